@@ -1,0 +1,187 @@
+"""CPU: the oracle restatement reproduces the reference-generated golden fixtures.
+
+Bit-exact for spikes, counts and (dyadic-weight) membranes; tolerance (stated per assert) for
+gradients, fractional-weight splats and loss values.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import encodings as oenc
+from oracle import firenet as ofn
+from oracle import iwe as oiwe
+from oracle import lif as olif
+from oracle import loss as oloss
+from snnflow_testutil import load_golden
+
+T = torch.from_numpy
+
+LAYER_FIXTURES = ["layer_ff_hard_arctan", "layer_ff_soft_super_res", "layer_rec_hard_arctan",
+                  "layer_rec_soft_triangle", "layer_rec_nodetach", "layer_head_counts", "layer_ff_c32",
+                  "layer_rec_c32", "layer_rec_c32_rand"]
+
+
+def run_layer(g, manual_backward=False):
+    rec, hard, detach, has_res = [bool(v) for v in g["meta"]]
+    act = str(g["activation"])
+    x = T(g["x"]).clone().requires_grad_(True)
+    w_ff = T(g["w_ff"]).clone().requires_grad_(True)
+    w_rec = T(g["w_rec"]).clone().requires_grad_(True) if rec else None
+    leak = T(g["leak"]).clone().requires_grad_(True)
+    thresh = T(g["thresh"]).clone().requires_grad_(True)
+    v = z = None
+    vs, zs, outs, loss = [], [], [], 0
+    for t in range(x.shape[0]):
+        out, v, z, _ = olif.lif_step(x[t], w_ff, leak, thresh, v, z, w_rec,
+                                     T(g["residual"][t]) if has_res else None,
+                                     hard_reset=hard, detach=detach, activation=act)
+        vs.append(v); zs.append(z); outs.append(out)
+        loss = loss + (out * T(g["gout"][t])).sum()
+    loss = loss + (v * T(g["gv_last"])).sum()
+    loss.backward()
+    return dict(v=torch.stack(vs), z=torch.stack(zs), out=torch.stack(outs), g_x=x.grad, dw_ff=w_ff.grad,
+                dw_rec=None if w_rec is None else w_rec.grad, dleak=leak.grad, dthresh=thresh.grad)
+
+
+@pytest.mark.parametrize("name", LAYER_FIXTURES)
+def test_layer_forward_backward(name):
+    g = load_golden(name)
+    r = run_layer(g)
+    exact = not name.endswith("_rand")
+    if exact:
+        assert np.array_equal(r["z"].detach().numpy(), g["z"])
+        assert np.array_equal(r["v"].detach().numpy(), g["v"])
+        assert np.array_equal(r["out"].detach().numpy(), g["out"])
+    else:
+        np.testing.assert_allclose(r["v"].detach().numpy(), g["v"], rtol=1e-5, atol=1e-6)
+    for k in ("g_x", "dw_ff", "dw_rec", "dleak", "dthresh"):
+        if r[k] is None:
+            continue
+        np.testing.assert_allclose(r[k].numpy(), g[k], rtol=1e-4, atol=1e-5, err_msg=k)
+
+
+@pytest.mark.parametrize("name", LAYER_FIXTURES)
+def test_layer_manual_backward_recurrences(name):
+    """The hand-derived BPTT recurrences (what the CUDA kernel implements) match reference autograd."""
+    g = load_golden(name)
+    rec, hard, detach, has_res = [bool(v) for v in g["meta"]]
+    act = str(g["activation"])
+    x, w_ff = T(g["x"]), T(g["w_ff"])
+    w_rec = T(g["w_rec"]) if rec else None
+    lam, theta = T(g["lam"]), T(g["theta"])
+    v_all, z_all = T(g["v"]), T(g["z"])
+    nT = x.shape[0]
+    zero = torch.zeros_like(v_all[0])
+    g_v, g_z_next = T(g["gv_last"]).clone(), zero.clone()
+    acc = dict(dw_ff=0, dw_rec=0, dlam=0, dtheta=0)
+    gxs = [None] * nT
+    for t in reversed(range(nT)):
+        v_in = v_all[t - 1] if t > 0 else zero
+        z_in = z_all[t - 1] if t > 0 else zero
+        import torch.nn.functional as F
+        cur = F.conv2d(x[t], w_ff, padding=1) + (F.conv2d(z_in, w_rec, padding=1) if rec else 0)
+        b = olif.lif_step_backward(x[t], w_ff, w_rec, lam, theta, v_in, z_in, v_all[t], cur,
+                                   T(g["gout"][t]) + g_z_next, g_v, hard_reset=hard, detach=detach, activation=act)
+        gxs[t] = b["g_x"]
+        g_v, g_z_next = b["g_v_in"], b["g_z_in"]
+        for k in acc:
+            if b[k] is not None:
+                acc[k] = acc[k] + b[k]
+    np.testing.assert_allclose(torch.stack(gxs).numpy(), g["g_x"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(acc["dw_ff"].numpy(), g["dw_ff"], rtol=1e-4, atol=1e-5)
+    if rec:
+        np.testing.assert_allclose(acc["dw_rec"].numpy(), g["dw_rec"], rtol=1e-4, atol=1e-5)
+    lamv = lam.reshape(-1)
+    dleak = acc["dlam"] * lamv * (1 - lamv)
+    dthresh = acc["dtheta"] * (T(g["thresh"]).reshape(-1) >= 0.01).float()
+    np.testing.assert_allclose(dleak.numpy(), g["dleak"].reshape(-1), rtol=2e-4, atol=1e-5)
+    np.testing.assert_allclose(dthresh.numpy(), g["dthresh"].reshape(-1), rtol=2e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["net_firenet_c8", "net_fireflownet_c8", "net_firenet_c32"])
+def test_network_forward(name):
+    g = load_golden(name)
+    params = {k[len("param."):]: T(v) for k, v in g.items() if k.startswith("param.")}
+    cnt = T(g["cnt"])
+    states = [None] * 7
+    with torch.no_grad():
+        for t in range(cnt.shape[0]):
+            flow, states, spikes = ofn.forward(params, cnt[t], states)
+            assert np.array_equal(flow.numpy(), g["flow"][t])
+            act = [float((cnt[t] != 0).float().mean())] + [float((s != 0).float().mean()) for s in spikes]
+            np.testing.assert_allclose(act, g["activity"][t][:8], rtol=0, atol=1e-12)
+    for i, (v, z) in enumerate(states):
+        assert np.array_equal(v.numpy(), g[f"state{i}"][0])
+        assert np.array_equal(z.numpy(), g[f"state{i}"][1])
+    # the fixture must exercise every layer (default init goes silent)
+    assert (g["activity"][-1][1:8] > 0.01).all(), g["activity"][-1]
+
+
+def test_encodings():
+    g = load_golden("encode_small")
+    xs, ys, ts, ps = (T(g[k]) for k in ("xs", "ys", "ts", "ps"))
+    H, W = g["cnt"].shape[1:]
+    cnt = oenc.events_to_channels(xs, ys, ps, (H, W)).numpy()
+    assert np.array_equal(cnt, g["cnt"])
+    assert np.array_equal(oenc.events_to_channels_np(g["xs"], g["ys"], g["ps"], (H, W)), g["cnt"])
+    assert cnt.sum() == len(g["xs"])
+    assert np.array_equal(oenc.events_to_image(xs, ys, ps.abs(), (H, W), accumulate=False).numpy(), g["mask"])
+    assert np.array_equal(oenc.events_to_image(xs, ys, ps, (H, W)).numpy(), g["img_acc"])
+    for key, nb, rnd in (("voxel5", 5, False), ("voxel2", 2, False), ("voxel5_round", 5, True)):
+        np.testing.assert_allclose(oenc.events_to_voxel(xs, ys, ts, ps, nb, (H, W), rnd).numpy(), g[key],
+                                   rtol=1e-6, atol=1e-6)
+
+
+def test_encodings_empty():
+    g = load_golden("encode_empty")
+    e = torch.zeros(0)
+    assert np.array_equal(oenc.events_to_channels(e, e, e, (8, 8)).numpy(), g["cnt"])
+    assert np.array_equal(oenc.events_to_voxel(e, e, e, e, 5, (8, 8)).numpy(), g["voxel5"])
+
+
+@pytest.mark.parametrize("name", ["iwe_rand", "iwe_zero_flow", "iwe_fractional"])
+def test_iwe(name):
+    g = load_golden(name)
+    H, W, S = [int(v) for v in g["params"]]
+    ev, pm = T(g["events"]), T(g["pol_mask"])
+    flow = T(g["flow"]).clone().requires_grad_(True)
+    ef = oiwe.gather_event_flow(flow, ev, (H, W))
+    assert np.array_equal(ef.detach().numpy(), g["ev_flow"])
+    for tag, tref, tsw in (("fw", 3, ev[:, :, 0:1]), ("bw", 0, 3 - ev[:, :, 0:1])):
+        idx, w = oiwe.interpolation(ev, ef, tref, (H, W), S)
+        assert np.array_equal(idx.detach().numpy(), g[f"{tag}_idx"])
+        np.testing.assert_allclose(w.detach().numpy(), g[f"{tag}_w"], rtol=0, atol=0)
+        img = oiwe.warp_images(ev, ef, pm, tref, (H, W), S, ts_weight=tsw)
+        np.testing.assert_allclose(img.detach().numpy(), g[f"{tag}_img"], rtol=1e-6, atol=1e-6)
+        flow.grad = None
+        (img * T(g[f"{tag}_gimg"])).sum().backward(retain_graph=True)
+        np.testing.assert_allclose(flow.grad.numpy(), g[f"{tag}_gflow"], rtol=1e-5, atol=1e-5)
+    ev1 = ev.clone()
+    ev1[:, :, 0] /= 3.0
+    with torch.no_grad():
+        for key, rnd in (("pol_iwe_round", True), ("pol_iwe_bilinear", False)):
+            out = oiwe.pol_iwe(flow, ev1, (H, W), pm[:, :, 0:1], pm[:, :, 1:2], S, rnd)
+            np.testing.assert_allclose(out.numpy(), g[key], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["train_firenet_c8", "train_fireflownet_c8_mask"])
+def test_train_window(name):
+    g = load_golden(name)
+    C, B, H, W, nT, n = [int(v) for v in g["dims"]]
+    params = {k[len("param."):]: T(v).clone().requires_grad_(True) for k, v in g.items() if k.startswith("param.")
+              if v.dtype == np.float32 and v.ndim > 0}
+    lossf = oloss.EventWarpingOracle((H, W), 0.001, mask_output=bool(g["mask_output"]))
+    states, flows = [None] * 7, []
+    for t in range(nT):
+        flow, states, _ = ofn.forward(params, T(g[f"cnt{t}"]), states)
+        flow.retain_grad()
+        flows.append(flow)
+        lossf.associate(flow, T(g[f"events{t}"]).clone(), T(g[f"pol{t}"]), T(g[f"mask{t}"]))
+    loss = lossf()
+    loss.backward()
+    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=1e-6)
+    np.testing.assert_allclose(torch.stack(flows).detach().numpy(), g["flow"], rtol=0, atol=0)
+    np.testing.assert_allclose(torch.stack([f.grad for f in flows]).numpy(), g["gflow"], rtol=1e-5, atol=1e-7)
+    for k, p in params.items():
+        if "grad." + k in g:
+            np.testing.assert_allclose(p.grad.numpy(), g["grad." + k], rtol=1e-4, atol=1e-6, err_msg=k)
