@@ -1,0 +1,154 @@
+/*
+ * snnflow.h - C ABI of the B200-native spiking-FireNet hot path (libsnnflow.so).
+ *
+ * This is the drop-in boundary: plain device pointers, sizes and a CUDA stream; no torch types.
+ * Every buffer (inputs, outputs, workspace) is owned and allocated by the caller; the library never
+ * allocates device memory, never synchronises the stream and keeps no mutable global state apart from
+ * the thread-local last-error string.  All tensors are fp32, contiguous, NCHW unless stated.  All
+ * functions return 0 on success and a negative SNNFLOW_E* code on failure (the message is available
+ * from snnflow_last_error()).  There is no CPU fallback.
+ *
+ * The reference (LSquarzoni/SNN_Event-based_Optical_Flow) has no FFI for this path - it is pure
+ * PyTorch - so each entry point cites the Python function it replaces (paths relative to the
+ * reference root).  The reference's only native-plugin convention is the libtorch custom op of
+ * ONNX_LIF_operator/src/lif_op.cpp:71-83; INTEGRATION.md shows the ctypes binding a maintainer adds.
+ */
+#ifndef SNNFLOW_H_
+#define SNNFLOW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNNFLOW_ABI_VERSION 1
+
+/* error codes */
+#define SNNFLOW_OK 0
+#define SNNFLOW_EINVAL (-1)   /* bad argument (null pointer, unsupported size) */
+#define SNNFLOW_ECUDA (-2)    /* a CUDA runtime call / kernel launch failed    */
+#define SNNFLOW_EWORKSPACE (-3) /* workspace too small                         */
+
+/* flags for the ConvLIF entry points */
+#define SNNFLOW_HARD_RESET 1u   /* v' = v*lam*(1-z) + (1-lam)*I ; else soft: v' = v*lam + (1-lam)*I - z*theta */
+#define SNNFLOW_DETACH_RESET 2u /* reset path does not carry gradient (spiking_submodules.py:139-140)      */
+#define SNNFLOW_NO_TENSOR_CORES 4u /* force the exact-fp32 CUDA-core convolution                           */
+
+/* surrogate gradient kinds (models/spiking_util.py) */
+#define SNNFLOW_SG_ARCTAN 0     /* 1/(1+w*u^2)      spiking_util.py:92 */
+#define SNNFLOW_SG_SUPERSPIKE 1 /* 1/(1+w*|u|)^2    spiking_util.py:42 */
+#define SNNFLOW_SG_TRIANGLE 2   /* relu(1-w*|u|)    spiking_util.py:78 */
+
+typedef void* snnflow_stream_t; /* cudaStream_t */
+
+int snnflow_abi_version(void);
+const char* snnflow_last_error(void);
+/* number of kernels this library has launched in the calling process (for bench accounting) */
+uint64_t snnflow_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * ConvLIF / ConvLIFRecurrent forward, one layer-step.
+ * Replaces ConvLIF.forward (models/spiking_submodules.py:121-151) and ConvLIFRecurrent.forward
+ * (:265-300): 3x3 conv (stride 1, pad 1, no bias) of x with w_ff [+ 3x3 conv of z_in with w_rec],
+ * leak, delayed reset, threshold, spike - fused in one kernel.
+ *   x [B,Cin,H,W]; w_ff [C,Cin,3,3]; w_rec [C,C,3,3] or NULL (feed-forward cell)
+ *   v_in, z_in [B,C,H,W] or both NULL (= zeros, :128-129)
+ *   lam [C] = sigmoid(leak), theta [C] = clamp_min(thresh, 0.01)      (:133,:136; computed by caller)
+ *   residual [B,C,H,W] or NULL; out [B,C,H,W] or NULL: out = z_out + residual (:151)
+ *   v_out, z_out [B,C,H,W]; cur_out [B,C,H,W] or NULL: the input current I, saved for the backward
+ * Rounding order follows the reference exactly (separately rounded mul/add, strict '>' compare).
+ * --------------------------------------------------------------------------------------------- */
+int snnflow_convlif_fwd(const float* x, const float* w_ff, const float* w_rec, const float* v_in,
+                        const float* z_in, const float* lam, const float* theta, const float* residual,
+                        float* v_out, float* z_out, float* out, float* cur_out, int B, int Cin, int C, int H,
+                        int W, unsigned flags, snnflow_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ConvLIF / ConvLIFRecurrent backward, one layer-step of BPTT.
+ * Replaces the autograd graph of the forward above incl. ArctanSpike/SuperSpike/TriangleSpike
+ * .backward (models/spiking_util.py:38-43,74-79,88-93).  Saved tensors: x, v_in, z_in (may be NULL =
+ * zeros), v_out, cur (from cur_out).  Incoming: g_out (grad of `out`, may be NULL), g_v_out, g_z_out
+ * (grads of the returned state, may be NULL).  Outgoing: g_x (NULL = not needed), g_v_in, g_z_in
+ * (NULL allowed when w_rec == NULL and DETACH_RESET).  dw_ff / dw_rec / dlam / dtheta are ACCUMULATED
+ * into (+=), in a fixed order (run-to-run deterministic).  dlam/dtheta are w.r.t. the effective
+ * lam/theta; the caller applies the sigmoid / clamp chain rule.
+ * workspace: snnflow_convlif_bwd_workspace_bytes() bytes, 256-byte aligned.
+ * --------------------------------------------------------------------------------------------- */
+size_t snnflow_convlif_bwd_workspace_bytes(int B, int Cin, int C, int H, int W, int recurrent);
+int snnflow_convlif_bwd(const float* x, const float* w_ff, const float* w_rec, const float* v_in,
+                        const float* z_in, const float* v_out, const float* cur, const float* lam,
+                        const float* theta, const float* g_out, const float* g_v_out, const float* g_z_out,
+                        float* g_x, float* g_v_in, float* g_z_in, float* dw_ff, float* dw_rec, float* dlam,
+                        float* dtheta, void* workspace, size_t workspace_bytes, int B, int Cin, int C, int H,
+                        int W, unsigned flags, int surrogate, float act_width, snnflow_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Flow prediction head: flow = tanh(conv1x1(x, w) + b)   (models/submodules.py:96-113 with
+ * kernel_size=1, activation="tanh"; LIFFireNet.pred, models/model.py:105-107,182).
+ *   x [B,C,H,W]; w [2,C]; b [2]; flow [B,2,H,W]
+ * Backward: g_x [B,C,H,W] (overwritten), dw [2,C] and db [2] accumulated (+=).
+ * workspace for the backward: snnflow_pred_bwd_workspace_bytes().
+ * --------------------------------------------------------------------------------------------- */
+int snnflow_pred_fwd(const float* x, const float* w, const float* b, float* flow, int B, int C, int H, int W,
+                     snnflow_stream_t stream);
+size_t snnflow_pred_bwd_workspace_bytes(int B, int C, int H, int W);
+int snnflow_pred_bwd(const float* x, const float* w, const float* flow, const float* g_flow, float* g_x,
+                     float* dw, float* db, void* workspace, size_t workspace_bytes, int B, int C, int H, int W,
+                     snnflow_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Event encodings (dataloader/encodings.py).  xs, ys, ts, ps: [N] fp32 device arrays (integer-valued
+ * coordinates, truncated like .long()); events outside the sensor are ignored.
+ * encode_cnt   : events_to_channels (:70-85)  -> out [2,H,W]  per-polarity counts (exact integers)
+ * encode_image : events_to_image (:30-45)     -> out [H,W];   accumulate=0 keeps the LAST event's value
+ *                per pixel (CPU index_put_ order); scratch = H*W int32 (only for accumulate=0)
+ * encode_voxel : events_to_voxel (:48-67)     -> out [nb,H,W]; deterministic: accumulated in 64-bit
+ *                fixed point (2^-32 resolution); scratch = nb*H*W int64
+ * All outputs are overwritten (zero-initialised inside).  batch variants take B independent windows
+ * of equal length N laid out [B,N] -> out [B,...].
+ * --------------------------------------------------------------------------------------------- */
+int snnflow_encode_cnt(const float* xs, const float* ys, const float* ps, float* out, int64_t N, int B, int H,
+                       int W, snnflow_stream_t stream);
+int snnflow_encode_image(const float* xs, const float* ys, const float* ps, float* out, int32_t* scratch,
+                         int64_t N, int H, int W, int accumulate, snnflow_stream_t stream);
+int snnflow_encode_voxel(const float* xs, const float* ys, const float* ts, const float* ps, float* out,
+                         int64_t* scratch, int64_t N, int num_bins, int H, int W, int round_ts,
+                         snnflow_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Image of warped events (utils/iwe.py, loss/flow.py).
+ * events [B,N,4] = (ts, y, x, p); flow [B,2,H,W] (channel 0 = x, 1 = y); ev_flow [B,N,2] = (fy, fx).
+ *
+ * flow_gather_fwd : per-event flow lookup of loss/flow.py:66-81 / utils/iwe.py:110-120; the flat
+ *   index is formed in fp32 as y*W + x and truncated, exactly like the reference.
+ * flow_gather_bwd : its adjoint, g_flow [B,2,H,W] += scatter(g_ev_flow)  (g_flow must be initialised).
+ *
+ * iwe_splat_fwd : get_interpolation (utils/iwe.py:20-71) + interpolate (:74-93) fused: warps every
+ *   event to tref, computes the 4 bilinear corners (or the rounded location when round_idx != 0),
+ *   purges out-of-range corners and accumulates into `n_img` images per sample:
+ *     img 0: sum w * pol_mask[..,0]          img 1: sum w * pol_mask[..,1]
+ *     img 2: sum w * tsw * pol_mask[..,0]    img 3: sum w * tsw * pol_mask[..,1]     (n_img == 4)
+ *   with tsw = ts (ts_mode 1) or ts_ref - ts (ts_mode 2): the four images of one direction of the
+ *   contrast loss (loss/flow.py:199-213, :232-246); n_img == 2 is compute_pol_iwe (utils/iwe.py:133-154).
+ *   out [B,n_img,H,W] is overwritten.  Accumulation is in 64-bit fixed point (deterministic);
+ *   scratch = B*n_img*H*W int64.
+ * iwe_splat_bwd : gradient w.r.t. ev_flow given g_img [B,n_img,H,W], with the reference's autograd
+ *   semantics (abs'(0) = 0; the max(0, 0) tie passes half the gradient).  g_ev_flow [B,N,2] overwritten.
+ * --------------------------------------------------------------------------------------------- */
+int snnflow_flow_gather_fwd(const float* flow, const float* events, float* ev_flow, int B, int64_t N, int H,
+                            int W, snnflow_stream_t stream);
+int snnflow_flow_gather_bwd(const float* g_ev_flow, const float* events, float* g_flow, int B, int64_t N, int H,
+                            int W, snnflow_stream_t stream);
+int snnflow_iwe_splat_fwd(const float* events, const float* ev_flow, const float* pol_mask, float* out,
+                          int64_t* scratch, int B, int64_t N, int H, int W, float tref, float flow_scaling,
+                          int n_img, int ts_mode, float ts_ref, int round_idx, snnflow_stream_t stream);
+int snnflow_iwe_splat_bwd(const float* events, const float* ev_flow, const float* pol_mask, const float* g_img,
+                          float* g_ev_flow, int B, int64_t N, int H, int W, float tref, float flow_scaling,
+                          int n_img, int ts_mode, float ts_ref, snnflow_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNNFLOW_H_ */

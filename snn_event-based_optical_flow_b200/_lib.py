@@ -1,0 +1,88 @@
+"""ctypes binding of libsnnflow.so (include/snnflow.h).  No fallback: a missing library is an error."""
+import ctypes
+import os
+from ctypes import c_float, c_int, c_int64, c_size_t, c_uint, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsnnflow.so")
+
+HARD_RESET = 1
+DETACH_RESET = 2
+NO_TENSOR_CORES = 4
+SURROGATE_ID = {"arctanspike": 0, "superspike": 1, "trianglespike": 2}
+
+P = c_void_p
+_PROTOS = {
+    "snnflow_abi_version": (c_int, []),
+    "snnflow_last_error": (ctypes.c_char_p, []),
+    "snnflow_launch_count": (c_uint64, []),
+    "snnflow_convlif_fwd": (c_int, [P] * 12 + [c_int] * 5 + [c_uint, P]),
+    "snnflow_convlif_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
+    "snnflow_convlif_bwd": (c_int, [P] * 19 + [P, c_size_t] + [c_int] * 5 + [c_uint, c_int, c_float, P]),
+    "snnflow_pred_fwd": (c_int, [P] * 4 + [c_int] * 4 + [P]),
+    "snnflow_pred_bwd_workspace_bytes": (c_size_t, [c_int] * 4),
+    "snnflow_pred_bwd": (c_int, [P] * 7 + [P, c_size_t] + [c_int] * 4 + [P]),
+    "snnflow_encode_cnt": (c_int, [P] * 4 + [c_int64, c_int, c_int, c_int, P]),
+    "snnflow_encode_image": (c_int, [P] * 5 + [c_int64, c_int, c_int, c_int, P]),
+    "snnflow_encode_voxel": (c_int, [P] * 6 + [c_int64, c_int, c_int, c_int, c_int, P]),
+    "snnflow_flow_gather_fwd": (c_int, [P] * 3 + [c_int, c_int64, c_int, c_int, P]),
+    "snnflow_flow_gather_bwd": (c_int, [P] * 3 + [c_int, c_int64, c_int, c_int, P]),
+    "snnflow_iwe_splat_fwd": (c_int, [P] * 5 + [c_int, c_int64, c_int, c_int, c_float, c_float, c_int, c_int, c_float,
+                                                c_int, P]),
+    "snnflow_iwe_splat_bwd": (c_int, [P] * 5 + [c_int, c_int64, c_int, c_int, c_float, c_float, c_int, c_int, c_float,
+                                                P]),
+}
+
+_lib = None
+
+
+class SnnflowError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    return sorted(_PROTOS)
+
+
+def lib():
+    """Load libsnnflow.so once.  Raises if it has not been built (python __graft_entry__.py / build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise SnnflowError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().snnflow_last_error().decode(errors="replace")
+        raise SnnflowError(f"{what} failed ({rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  The tensor must be a contiguous fp32/int CUDA tensor."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise SnnflowError("snnflow kernels need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise SnnflowError("snnflow kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(lib().snnflow_launch_count())

@@ -1,0 +1,76 @@
+// Shared helpers for the snnflow CUDA translation units (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/snnflow.h"
+
+namespace snnflow {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return SNNFLOW_ECUDA;
+  }
+  count_launch();
+  return SNNFLOW_OK;
+}
+
+#define SNNFLOW_REQUIRE(cond, msg)                    \
+  do {                                                \
+    if (!(cond)) {                                    \
+      snnflow::set_error("%s: %s", __func__, msg);    \
+      return SNNFLOW_EINVAL;                          \
+    }                                                 \
+  } while (0)
+
+#define SNNFLOW_CUDA(call)                                                   \
+  do {                                                                       \
+    cudaError_t e__ = (call);                                                \
+    if (e__ != cudaSuccess) {                                                \
+      snnflow::set_error("%s: %s", #call, cudaGetErrorString(e__));          \
+      return SNNFLOW_ECUDA;                                                  \
+    }                                                                        \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// number of SMs of the current device (cached)
+int sm_count();
+
+// ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, bool valid) {
+  unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  int sz = valid ? 4 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// surrogate gradient d spike / d u  (models/spiking_util.py:42,78,92)
+__device__ __forceinline__ float surrogate(float u, float width, int kind) {
+  if (kind == SNNFLOW_SG_ARCTAN) return 1.0f / (1.0f + width * u * u);
+  if (kind == SNNFLOW_SG_SUPERSPIKE) {
+    float d = 1.0f + width * fabsf(u);
+    return 1.0f / (d * d);
+  }
+  return fmaxf(1.0f - width * fabsf(u), 0.0f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace snnflow

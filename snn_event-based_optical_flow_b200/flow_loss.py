@@ -1,0 +1,107 @@
+"""Contrast-maximisation loss: host-side mirror of loss/flow.py:28-303 (EventWarping).
+
+Same constructor, ``event_flow_association`` / ``reset`` / ``num_events`` / ``forward`` behaviour as the
+reference (including the in-place timestamp shift of the event list, :91).  The eight
+``interpolate`` scatters of the reference forward (:199-213, :232-246) are two fused
+``snnflow_iwe_splat_fwd`` launches; their backward is ``snnflow_iwe_splat_bwd``.  The arithmetic after
+the splat (:214-301) is a handful of small torch ops on [B,4,H,W] images.
+"""
+import torch
+
+from .iwe import gather_event_flow, warp_images
+
+
+class EventWarping(torch.nn.Module):
+    def __init__(self, config, device, flow_scaling=None, loss_scaling=True):
+        super().__init__()
+        self.loss_scaling = loss_scaling
+        self.res = config["loader"]["resolution"]
+        self.flow_scaling = flow_scaling if flow_scaling is not None else max(config["loader"]["resolution"])
+        self.weight = config["loss"]["flow_regul_weight"]
+        self.smoothing_mask = config["model"].get("mask_output", False)
+        self.overwrite_intermediate = config["loss"].get("overwrite_intermediate", False)
+        if self.overwrite_intermediate:
+            raise NotImplementedError("snnflow EventWarping: overwrite_intermediate=True is not covered")
+        self.device = device
+        self.reset()
+
+    def reset(self):
+        self._passes = 0
+        self._event_list = None
+        self._flow_list = None
+        self._flow_maps_x = None
+        self._flow_maps_y = None
+        self._pol_mask_list = None
+        self._event_mask = None
+
+    @property
+    def num_events(self):
+        return 0 if self._event_list is None else self._event_list.shape[1]
+
+    @property
+    def event_mask(self):
+        return self._event_mask[:, -1:, :, :]
+
+    def event_flow_association(self, flow_list, event_list, pol_mask, event_mask):
+        """loss/flow.py:58-121."""
+        if self._flow_list is None:
+            self._flow_list, self._flow_maps_x, self._flow_maps_y = [], [], []
+        for i, flow in enumerate(flow_list):
+            ev_flow = gather_event_flow(flow, event_list, self.res)
+            if i == len(self._flow_list):
+                self._flow_list.append(ev_flow)
+                self._flow_maps_x.append(flow[:, 0:1])
+                self._flow_maps_y.append(flow[:, 1:2])
+            else:
+                self._flow_list[i] = torch.cat([self._flow_list[i], ev_flow], dim=1)
+                self._flow_maps_x[i] = torch.cat([self._flow_maps_x[i], flow[:, 0:1]], dim=1)
+                self._flow_maps_y[i] = torch.cat([self._flow_maps_y[i], flow[:, 1:2]], dim=1)
+        if self._event_list is None:
+            self._event_list, self._pol_mask_list, self._event_mask = event_list, pol_mask, event_mask
+        else:
+            event_list[:, :, 0:1] += self._passes
+            self._event_list = torch.cat([self._event_list, event_list], dim=1)
+            self._pol_mask_list = torch.cat([self._pol_mask_list, pol_mask], dim=1)
+            self._event_mask = torch.cat([self._event_mask, event_mask], dim=1)
+        self._passes += 1
+
+    def _direction(self, ev_flow, tref, ts_mode, max_ts):
+        img = warp_images(self._event_list, ev_flow, self._pol_mask_list, tref, self.res, self.flow_scaling,
+                          ts_mode=ts_mode, ts_ref=max_ts)
+        cnt_p, cnt_n = img[:, 0:1], img[:, 1:2]
+        ts_p = img[:, 2:3] / (cnt_p + 1e-9) / max_ts                       # loss/flow.py:214-217
+        ts_n = img[:, 3:4] / (cnt_n + 1e-9) / max_ts
+        B = img.shape[0]
+        loss = (ts_p.reshape(B, -1) ** 2).sum(1) + (ts_n.reshape(B, -1) ** 2).sum(1)
+        if self.loss_scaling:
+            tot = cnt_p + cnt_n                                            # :224-227 (zero entries keep their grad path)
+            loss = loss / torch.where(tot > 0, torch.ones_like(tot), tot).reshape(B, -1).sum(1)
+        return loss.sum()
+
+    def _smoothness(self, fx, fy):
+        def charb(a, b):
+            return torch.sqrt((a + b) ** 2 + 1e-6)
+
+        terms = [
+            charb(fx[:, :, :, :-1] - fx[:, :, :, 1:], fy[:, :, :, :-1] - fy[:, :, :, 1:]),
+            charb(fx[:, :, :-1, :] - fx[:, :, 1:, :], fy[:, :, :-1, :] - fy[:, :, 1:, :]),
+            charb(fx[:, :, :-1, :-1] - fx[:, :, 1:, 1:], fy[:, :, :-1, :-1] - fy[:, :, 1:, 1:]),
+            charb(fx[:, :, 1:, :-1] - fx[:, :, :-1, 1:], fy[:, :, 1:, :-1] - fy[:, :, :-1, 1:]),
+            charb(fx[:, :-1] - fx[:, 1:], fy[:, :-1] - fy[:, 1:]),
+        ]
+        if self.smoothing_mask:
+            m = self._event_mask
+            masks = [m[:, :, :, :-1] * m[:, :, :, 1:], m[:, :, :-1, :] * m[:, :, 1:, :],
+                     m[:, :, :-1, :-1] * m[:, :, 1:, 1:], m[:, :, 1:, :-1] * m[:, :, :-1, 1:], m[:, :-1] * m[:, 1:]]
+            terms = [a * b for a, b in zip(masks, terms)]
+        total = terms[0].sum() + terms[1].sum() + terms[2].sum() + terms[3].sum() + terms[4].sum()
+        return total / 5 / fx.shape[1]
+
+    def forward(self):
+        max_ts = self._passes
+        loss = 0
+        for i in range(len(self._flow_list)):
+            fw = self._direction(self._flow_list[i], max_ts, 1, max_ts)    # loss/flow.py:197-228
+            bw = self._direction(self._flow_list[i], 0, 2, max_ts)         # :230-261
+            loss = loss + fw + bw + self.weight * self._smoothness(self._flow_maps_x[i], self._flow_maps_y[i])
+        return loss / len(self._flow_list)

@@ -1,0 +1,104 @@
+"""LIFFireNet / LIFFireFlowNet: host-side mirror of models/model.py:29-207 and :387-554.
+
+On the GPU box the reference tree does not exist, so the benchmark and the GPU parity tests need
+the network container itself; this mirror keeps the reference's constructor (a ``unet_kwargs`` dict),
+the class-attribute seam ``head_neuron / ff_neuron / rec_neuron`` (models/model.py:37-39), the
+``states`` / ``detach_states`` / ``reset_states`` plumbing (:109-130), the layer order and the
+``{"flow": [flow], "activity": ...}`` return, and the reference's state_dict keys.  In a checkout that
+has the reference, the same cells drop into the reference's own classes:
+
+    class Net(models.model.LIFFireNet):
+        head_neuron = ff_neuron = snnflow.ConvLIF; rec_neuron = snnflow.ConvLIFRecurrent
+"""
+import torch
+import torch.nn as nn
+
+from .spiking_submodules import ConvLIF, ConvLIFRecurrent
+from .submodules import ConvLayer
+
+
+class LIFFireNet(nn.Module):
+    head_neuron = ConvLIF
+    ff_neuron = ConvLIF
+    rec_neuron = ConvLIFRecurrent
+    residual = False
+    num_recurrent_units = 7
+    w_scale_pred = 0.01
+
+    def __init__(self, unet_kwargs):
+        super().__init__()
+        self.num_bins = unet_kwargs["num_bins"]
+        self.encoding = unet_kwargs["encoding"]
+        self.norm_input = unet_kwargs.get("norm_input", False)
+        self.mask = unet_kwargs.get("mask_output", False)
+        C = unet_kwargs["base_num_channels"]
+        k = unet_kwargs["kernel_size"]
+        q = unet_kwargs.get("quantization", {})
+        # model.py never forwards `spiking_neuron` / `activations` to the cells;
+        # `neuron_kwargs` is this mirror's explicit way to set them (leak/thresh statistics etc.).
+        nk = dict(unet_kwargs.get("neuron_kwargs", {}))
+        mk = lambda cls, cin: cls(cin, C, k, quantization_config=q, **nk)
+        self.head = mk(self.head_neuron, self.num_bins)
+        self.G1 = mk(self.rec_neuron, C)
+        self.R1a = mk(self.ff_neuron, C)
+        self.R1b = mk(self.ff_neuron, C)
+        self.G2 = mk(self.rec_neuron, C)
+        self.R2a = mk(self.ff_neuron, C)
+        self.R2b = mk(self.ff_neuron, C)
+        self.pred = ConvLayer(C, out_channels=2, kernel_size=1, activation="tanh", w_scale=self.w_scale_pred,
+                              quantization_config=q)
+        self.reset_states()
+
+    # --- state plumbing (models/model.py:109-130) ---
+    @property
+    def states(self):
+        return [None if s is None else s.clone() for s in self._states]   # model_util.py:95-101
+
+    @states.setter
+    def states(self, states):
+        self._states = states
+
+    def detach_states(self):
+        self._states = [None if s is None else s.detach() for s in self._states]
+
+    def reset_states(self):
+        self._states = [None] * self.num_recurrent_units
+
+    def init_cropping(self, width, height):
+        pass
+
+    def forward(self, event_voxel=None, event_cnt=None, log=False, return_dict=True):
+        if self.encoding == "voxel":
+            x = event_voxel
+        elif self.encoding == "cnt" and self.num_bins == 2:
+            x = event_cnt
+        else:
+            raise AttributeError("Model error: Incorrect input encoding.")
+        if self.norm_input:                                               # model.py:165-170
+            nz = x != 0
+            mean, std = x[nz].mean(), x[nz].std()
+            x = x.clone()
+            x[nz] = (x[nz] - mean) / std
+        s = self._states
+        x1, s[0] = self.head(x, s[0])
+        x2, s[1] = self.G1(x1, s[1])
+        x3, s[2] = self.R1a(x2, s[2])
+        x4, s[3] = self.R1b(x3, s[3], residual=x2 if self.residual else 0)
+        x5, s[4] = self.G2(x4, s[4])
+        x6, s[5] = self.R2a(x5, s[5])
+        x7, s[6] = self.R2b(x6, s[6], residual=x5 if self.residual else 0)
+        flow = self.pred(x7)
+        if not return_dict:
+            return flow
+        activity = None
+        if isinstance(log, bool) and log:
+            names = ["0:input", "1:head", "2:G1", "3:R1a", "4:R1b", "5:G2", "6:R2a", "7:R2b", "8:pred"]
+            acts = torch.stack([t.detach().ne(0).float().mean() for t in (x, x1, x2, x3, x4, x5, x6, x7, flow)])
+            activity = dict(zip(names, acts.tolist()))                    # one host sync instead of nine
+        return {"flow": [flow], "activity": activity}
+
+
+class LIFFireFlowNet(LIFFireNet):
+    """Feed-forward variant: G1/G2 are plain ConvLIF cells (models/model.py:387-395)."""
+
+    rec_neuron = ConvLIF

@@ -1,0 +1,83 @@
+"""GPU parity: LIFFireNet / LIFFireFlowNet (7 fused layers + flow head) against the reference-generated
+network fixtures, and one full training window (forward, contrast loss, BPTT) against reference autograd."""
+import numpy as np
+import pytest
+import torch
+
+from snnflow_testutil import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def build_net(g, kind, C):
+    import snnflow_b200 as snnflow
+    cls = getattr(snnflow, kind)
+    net = cls(dict(num_bins=2, encoding="cnt", base_num_channels=C, kernel_size=3, mask_output=False)).cuda()
+    sd = {k[len("param."):]: dev(v) for k, v in g.items() if k.startswith("param.")}
+    net.load_state_dict(sd, strict=True)
+    return net
+
+
+@pytest.mark.parametrize("name,C", [("net_firenet_c8", 8), ("net_fireflownet_c8", 8), ("net_firenet_c32", 32)])
+def test_network_forward(name, C):
+    g = load_golden(name)
+    net = build_net(g, str(g["kind"]), C)
+    cnt = dev(g["cnt"])
+    with torch.no_grad():
+        for t in range(cnt.shape[0]):
+            o = net(None, cnt[t], log=True)
+            # flow goes through tanhf on the GPU vs the CPU's tanh: tolerance 1e-6 abs
+            np.testing.assert_allclose(o["flow"][0].cpu().numpy(), g["flow"][t], rtol=1e-5, atol=1e-6)
+            got = [o["activity"][k] for k in sorted(o["activity"])][:8]
+            np.testing.assert_allclose(got, g["activity"][t][:8], rtol=0, atol=1e-7)
+    for i, st in enumerate(net._states):
+        st = st.cpu().numpy()
+        assert np.array_equal(st[1], g[f"state{i}"][1]), f"layer {i}: spikes differ"
+        # lam = sigmoid(leak) is evaluated by torch on the GPU here (CPU in the fixture): allow 1-ulp-of-lam drift
+        np.testing.assert_allclose(st[0], g[f"state{i}"][0], rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["train_firenet_c8", "train_fireflownet_c8_mask"])
+def test_training_window(name):
+    import snnflow_b200 as snnflow
+    g = load_golden(name)
+    C, B, H, W, nT, n = [int(v) for v in g["dims"]]
+    net = build_net(g, str(g["kind"]), C)
+    mask_output = bool(g["mask_output"])
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": 0.001}, "model": {"mask_output": mask_output}}
+    lossf = snnflow.EventWarping(cfg, torch.device("cuda"))
+    flows = []
+    for t in range(nT):
+        out = net(None, dev(g[f"cnt{t}"]))
+        out["flow"][0].retain_grad()
+        flows.append(out["flow"][0])
+        lossf.event_flow_association(out["flow"], dev(g[f"events{t}"]), dev(g[f"pol{t}"]), dev(g[f"mask{t}"]))
+    loss = lossf()
+    loss.backward()
+    np.testing.assert_allclose(float(loss.detach()), float(g["loss"]), rtol=1e-5)
+    np.testing.assert_allclose(torch.stack(flows).detach().cpu().numpy(), g["flow"], rtol=1e-5, atol=1e-6)
+    gf = torch.stack([f.grad for f in flows]).cpu().numpy()
+    np.testing.assert_allclose(gf, g["gflow"], rtol=1e-4, atol=1e-5 * np.abs(g["gflow"]).max())
+    for k, p in net.named_parameters():
+        ref = g["grad." + k]
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ref, rtol=1e-4, atol=1e-4 * max(1e-3, np.abs(ref).max()),
+                                   err_msg=k)
+
+
+def test_state_plumbing():
+    import snnflow_b200 as snnflow
+    net = snnflow.LIFFireNet(dict(num_bins=2, encoding="cnt", base_num_channels=8, kernel_size=3)).cuda()
+    assert net.states == [None] * 7
+    x = torch.ones(1, 2, 16, 16, device="cuda")
+    net(None, x)
+    st = net.states
+    assert all(s.shape == (2, 1, 8, 16, 16) for s in st)
+    assert st[0].data_ptr() != net._states[0].data_ptr()      # clones, like model_util.copy_states
+    net.detach_states()
+    assert not any(s.requires_grad for s in net._states)
+    net.reset_states()
+    assert net._states == [None] * 7

@@ -179,7 +179,7 @@ def test_train_window(name):
         lossf.associate(flow, T(g[f"events{t}"]).clone(), T(g[f"pol{t}"]), T(g[f"mask{t}"]))
     loss = lossf()
     loss.backward()
-    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=1e-6)
+    np.testing.assert_allclose(float(loss.detach()), float(g["loss"]), rtol=1e-6)
     np.testing.assert_allclose(torch.stack(flows).detach().numpy(), g["flow"], rtol=0, atol=0)
     np.testing.assert_allclose(torch.stack([f.grad for f in flows]).numpy(), g["gflow"], rtol=1e-5, atol=1e-7)
     for k, p in params.items():
