@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py - LIFFireNet training throughput (samples/s) on the B200 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): LIFFireNet (C=32) training step with the event-warping contrast
+loss on synthetic UZH-FPV-shaped input: 128x128, batch 8 per GPU, 10 time bins x 1000 events per sample,
+clip 1.0, Adam.  One "step" = one optimizer step over one window (train_flow.py:232-279); "samples" are
+batch elements per window.  N > 1: data parallel, one process per GPU (torchrun), weak scaling (per-GPU
+batch fixed), SUM all-reduce of the flat gradient over NCCL.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident inputs, CUDA-event timed, max over ranks;
+`e2e` = the same step driven from pinned HOST buffers (H2D of the window's tensors and D2H of the loss inside
+the timed region); `roofline` = the dominant kernel of the step, timed live with CUDA events on its stream
+by the library's per-launch profiler; `cpu_baseline` = the CPU oracle port of the reference timed on this
+box's host cores on a bounded sample.  `--impl reference` times only that CPU path (rank 0).
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LIFFireNet train samples/s @128x128 (batch 8/GPU, 10 bins x 1000 events, IWE loss)"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--channels", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
+    ap.add_argument("--res", type=int, default=128)
+    ap.add_argument("--bins", type=int, default=10)
+    ap.add_argument("--events", type=int, default=1000, help="events per sample per bin")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {
+        "workload": f"LIFFireNet C={a.channels} train step, {a.res}x{a.res}, batch {a.batch}/GPU, {a.bins} bins x "
+                    f"{a.events} events/sample, EventWarping loss, clip 1.0, Adam (BASELINE.json configs[1])",
+        "global_batch": a.batch * n_gpus, "bins": a.bins, "events_per_sample_bin": a.events,
+        "resolution": [a.res, a.res], "channels": a.channels, "parallelism": f"dp{n_gpus}",
+        "params": "leak~N(0,1), thresh~N(0.3,0.1) (active network, SURVEY 0-5); random init",
+        "l2_policy": "no explicit flush: one step streams ~1.5 GB of saved activations (>> 126 MB L2) and the "
+                     "input windows rotate over a pool of 4",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data in the loader's layout (dataloader/base.py:261-278), built with torch on the CPU
+# ------------------------------------------------------------------------------------------------
+def make_window(a, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    T, B, N, H, W = a.bins, a.batch, a.events, a.res, a.res
+    xs = torch.randint(0, W, (T, B, N), generator=g).float()
+    ys = torch.randint(0, H, (T, B, N), generator=g).float()
+    ts = torch.sort(torch.rand(T, B, N, generator=g), dim=2).values
+    ts = (ts - ts.amin(2, keepdim=True)) / (ts.amax(2, keepdim=True) - ts.amin(2, keepdim=True))
+    ps = torch.randint(0, 2, (T, B, N), generator=g).float() * 2 - 1
+    lin = (ys.long() * W + xs.long())
+    cnt = torch.zeros(T, B, 2, H * W)
+    cnt[:, :, 0].scatter_add_(2, lin, (ps > 0).float())
+    cnt[:, :, 1].scatter_add_(2, lin, (ps < 0).float())
+    cnt = cnt.view(T, B, 2, H, W)
+    mask = (cnt.sum(2, keepdim=True) > 0).float()
+    return {
+        "event_cnt": cnt.contiguous(),
+        "event_list": torch.stack([ts, ys, xs, ps], dim=3).contiguous(),
+        "event_list_pol_mask": torch.stack([(ps > 0).float(), (ps < 0).float()], dim=3).contiguous(),
+        "event_mask": mask.contiguous(),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference (torch-CPU fp32, all host threads)
+# ------------------------------------------------------------------------------------------------
+def cpu_train_steps(a, n_steps, n_warm):
+    import torch
+    from oracle import firenet as ofn
+    from oracle.loss import EventWarpingOracle
+
+    torch.manual_seed(0)
+    params = ofn.init_params(a.channels, 2, recurrent=True, leak=(0.0, 1.0), thresh=(0.3, 0.1))
+    params = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    opt = torch.optim.Adam(params.values(), lr=2e-4)
+    lossf = EventWarpingOracle((a.res, a.res), 0.001)
+    states = [None] * 7
+    pool = [make_window(a, 100 + i) for i in range(2)]
+    times = []
+    for it in range(n_warm + n_steps):
+        w = pool[it % len(pool)]
+        t0 = time.perf_counter()
+        for t in range(a.bins):
+            flow, states, _ = ofn.forward(params, w["event_cnt"][t], states)
+            lossf.associate(flow, w["event_list"][t].clone(), w["event_list_pol_mask"][t], w["event_mask"][t])
+        loss = lossf()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
+        opt.step()
+        opt.zero_grad()
+        states = [(v.detach(), z.detach()) for v, z in states]
+        lossf.reset()
+        float(loss.detach())
+        if it >= n_warm:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def run_reference(a):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sec = cpu_train_steps(a, a.steps, a.warmup)
+    val = a.batch / sec
+    cores = torch.get_num_threads()
+    sample = f"{a.steps} full optimizer steps (batch {a.batch}, {a.bins} bins) of the same workload after {a.warmup} warm-up"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, 1),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU oracle port (torch-CPU fp32 restatement of the reference, oracle/firenet.py + oracle/loss.py); "
+                "the Python reference itself cannot travel to the GPU box",
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) running during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self._stop = [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, str(e)
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv:
+            self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.nv:
+            self.t.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    snnflow = importlib.import_module("snn_event-based_optical_flow_b200")
+    from snnflow_b200 import _lib
+    from snnflow_b200.train import TrainWindow
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    torch.manual_seed(0)   # identical replicas on every rank
+    net = snnflow.LIFFireNet(dict(num_bins=2, encoding="cnt", base_num_channels=a.channels, kernel_size=3,
+                                  neuron_kwargs=dict(leak=(0.0, 1.0), thresh=(0.3, 0.1)))).to(dev)
+    cfg = {"loader": {"resolution": [a.res, a.res]}, "loss": {"flow_regul_weight": 0.001}, "model": {"mask_output": False}}
+    lossf = snnflow.EventWarping(cfg, dev)
+    opt = torch.optim.Adam(net.parameters(), lr=2e-4)
+    tw = TrainWindow(net, lossf, opt, clip_grad=1.0)
+
+    host_pool = [{k: v.pin_memory() for k, v in make_window(a, 1000 * rank + i).items()} for i in range(4)]
+    dev_pool = [{k: v.to(dev) for k, v in w.items()} for w in host_pool]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_pool[0].values())
+
+    def step_resident(i):
+        w = dev_pool[i % len(dev_pool)]
+        # event_flow_association shifts event timestamps in place (loss/flow.py:91): work on a copy of the list
+        w = dict(w, event_list=w["event_list"].clone())
+        return tw.step(w)
+
+    def step_e2e(i):
+        hw = host_pool[i % len(host_pool)]
+        w = {k: v.to(dev, non_blocking=True) for k, v in hw.items()}
+        return float(tw.step(w).item())          # D2H of the loss, synchronises
+
+    # ---- device-resident timing ----
+    for i in range(a.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(a.steps):
+        loss = step_resident(i)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - l0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = a.batch * world * a.steps / (ms_total / 1e3)
+
+    # ---- end-to-end timing from pinned host buffers ----
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    ev0.record()
+    for i in range(a.steps):
+        last_loss = step_e2e(i)
+    ev1.record()
+    barrier()
+    ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = a.batch * world * a.steps / (float(ms2.item()) / 1e3)
+
+    # ---- per-kernel profile of two steps (live CUDA events on the launching stream) ----
+    roofline, kernels = None, None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        _lib.profile(True)
+        for i in range(2):
+            step_resident(i)
+        prof = _lib.profile_summary()
+        _lib.profile(False)
+        tot = sum(p["ms"] for p in prof.values()) or 1.0
+        kernels = {k: {"launches": p["launches"], "ms": round(p["ms"], 4), "share": round(p["ms"] / tot, 4),
+                       "GBps": round(p["bytes"] / (p["ms"] * 1e6), 1) if p["ms"] else None,
+                       "TFLOPs": round(p["flops"] / (p["ms"] * 1e9), 2) if p["ms"] else None}
+                   for k, p in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        top = max(prof, key=lambda k: prof[k]["ms"])
+        p = prof[top]
+        achieved = p["bytes"] / (p["ms"] * 1e6)   # GB/s
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+        except Exception:  # noqa: BLE001
+            pass
+        roofline = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
+                    "avg_launch_us": round(1e3 * p["ms"] / p["launches"], 2),
+                    "algorithmic_bytes_per_launch": p["bytes"] / p["launches"],
+                    "share_of_kernel_time": round(p["ms"] / tot, 4)}
+
+    # ---- eval (LIFFireFlowNet, 256x256, batch 16: BASELINE.json configs[2]) on rank 0's GPU, every rank ----
+    eval_info = None
+    if not a.no_eval:
+        eval_info = run_eval(a, snnflow, dev, world, barrier)
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        sec = cpu_train_steps(a, 2, 1)
+        cpu = {"value": a.batch / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"2 full optimizer steps (batch {a.batch}, {a.bins} bins, C={a.channels}) after 1 warm-up, "
+                         f"{sec:.2f} s/step"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "eval": eval_info,
+            "loss": last_loss,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_eval(a, snnflow, dev, world, barrier):
+    """eval frames/s: LIFFireFlowNet (feed-forward ConvLIF), 256x256, batch 16, no_grad (BASELINE configs[2])."""
+    import torch
+    import torch.distributed as dist
+    B, R, T = 16, 256, 10
+    torch.manual_seed(0)
+    net = snnflow.LIFFireFlowNet(dict(num_bins=2, encoding="cnt", base_num_channels=a.channels, kernel_size=3,
+                                      neuron_kwargs=dict(leak=(0.0, 1.0), thresh=(0.3, 0.1)))).to(dev)
+    g = torch.Generator().manual_seed(7)
+    cnt = torch.poisson(torch.full((T, B, 2, R, R), 0.06), generator=g).to(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for t in range(T):
+            net(None, cnt[t])
+        barrier()
+        ev0.record()
+        for rep in range(3):
+            for t in range(T):
+                net(None, cnt[t])
+        ev1.record()
+        barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    fps = B * world * 3 * T / (float(ms.item()) / 1e3)
+    return {"metric": "LIFFireFlowNet eval frames/s @256x256, batch 16/GPU", "value": fps, "unit": "frames/s",
+            "ms_per_forward": float(ms.item()) / (3 * T)}
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -47,6 +47,11 @@ int snnflow_abi_version(void);
 const char* snnflow_last_error(void);
 /* number of kernels this library has launched in the calling process (for bench accounting) */
 uint64_t snnflow_launch_count(void);
+/* Per-launch profiler: enable(1) clears old records and brackets every subsequent kernel launch with CUDA
+ * events on its own stream; summary() synchronises the device and writes one text line per kernel name,
+ * "name launches total_ms algorithmic_bytes algorithmic_flops".  Off by default (no events recorded). */
+int snnflow_profile_enable(int on);
+int snnflow_profile_summary(char* buf, size_t capacity);
 
 /* ---------------------------------------------------------------------------------------------
  * ConvLIF / ConvLIFRecurrent forward, one layer-step.

@@ -16,6 +16,8 @@ _PROTOS = {
     "snnflow_abi_version": (c_int, []),
     "snnflow_last_error": (ctypes.c_char_p, []),
     "snnflow_launch_count": (c_uint64, []),
+    "snnflow_profile_enable": (c_int, [c_int]),
+    "snnflow_profile_summary": (c_int, [ctypes.c_char_p, c_size_t]),
     "snnflow_convlif_fwd": (c_int, [P] * 12 + [c_int] * 5 + [c_uint, P]),
     "snnflow_convlif_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
     "snnflow_convlif_bwd": (c_int, [P] * 19 + [P, c_size_t] + [c_int] * 5 + [c_uint, c_int, c_float, P]),
@@ -86,3 +88,18 @@ def stream():
 
 def launch_count():
     return int(lib().snnflow_launch_count())
+
+
+def profile(on=True):
+    check(lib().snnflow_profile_enable(int(on)), "snnflow_profile_enable")
+
+
+def profile_summary():
+    """{kernel: dict(launches, ms, bytes, flops)} for the launches recorded since profile(True)."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().snnflow_profile_summary(buf, len(buf)), "snnflow_profile_summary")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms, by, fl = line.split()
+        out[name] = dict(launches=int(n), ms=float(ms), bytes=float(by), flops=float(fl))
+    return out

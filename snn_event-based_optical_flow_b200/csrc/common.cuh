@@ -10,6 +10,11 @@ namespace snnflow {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// Optional per-launch timing (snnflow_profile_enable): prof_begin records a CUDA event on the launching
+// stream before the kernel, prof_end one after it.  algo_bytes / algo_flops are the ALGORITHMIC traffic and
+// arithmetic of the launch (what DESIGN.md states per kernel), used for the roofline fractions in bench.py.
+void prof_begin(const char* name, cudaStream_t st, double algo_bytes, double algo_flops = 0.0);
+void prof_end();
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -18,6 +23,7 @@ inline int check_launch(const char* what) {
     return SNNFLOW_ECUDA;
   }
   count_launch();
+  prof_end();
   return SNNFLOW_OK;
 }
 

@@ -382,6 +382,11 @@ extern "C" int snnflow_convlif_fwd(const float* x, const float* w_ff, const floa
     attr_done = true;
   }
   dim3 grid(ceil_div(W, CT_W), ceil_div(H, CT_H), B * ceil_div(C, CT_CO));
+  {
+    const double px = (double)B * H * W;
+    const int planes = Cin + 2 * C + (v_in ? 2 * C : 0) + (out ? C : 0) + (residual ? C : 0) + (cur_out ? C : 0);
+    prof_begin("convlif_fwd_simt", (cudaStream_t)stream, 4.0 * px * planes, 18.0 * px * C * (Cin + (a.n_src == 2 ? C : 0)));
+  }
   convlif_fwd_simt_kernel<<<grid, CT_THREADS, CT_SMEM_BYTES, (cudaStream_t)stream>>>(a);
   return check_launch("convlif_fwd_simt_kernel");
 }
@@ -404,6 +409,10 @@ static int launch_dgrad(const float* g_cur, const float* w, int n_in_orig, float
     attr_done = true;
   }
   dim3 grid(ceil_div(W, CT_W), ceil_div(H, CT_H), B * ceil_div(n_in_orig, CT_CO));
+  {
+    const double px = (double)B * H * W;
+    prof_begin("dgrad_simt", st, 4.0 * px * (C + n_in_orig * (accumulate ? 2 : 1)), 18.0 * px * C * n_in_orig);
+  }
   conv3x3_plain_simt_kernel<<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(d);
   return check_launch("conv3x3_plain_simt_kernel");
 }
@@ -447,6 +456,10 @@ extern "C" int snnflow_convlif_bwd(const float* x, const float* w_ff, const floa
   // g_z_in gets the reset-path term here unless the recurrent dgrad overwrites it anyway
   p.write_gz = (g_z_in != nullptr) && !(recurrent && detach);
   p.surrogate = surrogate; p.width = act_width;
+  {
+    const int planes = 4 + (g_out ? 1 : 0) + (g_v_out ? 1 : 0) + (g_z_out ? 1 : 0) + (v_in ? 2 : 0) + (p.write_gz ? 1 : 0);
+    prof_begin("lif_bwd_pointwise", st, 4.0 * B * C * H * W * planes);
+  }
   convlif_bwd_pointwise_kernel<<<dim3(L.n_chunk, C, B), EW_THREADS, 0, st>>>(p);
   int rc = check_launch("convlif_bwd_pointwise_kernel");
   if (rc) return rc;
@@ -477,6 +490,11 @@ extern "C" int snnflow_convlif_bwd(const float* x, const float* w_ff, const floa
     WgradArgs ws1 = w;
     if (s == 1) { ws1.xsrc[0] = w.xsrc[1]; ws1.n_ci[0] = w.n_ci[1]; ws1.part[0] = w.part[1]; }
     dim3 grid(L.gx, ceil_div(C, WG_CO) * ceil_div(ws1.n_ci[0], WG_CI), 1);
+    {
+      const double px = (double)B * H * W;
+      prof_begin("wgrad_simt", st, 4.0 * px * (C + ws1.n_ci[0]) + 4.0 * L.gx * C * ws1.n_ci[0] * 9,
+                 18.0 * px * C * ws1.n_ci[0]);
+    }
     wgrad_simt_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(ws1);
     rc = check_launch("wgrad_simt_kernel");
     if (rc) return rc;
@@ -486,6 +504,7 @@ extern "C" int snnflow_convlif_bwd(const float* x, const float* w_ff, const floa
   r.wpart[1] = wpart1; r.wdst[1] = recurrent ? dw_rec : nullptr; r.wcount[1] = C * C * 9;
   r.n_wpart = L.gx;
   r.cpart = cpart; r.cdst[0] = dlam; r.cdst[1] = dtheta; r.C = C; r.n_cpart = B * L.n_chunk;
+  prof_begin("bwd_reduce", st, 4.0 * L.gx * C * (Cin + (recurrent ? C : 0)) * 9 + 8.0 * C * B * L.n_chunk);
   bwd_reduce_kernel<<<dim3(8, 3), 256, 0, st>>>(r);
   return check_launch("bwd_reduce_kernel");
 }

@@ -129,6 +129,7 @@ extern "C" int snnflow_encode_cnt(const float* xs, const float* ys, const float*
   if (N == 0) return SNNFLOW_OK;
   SNNFLOW_REQUIRE(xs && ys && ps, "null event arrays");
   const int vec_ok = ((N & 3) == 0) && ((((uintptr_t)xs | (uintptr_t)ys | (uintptr_t)ps) & 15) == 0);
+  prof_begin("encode_cnt", st, 12.0 * N * B + 8.0 * H * W * B);
   encode_cnt_kernel<<<dim3(event_grid(N, 4), B), EN_THREADS, 0, st>>>(xs, ys, ps, out, N, H, W, vec_ok);
   return check_launch("encode_cnt_kernel");
 }
@@ -141,14 +142,17 @@ extern "C" int snnflow_encode_image(const float* xs, const float* ys, const floa
   if (N == 0) return SNNFLOW_OK;
   SNNFLOW_REQUIRE(xs && ys && ps, "null event arrays");
   if (accumulate) {
+    prof_begin("encode_image_acc", st, 12.0 * N + 4.0 * H * W);
     encode_image_acc_kernel<<<event_grid(N, 1), EN_THREADS, 0, st>>>(xs, ys, ps, out, N, H, W);
     return check_launch("encode_image_acc_kernel");
   }
   SNNFLOW_REQUIRE(scratch, "scratch required for accumulate=0");
   SNNFLOW_CUDA(cudaMemsetAsync(scratch, 0, (size_t)H * W * sizeof(int32_t), st));
+  prof_begin("encode_image_last", st, 8.0 * N + 4.0 * H * W);
   encode_image_last_kernel<<<event_grid(N, 1), EN_THREADS, 0, st>>>(xs, ys, scratch, N, H, W);
   int rc = check_launch("encode_image_last_kernel");
   if (rc) return rc;
+  prof_begin("encode_image_pick", st, 12.0 * H * W);
   encode_image_pick_kernel<<<ceil_div(H * W, EN_THREADS), EN_THREADS, 0, st>>>(ps, scratch, out, H * W);
   return check_launch("encode_image_pick_kernel");
 }
@@ -162,10 +166,12 @@ extern "C" int snnflow_encode_voxel(const float* xs, const float* ys, const floa
   SNNFLOW_CUDA(cudaMemsetAsync(scratch, 0, (size_t)n * sizeof(int64_t), st));
   if (N > 0) {
     SNNFLOW_REQUIRE(xs && ys && ts && ps, "null event arrays");
+    prof_begin("encode_voxel", st, 16.0 * N + 4.0 * n);
     encode_voxel_kernel<<<event_grid(N, 1), EN_THREADS, 0, st>>>(xs, ys, ts, ps, scratch, N, num_bins, H, W, round_ts);
     int rc = check_launch("encode_voxel_kernel");
     if (rc) return rc;
   }
+  prof_begin("fix_to_float", st, 12.0 * n);
   fix_to_float_kernel<<<(unsigned)ceil_div64(n, EN_THREADS), EN_THREADS, 0, st>>>(scratch, out, n);
   return check_launch("fix_to_float_kernel");
 }

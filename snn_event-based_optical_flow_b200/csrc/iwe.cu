@@ -195,6 +195,7 @@ extern "C" int snnflow_flow_gather_fwd(const float* flow, const float* events, f
   if (rc) return rc;
   SNNFLOW_REQUIRE(ev_flow || N == 0, "null output");
   if (N == 0) return SNNFLOW_OK;
+  prof_begin("flow_gather_fwd", (cudaStream_t)stream, 32.0 * N * B);
   flow_gather_fwd_kernel<<<dim3((unsigned)ceil_div64(N, IW_THREADS), B), IW_THREADS, 0, (cudaStream_t)stream>>>(
       flow, (const float4*)events, (float2*)ev_flow, N, H, W);
   return check_launch("flow_gather_fwd_kernel");
@@ -206,6 +207,7 @@ extern "C" int snnflow_flow_gather_bwd(const float* g_ev_flow, const float* even
   if (rc) return rc;
   if (N == 0) return SNNFLOW_OK;
   SNNFLOW_REQUIRE(g_ev_flow, "null pointer");
+  prof_begin("flow_gather_bwd", (cudaStream_t)stream, 32.0 * N * B);
   flow_gather_bwd_kernel<<<dim3((unsigned)ceil_div64(N, IW_THREADS), B), IW_THREADS, 0, (cudaStream_t)stream>>>(
       (const float2*)g_ev_flow, (const float4*)events, g_flow, N, H, W);
   return check_launch("flow_gather_bwd_kernel");
@@ -224,12 +226,14 @@ extern "C" int snnflow_iwe_splat_fwd(const float* events, const float* ev_flow, 
   if (N > 0) {
     SNNFLOW_REQUIRE(events && ev_flow && pol_mask, "null pointer");
     SNNFLOW_REQUIRE((((uintptr_t)events) & 15) == 0 && (((uintptr_t)ev_flow | (uintptr_t)pol_mask) & 7) == 0, "misaligned");
+    prof_begin("iwe_splat_fwd", st, 32.0 * N * B + 4.0 * n);
     iwe_splat_fwd_kernel<<<dim3((unsigned)ceil_div64(N, IW_THREADS), B), IW_THREADS, 0, st>>>(
         (const float4*)events, (const float2*)ev_flow, (const float2*)pol_mask, scratch, N, H, W, tref, flow_scaling,
         n_img, ts_mode, ts_ref, round_idx);
     int rc = check_launch("iwe_splat_fwd_kernel");
     if (rc) return rc;
   }
+  prof_begin("iwe_fix_to_float", st, 12.0 * n);
   iwe_fix_to_float_kernel<<<(unsigned)ceil_div64(n, IW_THREADS), IW_THREADS, 0, st>>>(scratch, out, n);
   return check_launch("iwe_fix_to_float_kernel");
 }
@@ -243,6 +247,7 @@ extern "C" int snnflow_iwe_splat_bwd(const float* events, const float* ev_flow, 
   SNNFLOW_REQUIRE(events && ev_flow && pol_mask && g_img && g_ev_flow, "null pointer");
   SNNFLOW_REQUIRE((((uintptr_t)events) & 15) == 0 && (((uintptr_t)ev_flow | (uintptr_t)pol_mask | (uintptr_t)g_ev_flow) & 7) == 0,
                   "misaligned");
+  prof_begin("iwe_splat_bwd", (cudaStream_t)stream, 40.0 * N * B + 4.0 * B * n_img * H * W);
   iwe_splat_bwd_kernel<<<dim3((unsigned)ceil_div64(N, IW_THREADS), B), IW_THREADS, 0, (cudaStream_t)stream>>>(
       (const float4*)events, (const float2*)ev_flow, (const float2*)pol_mask, g_img, (float2*)g_ev_flow, N, H, W, tref,
       flow_scaling, n_img, ts_mode, ts_ref);

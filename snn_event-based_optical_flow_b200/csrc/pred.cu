@@ -93,6 +93,7 @@ extern "C" int snnflow_pred_fwd(const float* x, const float* w, const float* b, 
   SNNFLOW_REQUIRE(x && w && flow, "null pointer");
   SNNFLOW_REQUIRE(B > 0 && C > 0 && C <= PR_MAX_C && H > 0 && W > 0, "bad dims (C <= 64)");
   const int HW = H * W;
+  prof_begin("pred_fwd", (cudaStream_t)stream, 4.0 * B * HW * (C + 2), 4.0 * B * HW * C);
   pred_fwd_kernel<<<dim3(ceil_div(HW, PR_THREADS), B), PR_THREADS, 0, (cudaStream_t)stream>>>(x, w, b, flow, C, HW);
   return check_launch("pred_fwd_kernel");
 }
@@ -113,9 +114,11 @@ extern "C" int snnflow_pred_bwd(const float* x, const float* w, const float* flo
   }
   const int HW = H * W, gx = ceil_div(HW, PR_THREADS);
   float* part = (float*)workspace;
+  prof_begin("pred_bwd", (cudaStream_t)stream, 4.0 * B * HW * (2 * C + 4), 8.0 * B * HW * C);
   pred_bwd_kernel<<<dim3(gx, B), PR_THREADS, 0, (cudaStream_t)stream>>>(x, w, flow, g_flow, g_x, part, C, HW);
   int rc = check_launch("pred_bwd_kernel");
   if (rc) return rc;
+  prof_begin("pred_reduce", (cudaStream_t)stream, 4.0 * gx * B * (2 * C + 2));
   pred_reduce_kernel<<<ceil_div(2 * C + 2, 128), 128, 0, (cudaStream_t)stream>>>(part, dw, db, C, gx * B);
   return check_launch("pred_reduce_kernel");
 }

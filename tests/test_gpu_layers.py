@@ -168,6 +168,10 @@ def test_forward_vs_oracle_seeded(shape):
     L = _lib.lib()
     v = z = None
     vg = zg = None
+    # device copies are kept alive in named variables: a temporary's memory could be recycled by the caching
+    # allocator before the asynchronous kernel has read it
+    w_ff_d, w_rec_d = w_ff.cuda(), (w_rec.cuda() if rec else None)
+    lam_d, theta_d = lam.reshape(-1).cuda(), theta.reshape(-1).cuda()
     for t in range(3):
         x = (torch.rand(B, Cin, H, W, generator=gen) < 0.2).float()
         _, v, z, _ = olif.lif_step(x, w_ff, leak, thresh, v, z, w_rec)
@@ -175,8 +179,8 @@ def test_forward_vs_oracle_seeded(shape):
         zo = torch.empty_like(vo)
         xd = x.cuda()
         _lib.check(L.snnflow_convlif_fwd(
-            _lib.ptr(xd), _lib.ptr(w_ff.cuda()), _lib.ptr(w_rec.cuda()) if rec else None, _lib.ptr(vg), _lib.ptr(zg),
-            _lib.ptr(lam.reshape(-1).cuda()), _lib.ptr(theta.reshape(-1).cuda()), None, _lib.ptr(vo), _lib.ptr(zo),
+            _lib.ptr(xd), _lib.ptr(w_ff_d), _lib.ptr(w_rec_d), _lib.ptr(vg), _lib.ptr(zg),
+            _lib.ptr(lam_d), _lib.ptr(theta_d), None, _lib.ptr(vo), _lib.ptr(zo),
             None, None, B, Cin, C, H, W, _lib.HARD_RESET | _lib.DETACH_RESET, _lib.stream()), "fwd")
         vg, zg = vo, zo
         assert torch.equal(zo.cpu(), z), f"t={t}: {(zo.cpu() != z).sum()} spike mismatches"
