@@ -302,17 +302,32 @@ struct ReduceArgs {
 };
 
 __global__ void __launch_bounds__(256) bwd_reduce_kernel(ReduceArgs a) {
+  // block = 32 (elements) x 8 (partial-stripes); every thread sums a fixed stripe of partials, then the 8
+  // stripes are added in a fixed order: deterministic, coalesced, and short dependent chains.
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, stripe = threadIdx.x >> 5;
   const int job = blockIdx.y;
   if (job < 2) {
     if (a.wdst[job] == nullptr) return;
     const int n = a.wcount[job];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i0 = blockIdx.x * 32; i0 < n; i0 += gridDim.x * 32) {
+      const int i = i0 + lane;
       float s = 0.f;
-      for (int p = 0; p < a.n_wpart; ++p) s += a.wpart[job][(size_t)p * n + i];
-      a.wdst[job][i] += s;
+      if (i < n) {
+#pragma unroll 4
+        for (int p = stripe; p < a.n_wpart; p += 8) s += a.wpart[job][(size_t)p * n + i];
+      }
+      red[stripe][lane] = s;
+      __syncthreads();
+      if (stripe == 0 && i < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][lane];
+        a.wdst[job][i] += t;
+      }
+      __syncthreads();
     }
   } else {
-    const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int r = warp_global; r < 2 * a.C; r += n_warps) {
@@ -505,6 +520,6 @@ extern "C" int snnflow_convlif_bwd(const float* x, const float* w_ff, const floa
   r.n_wpart = L.gx;
   r.cpart = cpart; r.cdst[0] = dlam; r.cdst[1] = dtheta; r.C = C; r.n_cpart = B * L.n_chunk;
   prof_begin("bwd_reduce", st, 4.0 * L.gx * C * (Cin + (recurrent ? C : 0)) * 9 + 8.0 * C * B * L.n_chunk);
-  bwd_reduce_kernel<<<dim3(8, 3), 256, 0, st>>>(r);
+  bwd_reduce_kernel<<<dim3(ceil_div(C * (Cin > C ? Cin : C) * 9, 32), 3), 256, 0, st>>>(r);
   return check_launch("bwd_reduce_kernel");
 }

@@ -21,13 +21,16 @@ class _GatherFlow(torch.autograd.Function):
         out = torch.empty((B, N, 2), dtype=torch.float32, device=flow.device)
         _lib.check(_lib.lib().snnflow_flow_gather_fwd(_lib.ptr(flow), _lib.ptr(events), _lib.ptr(out), B, N, H, W,
                                                       _lib.stream()), "snnflow_flow_gather_fwd")
-        ctx.save_for_backward(events)
+        # Not save_for_backward: EventWarping.event_flow_association later shifts the timestamps of this very
+        # tensor in place (loss/flow.py:91), which would trip autograd's version check although the gather only
+        # reads the (unmodified) y/x columns.
+        ctx.events = events
         ctx.dims = (B, N, H, W)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        (events,) = ctx.saved_tensors
+        events = ctx.events
         B, N, H, W = ctx.dims
         g_flow = torch.zeros((B, 2, H, W), dtype=torch.float32, device=g.device)
         _lib.check(_lib.lib().snnflow_flow_gather_bwd(_lib.ptr(_f32c(g)), _lib.ptr(events), _lib.ptr(g_flow), B, N, H,
