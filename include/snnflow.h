@@ -71,6 +71,26 @@ int snnflow_convlif_fwd(const float* x, const float* w_ff, const float* w_rec, c
                         int W, unsigned flags, snnflow_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Tensor-core variant of the forward (tcgen05 implicit GEMM, accumulators in TMEM) for Cin, C multiples of
+ * 16 up to 64.  Same semantics and outputs as snnflow_convlif_fwd.  Precondition: every element of x (and of
+ * z_in) is exactly representable in fp16 - true for spikes {0,1}, spikes + residual and event counts; the
+ * kernel counts violations (snnflow_tc_inexact_count).  Weights are passed pre-packed:
+ *   packed_bytes(Cin, C, recurrent)  size of the packed blob (0 = shape not covered, use snnflow_convlif_fwd)
+ *   pack(w_ff, w_rec|NULL, packed)   fp32 [C,Cin,3,3] (+ [C,C,3,3]) -> power-of-two scaled fp16 hi+lo split in
+ *                                    the UMMA shared-memory layout; re-run whenever the weights change
+ * The conv result equals the fp32 conv to ~2^-22 relative per weight (bit-exact for 2^-12-grid weights).
+ * --------------------------------------------------------------------------------------------- */
+size_t snnflow_convlif_packed_bytes(int Cin, int C, int recurrent);
+int snnflow_convlif_pack(const float* w_ff, const float* w_rec, void* packed, int Cin, int C,
+                         snnflow_stream_t stream);
+int snnflow_convlif_fwd_tc(const float* x, const void* packed, int recurrent, const float* v_in,
+                           const float* z_in, const float* lam, const float* theta, const float* residual,
+                           float* v_out, float* z_out, float* out, float* cur_out, int B, int Cin, int C, int H,
+                           int W, unsigned flags, snnflow_stream_t stream);
+/* number of input elements the tensor-core path saw that were NOT fp16-exact (synchronises); reset != 0 clears */
+unsigned int snnflow_tc_inexact_count(int reset);
+
+/* ---------------------------------------------------------------------------------------------
  * ConvLIF / ConvLIFRecurrent backward, one layer-step of BPTT.
  * Replaces the autograd graph of the forward above incl. ArctanSpike/SuperSpike/TriangleSpike
  * .backward (models/spiking_util.py:38-43,74-79,88-93).  Saved tensors: x, v_in, z_in (may be NULL =

@@ -19,6 +19,10 @@ _PROTOS = {
     "snnflow_profile_enable": (c_int, [c_int]),
     "snnflow_profile_summary": (c_int, [ctypes.c_char_p, c_size_t]),
     "snnflow_convlif_fwd": (c_int, [P] * 12 + [c_int] * 5 + [c_uint, P]),
+    "snnflow_convlif_packed_bytes": (c_size_t, [c_int] * 3),
+    "snnflow_convlif_pack": (c_int, [P] * 3 + [c_int, c_int, P]),
+    "snnflow_convlif_fwd_tc": (c_int, [P, P, c_int] + [P] * 9 + [c_int] * 5 + [c_uint, P]),
+    "snnflow_tc_inexact_count": (c_uint, [c_int]),
     "snnflow_convlif_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
     "snnflow_convlif_bwd": (c_int, [P] * 19 + [P, c_size_t] + [c_int] * 5 + [c_uint, c_int, c_float, P]),
     "snnflow_pred_fwd": (c_int, [P] * 4 + [c_int] * 4 + [P]),

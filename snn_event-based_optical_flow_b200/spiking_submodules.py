@@ -38,7 +38,8 @@ class _ConvLIFStep(torch.autograd.Function):
     """(x, prev_state, w_ff, w_rec, leak, thresh, residual) -> (state [2,B,C,H,W], out or None)."""
 
     @staticmethod
-    def forward(ctx, x, prev_state, w_ff, w_rec, leak, thresh, residual, hard_reset, detach, surrogate, act_width):
+    def forward(ctx, x, prev_state, w_ff, w_rec, leak, thresh, residual, hard_reset, detach, surrogate, act_width,
+                packed=None):
         L = _lib.lib()
         x = _f32c(x)
         w_ff = _f32c(w_ff)
@@ -59,10 +60,16 @@ class _ConvLIFStep(torch.autograd.Function):
         flags = (_lib.HARD_RESET if hard_reset else 0) | (_lib.DETACH_RESET if detach else 0)
         v_in = prev_state[0] if prev_state is not None else None
         z_in = prev_state[1] if prev_state is not None else None
-        _lib.check(L.snnflow_convlif_fwd(
-            _lib.ptr(x), _lib.ptr(w_ff), _lib.ptr(w_rec), _lib.ptr(v_in), _lib.ptr(z_in), _lib.ptr(lam),
-            _lib.ptr(theta), _lib.ptr(residual), _lib.ptr(state[0]), _lib.ptr(state[1]), _lib.ptr(out),
-            _lib.ptr(cur), B, Cin, C, H, W, flags, _lib.stream()), "snnflow_convlif_fwd")
+        if packed is not None:   # tensor-core path: fp16-exact input (spikes), pre-packed weights
+            _lib.check(L.snnflow_convlif_fwd_tc(
+                _lib.ptr(x), _lib.ptr(packed), int(w_rec is not None), _lib.ptr(v_in), _lib.ptr(z_in), _lib.ptr(lam),
+                _lib.ptr(theta), _lib.ptr(residual), _lib.ptr(state[0]), _lib.ptr(state[1]), _lib.ptr(out),
+                _lib.ptr(cur), B, Cin, C, H, W, flags, _lib.stream()), "snnflow_convlif_fwd_tc")
+        else:
+            _lib.check(L.snnflow_convlif_fwd(
+                _lib.ptr(x), _lib.ptr(w_ff), _lib.ptr(w_rec), _lib.ptr(v_in), _lib.ptr(z_in), _lib.ptr(lam),
+                _lib.ptr(theta), _lib.ptr(residual), _lib.ptr(state[0]), _lib.ptr(state[1]), _lib.ptr(out),
+                _lib.ptr(cur), B, Cin, C, H, W, flags, _lib.stream()), "snnflow_convlif_fwd")
         if need_bwd:
             ctx.save_for_backward(x, prev_state, w_ff, w_rec, lam, theta, state, cur, thresh)
             ctx.cfg = (flags, surrogate, float(act_width), leak.shape, thresh.shape)
@@ -103,7 +110,7 @@ class _ConvLIFStep(torch.autograd.Function):
         d_thresh = (dtheta * (thresh.reshape(-1) >= 0.01).float()).reshape(thresh_shape)  # clamp_min'
         g_prev_ret = g_prev if (prev_state is not None and ctx.needs_input_grad[1]) else None
         g_res = g_out if ctx.has_residual else None
-        return (g_x, g_prev_ret, dw_ff, dw_rec, d_leak, d_thresh, g_res, None, None, None, None)
+        return (g_x, g_prev_ret, dw_ff, dw_rec, d_leak, d_thresh, g_res, None, None, None, None, None)
 
 
 class _LIFBase(nn.Module):
@@ -150,17 +157,46 @@ class _LIFBase(nn.Module):
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
         self._act_width = float(self.act_width)
 
+    use_tensor_cores = True   # class-level switch (tests flip it to compare both paths)
+
+    def _packed_weights(self):
+        """fp16 hi/lo split of the weights in the UMMA smem layout; rebuilt only when the weights change."""
+        w_ff = self.ff.weight
+        w_rec = self.rec.weight if self.recurrent else None
+        key = (w_ff.data_ptr(), w_ff._version, None if w_rec is None else (w_rec.data_ptr(), w_rec._version))
+        cached = getattr(self, "_packed_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        L = _lib.lib()
+        nbytes = L.snnflow_convlif_packed_bytes(self.input_size, self.hidden_size, int(self.recurrent))
+        if nbytes == 0:
+            return None
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=w_ff.device)
+        wf = _f32c(w_ff.detach())
+        wr = _f32c(w_rec.detach()) if w_rec is not None else None
+        _lib.check(L.snnflow_convlif_pack(_lib.ptr(wf), _lib.ptr(wr), blob.data_ptr(), self.input_size,
+                                          self.hidden_size, _lib.stream()), "snnflow_convlif_pack")
+        self._packed_cache = (key, blob)
+        return blob
+
     def _step(self, input_, prev_state, residual):
         if not input_.is_cuda:
             raise _lib.SnnflowError("snnflow ConvLIF runs on CUDA tensors only (no CPU fallback)")
         res = residual if torch.is_tensor(residual) else None
+        # The tensor-core kernel needs fp16-exact inputs.  Tensors produced by these cells (spikes, spikes +
+        # tagged residual) carry the tag `_snnflow_exact16`; anything else takes the exact-fp32 CUDA-core path.
+        exact16 = getattr(input_, "_snnflow_exact16", False)
+        packed = self._packed_weights() if (self.use_tensor_cores and exact16) else None
         state, out = _ConvLIFStep.apply(
             input_, prev_state, self.ff.weight, self.rec.weight if self.recurrent else None, self.leak, self.thresh,
-            res, self.hard_reset, self.detach, _lib.SURROGATE_ID[self.activation], self._act_width)
+            res, self.hard_reset, self.detach, _lib.SURROGATE_ID[self.activation], self._act_width, packed)
         if out is None:
             out = state[1]
             if not torch.is_tensor(residual) and residual != 0:
-                out = out + residual
+                return out + residual, state
+            out._snnflow_exact16 = True
+        elif getattr(res, "_snnflow_exact16", False):
+            out._snnflow_exact16 = True
         return out, state
 
 
