@@ -23,7 +23,7 @@
 
 namespace snnflow {
 
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;         // 8 warps: TMEM lane quarter = warp & 3, channel half = warp >> 2
 constexpr int TC_TW = 128;            // output pixels per tile = UMMA M
 constexpr int TC_P = TC_TW + 2;       // padded row pitch in slots
 constexpr int TC_SLOTS = 392;         // 3 rows * 130 = 390 slots, padded to a multiple of 8
@@ -178,16 +178,102 @@ __device__ __forceinline__ float lif_update_tc(float v, float z, float cur, floa
   return __fsub_rn(__fadd_rn(a, c), __fmul_rn(z, theta));
 }
 
-__global__ void __launch_bounds__(TC_THREADS) convlif_fwd_tc_kernel(TcFwdArgs a) {
+// Stage one source (x or z_prev: n_chunks 8-channel chunks) of the tile into the slot buffer: fp32 NCHW rows
+// y0-1..y0+1, columns x0-1..x0+128 -> fp16, slot s = rr*130 + cc.  Vector path: aligned float4 loads of 4
+// consecutive pixels for 8 channels (8 x 16 B in flight per task), then four 16-byte slot stores.
+__device__ __forceinline__ void stage_source(const float* __restrict__ src, int n_chunks, unsigned char* s_a, int H, int W,
+                                             int y0, int x0, bool vec_ok, unsigned int& inexact) {
+  const int tid = threadIdx.x;
+  const size_t plane = (size_t)H * W;
+  auto pack8 = [&](const float (&f)[8]) {
+    __half2 h[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      h[c] = __floats2half2_rn(f[2 * c], f[2 * c + 1]);
+      const float2 back = __half22float2(h[c]);
+      inexact += (back.x != f[2 * c]) + (back.y != f[2 * c + 1]);
+    }
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h[0]);
+    pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
+    pk.z = *reinterpret_cast<uint32_t*>(&h[2]);
+    pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
+    return pk;
+  };
+  if (vec_ok) {
+    // interior: columns cc = 1..128 (xx = x0 .. x0+127) as 32 groups of 4 pixels
+    const int n_tasks = n_chunks * 3 * 32;
+    for (int task = tid; task < n_tasks; task += TC_THREADS) {
+      const int q = task & 31, rr = (task >> 5) % 3, j = task / 96;
+      const int y = y0 - 1 + rr, xx = x0 + 4 * q;
+      const bool ok = (y >= 0) && (y < H) && (xx < W);
+      const float* p = src + (size_t)j * 8 * plane + (size_t)(ok ? y : 0) * W + (ok ? xx : 0);
+      float4 v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = ok ? __ldg(reinterpret_cast<const float4*>(p + (size_t)c * plane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      uint4* dst = reinterpret_cast<uint4*>(s_a + (size_t)j * (TC_SLOTS * 16)) + rr * TC_P + 1 + 4 * q;
+      {
+        const float f0[8] = {v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x};
+        const float f1[8] = {v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y};
+        const float f2[8] = {v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z};
+        const float f3[8] = {v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w};
+        dst[0] = pack8(f0); dst[1] = pack8(f1); dst[2] = pack8(f2); dst[3] = pack8(f3);
+      }
+    }
+    // the two halo columns cc = 0 and cc = 129
+    const int n_edge = n_chunks * 3 * 2;
+    for (int task = tid; task < n_edge; task += TC_THREADS) {
+      const int side = task & 1, rr = (task >> 1) % 3, j = task / 6;
+      const int cc = side ? TC_P - 1 : 0;
+      const int y = y0 - 1 + rr, xx = x0 - 1 + cc;
+      const bool ok = (y >= 0) && (y < H) && (xx >= 0) && (xx < W);
+      float f[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[c] = ok ? __ldg(src + ((size_t)j * 8 + c) * plane + (size_t)y * W + xx) : 0.f;
+      reinterpret_cast<uint4*>(s_a + (size_t)j * (TC_SLOTS * 16))[rr * TC_P + cc] = pack8(f);
+    }
+  } else {
+    const int n_tasks = n_chunks * 3 * TC_P;
+    for (int task = tid; task < n_tasks; task += TC_THREADS) {
+      const int cc = task % TC_P, rr = (task / TC_P) % 3, j = task / (3 * TC_P);
+      const int y = y0 - 1 + rr, xx = x0 - 1 + cc;
+      const bool ok = (y >= 0) && (y < H) && (xx >= 0) && (xx < W);
+      float f[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[c] = ok ? __ldg(src + ((size_t)j * 8 + c) * plane + (size_t)y * W + xx) : 0.f;
+      reinterpret_cast<uint4*>(s_a + (size_t)j * (TC_SLOTS * 16))[rr * TC_P + cc] = pack8(f);
+    }
+  }
+}
+
+// One thread issues the MMAs of one conv (9 taps x K/16 k-steps x 2 weight terms) into the accumulator.
+__device__ __forceinline__ void issue_conv(uint32_t tmem_d, uint32_t a_base, uint32_t w_base, int K, int C, uint32_t idesc,
+                                           uint32_t& accumulate) {
+  const uint32_t a_lbo = TC_SLOTS * 16, b_lbo = (uint32_t)(C >> 3) * 128, tile_bytes = (uint32_t)K * C * 2;
+  for (int tap = 0; tap < 9; ++tap) {
+    const uint32_t shift = (uint32_t)((tap / 3) * TC_P + (tap % 3)) * 16;
+    for (int kk = 0; kk < (K >> 4); ++kk) {
+      const uint64_t adesc = make_desc(a_base + (uint32_t)(2 * kk) * a_lbo + shift, a_lbo, 128);
+#pragma unroll
+      for (int term = 0; term < TC_TERMS; ++term) {
+        const uint64_t bdesc = make_desc(w_base + (uint32_t)(tap * TC_TERMS + term) * tile_bytes + (uint32_t)(2 * kk) * b_lbo, b_lbo, 128);
+        umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+        accumulate = 1;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2) convlif_fwd_tc_kernel(TcFwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem);          // weights landed
-  uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + 8);    // accumulator ready
+  uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + 8);    // MMAs of one conv complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
   unsigned char* s_w = smem + 1024;
-  unsigned char* s_a = s_w + ((a.blob_bytes + 1023) / 1024) * 1024;
+  unsigned char* s_a = s_w + ((a.blob_bytes + 1023) / 1024) * 1024;   // ONE slot buffer, reused by x then z_prev
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int kc_x = a.Cin >> 3, kc_z = a.n_conv == 2 ? (a.C >> 3) : 0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;   // TMEM lane quarter / which 16-channel groups this warp owns
   const uint32_t ncols = a.C <= 32 ? 32u : 64u;
 
   if (tid == 0) {
@@ -211,101 +297,57 @@ __global__ void __launch_bounds__(TC_THREADS) convlif_fwd_tc_kernel(TcFwdArgs a)
   const size_t plane = (size_t)a.H * a.W;
   // instruction descriptor (kind::f16): D = f32 [4,6)=1, A = B = f16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
   const uint32_t idesc = (1u << 4) | ((uint32_t)(a.C >> 3) << 17) | ((uint32_t)(TC_TW >> 4) << 24);
-  const uint32_t a_lbo = TC_SLOTS * 16;               // next 8-channel chunk
-  const uint32_t b_lbo = (uint32_t)(a.C >> 3) * 128;  // next 8-k chunk of the weight tile
+  const bool vec_ok = ((a.W & 3) == 0) && ((((uintptr_t)a.x) & 15) == 0) && (a.z_src == nullptr || (((uintptr_t)a.z_src) & 15) == 0);
+  const uint32_t ff_bytes = (uint32_t)tc_conv_bytes(a.Cin, a.C);
   uint32_t mma_parity = 0;
   unsigned int inexact = 0;
+  bool weights_ready = false;
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b = tile / (a.H * tiles_x);
     const int rem = tile - b * (a.H * tiles_x);
     const int y0 = rem / tiles_x, x0 = (rem - y0 * tiles_x) * TC_TW;
 
-    // ---- stage the input rows: fp32 NCHW -> fp16 slots -----------------------------------
-    for (int j = 0; j < kc_x + kc_z; ++j) {
-      const bool from_x = j < kc_x;
-      const float* src = from_x ? a.x + ((size_t)b * a.Cin + (size_t)j * 8) * plane
-                                : a.z_src + ((size_t)b * a.C + (size_t)(j - kc_x) * 8) * plane;
-      uint4* dstp = reinterpret_cast<uint4*>(s_a + (size_t)j * a_lbo);
-#pragma unroll
-      for (int rr = 0; rr < 3; ++rr) {
-        const int y = y0 - 1 + rr;
-        const bool yok = (y >= 0) && (y < a.H);
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          const int cc = pass == 0 ? tid : TC_TW + tid;
-          if (cc >= TC_P) continue;
-          const int xx = x0 - 1 + cc;
-          const bool ok = yok && (xx >= 0) && (xx < a.W);
-          float f[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) f[c] = ok ? __ldg(src + (size_t)c * plane + (size_t)y * a.W + xx) : 0.f;
-          __half2 h[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            h[c] = __floats2half2_rn(f[2 * c], f[2 * c + 1]);
-            const float2 back = __half22float2(h[c]);
-            inexact += (back.x != f[2 * c]) + (back.y != f[2 * c + 1]);
-          }
-          uint4 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&h[0]);
-          pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
-          pk.z = *reinterpret_cast<uint32_t*>(&h[2]);
-          pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
-          dstp[rr * TC_P + cc] = pk;
-        }
+    uint32_t accumulate = 0;
+    for (int conv = 0; conv < a.n_conv; ++conv) {
+      if (conv == 1) {   // the slot buffer is still being read by the ff MMAs
+        mbar_wait(bar_mma, mma_parity);
+        mma_parity ^= 1;
+      }
+      const float* src = conv == 0 ? a.x + (size_t)b * a.Cin * plane : a.z_src + (size_t)b * a.C * plane;
+      stage_source(src, (conv == 0 ? a.Cin : a.C) >> 3, s_a, a.H, a.W, y0, x0, vec_ok, inexact);
+      fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncthreads();
+      if (tid == 0) {
+        if (!weights_ready) { mbar_wait(bar_w, 0); weights_ready = true; }
+        tc_fence_after();
+        issue_conv(tmem_base, smem_u32(s_a), smem_u32(s_w) + (conv == 0 ? 0u : ff_bytes), conv == 0 ? a.Cin : a.C, a.C, idesc,
+                   accumulate);
+        umma_commit(bar_mma);   // implies tcgen05.fence::before_thread_sync
       }
     }
-    fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    __syncthreads();
 
-    // ---- one thread issues every MMA of the tile ------------------------------------------
-    if (tid == 0) {
-      mbar_wait(bar_w, 0);   // weights in smem (completes once; later waits return immediately)
-      tc_fence_after();
-      uint32_t accumulate = 0;
-      uint32_t w_off = 0;
-      for (int conv = 0; conv < a.n_conv; ++conv) {
-        const int K = conv == 0 ? a.Cin : a.C;
-        const int chunk0 = conv == 0 ? 0 : kc_x;
-        const uint32_t tile_bytes = (uint32_t)K * a.C * 2;
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t shift = (uint32_t)((tap / 3) * TC_P + (tap % 3)) * 16;
-          for (int kk = 0; kk < (K >> 4); ++kk) {
-            const uint64_t adesc = make_desc(smem_u32(s_a) + (uint32_t)(chunk0 + 2 * kk) * a_lbo + shift, a_lbo, 128);
-#pragma unroll
-            for (int term = 0; term < TC_TERMS; ++term) {
-              const uint64_t bdesc =
-                  make_desc(smem_u32(s_w) + w_off + (uint32_t)(tap * TC_TERMS + term) * tile_bytes + (uint32_t)(2 * kk) * b_lbo,
-                            b_lbo, 128);
-              umma_f16(tmem_base, adesc, bdesc, idesc, accumulate);
-              accumulate = 1;
-            }
-          }
-        }
-        w_off += 9 * TC_TERMS * tile_bytes;
-      }
-      umma_commit(bar_mma);   // implies tcgen05.fence::before_thread_sync
-    }
-
-    // ---- epilogue: TMEM -> registers -> LIF -> global --------------------------------------
-    const int xo = x0 + tid;
+    // ---- epilogue: TMEM -> registers -> LIF -> global; the state loads are issued before waiting ----
+    const int xo = x0 + quarter * 32 + lane;
     const bool px_ok = xo < a.W;
     const size_t pix = (size_t)y0 * a.W + xo;
-    mbar_wait(bar_mma, mma_parity);
-    mma_parity ^= 1;
-    tc_fence_after();
-    for (int g = 0; g < (a.C >> 4); ++g) {
-      float acc[16];
-      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 16), acc);
-      if (px_ok) {
-        float vin[16], zin[16];
+    bool waited = false;
+    for (int g = half; g < (a.C >> 4); g += 2) {
+      float vin[16], zin[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const size_t idx = ((size_t)b * a.C + g * 16 + c) * plane + pix;
-          vin[c] = a.v_in ? __ldg(a.v_in + idx) : 0.f;
-          zin[c] = a.z_in ? __ldg(a.z_in + idx) : 0.f;
-        }
+      for (int c = 0; c < 16; ++c) {
+        const size_t idx = ((size_t)b * a.C + g * 16 + c) * plane + pix;
+        vin[c] = (px_ok && a.v_in) ? __ldg(a.v_in + idx) : 0.f;
+        zin[c] = (px_ok && a.z_in) ? __ldg(a.z_in + idx) : 0.f;
+      }
+      if (!waited) {
+        mbar_wait(bar_mma, mma_parity);
+        tc_fence_after();
+        waited = true;
+      }
+      float acc[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * 16), acc);
+      if (px_ok) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const int co = g * 16 + c;
@@ -321,8 +363,10 @@ __global__ void __launch_bounds__(TC_THREADS) convlif_fwd_tc_kernel(TcFwdArgs a)
         }
       }
     }
+    if (!waited) mbar_wait(bar_mma, mma_parity);   // warps without a channel group still track the phase
+    mma_parity ^= 1;
     tc_fence_before();
-    __syncthreads();   // TMEM drained and A tile free before the next tile overwrites them
+    __syncthreads();   // TMEM drained and slot buffer free before the next tile overwrites them
     tc_fence_after();
   }
   if (inexact) atomicAdd(&g_tc_inexact, inexact);
@@ -340,15 +384,22 @@ static size_t tc_blob_weight_bytes(int Cin, int C, int recurrent) {
 }  // namespace snnflow
 using namespace snnflow;
 
+static size_t tc_smem_bytes(int Cin, int C, int recurrent) {
+  const size_t kc = (size_t)((recurrent && C > Cin ? C : Cin) >> 3);   // one slot buffer, reused by x and z_prev
+  return 1024 + align_up(tc_blob_weight_bytes(Cin, C, recurrent), 1024) + kc * TC_SLOTS * 16;
+}
+
 extern "C" size_t snnflow_convlif_packed_bytes(int Cin, int C, int recurrent) {
   if (!tc_shape_ok(Cin, C)) return 0;
+  if (tc_smem_bytes(Cin, C, recurrent) > 227 * 1024) return 0;   // weights + tile must fit in one SM's shared memory
   return tc_blob_weight_bytes(Cin, C, recurrent) + 16;
 }
 
 extern "C" int snnflow_convlif_pack(const float* w_ff, const float* w_rec, void* packed, int Cin, int C,
                                     snnflow_stream_t stream) {
   SNNFLOW_REQUIRE(w_ff && packed, "null pointer");
-  SNNFLOW_REQUIRE(tc_shape_ok(Cin, C), "shape not covered by the tensor-core path (Cin, C multiples of 16, <= 64)");
+  SNNFLOW_REQUIRE(snnflow_convlif_packed_bytes(Cin, C, w_rec != nullptr) > 0,
+                  "shape not covered by the tensor-core path (Cin, C multiples of 16, <= 64, fitting in shared memory)");
   SNNFLOW_REQUIRE(((uintptr_t)packed & 15) == 0, "packed buffer must be 16-byte aligned");
   prof_begin("convlif_pack", (cudaStream_t)stream, 4.0 * 9 * C * (Cin + (w_rec ? C : 0)) * 2);
   convlif_pack_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(w_ff, w_rec, (unsigned char*)packed, Cin, C);
@@ -371,7 +422,7 @@ extern "C" int snnflow_convlif_fwd_tc(const float* x, const void* packed, int re
                                       int H, int W, unsigned flags, snnflow_stream_t stream) {
   SNNFLOW_REQUIRE(x && packed && lam && theta && v_out && z_out, "null pointer");
   SNNFLOW_REQUIRE((v_in == nullptr) == (z_in == nullptr), "v_in and z_in must both be given or both be NULL");
-  SNNFLOW_REQUIRE(tc_shape_ok(Cin, C), "shape not covered by the tensor-core path");
+  SNNFLOW_REQUIRE(snnflow_convlif_packed_bytes(Cin, C, recurrent) > 0, "shape not covered by the tensor-core path");
   SNNFLOW_REQUIRE(B > 0 && H > 0 && W > 0, "bad dims");
   SNNFLOW_REQUIRE(!(residual && !out), "residual given without out");
   SNNFLOW_REQUIRE(((uintptr_t)packed & 15) == 0, "packed weights must be 16-byte aligned");
@@ -385,9 +436,7 @@ extern "C" int snnflow_convlif_fwd_tc(const float* x, const void* packed, int re
   a.hard_reset = (flags & SNNFLOW_HARD_RESET) ? 1 : 0;
   // the whole blob (ff + rec) is staged even on the first step; only the convs in use are issued
   a.blob_bytes = (uint32_t)tc_blob_weight_bytes(Cin, C, recurrent);
-  const size_t kc = (size_t)(Cin >> 3) + (a.n_conv == 2 ? (C >> 3) : 0);
-  const size_t smem = 1024 + align_up(a.blob_bytes, 1024) + kc * TC_SLOTS * 16;
-  SNNFLOW_REQUIRE(smem <= 227 * 1024, "tile does not fit in shared memory");
+  const size_t smem = tc_smem_bytes(Cin, C, recurrent);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     SNNFLOW_CUDA(cudaFuncSetAttribute(convlif_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -395,7 +444,7 @@ extern "C" int snnflow_convlif_fwd_tc(const float* x, const void* packed, int re
   }
   const int n_tiles = B * H * ceil_div(W, TC_TW);
   int per_sm = (int)((227 * 1024) / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);   // register-limited to 2 CTAs of 256 threads
   int grid = sm_count() * per_sm;
   if (grid > n_tiles) grid = n_tiles;
   {
