@@ -35,6 +35,8 @@ extern "C" {
 #define SNNFLOW_HARD_RESET 1u   /* v' = v*lam*(1-z) + (1-lam)*I ; else soft: v' = v*lam + (1-lam)*I - z*theta */
 #define SNNFLOW_DETACH_RESET 2u /* reset path does not carry gradient (spiking_submodules.py:139-140)      */
 #define SNNFLOW_NO_TENSOR_CORES 4u /* force the exact-fp32 CUDA-core convolution                           */
+#define SNNFLOW_INPUT_EXACT16 8u /* caller guarantees x holds spikes / small integers (exact in fp16 AND bf16):
+                                    lets the backward use the tensor-core weight-gradient kernel               */
 
 /* surrogate gradient kinds (models/spiking_util.py) */
 #define SNNFLOW_SG_ARCTAN 0     /* 1/(1+w*u^2)      spiking_util.py:92 */

@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(HERE, "libsnnflow.so")
 HARD_RESET = 1
 DETACH_RESET = 2
 NO_TENSOR_CORES = 4
+INPUT_EXACT16 = 8
 SURROGATE_ID = {"arctanspike": 0, "superspike": 1, "trianglespike": 2}
 
 P = c_void_p

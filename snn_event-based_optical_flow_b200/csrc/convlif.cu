@@ -5,6 +5,12 @@
 
 namespace snnflow {
 
+// tensor-core weight gradient (convlif_bwd_tc.cu)
+bool wgrad_tc_supported(int Cin, int C, int recurrent);
+int wgrad_tc_grid(int B, int H, int W);
+int launch_wgrad_tc(const float* g_cur, const float* x, const float* z, float* part_ff, float* part_rec, int B, int Cin,
+                    int C, int H, int W, cudaStream_t st);
+
 // ============================================================================================
 // Forward: conv (CUDA cores, exact fp32) + leak + delayed reset + threshold + spike.
 // ============================================================================================
@@ -490,36 +496,47 @@ extern "C" int snnflow_convlif_bwd(const float* x, const float* w_ff, const floa
   }
 
   // phase C: weight gradients (partials) + fixed-order reduction
-  WgradArgs w{};
-  w.g_cur = g_cur; w.xsrc[0] = x; w.n_ci[0] = Cin; w.part[0] = wpart0;
-  w.xsrc[1] = recurrent ? z_in : nullptr; w.n_ci[1] = C; w.part[1] = wpart1;  // z_in NULL => zero partials
-  w.B = B; w.C = C; w.H = H; w.W = W; w.n_src = recurrent ? 2 : 1;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SNNFLOW_CUDA(cudaFuncSetAttribute(wgrad_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)WG_SMEM_BYTES));
-    attr_done = true;
-  }
-  for (int s = 0; s < w.n_src; ++s) {
-    // one launch per source: the (co-block, ci-block) grid differs
-    WgradArgs ws1 = w;
-    if (s == 1) { ws1.xsrc[0] = w.xsrc[1]; ws1.n_ci[0] = w.n_ci[1]; ws1.part[0] = w.part[1]; }
-    dim3 grid(L.gx, ceil_div(C, WG_CO) * ceil_div(ws1.n_ci[0], WG_CI), 1);
-    {
-      const double px = (double)B * H * W;
-      prof_begin("wgrad_simt", st, 4.0 * px * (C + ws1.n_ci[0]) + 4.0 * L.gx * C * ws1.n_ci[0] * 9,
-                 18.0 * px * C * ws1.n_ci[0]);
-    }
-    wgrad_simt_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(ws1);
-    rc = check_launch("wgrad_simt_kernel");
+  int n_wpart = L.gx;
+  const bool use_tc = (flags & SNNFLOW_INPUT_EXACT16) && !(flags & SNNFLOW_NO_TENSOR_CORES) &&
+                      wgrad_tc_supported(Cin, C, recurrent);
+  if (use_tc) {
+    // x (tagged exact by the caller) and z_prev (spikes) are exact in bf16; g_I is split hi + lo
+    rc = launch_wgrad_tc(g_cur, x, recurrent ? z_in : nullptr, wpart0, wpart1, B, Cin, C, H, W, st);
     if (rc) return rc;
+    n_wpart = wgrad_tc_grid(B, H, W);
+  } else {
+    WgradArgs w{};
+    w.g_cur = g_cur; w.xsrc[0] = x; w.n_ci[0] = Cin; w.part[0] = wpart0;
+    w.xsrc[1] = recurrent ? z_in : nullptr; w.n_ci[1] = C; w.part[1] = wpart1;
+    w.B = B; w.C = C; w.H = H; w.W = W; w.n_src = (recurrent && z_in) ? 2 : 1;
+    static bool attr_done = false;
+    if (!attr_done) {
+      SNNFLOW_CUDA(cudaFuncSetAttribute(wgrad_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)WG_SMEM_BYTES));
+      attr_done = true;
+    }
+    for (int s = 0; s < w.n_src; ++s) {
+      // one launch per source: the (co-block, ci-block) grid differs
+      WgradArgs ws1 = w;
+      if (s == 1) { ws1.xsrc[0] = w.xsrc[1]; ws1.n_ci[0] = w.n_ci[1]; ws1.part[0] = w.part[1]; }
+      dim3 grid(L.gx, ceil_div(C, WG_CO) * ceil_div(ws1.n_ci[0], WG_CI), 1);
+      {
+        const double px = (double)B * H * W;
+        prof_begin("wgrad_simt", st, 4.0 * px * (C + ws1.n_ci[0]) + 4.0 * L.gx * C * ws1.n_ci[0] * 9,
+                   18.0 * px * C * ws1.n_ci[0]);
+      }
+      wgrad_simt_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(ws1);
+      rc = check_launch("wgrad_simt_kernel");
+      if (rc) return rc;
+    }
   }
   ReduceArgs r{};
   r.wpart[0] = wpart0; r.wdst[0] = dw_ff; r.wcount[0] = C * Cin * 9;
-  r.wpart[1] = wpart1; r.wdst[1] = recurrent ? dw_rec : nullptr; r.wcount[1] = C * C * 9;
-  r.n_wpart = L.gx;
+  // with a zero initial state (z_in == NULL) the recurrent weight gradient of this step vanishes
+  r.wpart[1] = wpart1; r.wdst[1] = (recurrent && z_in) ? dw_rec : nullptr; r.wcount[1] = C * C * 9;
+  r.n_wpart = n_wpart;
   r.cpart = cpart; r.cdst[0] = dlam; r.cdst[1] = dtheta; r.C = C; r.n_cpart = B * L.n_chunk;
-  prof_begin("bwd_reduce", st, 4.0 * L.gx * C * (Cin + (recurrent ? C : 0)) * 9 + 8.0 * C * B * L.n_chunk);
+  prof_begin("bwd_reduce", st, 4.0 * n_wpart * C * (Cin + (recurrent ? C : 0)) * 9 + 8.0 * C * B * L.n_chunk);
   bwd_reduce_kernel<<<dim3(ceil_div(C * (Cin > C ? Cin : C) * 9, 32), 3), 256, 0, st>>>(r);
   return check_launch("bwd_reduce_kernel");
 }

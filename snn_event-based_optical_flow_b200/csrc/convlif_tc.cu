@@ -17,97 +17,11 @@
 //    (leak, delayed reset, threshold, spike) straight out of the accumulator - v/z state is read and written
 //    exactly once, coalesced along x.
 //  * Persistent CTAs (several per SM, so one CTA's loads overlap another's epilogue) stride over the tiles.
-#include <cuda_fp16.h>
-
-#include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace snnflow {
 
-constexpr int TC_THREADS = 256;         // 8 warps: TMEM lane quarter = warp & 3, channel half = warp >> 2
-constexpr int TC_TW = 128;            // output pixels per tile = UMMA M
-constexpr int TC_P = TC_TW + 2;       // padded row pitch in slots
-constexpr int TC_SLOTS = 392;         // 3 rows * 130 = 390 slots, padded to a multiple of 8
-constexpr int TC_TERMS = 2;           // fp16 hi + lo
-constexpr int TC_MAX_C = 64;
-
 __device__ unsigned int g_tc_inexact = 0;   // inputs that were not exactly representable in fp16
-
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra.uni WAIT_DONE;\n"
-      "bra.uni WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
-  uint32_t u[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
-}
-
-// K-major, no-swizzle shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor):
-//   [0,14) start>>4   [16,30) LBO>>4 = byte distance between the two 8-element K chunks of one MMA
-//   [32,46) SBO>>4 = byte distance between 8-row groups   [46,48) version = 1   [61,64) layout = 0
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
-         (1ull << 46);
-}
 
 // ---- weight packing ---------------------------------------------------------------------------
 // blob = for conv in (ff[, rec]): for tap 0..8: for term (hi, lo): fp16 [K/8][C/8][8 n][8 k]   then 1 float: 1/scale
@@ -176,74 +90,6 @@ __device__ __forceinline__ float lif_update_tc(float v, float z, float cur, floa
   float c = __fmul_rn(__fsub_rn(1.0f, lam), cur);
   if (hard) return __fadd_rn(__fmul_rn(a, __fsub_rn(1.0f, z)), c);
   return __fsub_rn(__fadd_rn(a, c), __fmul_rn(z, theta));
-}
-
-// Stage one source (x or z_prev: n_chunks 8-channel chunks) of the tile into the slot buffer: fp32 NCHW rows
-// y0-1..y0+1, columns x0-1..x0+128 -> fp16, slot s = rr*130 + cc.  Vector path: aligned float4 loads of 4
-// consecutive pixels for 8 channels (8 x 16 B in flight per task), then four 16-byte slot stores.
-__device__ __forceinline__ void stage_source(const float* __restrict__ src, int n_chunks, unsigned char* s_a, int H, int W,
-                                             int y0, int x0, bool vec_ok, unsigned int& inexact) {
-  const int tid = threadIdx.x;
-  const size_t plane = (size_t)H * W;
-  auto pack8 = [&](const float (&f)[8]) {
-    __half2 h[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      h[c] = __floats2half2_rn(f[2 * c], f[2 * c + 1]);
-      const float2 back = __half22float2(h[c]);
-      inexact += (back.x != f[2 * c]) + (back.y != f[2 * c + 1]);
-    }
-    uint4 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&h[0]);
-    pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
-    pk.z = *reinterpret_cast<uint32_t*>(&h[2]);
-    pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
-    return pk;
-  };
-  if (vec_ok) {
-    // interior: columns cc = 1..128 (xx = x0 .. x0+127) as 32 groups of 4 pixels
-    const int n_tasks = n_chunks * 3 * 32;
-    for (int task = tid; task < n_tasks; task += TC_THREADS) {
-      const int q = task & 31, rr = (task >> 5) % 3, j = task / 96;
-      const int y = y0 - 1 + rr, xx = x0 + 4 * q;
-      const bool ok = (y >= 0) && (y < H) && (xx < W);
-      const float* p = src + (size_t)j * 8 * plane + (size_t)(ok ? y : 0) * W + (ok ? xx : 0);
-      float4 v[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) v[c] = ok ? __ldg(reinterpret_cast<const float4*>(p + (size_t)c * plane)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      uint4* dst = reinterpret_cast<uint4*>(s_a + (size_t)j * (TC_SLOTS * 16)) + rr * TC_P + 1 + 4 * q;
-      {
-        const float f0[8] = {v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x};
-        const float f1[8] = {v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y};
-        const float f2[8] = {v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z};
-        const float f3[8] = {v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w};
-        dst[0] = pack8(f0); dst[1] = pack8(f1); dst[2] = pack8(f2); dst[3] = pack8(f3);
-      }
-    }
-    // the two halo columns cc = 0 and cc = 129
-    const int n_edge = n_chunks * 3 * 2;
-    for (int task = tid; task < n_edge; task += TC_THREADS) {
-      const int side = task & 1, rr = (task >> 1) % 3, j = task / 6;
-      const int cc = side ? TC_P - 1 : 0;
-      const int y = y0 - 1 + rr, xx = x0 - 1 + cc;
-      const bool ok = (y >= 0) && (y < H) && (xx >= 0) && (xx < W);
-      float f[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) f[c] = ok ? __ldg(src + ((size_t)j * 8 + c) * plane + (size_t)y * W + xx) : 0.f;
-      reinterpret_cast<uint4*>(s_a + (size_t)j * (TC_SLOTS * 16))[rr * TC_P + cc] = pack8(f);
-    }
-  } else {
-    const int n_tasks = n_chunks * 3 * TC_P;
-    for (int task = tid; task < n_tasks; task += TC_THREADS) {
-      const int cc = task % TC_P, rr = (task / TC_P) % 3, j = task / (3 * TC_P);
-      const int y = y0 - 1 + rr, xx = x0 - 1 + cc;
-      const bool ok = (y >= 0) && (y < H) && (xx >= 0) && (xx < W);
-      float f[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) f[c] = ok ? __ldg(src + ((size_t)j * 8 + c) * plane + (size_t)y * W + xx) : 0.f;
-      reinterpret_cast<uint4*>(s_a + (size_t)j * (TC_SLOTS * 16))[rr * TC_P + cc] = pack8(f);
-    }
-  }
 }
 
 // One thread issues the MMAs of one conv (9 taps x K/16 k-steps x 2 weight terms) into the accumulator.
@@ -315,7 +161,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) convlif_fwd_tc_kernel(TcFwdArgs
         mma_parity ^= 1;
       }
       const float* src = conv == 0 ? a.x + (size_t)b * a.Cin * plane : a.z_src + (size_t)b * a.C * plane;
-      stage_source(src, (conv == 0 ? a.Cin : a.C) >> 3, s_a, a.H, a.W, y0, x0, vec_ok, inexact);
+      stage_source<false>(src, (conv == 0 ? a.Cin : a.C) >> 3, s_a, a.H, a.W, y0, x0, vec_ok, inexact);
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncthreads();
       if (tid == 0) {

@@ -72,7 +72,9 @@ class _ConvLIFStep(torch.autograd.Function):
                 _lib.ptr(cur), B, Cin, C, H, W, flags, _lib.stream()), "snnflow_convlif_fwd")
         if need_bwd:
             ctx.save_for_backward(x, prev_state, w_ff, w_rec, lam, theta, state, cur, thresh)
-            ctx.cfg = (flags, surrogate, float(act_width), leak.shape, thresh.shape)
+            # packed is only passed for inputs tagged fp16/bf16-exact (spikes): the backward may use tensor cores too
+            bwd_flags = flags | (_lib.INPUT_EXACT16 if packed is not None else 0)
+            ctx.cfg = (bwd_flags, surrogate, float(act_width), leak.shape, thresh.shape)
             ctx.has_residual = residual is not None
         return state, out
 

@@ -61,7 +61,7 @@ def test_forward_capi(name):
         assert np.array_equal(out, g["out"])
 
 
-def capi_backward(g, v, cur):
+def capi_backward(g, v, cur, flags_extra=0):
     from snnflow_b200 import _lib
     L = _lib.lib()
     rec, hard, detach, has_res = [bool(v_) for v_ in g["meta"]]
@@ -73,7 +73,7 @@ def capi_backward(g, v, cur):
     gout = dev(g["gout"])
     T, B, Cin, H, W = x.shape
     C = w_ff.shape[0]
-    flags = (_lib.HARD_RESET if hard else 0) | (_lib.DETACH_RESET if detach else 0)
+    flags = (_lib.HARD_RESET if hard else 0) | (_lib.DETACH_RESET if detach else 0) | flags_extra
     nbytes = L.snnflow_convlif_bwd_workspace_bytes(B, Cin, C, H, W, int(rec))
     ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     g_x = torch.empty_like(x)

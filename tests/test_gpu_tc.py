@@ -159,3 +159,55 @@ def test_module_uses_tensor_cores_and_matches_simt():
     for a, b in zip(s_tc, s_simt):
         assert torch.equal(a, b)
     assert float(s_tc[-1][1].mean()) > 0.01
+
+
+@pytest.mark.parametrize("name", ["layer_ff_c32", "layer_rec_c32", "layer_rec_c32_rand"])
+def test_tc_backward_golden(name):
+    """Tensor-core weight gradient (bf16 hi/lo split of g_I, spikes exact) vs reference autograd: rel 1e-4."""
+    from snnflow_b200 import _lib
+    from test_gpu_layers import capi_backward, capi_forward
+    g = load_golden(name)
+    _, _, _, cur = capi_forward(g)
+    _lib.profile(True)
+    r = capi_backward(g, dev(g["v"]), cur, flags_extra=_lib.INPUT_EXACT16)
+    prof = _lib.profile_summary()
+    _lib.profile(False)
+    assert "wgrad_tc" in prof and "wgrad_simt" not in prof
+    for k in ("g_x", "dw_ff", "dw_rec", "dleak", "dthresh"):
+        if r[k] is None:
+            continue
+        ref = g[k].reshape(r[k].shape)
+        scale = max(1.0, float(np.abs(ref).max()))
+        np.testing.assert_allclose(r[k].cpu().numpy(), ref, rtol=1e-4, atol=1e-5 * scale, err_msg=k)
+
+
+def test_tc_wgrad_matches_simt_large():
+    """128x128, batch 4, recurrent: tensor-core partial sums vs the exact-fp32 CUDA-core kernel, rel 1e-4 of max."""
+    from snnflow_b200 import _lib
+    L = _lib.lib()
+    B, C, H, W = 4, 32, 128, 128
+    gen = torch.Generator().manual_seed(11)
+    x = (torch.rand(B, C, H, W, generator=gen) < 0.2).float().cuda()
+    z = (torch.rand(B, C, H, W, generator=gen) < 0.15).float().cuda()
+    v_in = torch.randn(B, C, H, W, generator=gen).cuda()
+    v_out = (torch.randn(B, C, H, W, generator=gen) * 0.3 + 0.2).cuda()
+    cur = torch.randn(B, C, H, W, generator=gen).cuda()
+    g_out = torch.randn(B, C, H, W, generator=gen).cuda()
+    w_ff = ((torch.rand(C, C, 3, 3, generator=gen) - 0.5) * 0.3).cuda()
+    w_rec = ((torch.rand(C, C, 3, 3, generator=gen) - 0.5) * 0.3).cuda()
+    lam, theta = torch.full((C,), 0.6).cuda(), torch.full((C,), 0.3).cuda()
+    ws = torch.empty(L.snnflow_convlif_bwd_workspace_bytes(B, C, C, H, W, 1), dtype=torch.uint8, device="cuda")
+    outs = []
+    for extra in (0, _lib.INPUT_EXACT16):
+        g_x, g_v, g_z = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        dwf, dwr = torch.zeros_like(w_ff), torch.zeros_like(w_rec)
+        dl, dt = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        _lib.check(L.snnflow_convlif_bwd(
+            _lib.ptr(x), _lib.ptr(w_ff), _lib.ptr(w_rec), _lib.ptr(v_in), _lib.ptr(z), _lib.ptr(v_out), _lib.ptr(cur),
+            _lib.ptr(lam), _lib.ptr(theta), _lib.ptr(g_out), None, None, _lib.ptr(g_x), _lib.ptr(g_v), _lib.ptr(g_z),
+            _lib.ptr(dwf), _lib.ptr(dwr), _lib.ptr(dl), _lib.ptr(dt), ws.data_ptr(), ws.numel(), B, C, C, H, W,
+            _lib.HARD_RESET | _lib.DETACH_RESET | extra, 0, 10.0, _lib.stream()), "bwd")
+        torch.cuda.synchronize()
+        outs.append((dwf.cpu().numpy(), dwr.cpu().numpy()))
+    for a, b in zip(outs[0], outs[1]):
+        np.testing.assert_allclose(b, a, rtol=1e-4, atol=1e-4 * np.abs(a).max())
