@@ -356,7 +356,7 @@ static int wgrad_grid_x(int B, int H, int W) {
 
 struct BwdLayout {
   size_t off_gcur, off_cpart, off_wpart0, off_wpart1, total;
-  int n_chunk, gx;
+  int n_chunk, gx;   // gx: grid of the CUDA-core wgrad; the partial buffers hold max(gx, tensor-core grid) blocks
 };
 
 static BwdLayout bwd_layout(int B, int Cin, int C, int H, int W, int recurrent) {
@@ -367,8 +367,10 @@ static BwdLayout bwd_layout(int B, int Cin, int C, int H, int W, int recurrent) 
   size_t o = 0;
   L.off_gcur = o; o += align_up(n * sizeof(float), 256);
   L.off_cpart = o; o += align_up((size_t)2 * C * B * L.n_chunk * sizeof(float), 256);
-  L.off_wpart0 = o; o += align_up((size_t)L.gx * C * Cin * 9 * sizeof(float), 256);
-  L.off_wpart1 = o; if (recurrent) o += align_up((size_t)L.gx * C * C * 9 * sizeof(float), 256);
+  const int tcg = wgrad_tc_grid(B, H, W);
+  const int n_part = L.gx > tcg ? L.gx : tcg;
+  L.off_wpart0 = o; o += align_up((size_t)n_part * C * Cin * 9 * sizeof(float), 256);
+  L.off_wpart1 = o; if (recurrent) o += align_up((size_t)n_part * C * C * 9 * sizeof(float), 256);
   L.total = o;
   return L;
 }
