@@ -10,6 +10,11 @@ bool wgrad_tc_supported(int Cin, int C, int recurrent);
 int wgrad_tc_grid(int B, int H, int W);
 int launch_wgrad_tc(const float* g_cur, const float* x, const float* z, float* part_ff, float* part_rec, int B, int Cin,
                     int C, int H, int W, cudaStream_t st);
+// tensor-core data gradient (convlif_bwd_tc.cu)
+bool dgrad_tc_supported(int Cin, int C, int n_rec, bool need_gx);
+size_t dgrad_tc_workspace_bytes(int Cin, int C, int n_rec);
+int launch_dgrad_tc(const float* g_cur, const float* w_ff, const float* w_rec, float* g_x, float* g_z, int accumulate_z,
+                    void* blob_ws, int B, int Cin, int C, int n_rec, int H, int W, cudaStream_t st);
 
 // ============================================================================================
 // Forward: conv (CUDA cores, exact fp32) + leak + delayed reset + threshold + spike.
@@ -355,7 +360,7 @@ static int wgrad_grid_x(int B, int H, int W) {
 }
 
 struct BwdLayout {
-  size_t off_gcur, off_cpart, off_wpart0, off_wpart1, total;
+  size_t off_gcur, off_cpart, off_wpart0, off_wpart1, off_dgblob, total;
   int n_chunk, gx;   // gx: grid of the CUDA-core wgrad; the partial buffers hold max(gx, tensor-core grid) blocks
 };
 
@@ -371,6 +376,7 @@ static BwdLayout bwd_layout(int B, int Cin, int C, int H, int W, int recurrent) 
   const int n_part = L.gx > tcg ? L.gx : tcg;
   L.off_wpart0 = o; o += align_up((size_t)n_part * C * Cin * 9 * sizeof(float), 256);
   L.off_wpart1 = o; if (recurrent) o += align_up((size_t)n_part * C * C * 9 * sizeof(float), 256);
+  L.off_dgblob = o; o += dgrad_tc_workspace_bytes(Cin, C, recurrent ? C : 0);
   L.total = o;
   return L;
 }
@@ -487,14 +493,22 @@ extern "C" int snnflow_convlif_bwd(const float* x, const float* w_ff, const floa
   int rc = check_launch("convlif_bwd_pointwise_kernel");
   if (rc) return rc;
 
-  // phase B: data gradients
-  if (g_x) {
-    rc = launch_dgrad(g_cur, w_ff, Cin, g_x, 0, B, C, H, W, st);
-    if (rc) return rc;
-  }
-  if (recurrent) {
-    rc = launch_dgrad(g_cur, w_rec, C, g_z_in, detach ? 0 : 1, B, C, H, W, st);
-    if (rc) return rc;
+  // phase B: data gradients (g_x through W_ff, g_z_in through W_rec)
+  if (g_x || recurrent) {
+    if (!(flags & SNNFLOW_NO_TENSOR_CORES) && dgrad_tc_supported(Cin, C, recurrent ? C : 0, g_x != nullptr)) {
+      rc = launch_dgrad_tc(g_cur, w_ff, w_rec, g_x, recurrent ? g_z_in : nullptr, detach ? 0 : 1, ws + L.off_dgblob, B,
+                           Cin, C, recurrent ? C : 0, H, W, st);
+      if (rc) return rc;
+    } else {
+      if (g_x) {
+        rc = launch_dgrad(g_cur, w_ff, Cin, g_x, 0, B, C, H, W, st);
+        if (rc) return rc;
+      }
+      if (recurrent) {
+        rc = launch_dgrad(g_cur, w_rec, C, g_z_in, detach ? 0 : 1, B, C, H, W, st);
+        if (rc) return rc;
+      }
+    }
   }
 
   // phase C: weight gradients (partials) + fixed-order reduction

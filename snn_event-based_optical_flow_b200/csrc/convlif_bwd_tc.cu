@@ -1,4 +1,4 @@
-// ConvLIF backward on the tensor cores (tcgen05 + TMEM): weight gradient.
+// ConvLIF backward on the tensor cores (tcgen05 + TMEM): weight gradient and data gradient.
 //
 //   dW[co][ci][ky][kx] = sum over pixels  g_I[b,co,y,x] * X[b,ci,y+ky-1,x+kx-1]        (X = x for ff, z_prev for rec)
 //
@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(TcWgradArgs a) 
     unsigned char* xb = stages + (size_t)s * stage_bytes;
     unsigned char* gb = xb + WG_TC_XBYTES;
     if (it >= WG_TC_STAGES) mbar_wait(&bar[s], (uint32_t)(((it >> 1) - 1) & 1));   // stage s free again
-    stage_source<true>(a.x + (size_t)b * a.Cin * plane, n_x, xb, a.H, a.W, y0, x0, vec_ok, inexact);
-    if (a.n_z) stage_source<true>(a.z + (size_t)b * a.C * plane, a.n_z, xb + (size_t)n_x * TC_SLOTS * 16, a.H, a.W, y0, x0, vec_ok, inexact);
+    stage_source<1>(a.x + (size_t)b * a.Cin * plane, n_x, xb, a.H, a.W, y0, x0, vec_ok, inexact);
+    if (a.n_z) stage_source<1>(a.z + (size_t)b * a.C * plane, a.n_z, xb + (size_t)n_x * TC_SLOTS * 16, a.H, a.W, y0, x0, vec_ok, inexact);
     stage_grad(a.g_cur + (size_t)b * a.C * plane, a.C, gb, a.W, plane, (size_t)y0 * a.W, x0, vec_ok);
     fence_proxy_async();
     __syncthreads();
@@ -203,6 +203,190 @@ int launch_wgrad_tc(const float* g_cur, const float* x, const float* z, float* p
              18.0 * px * C * (Cin + (z ? C : 0)));
   wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
   return check_launch("wgrad_tc_kernel");
+}
+
+
+// ================================================================================================
+// Data gradient on the tensor cores.
+//   g_x[b,ci,y,x]      = sum_{co,ky,kx} g_I[b,co,y+1-ky,x+1-kx] * W_ff [co][ci][ky][kx]
+//   g_zprev[b,cz,y,x]  = the same with W_rec                       (recurrent cells)
+// = one implicit GEMM per row tile: D[m = pixel][n = ci | Cin + cz] += A_tap[m][k = co] * B_tap[n][k], A = g_I in the
+// K-major slot layout (3 rows + halo, bf16 hi + lo planes), B = the transposed, tap-flipped weights (bf16 hi + lo,
+// packed by dgrad_pack_kernel into the UMMA image, one TMA bulk copy per CTA).  Three MMAs per (tap, k-step):
+// hi*hi + hi*lo + lo*hi (the lo*lo term is below 2^-32 relative).  One persistent CTA per SM with two smem stages
+// and two TMEM accumulators: the MMAs of tile i run while tile i-1 is drained to global and tile i+1 is staged.
+// ================================================================================================
+struct TcDgradArgs {
+  const float* g_cur;
+  const unsigned char* blob;
+  float *g_x, *g_z;
+  int B, C, Cin, n_rec, H, W, accumulate_z;
+  uint32_t blob_bytes;
+};
+
+__host__ __device__ inline size_t dg_tc_blob_bytes(int C, int N) { return (size_t)9 * 2 * N * C * 2; }
+
+// blob: for tap' 0..8: for term (hi, lo): bf16 [C/8][N/8][8 n][8 k];  value(n, k) = W[k][n][8 - tap']
+__global__ void __launch_bounds__(256) dgrad_pack_kernel(const float* __restrict__ w_ff, const float* __restrict__ w_rec,
+                                                         __nv_bfloat16* __restrict__ blob, int C, int Cin, int n_rec) {
+  const int N = Cin + n_rec, per_tile = N * C;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < 9 * per_tile; i += gridDim.x * 256) {
+    const int tap = i / per_tile, r = i - tap * per_tile;
+    const int n = r / C, k = r - n * C;
+    const float v = n < Cin ? w_ff[((size_t)k * Cin + n) * 9 + (8 - tap)] : w_rec[((size_t)k * n_rec + (n - Cin)) * 9 + (8 - tap)];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const int idx = ((k >> 3) * (N >> 3) + (n >> 3)) * 64 + (n & 7) * 8 + (k & 7);
+    blob[(size_t)(tap * 2 + 0) * per_tile + idx] = hi;
+    blob[(size_t)(tap * 2 + 1) * per_tile + idx] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(TcDgradArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 8);   // bar[0..1]: MMAs of the tile in stage s complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
+  unsigned char* s_w = smem + 1024;
+  const int n_ch = a.C >> 3;
+  const uint32_t plane_bytes = (uint32_t)n_ch * TC_SLOTS * 16;        // one term of one stage
+  unsigned char* s_a = s_w + ((a.blob_bytes + 1023) / 1024) * 1024;    // [stage][term][chunk][slot][8]
+  const int N = a.Cin + a.n_rec;
+  const uint32_t ncols = 2 * N <= 32 ? 32u : (2 * N <= 64 ? 64u : (2 * N <= 128 ? 128u : 256u));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, a.blob_bytes);
+    tma_bulk_g2s(s_w, a.blob, a.blob_bytes, bar_w);
+  }
+
+  const int tiles_x = (a.W + TC_TW - 1) / TC_TW;
+  const int n_tiles = a.B * a.H * tiles_x;
+  const size_t plane = (size_t)a.H * a.W;
+  const uint32_t idesc = make_idesc(TC_TW, N, /*bf16*/ 1, 0, 0);
+  const bool vec_ok = ((a.W & 3) == 0) && ((((uintptr_t)a.g_cur) & 15) == 0);
+  const uint32_t a_lbo = TC_SLOTS * 16, b_lbo = (uint32_t)(N >> 3) * 128, w_tile = (uint32_t)N * a.C * 2;
+  unsigned int unused = 0;
+  bool weights_ready = false;
+
+  for (int it = 0;; ++it) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    const bool have = tile < n_tiles;
+    const int s = it & 1;
+    if (have) {
+      const int b = tile / (a.H * tiles_x);
+      const int rem = tile - b * (a.H * tiles_x);
+      const int y0 = rem / tiles_x, x0 = (rem - y0 * tiles_x) * TC_TW;
+      unsigned char* hi = s_a + (size_t)s * 2 * plane_bytes;
+      stage_source<2>(a.g_cur + (size_t)b * a.C * plane, n_ch, hi, a.H, a.W, y0, x0, vec_ok, unused, hi + plane_bytes);
+      fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();   // stage s written; the epilogue of tile it-2 has drained accumulator s
+    if (have && tid == 0) {
+      if (!weights_ready) { mbar_wait(bar_w, 0); weights_ready = true; }
+      tc_fence_after();
+      const uint32_t hi_addr = smem_u32(s_a) + (uint32_t)s * 2 * plane_bytes, lo_addr = hi_addr + plane_bytes;
+      const uint32_t d = tmem_base + (uint32_t)(s * N);
+      uint32_t accumulate = 0;
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t shift = (uint32_t)((tap / 3) * TC_P + (tap % 3)) * 16;
+        const uint32_t wb = smem_u32(s_w) + (uint32_t)(tap * 2) * w_tile;
+        for (int kk = 0; kk < (a.C >> 4); ++kk) {
+          const uint64_t a_hi = make_desc(hi_addr + (uint32_t)(2 * kk) * a_lbo + shift, a_lbo, 128);
+          const uint64_t a_lo = make_desc(lo_addr + (uint32_t)(2 * kk) * a_lbo + shift, a_lbo, 128);
+          const uint64_t b_hi = make_desc(wb + (uint32_t)(2 * kk) * b_lbo, b_lbo, 128);
+          const uint64_t b_lo = make_desc(wb + w_tile + (uint32_t)(2 * kk) * b_lbo, b_lbo, 128);
+          umma_f16(d, a_hi, b_hi, idesc, accumulate);
+          umma_f16(d, a_hi, b_lo, idesc, 1u);
+          umma_f16(d, a_lo, b_hi, idesc, 1u);
+          accumulate = 1;
+        }
+      }
+      umma_commit(&bar[s]);
+    }
+    if (it >= 1) {   // drain tile it-1 while the MMAs of tile it run
+      const int pt = blockIdx.x + (it - 1) * gridDim.x, ps = (it - 1) & 1;
+      const int b = pt / (a.H * tiles_x);
+      const int rem = pt - b * (a.H * tiles_x);
+      const int y0 = rem / tiles_x, x0 = (rem - y0 * tiles_x) * TC_TW;
+      const int xo = x0 + quarter * 32 + lane;
+      const bool px_ok = xo < a.W;
+      const size_t pix = (size_t)y0 * a.W + xo;
+      mbar_wait(&bar[ps], (uint32_t)(((it - 1) >> 1) & 1));
+      tc_fence_after();
+      for (int g = half; g < (N >> 4); g += 2) {
+        float acc[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ps * N + g * 16), acc);
+        if (px_ok) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int n = g * 16 + c;
+            if (n < a.Cin) {
+              if (a.g_x) a.g_x[((size_t)b * a.Cin + n) * plane + pix] = acc[c];
+            } else {
+              float* p = a.g_z + ((size_t)b * a.n_rec + (n - a.Cin)) * plane + pix;
+              *p = a.accumulate_z ? *p + acc[c] : acc[c];
+            }
+          }
+        }
+      }
+    }
+    if (!have) break;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+}
+
+static size_t dg_tc_smem(int C, int N) {
+  return 1024 + align_up(dg_tc_blob_bytes(C, N), 1024) + (size_t)2 * 2 * (C >> 3) * TC_SLOTS * 16;
+}
+
+bool dgrad_tc_supported(int Cin, int C, int n_rec, bool need_gx) {
+  if ((C % 16) || C > 64 || C < 16) return false;
+  const int N = (need_gx || n_rec == 0 ? Cin : Cin) + n_rec;   // the g_x columns are always computed
+  if ((Cin % 8) || (N % 16) || N > 128 || N < 16) return false;
+  return dg_tc_smem(C, N) <= 227 * 1024;
+}
+
+size_t dgrad_tc_workspace_bytes(int Cin, int C, int n_rec) { return align_up(dg_tc_blob_bytes(C, Cin + n_rec), 256); }
+
+int launch_dgrad_tc(const float* g_cur, const float* w_ff, const float* w_rec, float* g_x, float* g_z, int accumulate_z,
+                    void* blob_ws, int B, int Cin, int C, int n_rec, int H, int W, cudaStream_t st) {
+  const int N = Cin + n_rec;
+  prof_begin("dgrad_pack", st, 4.0 * 9 * C * N + 2.0 * 2 * 9 * C * N);
+  dgrad_pack_kernel<<<ceil_div(9 * N * C, 256 * 4), 256, 0, st>>>(w_ff, w_rec, (__nv_bfloat16*)blob_ws, C, Cin, n_rec);
+  int rc = check_launch("dgrad_pack_kernel");
+  if (rc) return rc;
+  TcDgradArgs a{};
+  a.g_cur = g_cur; a.blob = (const unsigned char*)blob_ws; a.g_x = g_x; a.g_z = g_z;
+  a.B = B; a.C = C; a.Cin = Cin; a.n_rec = n_rec; a.H = H; a.W = W; a.accumulate_z = accumulate_z;
+  a.blob_bytes = (uint32_t)dg_tc_blob_bytes(C, N);
+  const size_t smem = dg_tc_smem(C, N);
+  static size_t attr = 0;
+  if (smem > attr) {
+    SNNFLOW_CUDA(cudaFuncSetAttribute(dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int n_tiles = B * H * ceil_div(W, TC_TW);
+  const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+  const double px = (double)B * H * W;
+  prof_begin("dgrad_tc", st, 4.0 * px * (C + (g_x ? Cin : 0) + n_rec * (accumulate_z ? 2 : 1)), 18.0 * px * C * N);
+  dgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+  return check_launch("dgrad_tc_kernel");
 }
 
 }  // namespace snnflow

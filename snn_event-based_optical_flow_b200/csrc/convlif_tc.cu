@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) convlif_fwd_tc_kernel(TcFwdArgs
         mma_parity ^= 1;
       }
       const float* src = conv == 0 ? a.x + (size_t)b * a.Cin * plane : a.z_src + (size_t)b * a.C * plane;
-      stage_source<false>(src, (conv == 0 ? a.Cin : a.C) >> 3, s_a, a.H, a.W, y0, x0, vec_ok, inexact);
+      stage_source<0>(src, (conv == 0 ? a.Cin : a.C) >> 3, s_a, a.H, a.W, y0, x0, vec_ok, inexact);
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncthreads();
       if (tid == 0) {

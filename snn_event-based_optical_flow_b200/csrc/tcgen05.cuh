@@ -105,31 +105,40 @@ constexpr int TC_TERMS = 2;           // fp16 hi + lo
 constexpr int TC_MAX_C = 64;
 
 
-// Stage one source (x or z_prev: n_chunks 8-channel chunks) of the tile into the slot buffer: fp32 NCHW rows
-// y0-1..y0+1, columns x0-1..x0+128 -> fp16, slot s = rr*130 + cc.  Vector path: aligned float4 loads of 4
-// consecutive pixels for 8 channels (8 x 16 B in flight per task), then four 16-byte slot stores.
-template <bool BF16>
+// Stage one source (n_chunks 8-channel chunks of an fp32 NCHW tensor) of a row tile into the slot buffer:
+// rows y0-1..y0+1, columns x0-1..x0+128 -> 16-bit, slot s = rr*130 + cc holds 8 channels (16 B).
+//   MODE 0: fp16 (one term)   MODE 1: bf16 (one term)   MODE 2: bf16 hi + lo (lo planes go to s_lo)
+// `inexact` counts values that a single term does not represent exactly (MODE 0/1).
+// Vector path: aligned float4 loads of 4 consecutive pixels for 8 channels (8 x 16 B in flight per task).
+template <int MODE>
 __device__ __forceinline__ void stage_source(const float* __restrict__ src, int n_chunks, unsigned char* s_a, int H, int W,
-                                             int y0, int x0, bool vec_ok, unsigned int& inexact) {
+                                             int y0, int x0, bool vec_ok, unsigned int& inexact,
+                                             unsigned char* s_lo = nullptr) {
   const int tid = threadIdx.x;
   const size_t plane = (size_t)H * W;
-  auto pack8 = [&](const float (&f)[8]) {
-    uint32_t u[4];
+  auto put = [&](const float (&f)[8], int j, int slot) {
+    uint32_t u[4], l[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       float2 back;
-      if (BF16) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * c], f[2 * c + 1]);
-        back = __bfloat1622float2(h);
-        u[c] = *reinterpret_cast<uint32_t*>(&h);
-      } else {
+      if (MODE == 0) {
         __half2 h = __floats2half2_rn(f[2 * c], f[2 * c + 1]);
         back = __half22float2(h);
         u[c] = *reinterpret_cast<uint32_t*>(&h);
+      } else {
+        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * c], f[2 * c + 1]);
+        back = __bfloat1622float2(h);
+        u[c] = *reinterpret_cast<uint32_t*>(&h);
       }
-      inexact += (back.x != f[2 * c]) + (back.y != f[2 * c + 1]);
+      if (MODE == 2) {
+        __nv_bfloat162 r = __floats2bfloat162_rn(f[2 * c] - back.x, f[2 * c + 1] - back.y);
+        l[c] = *reinterpret_cast<uint32_t*>(&r);
+      } else {
+        inexact += (back.x != f[2 * c]) + (back.y != f[2 * c + 1]);
+      }
     }
-    return make_uint4(u[0], u[1], u[2], u[3]);
+    reinterpret_cast<uint4*>(s_a + (size_t)j * (TC_SLOTS * 16))[slot] = make_uint4(u[0], u[1], u[2], u[3]);
+    if (MODE == 2) reinterpret_cast<uint4*>(s_lo + (size_t)j * (TC_SLOTS * 16))[slot] = make_uint4(l[0], l[1], l[2], l[3]);
   };
   if (vec_ok) {
     // interior: columns cc = 1..128 (xx = x0 .. x0+127) as 32 groups of 4 pixels
@@ -142,14 +151,12 @@ __device__ __forceinline__ void stage_source(const float* __restrict__ src, int 
       float4 v[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) v[c] = ok ? __ldg(reinterpret_cast<const float4*>(p + (size_t)c * plane)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      uint4* dst = reinterpret_cast<uint4*>(s_a + (size_t)j * (TC_SLOTS * 16)) + rr * TC_P + 1 + 4 * q;
-      {
-        const float f0[8] = {v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x};
-        const float f1[8] = {v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y};
-        const float f2[8] = {v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z};
-        const float f3[8] = {v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w};
-        dst[0] = pack8(f0); dst[1] = pack8(f1); dst[2] = pack8(f2); dst[3] = pack8(f3);
-      }
+      const int slot = rr * TC_P + 1 + 4 * q;
+      const float f0[8] = {v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x};
+      const float f1[8] = {v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y};
+      const float f2[8] = {v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z};
+      const float f3[8] = {v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w};
+      put(f0, j, slot); put(f1, j, slot + 1); put(f2, j, slot + 2); put(f3, j, slot + 3);
     }
     // the two halo columns cc = 0 and cc = 129
     const int n_edge = n_chunks * 3 * 2;
@@ -161,7 +168,7 @@ __device__ __forceinline__ void stage_source(const float* __restrict__ src, int 
       float f[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) f[c] = ok ? __ldg(src + ((size_t)j * 8 + c) * plane + (size_t)y * W + xx) : 0.f;
-      reinterpret_cast<uint4*>(s_a + (size_t)j * (TC_SLOTS * 16))[rr * TC_P + cc] = pack8(f);
+      put(f, j, rr * TC_P + cc);
     }
   } else {
     const int n_tasks = n_chunks * 3 * TC_P;
@@ -172,10 +179,9 @@ __device__ __forceinline__ void stage_source(const float* __restrict__ src, int 
       float f[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) f[c] = ok ? __ldg(src + ((size_t)j * 8 + c) * plane + (size_t)y * W + xx) : 0.f;
-      reinterpret_cast<uint4*>(s_a + (size_t)j * (TC_SLOTS * 16))[rr * TC_P + cc] = pack8(f);
+      put(f, j, rr * TC_P + cc);
     }
   }
 }
-
 
 }  // namespace snnflow

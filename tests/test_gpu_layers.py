@@ -105,7 +105,9 @@ def test_backward_capi(name):
     v, z, out, cur = capi_forward(g)
     if not name.endswith("_rand"):
         assert np.array_equal(z.cpu().numpy(), g["z"])
-    r = capi_backward(g, dev(g["v"]), cur)   # teacher-forced membranes from the reference
+    from snnflow_b200 import _lib
+    # teacher-forced membranes from the reference; CUDA-core (exact fp32) data/weight gradients
+    r = capi_backward(g, dev(g["v"]), cur, flags_extra=_lib.NO_TENSOR_CORES)
     for k in ("g_x", "dw_ff", "dw_rec", "dleak", "dthresh"):
         if r[k] is None:
             continue

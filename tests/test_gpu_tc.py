@@ -173,6 +173,7 @@ def test_tc_backward_golden(name):
     prof = _lib.profile_summary()
     _lib.profile(False)
     assert "wgrad_tc" in prof and "wgrad_simt" not in prof
+    assert "dgrad_tc" in prof and "dgrad_simt" not in prof
     for k in ("g_x", "dw_ff", "dw_rec", "dleak", "dthresh"):
         if r[k] is None:
             continue
@@ -198,7 +199,7 @@ def test_tc_wgrad_matches_simt_large():
     lam, theta = torch.full((C,), 0.6).cuda(), torch.full((C,), 0.3).cuda()
     ws = torch.empty(L.snnflow_convlif_bwd_workspace_bytes(B, C, C, H, W, 1), dtype=torch.uint8, device="cuda")
     outs = []
-    for extra in (0, _lib.INPUT_EXACT16):
+    for extra in (_lib.NO_TENSOR_CORES, _lib.INPUT_EXACT16):
         g_x, g_v, g_z = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
         dwf, dwr = torch.zeros_like(w_ff), torch.zeros_like(w_rec)
         dl, dt = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
@@ -208,6 +209,42 @@ def test_tc_wgrad_matches_simt_large():
             _lib.ptr(dwf), _lib.ptr(dwr), _lib.ptr(dl), _lib.ptr(dt), ws.data_ptr(), ws.numel(), B, C, C, H, W,
             _lib.HARD_RESET | _lib.DETACH_RESET | extra, 0, 10.0, _lib.stream()), "bwd")
         torch.cuda.synchronize()
-        outs.append((dwf.cpu().numpy(), dwr.cpu().numpy()))
+        outs.append((dwf.cpu().numpy(), dwr.cpu().numpy(), g_x.cpu().numpy(), g_z.cpu().numpy()))
     for a, b in zip(outs[0], outs[1]):
         np.testing.assert_allclose(b, a, rtol=1e-4, atol=1e-4 * np.abs(a).max())
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 20, 200, True, True), (1, 16, 32, 9, 130, False, True), (2, 32, 32, 7, 64, True, False)])
+def test_tc_dgrad_matches_simt(shape):
+    """Odd widths / channel mixes / non-detached reset (g_z_in accumulates onto the reset term)."""
+    from snnflow_b200 import _lib
+    L = _lib.lib()
+    B, Cin, C, H, W, rec, detach = shape
+    gen = torch.Generator().manual_seed(21 + W)
+    x = (torch.rand(B, Cin, H, W, generator=gen) < 0.2).float().cuda()
+    z = (torch.rand(B, C, H, W, generator=gen) < 0.15).float().cuda()
+    v_in = torch.randn(B, C, H, W, generator=gen).cuda()
+    v_out = (torch.randn(B, C, H, W, generator=gen) * 0.3 + 0.2).cuda()
+    cur = torch.randn(B, C, H, W, generator=gen).cuda()
+    g_out = (torch.randn(B, C, H, W, generator=gen) * torch.rand(B, C, H, W, generator=gen) ** 8).cuda()   # wide dynamic range
+    w_ff = ((torch.rand(C, Cin, 3, 3, generator=gen) - 0.5) * 0.3).cuda()
+    w_rec = ((torch.rand(C, C, 3, 3, generator=gen) - 0.5) * 0.3).cuda() if rec else None
+    lam, theta = torch.full((C,), 0.6).cuda(), torch.full((C,), 0.3).cuda()
+    ws = torch.empty(L.snnflow_convlif_bwd_workspace_bytes(B, Cin, C, H, W, int(rec)), dtype=torch.uint8, device="cuda")
+    base = _lib.HARD_RESET | (_lib.DETACH_RESET if detach else 0)
+    outs = []
+    for extra in (_lib.NO_TENSOR_CORES, 0):
+        g_x, g_v, g_z = torch.empty_like(x), torch.empty_like(z), torch.empty_like(z)
+        dwf = torch.zeros_like(w_ff)
+        dwr = torch.zeros_like(w_rec) if rec else None
+        dl, dt = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        _lib.check(L.snnflow_convlif_bwd(
+            _lib.ptr(x), _lib.ptr(w_ff), _lib.ptr(w_rec), _lib.ptr(v_in), _lib.ptr(z), _lib.ptr(v_out), _lib.ptr(cur),
+            _lib.ptr(lam), _lib.ptr(theta), _lib.ptr(g_out), None, None, _lib.ptr(g_x), _lib.ptr(g_v), _lib.ptr(g_z),
+            _lib.ptr(dwf), _lib.ptr(dwr), _lib.ptr(dl), _lib.ptr(dt), ws.data_ptr(), ws.numel(), B, Cin, C, H, W,
+            base | extra, 0, 10.0, _lib.stream()), "bwd")
+        torch.cuda.synchronize()
+        outs.append((g_x.cpu().numpy(), g_z.cpu().numpy()))
+    np.testing.assert_allclose(outs[1][0], outs[0][0], rtol=1e-4, atol=1e-5 * np.abs(outs[0][0]).max())
+    if rec or not detach:
+        np.testing.assert_allclose(outs[1][1], outs[0][1], rtol=1e-4, atol=1e-5 * np.abs(outs[0][1]).max())
