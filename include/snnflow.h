@@ -126,6 +126,48 @@ int snnflow_pred_bwd(const float* x, const float* w, const float* flow, const fl
                      snnflow_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Whole-network window: LIFFireNet / LIFFireFlowNet forward over T time bins and the matching BPTT, as ONE
+ * host call each (no Python between the ~80 + ~300 kernel launches; capturable in a CUDA graph).
+ * Replaces T calls of LIFFireNet.forward (models/model.py:172-182: head -> G1 -> R1a -> R1b -> G2 -> R2a -> R2b
+ * -> 1x1 tanh pred) plus the autograd graph torch would build for them (train_flow.py:232,262).
+ *
+ * Layers are indexed 0..6 in that order; bit l of recurrent_mask marks a ConvLIFRecurrent (FireNet: 0x12).
+ * acts: activation arena of snnflow_net_acts_floats() floats.  With save != 0 it keeps, for every layer l and bin
+ *   t, the block [v | z | I] (3 * B*C*H*W floats) at offset ((l*T + t) * 3) * B*C*H*W: the [v | z] pair of (l, T-1)
+ *   is the layer's state [2,B,C,H,W] after the window.  With save == 0 (inference) only two bins are kept
+ *   (ping-pong) and I is not stored; the final state of layer l is at slot (T-1) % 2.
+ * state_in: NULL (zero state) or 7 pointers to [2,B,C,H,W] states from the previous window.
+ * input [T,B,num_bins,H,W]; flow [T,B,2,H,W].  exact_input != 0: the caller guarantees the input holds small
+ *   integers (event counts), which lets layer 0's weight gradient use bf16 operands (it does not today).
+ * Backward: g_flow [T,B,2,H,W] -> accumulates (+=) into the d* pointers of every layer and d_pred_w / d_pred_b;
+ *   gradients w.r.t. state_in and input are not produced (the reference detaches states at window boundaries,
+ *   train_flow.py:278, and the event counts need no gradient).  model.residual (default False) is not covered.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, C, H, W, T, num_bins;
+  unsigned recurrent_mask;
+  unsigned flags;       /* SNNFLOW_HARD_RESET | SNNFLOW_DETACH_RESET | SNNFLOW_NO_TENSOR_CORES */
+  int surrogate;
+  float act_width;
+} snnflow_net_desc;
+
+typedef struct {
+  const float *w_ff, *w_rec, *lam, *theta; /* parameters (lam/theta already sigmoid'ed / clamped)        */
+  const void* packed;                      /* snnflow_convlif_pack blob or NULL (CUDA-core forward)      */
+  float *dw_ff, *dw_rec, *dlam, *dtheta;   /* gradient accumulators (backward only; may be NULL forward) */
+} snnflow_layer_ptrs;
+
+size_t snnflow_net_acts_floats(const snnflow_net_desc* d, int save);
+size_t snnflow_net_bwd_workspace_bytes(const snnflow_net_desc* d);
+int snnflow_net_forward(const snnflow_net_desc* d, const snnflow_layer_ptrs* layers, const float* pred_w,
+                        const float* pred_b, const float* input, const float* const* state_in, float* acts,
+                        float* flow, int save, snnflow_stream_t stream);
+int snnflow_net_backward(const snnflow_net_desc* d, const snnflow_layer_ptrs* layers, const float* pred_w,
+                         const float* input, const float* const* state_in, const float* acts, const float* flow,
+                         const float* g_flow, float* d_pred_w, float* d_pred_b, void* workspace,
+                         size_t workspace_bytes, snnflow_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Event encodings (dataloader/encodings.py).  xs, ys, ts, ps: [N] fp32 device arrays (integer-valued
  * coordinates, truncated like .long()); events outside the sensor are ignored.
  * encode_cnt   : events_to_channels (:70-85)  -> out [2,H,W]  per-polarity counts (exact integers)

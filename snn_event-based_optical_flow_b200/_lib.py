@@ -47,8 +47,12 @@ class SnnflowError(RuntimeError):
     pass
 
 
+_ENGINE_SYMBOLS = ["snnflow_net_acts_floats", "snnflow_net_bwd_workspace_bytes", "snnflow_net_forward",
+                   "snnflow_net_backward"]   # struct-taking entry points, bound in engine.py
+
+
 def exported_symbols():
-    return sorted(_PROTOS)
+    return sorted(list(_PROTOS) + _ENGINE_SYMBOLS)
 
 
 def lib():

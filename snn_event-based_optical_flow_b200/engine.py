@@ -1,0 +1,192 @@
+"""Whole-window execution of LIFFireNet / LIFFireFlowNet: T time bins forward (and the matching BPTT) as one
+C call each (``snnflow_net_forward`` / ``snnflow_net_backward``, include/snnflow.h), wrapped in a single
+``torch.autograd.Function``.
+
+The per-layer modules stay the drop-in face (models/model.py calls them once per bin); this is the fast path for
+a caller that has the T bins of a loss window at hand (train_flow.py:232-279 processes them back to back anyway).
+Saved activations live in a preallocated arena ([v | z | I] per layer and bin), so nothing is allocated, stacked
+or cloned per layer-step, and gradients accumulate straight into per-parameter buffers.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+N_LAYERS = 7
+
+
+class NetDesc(ctypes.Structure):
+    _fields_ = [("B", ctypes.c_int), ("C", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("T", ctypes.c_int),
+                ("num_bins", ctypes.c_int), ("recurrent_mask", ctypes.c_uint), ("flags", ctypes.c_uint),
+                ("surrogate", ctypes.c_int), ("act_width", ctypes.c_float)]
+
+
+class LayerPtrs(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("w_ff", "w_rec", "lam", "theta", "packed", "dw_ff", "dw_rec", "dlam",
+                                               "dtheta")]
+
+
+def _bind(L):
+    if getattr(L, "_net_bound", False):
+        return
+    P = ctypes.c_void_p
+    L.snnflow_net_acts_floats.restype = ctypes.c_size_t
+    L.snnflow_net_acts_floats.argtypes = [ctypes.POINTER(NetDesc), ctypes.c_int]
+    L.snnflow_net_bwd_workspace_bytes.restype = ctypes.c_size_t
+    L.snnflow_net_bwd_workspace_bytes.argtypes = [ctypes.POINTER(NetDesc)]
+    L.snnflow_net_forward.restype = ctypes.c_int
+    L.snnflow_net_forward.argtypes = [ctypes.POINTER(NetDesc), ctypes.POINTER(LayerPtrs), P, P, P, ctypes.POINTER(P), P, P,
+                                      ctypes.c_int, P]
+    L.snnflow_net_backward.restype = ctypes.c_int
+    L.snnflow_net_backward.argtypes = [ctypes.POINTER(NetDesc), ctypes.POINTER(LayerPtrs), P, P, ctypes.POINTER(P), P, P, P,
+                                       P, P, P, ctypes.c_size_t, P]
+    L._net_bound = True
+
+
+def _state_ptrs(states):
+    arr = (ctypes.c_void_p * N_LAYERS)()
+    if states is None or all(s is None for s in states):
+        return None, arr
+    for i, s in enumerate(states):
+        arr[i] = None if s is None else s.data_ptr()
+    return arr, arr
+
+
+class _WindowFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner, cnt, *params):
+        L = _lib.lib()
+        _bind(L)
+        net = runner.net
+        layers = runner.layers
+        T, B, nb, H, W = cnt.shape
+        C = layers[0].hidden_size
+        dev = cnt.device
+        cnt = cnt.float().contiguous()
+        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params if p is not None)
+        # effective leak / threshold of all layers in two launches (spiking_submodules.py:133,136)
+        lam = torch.sigmoid(torch.stack([l.leak.detach().reshape(-1) for l in layers]))
+        theta = torch.stack([l.thresh.detach().reshape(-1) for l in layers]).clamp_min(0.01)
+        first = layers[0]
+        flags = (_lib.HARD_RESET if first.hard_reset else 0) | (_lib.DETACH_RESET if first.detach else 0)
+        if not first.use_tensor_cores:
+            flags |= _lib.NO_TENSOR_CORES
+        mask = sum(1 << i for i, l in enumerate(layers) if l.recurrent)
+        desc = NetDesc(B, C, H, W, T, nb, mask, flags, _lib.SURROGATE_ID[first.activation], first._act_width)
+        packed = [None if (i == 0 or not l.use_tensor_cores) else l._packed_weights() for i, l in enumerate(layers)]
+        lp = (LayerPtrs * N_LAYERS)()
+        for i, l in enumerate(layers):
+            lp[i].w_ff = l.ff.weight.data_ptr()
+            lp[i].w_rec = l.rec.weight.data_ptr() if l.recurrent else None
+            lp[i].lam = lam[i].data_ptr()
+            lp[i].theta = theta[i].data_ptr()
+            lp[i].packed = None if packed[i] is None else packed[i].data_ptr()
+        acts = runner.arena(desc, need_bwd, dev)
+        flow = torch.empty((T, B, 2, H, W), dtype=torch.float32, device=dev)
+        states = net._states
+        sp, keep = _state_ptrs(states)
+        pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
+        _lib.check(L.snnflow_net_forward(ctypes.byref(desc), lp, pw.data_ptr(), None if pb is None else pb.data_ptr(),
+                                         cnt.data_ptr(), sp, acts.data_ptr(), flow.data_ptr(), int(need_bwd),
+                                         _lib.stream()), "snnflow_net_forward")
+        # new states: zero-copy views into the arena ([v | z] of the last bin)
+        n = B * C * H * W
+        new_states = []
+        for i in range(N_LAYERS):
+            off = ((i * T + (T - 1)) * 3 * n) if need_bwd else ((i * 2 + ((T - 1) & 1)) * 2 * n)
+            new_states.append(acts[off:off + 2 * n].view(2, B, C, H, W))
+        runner.new_states = new_states
+        if need_bwd:
+            ctx.runner, ctx.desc, ctx.lam, ctx.theta, ctx.packed = runner, desc, lam, theta, packed
+            ctx.cnt, ctx.acts, ctx.flow, ctx.states_in = cnt, acts, flow, list(states)
+        return flow
+
+    @staticmethod
+    def backward(ctx, g_flow):
+        L = _lib.lib()
+        runner, desc, lam, theta = ctx.runner, ctx.desc, ctx.lam, ctx.theta
+        layers, net = runner.layers, runner.net
+        dev = g_flow.device
+        C = desc.C
+        g_flow = g_flow.float().contiguous()
+        dlam = torch.zeros_like(lam)
+        dtheta = torch.zeros_like(theta)
+        dws = []
+        lp = (LayerPtrs * N_LAYERS)()
+        for i, l in enumerate(layers):
+            dwf = torch.zeros_like(l.ff.weight)
+            dwr = torch.zeros_like(l.rec.weight) if l.recurrent else None
+            dws.append((dwf, dwr))
+            lp[i].w_ff = l.ff.weight.data_ptr()
+            lp[i].w_rec = l.rec.weight.data_ptr() if l.recurrent else None
+            lp[i].lam = lam[i].data_ptr()
+            lp[i].theta = theta[i].data_ptr()
+            lp[i].packed = None if ctx.packed[i] is None else ctx.packed[i].data_ptr()
+            lp[i].dw_ff = dwf.data_ptr()
+            lp[i].dw_rec = None if dwr is None else dwr.data_ptr()
+            lp[i].dlam = dlam[i].data_ptr()
+            lp[i].dtheta = dtheta[i].data_ptr()
+        pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
+        d_pw = torch.zeros_like(pw)
+        d_pb = torch.zeros(2, dtype=torch.float32, device=dev)
+        ws = runner.workspace(desc, dev)
+        sp, keep = _state_ptrs(ctx.states_in)
+        _lib.check(L.snnflow_net_backward(ctypes.byref(desc), lp, pw.data_ptr(), ctx.cnt.data_ptr(), sp, ctx.acts.data_ptr(),
+                                          ctx.flow.data_ptr(), g_flow.data_ptr(), d_pw.data_ptr(), d_pb.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), _lib.stream()), "snnflow_net_backward")
+        d_leak = dlam * lam * (1.0 - lam)                                           # sigmoid'
+        thr = torch.stack([l.thresh.detach().reshape(-1) for l in layers])
+        d_thresh = dtheta * (thr >= 0.01).float()                                   # clamp_min'
+        grads = []
+        for i, l in enumerate(layers):
+            grads += [dws[i][0], dws[i][1], d_leak[i].reshape(l.leak.shape), d_thresh[i].reshape(l.thresh.shape)]
+        grads += [d_pw, d_pb if pb is not None else None]
+        return (None, None) + tuple(grads)
+
+
+class WindowRunner:
+    """Runs windows of T bins through a snnflow LIFFireNet / LIFFireFlowNet with one C call per direction."""
+
+    def __init__(self, net):
+        self.net = net
+        self.layers = [net.head, net.G1, net.R1a, net.R1b, net.G2, net.R2a, net.R2b]
+        self._arenas = {}
+        self._flip = 0
+        self._ws = None
+        self.new_states = None
+
+    def supported(self):
+        l0 = self.layers[0]
+        same = all((l.hard_reset, l.detach, l.activation, l._act_width) ==
+                   (l0.hard_reset, l0.detach, l0.activation, l0._act_width) for l in self.layers)
+        return same and not self.net.residual and not self.net.norm_input and not self.layers[0].recurrent
+
+    def arena(self, desc, save, dev):
+        # two arenas per shape: the states of window k (views into arena k%2) feed window k+1 (arena (k+1)%2)
+        n = _lib.lib().snnflow_net_acts_floats(ctypes.byref(desc), int(save))
+        self._flip ^= 1
+        key = (self._flip, bool(save))
+        buf = self._arenas.get(key)
+        if buf is None or buf.numel() < n or buf.device != dev:
+            buf = torch.empty(n, dtype=torch.float32, device=dev)
+            self._arenas[key] = buf
+        return buf
+
+    def workspace(self, desc, dev):
+        n = _lib.lib().snnflow_net_bwd_workspace_bytes(ctypes.byref(desc))
+        if self._ws is None or self._ws.numel() < n or self._ws.device != dev:
+            self._ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        return self._ws
+
+    def __call__(self, cnt_window):
+        """cnt_window [T,B,num_bins,H,W] -> flow [T,B,2,H,W]; updates net._states like T forward calls would."""
+        if not cnt_window.is_cuda:
+            raise _lib.SnnflowError("snnflow WindowRunner runs on CUDA tensors only (no CPU fallback)")
+        params = []
+        for l in self.layers:
+            params += [l.ff.weight, l.rec.weight if l.recurrent else None, l.leak, l.thresh]
+        params += [self.net.pred.conv2d.weight, self.net.pred.conv2d.bias]
+        flow = _WindowFn.apply(self, cnt_window, *params)
+        self.net._states = self.new_states
+        return flow

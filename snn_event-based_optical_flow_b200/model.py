@@ -67,6 +67,18 @@ class LIFFireNet(nn.Module):
     def init_cropping(self, width, height):
         pass
 
+    def forward_window(self, event_cnt_window):
+        """T bins at once: [T,B,num_bins,H,W] -> flow [T,B,2,H,W], equivalent to T calls of forward() (same states,
+        same gradients) but executed as one C call per direction (engine.WindowRunner)."""
+        from .engine import WindowRunner
+        runner = getattr(self, "_window_runner", None)
+        if runner is None:
+            runner = WindowRunner(self)
+            object.__setattr__(self, "_window_runner", runner)
+        if not runner.supported():
+            return torch.stack([self.forward(None, event_cnt_window[t])["flow"][0] for t in range(event_cnt_window.shape[0])])
+        return runner(event_cnt_window)
+
     def forward(self, event_voxel=None, event_cnt=None, log=False, return_dict=True):
         if self.encoding == "voxel":
             x = event_voxel

@@ -45,11 +45,12 @@ class TrainWindow:
         self.model, self.loss_fn, self.opt, self.clip = model, loss_fn, optimizer, clip_grad
         self.reducer = FlatGradAllReduce(model.parameters(), group)
 
-    def step(self, batch):
+    def step(self, batch, use_window=True):
         T = batch["event_cnt"].shape[0]
+        flows = self.model.forward_window(batch["event_cnt"]) if (use_window and hasattr(self.model, "forward_window")) else None
         for t in range(T):
-            out = self.model(None, batch["event_cnt"][t])
-            self.loss_fn.event_flow_association(out["flow"], batch["event_list"][t], batch["event_list_pol_mask"][t],
+            flow = flows[t] if flows is not None else self.model(None, batch["event_cnt"][t])["flow"][0]
+            self.loss_fn.event_flow_association([flow], batch["event_list"][t], batch["event_list_pol_mask"][t],
                                                 batch["event_mask"][t])
         loss = self.loss_fn()
         loss.backward()
