@@ -64,7 +64,7 @@ class _WindowFn(torch.autograd.Function):
         C = layers[0].hidden_size
         dev = cnt.device
         cnt = cnt.float().contiguous()
-        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params if p is not None)
+        need_bwd = any(ctx.needs_input_grad)   # (grad mode is off inside Function.forward)
         # effective leak / threshold of all layers in two launches (spiking_submodules.py:133,136)
         lam = torch.sigmoid(torch.stack([l.leak.detach().reshape(-1) for l in layers]))
         theta = torch.stack([l.thresh.detach().reshape(-1) for l in layers]).clamp_min(0.01)
