@@ -168,6 +168,39 @@ int snnflow_net_backward(const snnflow_net_desc* d, const snnflow_layer_ptrs* la
                          size_t workspace_bytes, snnflow_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Layer-major window engine: the same window (same arguments, same results) executed layer by layer instead of
+ * bin by bin.  A layer at bin t depends only on the layer below at bin t and on its own state, so a feed-forward
+ * ConvLIF runs all T bins in ONE launch with its membrane in registers, a ConvLIFRecurrent takes one launch per
+ * bin, and the backward pass computes the data gradient and the weight gradient of a layer in one launch each over
+ * all T*B images.  Spikes travel between layers as bf16 planes with a zero border (TMA-staged straight into the
+ * tensor-core layout); weights are split into three bf16 terms (every product exact, fp32 accumulation), gradients
+ * into bf16 hi + lo.  Covers C in {16, 32, 64}, num_bins <= 16 with bf16-exact input values (event counts),
+ * SNNFLOW_DETACH_RESET set, feed-forward head; snnflow_window_supported() tells, everything else stays on
+ * snnflow_net_forward / snnflow_net_backward.
+ *
+ * arena: snnflow_window_arena_bytes() bytes, 256-byte aligned, ZERO-FILLED ONCE by the caller when it is allocated
+ *   (or when the descriptor changes): the plane borders are never written by the kernels and must read as zero.
+ *   The state [2,B,C,H,W] of layer l after the window lives inside the arena at the byte offset reported by
+ *   snnflow_window_state_offsets() (zero copy).  With save != 0 the arena also keeps what the backward needs.
+ * workspace (backward): snnflow_window_workspace_bytes() bytes, 256-byte aligned, zero-filled once as well.
+ * state_in, layers, pred_*, input, flow, g_flow and the gradient accumulation semantics are those of
+ * snnflow_net_forward / snnflow_net_backward (layers[l].packed is ignored: the engine packs per window).
+ * snnflow_window_inexact_count: number of input values seen so far that were not bf16-exact (synchronises).
+ * --------------------------------------------------------------------------------------------- */
+int snnflow_window_supported(const snnflow_net_desc* d, int backward /* 0: forward (save == 0) only */);
+size_t snnflow_window_arena_bytes(const snnflow_net_desc* d, int save);
+size_t snnflow_window_workspace_bytes(const snnflow_net_desc* d);
+int snnflow_window_state_offsets(const snnflow_net_desc* d, int save, size_t* offsets_bytes /* [7] */);
+unsigned int snnflow_window_inexact_count(int reset);
+int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_layer_ptrs* layers, const float* pred_w,
+                           const float* pred_b, const float* input, const float* const* state_in, void* arena,
+                           float* flow, int save, snnflow_stream_t stream);
+int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_layer_ptrs* layers, const float* pred_w,
+                            const float* const* state_in, const void* arena, const float* flow, const float* g_flow,
+                            float* d_pred_w, float* d_pred_b, void* workspace, size_t workspace_bytes,
+                            snnflow_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Event encodings (dataloader/encodings.py).  xs, ys, ts, ps: [N] fp32 device arrays (integer-valued
  * coordinates, truncated like .long()); events outside the sensor are ignored.
  * encode_cnt   : events_to_channels (:70-85)  -> out [2,H,W]  per-polarity counts (exact integers)

@@ -221,10 +221,15 @@ def train_fixture(ref, name, *, kind, C, B, H, W, T, n, seed, mask_output=False)
     _save(name, kind=kind, dims=np.array([C, B, H, W, T, n]), mask_output=int(mask_output), **arrs)
 
 
-def main():
+def main(only=None):
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     ref = ref_shim.load()
+    if only:   # regenerate selected fixtures only (python oracle/make_golden.py --only name[,name])
+        g = globals()
+        for fn in ("layer_fixture", "net_fixture", "encode_fixture", "iwe_fixture", "train_fixture"):
+            orig = g[fn]
+            g[fn] = (lambda o: (lambda r, name, **kw: o(r, name, **kw) if name in only else None))(orig)
     # --- single layers (fwd + bwd), bit-exact tier (dyadic weights, spike inputs) ---
     layer_fixture(ref, "layer_ff_hard_arctan", recurrent=False, Cin=4, C=8, B=2, H=11, W=13, T=4,
                   hard_reset=True, activation="arctanspike", seed=10)
@@ -259,7 +264,14 @@ def main():
     train_fixture(ref, "train_firenet_c8", kind="LIFFireNet", C=8, B=2, H=16, W=16, T=3, n=120, seed=50)
     train_fixture(ref, "train_fireflownet_c8_mask", kind="LIFFireFlowNet", C=8, B=1, H=16, W=16, T=3, n=150,
                   seed=51, mask_output=True)
+    # C = 16 / 32: inside the envelope of the layer-major window engine (tensor-core head layer included)
+    train_fixture(ref, "train_firenet_c16", kind="LIFFireNet", C=16, B=2, H=16, W=16, T=3, n=120, seed=52)
+    train_fixture(ref, "train_fireflownet_c32", kind="LIFFireFlowNet", C=32, B=1, H=12, W=20, T=4, n=150, seed=53)
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    sel = None
+    if "--only" in sys.argv:
+        sel = set(sys.argv[sys.argv.index("--only") + 1].split(","))
+    main(sel)

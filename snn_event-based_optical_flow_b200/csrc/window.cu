@@ -1,0 +1,389 @@
+// Layer-major window engine: host-side sequencing of one loss window of LIFFireNet / LIFFireFlowNet.
+//
+// The reference calls the network once per time bin and lets autograd replay the graph (models/model.py:172-182,
+// train_flow.py:232-279).  A layer at bin t only depends on the layer below at bin t and on its own state, so the
+// window can be executed LAYER BY LAYER: a feed-forward ConvLIF processes all T bins in one launch with its
+// membrane in registers, a ConvLIFRecurrent takes one launch per bin, and in the backward pass the data gradient
+// and the weight gradient of a layer are single launches over all T*B images.  ~30 + ~50 launches per window instead
+// of ~80 + ~380.  Layouts are described in window.cuh.
+#include "window.cuh"
+
+namespace snnflow {
+
+struct WinLayout {
+  PlaneGeom g;
+  size_t n;                       // B*C*H*W
+  int Kin[WIN_LAYERS];            // allocated input channels (multiple of 16)
+  int Cin[WIN_LAYERS];            // real input channels
+  bool rec[WIN_LAYERS];
+  size_t off_inplanes;
+  size_t off_zp[WIN_LAYERS], zp_img_stride;   // bf16 planes; recurrent layers have B leading images (initial spikes)
+  size_t off_v[WIN_LAYERS], off_cur[WIN_LAYERS];
+  size_t off_fwd_blob[WIN_LAYERS], off_dg_blob[WIN_LAYERS], off_rb_blob[WIN_LAYERS], off_par[WIN_LAYERS];
+  uint32_t fwd_blob_bytes[WIN_LAYERS], dg_blob_bytes[WIN_LAYERS], rb_blob_bytes[WIN_LAYERS], rec_w_off[WIN_LAYERS];
+  size_t total;
+};
+
+static WinLayout win_layout(const snnflow_net_desc* d, int save) {
+  WinLayout L{};
+  L.g = plane_geom(d->H, d->W);
+  const int C = d->C, T = d->T, B = d->B;
+  L.n = (size_t)B * C * d->H * d->W;
+  L.zp_img_stride = (size_t)(C / 8) * L.g.plane_bytes;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
+  L.off_inplanes = take((size_t)T * B * 2 * L.g.plane_bytes);
+  for (int l = 0; l < WIN_LAYERS; ++l) {
+    L.rec[l] = (d->recurrent_mask >> l) & 1u;
+    L.Cin[l] = l == 0 ? d->num_bins : C;
+    L.Kin[l] = l == 0 ? 16 : C;
+    L.off_zp[l] = take((size_t)(L.rec[l] ? T + 1 : T) * B * L.zp_img_stride);
+    if (save) {
+      L.off_v[l] = take((size_t)(T + 1) * L.n * sizeof(float));   // v[0..T-1] then z of the last bin
+      L.off_cur[l] = take((size_t)T * L.n * sizeof(float));
+    } else {
+      L.off_v[l] = take((size_t)(L.rec[l] ? 4 : 2) * L.n * sizeof(float));   // [pp0 pp1] v_last z_last
+      L.off_cur[l] = 0;
+    }
+    const size_t ffb = (size_t)9 * 3 * L.Kin[l] * C * 2, recb = L.rec[l] ? (size_t)9 * 3 * C * C * 2 : 0;
+    L.rec_w_off[l] = (uint32_t)ffb;
+    L.fwd_blob_bytes[l] = (uint32_t)(ffb + recb);
+    L.off_fwd_blob[l] = take(L.fwd_blob_bytes[l]);
+    L.dg_blob_bytes[l] = l > 0 ? (uint32_t)((size_t)9 * 2 * L.Kin[l] * C * 2) : 0;
+    L.off_dg_blob[l] = take(L.dg_blob_bytes[l]);
+    L.rb_blob_bytes[l] = L.rec[l] ? (uint32_t)((size_t)9 * 2 * C * C * 2) : 0;
+    L.off_rb_blob[l] = take(L.rb_blob_bytes[l]);
+    L.off_par[l] = take((size_t)C * 4 * sizeof(float));
+  }
+  L.total = o;
+  return L;
+}
+
+struct WinPlan {   // tile plans of the tensor-core kernels for this shape
+  int R_ff, S_ff, R_head, S_head, R_rec, S_rec, R_dg, S_dg, R_rb, S_rb;
+  uint32_t sub_ff, cs_ff, st_ff, sub_head, cs_head, st_head, sub_rec, cs_rec, st_rec, sub_dg, cs_dg, st_dg, sub_rb, cs_rb, st_rb;
+  bool ok;
+};
+
+static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool backward = true) {
+  WinPlan P{};
+  const int C = d->C;
+  bool any_rec = false;
+  for (int l = 0; l < WIN_LAYERS; ++l) any_rec |= L.rec[l];
+  uint32_t max_fwd_rec_blob = 0;
+  for (int l = 0; l < WIN_LAYERS; ++l)
+    if (L.rec[l] && L.fwd_blob_bytes[l] > max_fwd_rec_blob) max_fwd_rec_blob = L.fwd_blob_bytes[l];
+  P.ok = wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 3 * C * C * 2), true, &P.R_ff, &P.S_ff, &P.sub_ff, &P.cs_ff, &P.st_ff);
+  P.ok = P.ok && wt_plan(d->H, d->W, 2, C, (uint32_t)((size_t)9 * 3 * 16 * C * 2), true, &P.R_head, &P.S_head, &P.sub_head,
+                         &P.cs_head, &P.st_head);
+  if (any_rec)
+    P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, max_fwd_rec_blob, true, &P.R_rec, &P.S_rec, &P.sub_rec, &P.cs_rec, &P.st_rec);
+  if (!backward) return P;
+  if (any_rec) {
+    P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, &P.R_rb, &P.S_rb, &P.sub_rb,
+                           &P.cs_rb, &P.st_rb);
+  }
+  P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, &P.R_dg, &P.S_dg, &P.sub_dg,
+                         &P.cs_dg, &P.st_dg);
+  return P;
+}
+
+static bool win_supported(const snnflow_net_desc* d, bool backward = true) {
+  if (!d || d->B <= 0 || d->H <= 0 || d->W <= 0 || d->T <= 0) return false;
+  if (d->C != 16 && d->C != 32 && d->C != 64) return false;
+  if (d->num_bins <= 0 || d->num_bins > 16) return false;
+  if (!(d->flags & SNNFLOW_DETACH_RESET)) return false;        // the non-detached reset path stays on the per-step engine
+  if (d->flags & SNNFLOW_NO_TENSOR_CORES) return false;
+  if (d->recurrent_mask & 1u) return false;
+  if (d->surrogate < 0 || d->surrogate > 2) return false;
+  const WinLayout L = win_layout(d, 1);
+  if (!win_plan(d, L, backward).ok) return false;
+  if (!backward) return true;
+  for (int l = 0; l < WIN_LAYERS; ++l)
+    if (!wg_supported(d->C, L.Kin[l] / 8, L.rec[l] ? d->C / 8 : 0, d->H, d->W)) return false;
+  return true;
+}
+
+struct WinWorkspace {
+  size_t off_g[2], off_gp, gp_term_stride, off_gv, off_wpart[2], off_cpart, off_ppart, total;
+  int wg_grid_max, rb_grid, pw_parts, pred_parts;
+};
+
+static WinWorkspace win_workspace(const snnflow_net_desc* d, const WinLayout& L, const WinPlan& P) {
+  WinWorkspace W{};
+  const int C = d->C, T = d->T, B = d->B;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
+  W.off_g[0] = take((size_t)T * L.n * sizeof(float));
+  W.off_g[1] = take((size_t)T * L.n * sizeof(float));
+  W.gp_term_stride = align_up((size_t)T * B * L.zp_img_stride, 256);
+  W.off_gp = take(2 * W.gp_term_stride);
+  W.off_gv = take(L.n * sizeof(float));
+  W.wg_grid_max = 0;
+  for (int l = 0; l < WIN_LAYERS; ++l) {
+    const int g = wg_grid(T * B, d->H, d->W, C, L.Kin[l] / 8, L.rec[l] ? C / 8 : 0);
+    if (g > W.wg_grid_max) W.wg_grid_max = g;
+  }
+  W.off_wpart[0] = take((size_t)W.wg_grid_max * 9 * C * C * sizeof(float));
+  W.off_wpart[1] = take((size_t)W.wg_grid_max * 9 * C * C * sizeof(float));
+  W.rb_grid = P.R_rb ? wt_grid(B * (d->H / P.R_rb)) : 0;
+  W.pw_parts = B * ceil_div(d->H * d->W, 256);
+  const size_t c1 = (size_t)2 * C * W.pw_parts, c2 = (size_t)T * W.rb_grid * 2 * C;
+  W.off_cpart = take((c1 > c2 ? c1 : c2) * sizeof(float));
+  W.pred_parts = pred_planes_parts(T * B, d->H, d->W);
+  W.off_ppart = take((size_t)W.pred_parts * (2 * C + 2) * sizeof(float));
+  W.total = o;
+  return W;
+}
+
+}  // namespace snnflow
+using namespace snnflow;
+
+extern "C" int snnflow_window_supported(const snnflow_net_desc* d, int backward) { return win_supported(d, backward != 0) ? 1 : 0; }
+
+extern "C" size_t snnflow_window_arena_bytes(const snnflow_net_desc* d, int save) {
+  if (!win_supported(d, save != 0)) return 0;
+  return win_layout(d, save).total;
+}
+
+extern "C" size_t snnflow_window_workspace_bytes(const snnflow_net_desc* d) {
+  if (!win_supported(d)) return 0;
+  const WinLayout L = win_layout(d, 1);
+  return win_workspace(d, L, win_plan(d, L)).total;
+}
+
+extern "C" unsigned int snnflow_window_inexact_count(int reset) { return win_inexact_count(reset); }
+
+extern "C" int snnflow_window_state_offsets(const snnflow_net_desc* d, int save, size_t* offsets_bytes) {
+  SNNFLOW_REQUIRE(win_supported(d, save != 0) && offsets_bytes, "unsupported shape or null pointer");
+  const WinLayout L = win_layout(d, save);
+  for (int l = 0; l < WIN_LAYERS; ++l) {
+    if (save) offsets_bytes[l] = L.off_v[l] + (size_t)(d->T - 1) * L.n * sizeof(float);
+    else offsets_bytes[l] = L.off_v[l] + (L.rec[l] ? 2 : 0) * L.n * sizeof(float);
+  }
+  return SNNFLOW_OK;
+}
+
+extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_layer_ptrs* layers, const float* pred_w,
+                                      const float* pred_b, const float* input, const float* const* state_in, void* arena,
+                                      float* flow, int save, snnflow_stream_t stream) {
+  SNNFLOW_REQUIRE(win_supported(d, save != 0), "shape / options not covered by the window engine (use snnflow_net_forward)");
+  SNNFLOW_REQUIRE(layers && pred_w && input && arena && flow, "null pointer");
+  SNNFLOW_REQUIRE(((uintptr_t)arena & 255) == 0, "arena must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const WinLayout L = win_layout(d, save);
+  const WinPlan P = win_plan(d, L, save != 0);
+  unsigned char* A = (unsigned char*)arena;
+  const int C = d->C, T = d->T, B = d->B, H = d->H, W = d->W;
+  const size_t n = L.n;
+  const double px = (double)B * H * W;
+
+  PackArgs pk{};
+  for (int l = 0; l < WIN_LAYERS; ++l) {
+    const snnflow_layer_ptrs& P_ = layers[l];
+    SNNFLOW_REQUIRE(P_.w_ff && P_.lam && P_.theta && (!L.rec[l] || P_.w_rec), "null layer parameter");
+    pk.L[l].w_ff = P_.w_ff; pk.L[l].w_rec = L.rec[l] ? P_.w_rec : nullptr;
+    pk.L[l].fwd_blob = A + L.off_fwd_blob[l];
+    pk.L[l].dg_blob = (save && l > 0) ? A + L.off_dg_blob[l] : nullptr;
+    pk.L[l].rb_blob = (save && L.rec[l]) ? A + L.off_rb_blob[l] : nullptr;
+    pk.L[l].Cin = L.Cin[l]; pk.L[l].Kin = L.Kin[l]; pk.L[l].C = C;
+    pk.L[l].leak_lam = P_.lam; pk.L[l].theta = P_.theta;
+    pk.L[l].par = (float*)(A + L.off_par[l]);
+  }
+  int rc = launch_pack_weights(pk, st);
+  if (rc) return rc;
+  rc = launch_pack_input(input, A + L.off_inplanes, T * B, d->num_bins, 2, H, W, st);
+  if (rc) return rc;
+
+  for (int l = 0; l < WIN_LAYERS; ++l) {
+    const float* v_init = (state_in && state_in[l]) ? state_in[l] : nullptr;
+    const float* z_init = v_init ? v_init + n : nullptr;
+    float* vbase = (float*)(A + L.off_v[l]);
+    float* cbase = save ? (float*)(A + L.off_cur[l]) : nullptr;
+    // input planes of this layer: the packed event counts, or the spikes of the layer below
+    const unsigned char* xin;
+    size_t x_img_stride;
+    if (l == 0) { xin = A + L.off_inplanes; x_img_stride = 2 * L.g.plane_bytes; }
+    else { xin = A + L.off_zp[l - 1] + (L.rec[l - 1] ? (size_t)B * L.zp_img_stride : 0); x_img_stride = L.zp_img_stride; }
+    WtArgs a{};
+    a.src[0].planes = xin; a.src[0].img_stride = x_img_stride;
+    a.src[0].n_chunks = (uint32_t)(L.Kin[l] / 8); a.src[0].w_off = 0; a.src[0].w_terms = 3; a.src[0].w_used = 3;
+    a.n_src = 1;
+    a.wblob = A + L.off_fwd_blob[l]; a.wblob_bytes = L.fwd_blob_bytes[l];
+    a.B = B; a.H = H; a.W = W; a.Wp = W + 2; a.n_seg = ceil_div(W, 128); a.N = C;
+    a.hard_reset = (d->flags & SNNFLOW_HARD_RESET) ? 1 : 0;
+    a.par = (const float*)(A + L.off_par[l]);
+    a.zp_img_stride = L.zp_img_stride;
+    if (!L.rec[l]) {
+      a.n_outer = B; a.T = T;
+      if (l == 0) { a.R = P.R_head; a.S = P.S_head; a.sub_bytes = P.sub_head; a.chunk_stride = P.cs_head; a.stage_bytes = P.st_head; }
+      else { a.R = P.R_ff; a.S = P.S_ff; a.sub_bytes = P.sub_ff; a.chunk_stride = P.cs_ff; a.stage_bytes = P.st_ff; }
+      a.v_init = v_init; a.z_init = z_init;
+      a.v_out = save ? vbase : nullptr; a.cur_out = cbase;
+      a.zp_out = A + L.off_zp[l];
+      a.v_last = save ? nullptr : vbase;
+      a.z_last = save ? vbase + (size_t)T * n : vbase + n;
+      rc = launch_wt_fwd(a, true, st, "win_fwd_seq", 4.0 * T * px * (L.Cin[l] + 4 * C + (save ? C : 0)),
+                         18.0 * T * px * C * L.Cin[l]);
+      if (rc) return rc;
+    } else {
+      // initial spikes of the window -> image block 0 of this layer's planes (zeros when there is no state)
+      rc = launch_pack_spikes(z_init, A + L.off_zp[l], B, C, H, W, st);
+      if (rc) return rc;
+      a.n_outer = B; a.T = 1;
+      a.R = P.R_rec; a.S = P.S_rec; a.sub_bytes = P.sub_rec; a.chunk_stride = P.cs_rec; a.stage_bytes = P.st_rec;
+      a.n_src = 2;
+      a.src[1] = a.src[0];
+      a.src[1].img_stride = L.zp_img_stride; a.src[1].n_chunks = (uint32_t)(C / 8); a.src[1].w_off = L.rec_w_off[l];
+      for (int t = 0; t < T; ++t) {
+        a.src[0].planes = xin + (size_t)t * B * x_img_stride;
+        a.src[1].planes = A + L.off_zp[l] + (size_t)t * B * L.zp_img_stride;
+        a.zin_planes = a.src[1].planes; a.zin_img_stride = L.zp_img_stride;
+        const bool last = t == T - 1;
+        if (save) {
+          a.v_prev = t > 0 ? vbase + (size_t)(t - 1) * n : v_init;
+          a.v_out = vbase + (size_t)t * n; a.cur_out = cbase + (size_t)t * n;
+          a.v_last = nullptr; a.z_last = last ? vbase + (size_t)T * n : nullptr;
+        } else {
+          a.v_prev = t > 0 ? vbase + (size_t)((t - 1) & 1) * n : v_init;
+          a.v_out = vbase + (size_t)(t & 1) * n; a.cur_out = nullptr;
+          a.v_last = last ? vbase + 2 * n : nullptr; a.z_last = last ? vbase + 3 * n : nullptr;
+        }
+        a.zp_out = A + L.off_zp[l] + (size_t)(t + 1) * B * L.zp_img_stride;
+        rc = launch_wt_fwd(a, false, st, "win_fwd_rec", 4.0 * px * (L.Cin[l] + 4 * C + (save ? C : 0)),
+                           18.0 * px * C * (L.Cin[l] + C));
+        if (rc) return rc;
+      }
+    }
+  }
+  const int top = WIN_LAYERS - 1;
+  return launch_pred_fwd_planes(A + L.off_zp[top] + (L.rec[top] ? (size_t)B * L.zp_img_stride : 0), L.zp_img_stride, pred_w,
+                                pred_b, flow, T * B, C, H, W, st);
+}
+
+extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_layer_ptrs* layers, const float* pred_w,
+                                       const float* const* state_in, const void* arena, const float* flow,
+                                       const float* g_flow, float* d_pred_w, float* d_pred_b, void* workspace,
+                                       size_t workspace_bytes, snnflow_stream_t stream) {
+  SNNFLOW_REQUIRE(win_supported(d), "shape / options not covered by the window engine (use snnflow_net_backward)");
+  SNNFLOW_REQUIRE(layers && pred_w && arena && flow && g_flow && workspace, "null pointer");
+  SNNFLOW_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)arena & 255) == 0, "arena / workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const WinLayout L = win_layout(d, 1);
+  const WinPlan P = win_plan(d, L);
+  const WinWorkspace WS = win_workspace(d, L, P);
+  if (workspace_bytes < WS.total) {
+    set_error("snnflow_window_backward: workspace %zu < %zu", workspace_bytes, WS.total);
+    return SNNFLOW_EWORKSPACE;
+  }
+  const unsigned char* A = (const unsigned char*)arena;
+  unsigned char* Wk = (unsigned char*)workspace;
+  const int C = d->C, T = d->T, B = d->B, H = d->H, W = d->W;
+  const size_t n = L.n;
+  const double px = (double)B * H * W;
+  float* gbuf[2] = {(float*)(Wk + WS.off_g[0]), (float*)(Wk + WS.off_g[1])};
+  unsigned char* gp = Wk + WS.off_gp;
+  float* g_v = (float*)(Wk + WS.off_gv);
+  float* wpart[2] = {(float*)(Wk + WS.off_wpart[0]), (float*)(Wk + WS.off_wpart[1])};
+  float* cpart = (float*)(Wk + WS.off_cpart);
+  float* ppart = (float*)(Wk + WS.off_ppart);
+  const int hard = (d->flags & SNNFLOW_HARD_RESET) ? 1 : 0;
+
+  const int top = WIN_LAYERS - 1;
+  int cur = 0;
+  int rc = launch_pred_bwd_planes(A + L.off_zp[top] + (L.rec[top] ? (size_t)B * L.zp_img_stride : 0), L.zp_img_stride, pred_w,
+                                  flow, g_flow, gbuf[cur], ppart, T * B, C, H, W, st);
+  if (rc) return rc;
+  rc = launch_pred_reduce_planes(ppart, d_pred_w, d_pred_b, C, WS.pred_parts, st);
+  if (rc) return rc;
+
+  for (int l = top; l >= 0; --l) {
+    const snnflow_layer_ptrs& P_ = layers[l];
+    const float* v_init = (state_in && state_in[l]) ? state_in[l] : nullptr;
+    const float* z_init = v_init ? v_init + n : nullptr;
+    const float* vbase = (const float*)(A + L.off_v[l]);
+    const float* cbase = (const float*)(A + L.off_cur[l]);
+    const float* par = (const float*)(A + L.off_par[l]);
+    const float* g_out = gbuf[cur];
+    int n_cpart, cpart_layout;
+    if (L.rec[l]) {
+      WtArgs a{};
+      // hi planes x (w_hi, w_lo), then lo planes x w_hi: two pipeline units per tile
+      a.src[0].img_stride = L.zp_img_stride; a.src[0].n_chunks = (uint32_t)(C / 8);
+      a.src[0].w_off = 0; a.src[0].w_terms = 2; a.src[0].w_used = 2;
+      a.src[1] = a.src[0]; a.src[1].w_used = 1;
+      a.n_src = 2;
+      a.wblob = A + L.off_rb_blob[l]; a.wblob_bytes = L.rb_blob_bytes[l];
+      a.n_outer = B; a.T = 1; a.B = B; a.H = H; a.W = W; a.Wp = W + 2; a.n_seg = ceil_div(W, 128); a.N = C;
+      a.R = P.R_rb; a.S = P.S_rb; a.sub_bytes = P.sub_rb; a.chunk_stride = P.cs_rb; a.stage_bytes = P.st_rb;
+      a.hard_reset = hard; a.surrogate = d->surrogate; a.width = d->act_width;
+      a.par = par;
+      a.g_v = g_v; a.gp_img_stride = L.zp_img_stride; a.gp_term_stride = WS.gp_term_stride;
+      for (int t = T - 1; t >= 0; --t) {
+        a.has_gz = t < T - 1; a.first_step = t == T - 1;
+        a.src[0].planes = gp + (size_t)(t + 1) * B * L.zp_img_stride;
+        a.src[1].planes = a.src[0].planes + WS.gp_term_stride;
+        a.g_out = g_out + (size_t)t * n; a.v_t = vbase + (size_t)t * n; a.cur_t = cbase + (size_t)t * n;
+        a.v_in = t > 0 ? vbase + (size_t)(t - 1) * n : v_init;
+        a.z_from_v = t > 0; a.z_init = z_init;
+        a.gp_out = gp + (size_t)t * B * L.zp_img_stride;
+        a.part = cpart + (size_t)t * WS.rb_grid * 2 * C;
+        rc = launch_wt_recbwd(a, st, 4.0 * px * C * (a.has_gz ? 8 : 7), a.has_gz ? 18.0 * px * C * C : 0.0);
+        if (rc) return rc;
+      }
+      n_cpart = T * WS.rb_grid; cpart_layout = 1;
+    } else {
+      PwSeqArgs a{};
+      a.v = vbase; a.cur = cbase; a.g_out = g_out; a.v_init = v_init; a.z_init = z_init; a.par = par;
+      a.gp = gp; a.gp_img_stride = L.zp_img_stride; a.gp_term_stride = WS.gp_term_stride;
+      a.part = cpart; a.T = T; a.B = B; a.C = C; a.H = H; a.W = W; a.hard_reset = hard; a.surrogate = d->surrogate;
+      a.n_part = WS.pw_parts; a.width = d->act_width;
+      rc = launch_pw_seq(a, st);
+      if (rc) return rc;
+      n_cpart = WS.pw_parts; cpart_layout = 0;
+    }
+    // data gradient through W_ff: the spike gradient of the layer below, all T*B images at once
+    if (l > 0) {
+      WtArgs a{};
+      a.src[0].planes = gp; a.src[0].img_stride = L.zp_img_stride; a.src[0].n_chunks = (uint32_t)(C / 8);
+      a.src[0].w_off = 0; a.src[0].w_terms = 2; a.src[0].w_used = 2;
+      a.src[1] = a.src[0]; a.src[1].planes = gp + WS.gp_term_stride; a.src[1].w_used = 1;
+      a.n_src = 2;
+      a.wblob = A + L.off_dg_blob[l]; a.wblob_bytes = L.dg_blob_bytes[l];
+      a.n_outer = T * B; a.T = 1; a.B = B; a.H = H; a.W = W; a.Wp = W + 2; a.n_seg = ceil_div(W, 128); a.N = L.Kin[l];
+      a.R = P.R_dg; a.S = P.S_dg; a.sub_bytes = P.sub_dg; a.chunk_stride = P.cs_dg; a.stage_bytes = P.st_dg;
+      a.g_x = gbuf[cur ^ 1];
+      rc = launch_wt_dgrad(a, st, 4.0 * T * px * (C + L.Kin[l]), 18.0 * T * px * C * L.Kin[l]);
+      if (rc) return rc;
+    }
+    // weight gradients over all T*B images, then the fixed-order reduction into the caller's accumulators
+    {
+      WgArgs a{};
+      if (l == 0) { a.xp[0] = A + L.off_inplanes; a.x_img_stride[0] = 2 * L.g.plane_bytes; }
+      else { a.xp[0] = A + L.off_zp[l - 1] + (L.rec[l - 1] ? (size_t)B * L.zp_img_stride : 0); a.x_img_stride[0] = L.zp_img_stride; }
+      a.x_chunks[0] = L.Kin[l] / 8; a.cin_alloc[0] = L.Kin[l]; a.cin_real[0] = L.Cin[l];
+      a.n_xsrc = 1;
+      if (L.rec[l]) {
+        a.xp[1] = A + L.off_zp[l]; a.x_img_stride[1] = L.zp_img_stride;   // image t*B + b = spikes before bin t
+        a.x_chunks[1] = C / 8; a.cin_alloc[1] = C; a.cin_real[1] = C;
+        a.n_xsrc = 2;
+      }
+      a.gp = gp; a.g_img_stride = L.zp_img_stride; a.g_term_stride = WS.gp_term_stride;
+      a.part[0] = wpart[0]; a.part[1] = wpart[1];
+      a.n_img = T * B; a.H = H; a.W = W; a.C = C;
+      rc = launch_wgrad_planes(a, st, 4.0 * T * px * (C + L.Cin[l] + (L.rec[l] ? C : 0)),
+                               18.0 * T * px * C * (L.Cin[l] + (L.rec[l] ? C : 0)));
+      if (rc) return rc;
+      WinReduceArgs r{};
+      r.wpart[0] = wpart[0]; r.wdst[0] = P_.dw_ff; r.cin_alloc[0] = L.Kin[l]; r.cin_real[0] = L.Cin[l];
+      r.wpart[1] = wpart[1]; r.wdst[1] = L.rec[l] ? P_.dw_rec : nullptr; r.cin_alloc[1] = C; r.cin_real[1] = C;
+      r.n_wpart = wg_grid(T * B, H, W, C, L.Kin[l] / 8, L.rec[l] ? C / 8 : 0);
+      r.cpart = cpart; r.n_cpart = n_cpart; r.cpart_layout = cpart_layout;
+      r.dlam = P_.dlam; r.dtheta = P_.dtheta; r.C = C;
+      rc = launch_win_reduce(r, st);
+      if (rc) return rc;
+    }
+    if (l > 0) cur ^= 1;
+  }
+  return SNNFLOW_OK;
+}

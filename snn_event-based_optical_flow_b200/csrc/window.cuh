@@ -1,0 +1,137 @@
+// Shared declarations of the layer-major window engine (window.cu, window_tc.cu, window_wgrad.cu, window_simt.cu).
+//
+// Data layout of the engine (all library-private, inside the caller-owned arena / workspace):
+//   * spike planes: bf16 [image][chunk = C/8][H+2][W+2][8 channels]  - one 16-byte "slot" per pixel and 8-channel
+//     chunk, with a one-pixel zero border around every image.  A row tile with its halo is therefore ONE contiguous
+//     byte range per chunk: it is staged by a TMA bulk copy straight into the canonical no-swizzle UMMA layout
+//     (K-major for the forward / data gradient, MN-major for the weight gradient) with no register staging, and the
+//     zero border supplies the convolution padding and isolates images from each other.  Spikes {0,1} and event
+//     counts are exact in bf16.  The borders are zeroed once (the arena is allocated zero-filled) and never written.
+//   * gradient planes: the input-current gradient g_I as bf16 hi + lo planes of the same geometry (16 mantissa bits).
+//   * membranes v, input currents I, gradients w.r.t. spikes: fp32 NCHW like the reference tensors.
+#pragma once
+#include "common.cuh"
+
+namespace snnflow {
+
+constexpr int WIN_LAYERS = 7;
+
+struct PlaneGeom {
+  int H, W, Hp, Wp;
+  size_t plane_bytes;   // one chunk of one image
+};
+inline PlaneGeom plane_geom(int H, int W) {
+  PlaneGeom g;
+  g.H = H; g.W = W; g.Hp = H + 2; g.Wp = W + 2;
+  g.plane_bytes = (size_t)g.Hp * g.Wp * 16;
+  return g;
+}
+
+// ---- tensor-core tile pipeline (window_tc.cu) ------------------------------------------------------
+struct WtSrc {
+  const unsigned char* planes;   // image 0, term 0, chunk 0, padded row 0
+  unsigned long long img_stride;   // bytes
+  uint32_t n_chunks;             // K/8
+  uint32_t w_off, w_terms, w_used;   // byte offset of this source's weights in the blob ; terms stored per tap (3 forward,
+                                     // 2 gradients) ; terms multiplied with this source (gradients: hi planes x {hi, lo}, lo planes x {hi})
+};
+
+struct WtArgs {
+  WtSrc src[2];
+  int n_src;
+  const unsigned char* wblob;
+  uint32_t wblob_bytes;
+  int n_outer;   // sequence mode: B sequences (image = t*B + b) ; otherwise the number of images
+  int T, B;
+  int H, W, Wp, R, S, n_seg, N;   // R rows per tile, S pipeline stages, n_seg 128-pixel segments per row, N = MMA N
+  uint32_t sub_bytes, chunk_stride, stage_bytes;
+  int hard_reset, surrogate;
+  float width;
+  const float* par;   // [N][4] = (lam, 1 - lam, theta, 0)
+  // forward
+  const float *v_init, *z_init;   // sequence mode, t == 0: [B][N][H][W] or NULL (zeros)
+  const float* v_prev;            // step mode: membrane before this step [B][N][H][W] or NULL (zeros)
+  const unsigned char* zin_planes;   // step mode: spikes before this step (planes, image b) or NULL (zeros)
+  unsigned long long zin_img_stride;
+  float *v_out, *cur_out;         // [images][N][H][W] or NULL
+  unsigned char* zp_out;          // spike planes written by this launch (image 0 = first image of the launch)
+  unsigned long long zp_img_stride;
+  float *v_last, *z_last;         // [B][N][H][W] or NULL: state after the last step
+  // data gradient
+  float* g_x;                     // [images][N][H][W]
+  // recurrent backward step
+  const float *g_out, *v_t, *cur_t, *v_in;   // v_in: membrane before the step or NULL ; z_init: spikes before step 0
+  float* g_v;                     // [B][N][H][W] in/out: gradient w.r.t. the membrane carried to the previous step
+  unsigned char* gp_out;          // g_I planes of this step (hi ; lo at + gp_term_stride)
+  unsigned long long gp_img_stride, gp_term_stride;
+  float* part;                    // [grid][2][N] partial sums of dlam, dtheta
+  int has_gz, first_step, z_from_v;   // first_step: g_v starts at zero ; z_from_v: z_in = spike(v_in) else from z_init
+};
+
+int launch_wt_fwd(const WtArgs& a, bool seq, cudaStream_t st, const char* prof_name, double bytes, double flops);
+int launch_wt_dgrad(const WtArgs& a, cudaStream_t st, double bytes, double flops);
+int launch_wt_recbwd(const WtArgs& a, cudaStream_t st, double bytes, double flops);
+// picks rows-per-tile / stages for the given shapes; returns false when the shape does not fit
+bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int* R, int* S,
+             uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes);
+int wt_grid(int n_tiles);
+
+// ---- weight gradient (window_wgrad.cu) --------------------------------------------------------------
+struct WgArgs {
+  const unsigned char* xp[2];
+  unsigned long long x_img_stride[2];
+  int x_chunks[2], cin_alloc[2], cin_real[2], n_xsrc;
+  const unsigned char* gp;
+  unsigned long long g_img_stride, g_term_stride;
+  float* part[2];   // per source: [grid][9][cin_alloc][C]
+  int n_img, H, W, Wp, R, S, C, P, n_cg, rpm, n_kyg, ksteps, x_rows;
+  uint32_t stage_bytes, g_off;
+};
+bool wg_supported(int C, int cin_chunks, int rec_chunks, int H, int W);
+int wg_grid(int n_img, int H, int W, int C, int cin_chunks, int rec_chunks);
+int launch_wgrad_planes(WgArgs a, cudaStream_t st, double bytes, double flops);
+
+// ---- CUDA-core helpers (window_simt.cu) ---------------------------------------------------------------
+int launch_pack_input(const float* in, unsigned char* planes, int n_img, int nb, int n_chunks, int H, int W,
+                      cudaStream_t st);
+unsigned int win_inexact_count(int reset);
+int launch_pack_spikes(const float* z, unsigned char* planes, int n_img, int C, int H, int W, cudaStream_t st);
+struct PackLayer {
+  const float *w_ff, *w_rec;
+  unsigned char *fwd_blob, *dg_blob, *rb_blob;   // forward (ff [+ rec]) ; data gradient through W_ff ; through W_rec
+  int Cin, Kin, C;   // Cin real input channels, Kin = allocated (multiple of 16), C output channels
+  const float *leak_lam, *theta;   // effective lam / theta (already sigmoid'ed / clamped)
+  float* par;                      // [C][4]
+};
+struct PackArgs { PackLayer L[WIN_LAYERS]; };
+int launch_pack_weights(const PackArgs& p, cudaStream_t st);
+struct PwSeqArgs {
+  const float *v, *cur, *g_out;    // [T*B][C][H][W]
+  const float *v_init, *z_init;    // [B][C][H][W] or NULL
+  const float* par;                // [C][4]
+  unsigned char* gp;               // g_I planes (hi ; lo at + term_stride), image t*B + b
+  unsigned long long gp_img_stride, gp_term_stride;
+  float* part;                     // [2][C][n_part]
+  int T, B, C, H, W, hard_reset, surrogate, n_part;
+  float width;
+};
+int launch_pw_seq(const PwSeqArgs& a, cudaStream_t st);
+int launch_pred_fwd_planes(const unsigned char* zp, unsigned long long img_stride, const float* w, const float* b,
+                           float* flow, int n_img, int C, int H, int W, cudaStream_t st);
+int launch_pred_bwd_planes(const unsigned char* zp, unsigned long long img_stride, const float* w, const float* flow,
+                           const float* g_flow, float* g_x, float* part, int n_img, int C, int H, int W,
+                           cudaStream_t st);
+int pred_planes_parts(int n_img, int H, int W);
+struct WinReduceArgs {
+  const float* wpart[2];   // [n_wpart][9][cin_alloc][C]
+  float* wdst[2];          // [C][cin_real][9]  (+=)
+  int cin_alloc[2], cin_real[2], n_wpart;
+  const float* cpart;      // channel partials, rows of length n_cpart: row r < 2C
+  int n_cpart, cpart_layout;   // layout 0: [2][C][n_cpart] ; 1: [n_cpart][2][C]
+  float *dlam, *dtheta;    // (+=)
+  int C;
+};
+int launch_win_reduce(const WinReduceArgs& a, cudaStream_t st);
+int launch_pred_reduce_planes(const float* part, float* dw, float* db, int C, int n_part, cudaStream_t st);
+
+}  // namespace snnflow

@@ -1,0 +1,417 @@
+// Layer-major window engine: CUDA-core kernels (packing, time-fused pointwise BPTT, flow head on planes, reductions).
+#include <cuda_bf16.h>
+
+#include "window.cuh"
+
+namespace snnflow {
+
+__device__ unsigned int g_win_inexact = 0;   // window inputs that one bf16 term does not represent exactly
+
+// ---- fp32 NCHW -> bf16 planes ------------------------------------------------------------------------
+// thread = one pixel of one (image, chunk): reads up to 8 channel planes (coalesced along x), writes one 16-B slot
+__global__ void __launch_bounds__(256) pack_planes_kernel(const float* __restrict__ in, unsigned char* __restrict__ planes,
+                                                          int n_ch, int n_chunks, int H, int W, int count_inexact) {
+  const int HW = H * W, Wp = W + 2;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  const int chunk = blockIdx.y, img = blockIdx.z;
+  if (p >= HW) return;
+  const int y = p / W, x = p - y * W;
+  uint32_t u[4] = {0, 0, 0, 0};
+  unsigned int bad = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int ch = chunk * 8 + c;
+    float v = 0.f;
+    if (in != nullptr && ch < n_ch) v = __ldg(in + ((size_t)img * n_ch + ch) * HW + p);
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    bad += (__bfloat162float(b) != v);
+    u[c >> 1] |= (uint32_t)__bfloat16_as_ushort(b) << ((c & 1) * 16);
+  }
+  const size_t plane_bytes = (size_t)(H + 2) * Wp * 16;
+  unsigned char* dst = planes + ((size_t)img * n_chunks + chunk) * plane_bytes + ((size_t)(y + 1) * Wp + x + 1) * 16;
+  *reinterpret_cast<uint4*>(dst) = make_uint4(u[0], u[1], u[2], u[3]);
+  if (count_inexact && bad) atomicAdd(&g_win_inexact, bad);
+}
+
+unsigned int win_inexact_count(int reset) {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, g_win_inexact, sizeof(v));
+  if (reset) {
+    unsigned int z = 0;
+    cudaMemcpyToSymbol(g_win_inexact, &z, sizeof(z));
+  }
+  return v;
+}
+
+int launch_pack_input(const float* in, unsigned char* planes, int n_img, int nb, int n_chunks, int H, int W,
+                      cudaStream_t st) {
+  prof_begin("win_pack_input", st, (double)n_img * H * W * (4.0 * nb + 16.0 * n_chunks));
+  pack_planes_kernel<<<dim3(ceil_div(H * W, 256), n_chunks, n_img), 256, 0, st>>>(in, planes, nb, n_chunks, H, W, 1);
+  return check_launch("pack_planes_kernel");
+}
+
+int launch_pack_spikes(const float* z, unsigned char* planes, int n_img, int C, int H, int W, cudaStream_t st) {
+  prof_begin("win_pack_state", st, (double)n_img * H * W * (4.0 * C + 2.0 * C));
+  pack_planes_kernel<<<dim3(ceil_div(H * W, 256), C / 8, n_img), 256, 0, st>>>(z, planes, C, C / 8, H, W, 0);
+  return check_launch("pack_planes_kernel");
+}
+
+// ---- weights -> UMMA shared-memory images, per-channel parameters ---------------------------------------
+// forward blob : for conv in (ff[, rec]): [tap][term 0..2][K/8][C/8][8 n][8 k] bf16, value(n = co, k = ci) = w[co][ci][tap]
+// gradient blob: [tap'][term 0..1][C/8][N/8][8 n][8 k] bf16, value(n = ci, k = co) = w[co][ci][8 - tap']
+__device__ __forceinline__ void split3(float v, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
+  a = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(a);
+  b = __float2bfloat16_rn(r1);
+  c = __float2bfloat16_rn(r1 - __bfloat162float(b));
+}
+
+__global__ void __launch_bounds__(256) window_pack_weights_kernel(const PackArgs p) {
+  const PackLayer& L = p.L[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int C = L.C;
+  // forward
+  size_t off = 0;
+  for (int conv = 0; conv < (L.w_rec ? 2 : 1); ++conv) {
+    const float* w = conv == 0 ? L.w_ff : L.w_rec;
+    const int K = conv == 0 ? L.Kin : C, Kreal = conv == 0 ? L.Cin : C;
+    const int per_tile = K * C;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(L.fwd_blob + off);
+    for (int i = tid; i < 9 * per_tile; i += 256) {
+      const int tap = i / per_tile, r = i - tap * per_tile;
+      const int n = r / K, k = r - n * K;
+      const float v = k < Kreal ? w[((size_t)n * Kreal + k) * 9 + tap] : 0.f;
+      __nv_bfloat16 t0, t1, t2;
+      split3(v, t0, t1, t2);
+      const int idx = ((k >> 3) * (C >> 3) + (n >> 3)) * 64 + (n & 7) * 8 + (k & 7);
+      dst[(size_t)(tap * 3 + 0) * per_tile + idx] = t0;
+      dst[(size_t)(tap * 3 + 1) * per_tile + idx] = t1;
+      dst[(size_t)(tap * 3 + 2) * per_tile + idx] = t2;
+    }
+    off += (size_t)9 * 3 * per_tile * 2;
+  }
+  // gradient blobs (K = co)
+  for (int which = 0; which < 2; ++which) {
+    unsigned char* blob = which == 0 ? L.dg_blob : L.rb_blob;
+    const float* w = which == 0 ? L.w_ff : L.w_rec;
+    if (blob == nullptr || w == nullptr) continue;
+    const int N = which == 0 ? L.Kin : C, Nreal = which == 0 ? L.Cin : C;
+    const int per_tile = N * C;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(blob);
+    for (int i = tid; i < 9 * per_tile; i += 256) {
+      const int tap = i / per_tile, r = i - tap * per_tile;
+      const int n = r / C, k = r - n * C;
+      const float v = n < Nreal ? w[((size_t)k * Nreal + n) * 9 + (8 - tap)] : 0.f;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      const int idx = ((k >> 3) * (N >> 3) + (n >> 3)) * 64 + (n & 7) * 8 + (k & 7);
+      dst[(size_t)(tap * 2 + 0) * per_tile + idx] = hi;
+      dst[(size_t)(tap * 2 + 1) * per_tile + idx] = lo;
+    }
+  }
+  for (int c = tid; c < C; c += 256) {
+    const float lam = L.leak_lam[c];
+    reinterpret_cast<float4*>(L.par)[c] = make_float4(lam, __fsub_rn(1.0f, lam), L.theta[c], 0.f);
+  }
+}
+
+int launch_pack_weights(const PackArgs& p, cudaStream_t st) {
+  prof_begin("win_pack_weights", st, 0.0);
+  window_pack_weights_kernel<<<WIN_LAYERS, 256, 0, st>>>(p);
+  return check_launch("window_pack_weights_kernel");
+}
+
+// ---- time-fused pointwise BPTT of a feed-forward ConvLIF layer --------------------------------------------
+// thread = one pixel x 8 channels of one sample, walking t = T-1 .. 0 with the membrane gradient in registers:
+//   gs = g_out[t] * sg(v[t] - theta);  gv = carry + gs;  g_I[t] = gv * (1 - lam)  -> bf16 hi/lo planes
+//   hard: carry = gv*lam*(1-z_in); dlam += gv*(v_in*(1-z_in) - I[t]); dtheta -= gs
+//   soft: carry = gv*lam;          dlam += gv*(v_in - I[t]);          dtheta -= gs + gv*z_in
+// with v_in = v[t-1] (the window's initial state at t = 0) and z_in = spike(v_in) (z_init at t = 0).
+__global__ void __launch_bounds__(256) pw_seq_kernel(const PwSeqArgs a) {
+  const int HW = a.H * a.W, Wp = a.W + 2;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  const bool ok = p < HW;
+  const int y = ok ? p / a.W : 0, x = ok ? p - y * a.W : 0;
+  const size_t plane_bytes = (size_t)(a.H + 2) * Wp * 16;
+  float lam[8], oml[8], th[8], carry[8], s_lam[8], s_th[8], v_cur[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 pr = __ldg(reinterpret_cast<const float4*>(a.par) + chunk * 8 + c);
+    lam[c] = pr.x; oml[c] = pr.y; th[c] = pr.z;
+    carry[c] = 0.f; s_lam[c] = 0.f; s_th[c] = 0.f;
+  }
+  const size_t n_img_elems = (size_t)a.C * HW;
+  const size_t ch_off = (size_t)(chunk * 8) * HW + p;
+  if (ok) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v_cur[c] = __ldg(a.v + (size_t)((a.T - 1) * a.B + b) * n_img_elems + ch_off + (size_t)c * HW);
+  }
+  for (int t = a.T - 1; t >= 0; --t) {
+    const size_t img = (size_t)(t * a.B + b);
+    float v_in[8], z_in[8], go[8], cu[8];
+    if (ok) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const size_t i = img * n_img_elems + ch_off + (size_t)c * HW;
+        go[c] = __ldg(a.g_out + i);
+        cu[c] = __ldg(a.cur + i);
+        if (t > 0) {
+          v_in[c] = __ldg(a.v + (img - a.B) * n_img_elems + ch_off + (size_t)c * HW);
+          z_in[c] = (__fsub_rn(v_in[c], th[c]) > 0.f) ? 1.f : 0.f;
+        } else {
+          const size_t i0 = (size_t)b * n_img_elems + ch_off + (size_t)c * HW;
+          v_in[c] = a.v_init ? __ldg(a.v_init + i0) : 0.f;
+          z_in[c] = a.z_init ? __ldg(a.z_init + i0) : 0.f;
+        }
+      }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float gs = go[c] * surrogate(v_cur[c] - th[c], a.width, a.surrogate);
+        const float gv = carry[c] + gs;
+        const float gi = gv * oml[c];
+        if (a.hard_reset) {
+          carry[c] = gv * lam[c] * (1.0f - z_in[c]);
+          s_lam[c] += gv * (v_in[c] * (1.0f - z_in[c]) - cu[c]);
+          s_th[c] -= gs;
+        } else {
+          carry[c] = gv * lam[c];
+          s_lam[c] += gv * (v_in[c] - cu[c]);
+          s_th[c] -= gs + gv * z_in[c];
+        }
+        const __nv_bfloat16 bh = __float2bfloat16_rn(gi);
+        const __nv_bfloat16 bl = __float2bfloat16_rn(gi - __bfloat162float(bh));
+        const uint32_t uh = (uint32_t)__bfloat16_as_ushort(bh), ul = (uint32_t)__bfloat16_as_ushort(bl);
+        if (c & 1) { hi[c >> 1] |= uh << 16; lo[c >> 1] |= ul << 16; }
+        else { hi[c >> 1] = uh; lo[c >> 1] = ul; }
+        v_cur[c] = v_in[c];
+      }
+      unsigned char* gp = a.gp + img * a.gp_img_stride + (size_t)chunk * plane_bytes + ((size_t)(y + 1) * Wp + x + 1) * 16;
+      *reinterpret_cast<uint4*>(gp) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(gp + a.gp_term_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  // fixed-order block reduction of the per-channel sums
+  __shared__ float red[8][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float l = warp_sum(ok ? s_lam[c] : 0.f), t = warp_sum(ok ? s_th[c] : 0.f);
+    if (lane == 0) { red[warp][c] = l; red[warp][8 + c] = t; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    const int which = threadIdx.x >> 3, c = threadIdx.x & 7;
+    const int j = b * gridDim.x + blockIdx.x;
+    a.part[((size_t)which * a.C + chunk * 8 + c) * a.n_part + j] = t;
+  }
+}
+
+int launch_pw_seq(const PwSeqArgs& a, cudaStream_t st) {
+  const int gx = ceil_div(a.H * a.W, 256);
+  if (a.n_part != a.B * gx) {
+    set_error("launch_pw_seq: n_part mismatch");
+    return SNNFLOW_EINVAL;
+  }
+  prof_begin("win_pw_seq", st, (double)a.T * a.B * a.C * a.H * a.W * 16.0);
+  pw_seq_kernel<<<dim3(gx, a.C / 8, a.B), 256, 0, st>>>(a);
+  return check_launch("pw_seq_kernel");
+}
+
+// ---- flow head on spike planes: flow = tanh(conv1x1(z) + b)  (models/submodules.py:96-113) ----------------
+constexpr int PP_MAX_C = 64;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+
+__global__ void __launch_bounds__(256) pred_fwd_planes_kernel(const unsigned char* __restrict__ zp, unsigned long long img_stride,
+                                                              const float* __restrict__ w, const float* __restrict__ bias,
+                                                              float* __restrict__ flow, int C, int H, int W) {
+  __shared__ float sw[2 * PP_MAX_C + 2];
+  for (int i = threadIdx.x; i < 2 * C; i += 256) sw[i] = w[i];
+  if (threadIdx.x < 2) sw[2 * C + threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int HW = H * W, Wp = W + 2;
+  const int p = blockIdx.x * 256 + threadIdx.x, img = blockIdx.y;
+  if (p >= HW) return;
+  const int y = p / W, x = p - y * W;
+  const size_t plane_bytes = (size_t)(H + 2) * Wp * 16;
+  const unsigned char* src = zp + (size_t)img * img_stride + ((size_t)(y + 1) * Wp + x + 1) * 16;
+  float a0 = 0.f, a1 = 0.f;
+  for (int ch = 0; ch < (C >> 3); ++ch) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(src + ch * plane_bytes)), f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {   // same accumulation order as pred_fwd_kernel (pred.cu)
+      a0 = fmaf(f[c], sw[ch * 8 + c], a0);
+      a1 = fmaf(f[c], sw[C + ch * 8 + c], a1);
+    }
+  }
+  flow[((size_t)img * 2 + 0) * HW + p] = tanhf(a0 + sw[2 * C]);
+  flow[((size_t)img * 2 + 1) * HW + p] = tanhf(a1 + sw[2 * C + 1]);
+}
+
+int launch_pred_fwd_planes(const unsigned char* zp, unsigned long long img_stride, const float* w, const float* b,
+                           float* flow, int n_img, int C, int H, int W, cudaStream_t st) {
+  if (C > PP_MAX_C) {
+    set_error("pred planes: C <= 64");
+    return SNNFLOW_EINVAL;
+  }
+  prof_begin("win_pred_fwd", st, (double)n_img * H * W * (2.0 * C + 8.0), 4.0 * n_img * H * W * C);
+  pred_fwd_planes_kernel<<<dim3(ceil_div(H * W, 256), n_img), 256, 0, st>>>(zp, img_stride, w, b, flow, C, H, W);
+  return check_launch("pred_fwd_planes_kernel");
+}
+
+// g_pre = g_flow * (1 - flow^2); g_x[c] = g_pre0*w[0][c] + g_pre1*w[1][c]; per-CTA partials of dw [2][C], db [2]
+__global__ void __launch_bounds__(256) pred_bwd_planes_kernel(const unsigned char* __restrict__ zp, unsigned long long img_stride,
+                                                              const float* __restrict__ w, const float* __restrict__ flow,
+                                                              const float* __restrict__ g_flow, float* __restrict__ g_x,
+                                                              float* __restrict__ part, int C, int H, int W) {
+  __shared__ float sw[2 * PP_MAX_C];
+  __shared__ float red[8][2 * PP_MAX_C + 2];
+  for (int i = threadIdx.x; i < 2 * C; i += 256) sw[i] = w[i];
+  __syncthreads();
+  const int HW = H * W, Wp = W + 2;
+  const int p = blockIdx.x * 256 + threadIdx.x, img = blockIdx.y;
+  const bool ok = p < HW;
+  const int y = ok ? p / W : 0, x = ok ? p - y * W : 0;
+  const size_t plane_bytes = (size_t)(H + 2) * Wp * 16;
+  float g0 = 0.f, g1 = 0.f;
+  if (ok) {
+    const float f0 = flow[((size_t)img * 2 + 0) * HW + p], f1 = flow[((size_t)img * 2 + 1) * HW + p];
+    g0 = g_flow[((size_t)img * 2 + 0) * HW + p] * (1.0f - f0 * f0);
+    g1 = g_flow[((size_t)img * 2 + 1) * HW + p] * (1.0f - f1 * f1);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned char* src = zp + (size_t)img * img_stride + ((size_t)(y + 1) * Wp + x + 1) * 16;
+  float* gxp = g_x + (size_t)img * C * HW + p;
+  for (int ch = 0; ch < (C >> 3); ++ch) {
+    float f[8];
+    if (ok) unpack8(__ldg(reinterpret_cast<const uint4*>(src + ch * plane_bytes)), f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int co = ch * 8 + c;
+      const float zv = ok ? f[c] : 0.f;
+      if (ok) gxp[(size_t)co * HW] = g0 * sw[co] + g1 * sw[C + co];
+      const float s0 = warp_sum(g0 * zv), s1 = warp_sum(g1 * zv);
+      if (lane == 0) { red[warp][co] = s0; red[warp][C + co] = s1; }
+    }
+  }
+  const float s0 = warp_sum(g0), s1 = warp_sum(g1);
+  if (lane == 0) { red[warp][2 * C] = s0; red[warp][2 * C + 1] = s1; }
+  __syncthreads();
+  float* mypart = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (2 * C + 2);
+  for (int i = threadIdx.x; i < 2 * C + 2; i += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][i];
+    mypart[i] = t;
+  }
+}
+
+int pred_planes_parts(int n_img, int H, int W) { return n_img * ceil_div(H * W, 256); }
+
+int launch_pred_bwd_planes(const unsigned char* zp, unsigned long long img_stride, const float* w, const float* flow,
+                           const float* g_flow, float* g_x, float* part, int n_img, int C, int H, int W,
+                           cudaStream_t st) {
+  if (C > PP_MAX_C) {
+    set_error("pred planes: C <= 64");
+    return SNNFLOW_EINVAL;
+  }
+  prof_begin("win_pred_bwd", st, (double)n_img * H * W * (2.0 * C + 4.0 * C + 16.0), 8.0 * n_img * H * W * C);
+  pred_bwd_planes_kernel<<<dim3(ceil_div(H * W, 256), n_img), 256, 0, st>>>(zp, img_stride, w, flow, g_flow, g_x, part, C, H, W);
+  return check_launch("pred_bwd_planes_kernel");
+}
+
+// dw[i] += sum_p part[p][i]  (i < 2C), db[i - 2C] += ...   : one warp per output, fixed shuffle tree
+__global__ void __launch_bounds__(256) pred_reduce_planes_kernel(const float* __restrict__ part, float* dw, float* db, int C,
+                                                                 int n_part) {
+  const int n = 2 * C + 2;
+  const int wid = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= n) return;
+  float s = 0.f;
+  for (int p = lane; p < n_part; p += 32) s += part[(size_t)p * n + wid];
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (wid < 2 * C) { if (dw) dw[wid] += s; }
+    else if (db) db[wid - 2 * C] += s;
+  }
+}
+
+int launch_pred_reduce_planes(const float* part, float* dw, float* db, int C, int n_part, cudaStream_t st) {
+  prof_begin("win_pred_reduce", st, 4.0 * n_part * (2 * C + 2));
+  pred_reduce_planes_kernel<<<ceil_div((2 * C + 2) * 32, 256), 256, 0, st>>>(part, dw, db, C, n_part);
+  return check_launch("pred_reduce_planes_kernel");
+}
+
+// ---- reductions of the per-CTA partials (fixed order: run-to-run deterministic) --------------------------
+//   blockIdx.y 0/1: dW_ff / dW_rec[co][ci][tap] += sum_p part[p][tap][ci][co]
+//   blockIdx.y 2  : dlam / dtheta[c] += sum_j cpart
+__global__ void __launch_bounds__(256) win_reduce_kernel(const WinReduceArgs a) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, stripe = threadIdx.x >> 5;
+  const int job = blockIdx.y;
+  if (job < 2) {
+    if (a.wdst[job] == nullptr) return;
+    const int C = a.C, cr = a.cin_real[job], ca = a.cin_alloc[job];
+    const int n = C * cr * 9;                 // outputs
+    const size_t pstride = (size_t)9 * ca * C;
+    for (int i0 = blockIdx.x * 32; i0 < n; i0 += gridDim.x * 32) {
+      // consecutive lanes take consecutive co (contiguous in the partials)
+      const int i = i0 + lane;
+      const int co = i % C, rest = i / C, ci = rest % cr, tap = rest / cr;
+      float s = 0.f;
+      if (i < n) {
+        const float* src = a.wpart[job] + ((size_t)tap * ca + ci) * C + co;
+#pragma unroll 4
+        for (int p = stripe; p < a.n_wpart; p += 8) s += src[(size_t)p * pstride];
+      }
+      red[stripe][lane] = s;
+      __syncthreads();
+      if (stripe == 0 && i < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][lane];
+        a.wdst[job][((size_t)co * cr + ci) * 9 + tap] += t;
+      }
+      __syncthreads();
+    }
+  } else {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp_global; r < 2 * a.C; r += n_warps) {
+      float s = 0.f;
+      if (a.cpart_layout == 0) {
+        for (int j = lane; j < a.n_cpart; j += 32) s += a.cpart[(size_t)r * a.n_cpart + j];
+      } else {
+        for (int j = lane; j < a.n_cpart; j += 32) s += a.cpart[(size_t)j * 2 * a.C + r];
+      }
+      s = warp_sum(s);
+      if (lane == 0) {
+        float* dst = r < a.C ? a.dlam : a.dtheta;
+        if (dst) dst[r % a.C] += s;
+      }
+    }
+  }
+}
+
+int launch_win_reduce(const WinReduceArgs& a, cudaStream_t st) {
+  const int cmax = a.cin_real[0] > a.cin_real[1] ? a.cin_real[0] : a.cin_real[1];
+  int gx = ceil_div(a.C * cmax * 9, 32);
+  if (gx > 4 * sm_count()) gx = 4 * sm_count();
+  prof_begin("win_reduce", st, 4.0 * a.n_wpart * 9.0 * a.C * (a.cin_alloc[0] + (a.wdst[1] ? a.cin_alloc[1] : 0)) + 8.0 * a.C * a.n_cpart);
+  win_reduce_kernel<<<dim3(gx, 3), 256, 0, st>>>(a);
+  return check_launch("win_reduce_kernel");
+}
+
+}  // namespace snnflow

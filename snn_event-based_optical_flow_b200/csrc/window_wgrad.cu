@@ -1,0 +1,237 @@
+// Layer-major window engine: weight gradient of one layer over ALL T*B images of a window in one launch
+// (tcgen05, accumulators resident in TMEM for the whole kernel).
+//
+//   dW[co][ci][ky][kx] = sum over images, pixels  g_I[co][y][x] * X[ci][y+ky-1][x+kx-1]        (X = layer input; z_prev)
+//
+// Per image row this is a GEMM with K = pixels:  D[m][n = co] += A[m][k] * B[n][k],  both operands MN-major
+// (8 channels = 16 B contiguous per pixel slot).  The trick that fills the 128-row MMA: shared memory holds the input
+// rows interleaved as [row][chunk][P slots], so the M index (16 chunk-groups of 8 channels, a fixed byte stride
+// apart) runs first over the chunks of row r and then over the chunks of rows r+1, r+2, ...: ONE tcgen05.mma
+// computes several vertical taps (ky) at once - all three for a 32-channel feed-forward layer, two for a
+// recurrent layer (x and z_prev chunks side by side).  The horizontal tap kx is a one-slot shift of the start
+// address.  g_I comes as bf16 hi + lo planes (two MMAs per k-step); its zero border column and the zeroed pad slots
+// make the k-steps that run past the end of a row contribute nothing.
+// Each persistent CTA writes one partial block [tap][ci][co]; window_reduce sums them in a fixed order.
+#include "tcgen05.cuh"
+#include "window.cuh"
+
+#include <stdlib.h>
+
+namespace snnflow {
+
+constexpr int WG_EPI_WARPS = 8;
+constexpr int WG_THREADS = (WG_EPI_WARPS + 2) * 32;
+constexpr int WG_MAX_STAGES = 4;
+constexpr int WG_HDR = 1024;
+
+static int wg_env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+__device__ __forceinline__ int wg_n_items(const WgArgs& a) {
+  const int n_tiles = a.n_img * (a.H / a.R);
+  return ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+}
+
+__device__ __forceinline__ uint32_t wg_tmem_cols(const WgArgs& a) {
+  const uint32_t need = (uint32_t)(a.n_kyg * 3 * a.C);
+  uint32_t c = 32;
+  while (c < need) c <<= 1;
+  return c;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_constant__ WgArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + WG_MAX_STAGES;
+  uint64_t* done = empty + WG_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 128);
+  unsigned char* stages = smem + WG_HDR;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < WG_MAX_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, wg_tmem_cols(a));
+  // pad slots, spare rows and unused chunk groups must read as zeros: clear the whole ring once
+  {
+    uint4* p = reinterpret_cast<uint4*>(stages);
+    const size_t n = (size_t)a.S * a.stage_bytes / 16;
+    for (size_t i = tid; i < n; i += WG_THREADS) p[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_items = wg_n_items(a);
+  const int tpi = a.H / a.R;
+  const size_t plane_bytes = (size_t)(a.H + 2) * a.Wp * 16;
+  const uint32_t row_bytes = (uint32_t)a.Wp * 16, pitch = (uint32_t)a.P * 16;
+  const int g_chunks = a.C >> 3;
+
+  if (warp == WG_EPI_WARPS) {
+    if (lane == 0) {
+      for (int k = 0; k < n_items; ++k) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        const int img = tile / tpi, y0 = (tile - img * tpi) * a.R;
+        const uint32_t st = (uint32_t)k % (uint32_t)a.S, use = (uint32_t)k / (uint32_t)a.S;
+        if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
+        unsigned char* xs = stages + (size_t)st * a.stage_bytes;
+        unsigned char* gs = xs + a.g_off;
+        mbar_expect_tx(&full[st], (uint32_t)((a.R + 2) * a.n_cg + a.R * 2 * g_chunks) * row_bytes);
+        for (int row = 0; row < a.R + 2; ++row) {
+          int cg = 0;
+          for (int si = 0; si < a.n_xsrc; ++si) {
+            const unsigned char* src = a.xp[si] + (size_t)img * a.x_img_stride[si] + (size_t)(y0 + row) * row_bytes;
+            for (int ch = 0; ch < a.x_chunks[si]; ++ch, ++cg)
+              tma_bulk_g2s(xs + (size_t)(row * a.n_cg + cg) * pitch, src + ch * plane_bytes, row_bytes, &full[st]);
+          }
+        }
+        for (int r = 0; r < a.R; ++r)
+          for (int term = 0; term < 2; ++term) {
+            const unsigned char* src = a.gp + term * a.g_term_stride + (size_t)img * a.g_img_stride + (size_t)(y0 + 1 + r) * row_bytes;
+            for (int ch = 0; ch < g_chunks; ++ch)
+              tma_bulk_g2s(gs + (size_t)((r * 2 + term) * g_chunks + ch) * pitch, src + ch * plane_bytes, row_bytes, &full[st]);
+          }
+      }
+    }
+    __syncwarp();
+  } else if (warp == WG_EPI_WARPS + 1) {
+    if (lane == 0 && n_items > 0) {
+      const uint32_t idesc = make_idesc(128, a.C, /*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1);
+      const uint32_t stages_addr = smem_u32(stages);
+      for (int k = 0; k < n_items; ++k) {
+        const uint32_t st = (uint32_t)k % (uint32_t)a.S, use = (uint32_t)k / (uint32_t)a.S;
+        mbar_wait(&full[st], use & 1);
+        tc_fence_after();
+        const uint32_t xs = stages_addr + st * a.stage_bytes, gs = xs + a.g_off;
+        for (int r = 0; r < a.R; ++r) {
+          for (int j = 0; j < a.n_kyg; ++j) {
+            const uint32_t arow = xs + (uint32_t)((r + j * a.rpm) * a.n_cg) * pitch;
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint32_t d = tmem_base + (uint32_t)((j * 3 + kx) * a.C);
+              for (int kk = 0; kk < a.ksteps; ++kk) {
+                // g slot c (padded column) pairs with input slot c + kx - 1; the k range starts at c = 1
+                const uint64_t adesc = make_desc_mn(arow + (uint32_t)(kx + kk * 16) * 16u, 128, pitch);
+#pragma unroll
+                for (int term = 0; term < 2; ++term) {
+                  const uint64_t bdesc = make_desc_mn(gs + (uint32_t)((r * 2 + term) * g_chunks) * pitch + (uint32_t)(1 + kk * 16) * 16u, 128, pitch);
+                  umma_f16(d, adesc, bdesc, idesc, (k > 0 || r > 0 || kk > 0 || term > 0) ? 1u : 0u);
+                }
+              }
+            }
+          }
+        }
+        umma_commit(&empty[st]);
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+  } else if (n_items > 0) {
+    // ---- read-out: D[(j, kx)] row M = (ky - j*rpm) * n_cg*8 + cg*8 + c  ->  part[tap][ci][co] ----
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const int q = warp & 3, par = warp >> 2;
+    const int M = q * 32 + lane;
+    const int i = M / (a.n_cg * 8), cg = (M >> 3) % a.n_cg, c = M & 7;
+    const int si = (cg < a.x_chunks[0]) ? 0 : 1;
+    const int ci = (si == 0 ? cg : cg - a.x_chunks[0]) * 8 + c;
+    const bool row_used = i < a.rpm;
+    for (int acc_id = par; acc_id < a.n_kyg * 3; acc_id += 2) {
+      const int j = acc_id / 3, kx = acc_id - j * 3;
+      const int ky = j * a.rpm + i;
+      const bool ok = row_used && ky < 3 && ci < a.cin_real[si];
+      float* dst = a.part[si] + ((size_t)blockIdx.x * 9 + (ky * 3 + kx)) * a.cin_alloc[si] * a.C + (size_t)ci * a.C;
+      for (int g = 0; g < (a.C >> 4); ++g) {
+        float acc[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_id * a.C + g * 16), acc);
+        if (ok) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            reinterpret_cast<float4*>(dst + g * 16)[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, wg_tmem_cols(a));
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------
+struct WgPlan {
+  int n_cg, rpm, n_kyg, ksteps, P, x_rows, R, S;
+  uint32_t stage_bytes, g_off;
+  bool ok;
+};
+
+static WgPlan wg_plan(int C, int cin_chunks, int rec_chunks, int H, int W) {
+  WgPlan p{};
+  p.ok = false;
+  p.n_cg = cin_chunks + rec_chunks;
+  if (p.n_cg <= 0 || p.n_cg > 16 || (16 % p.n_cg) != 0) return p;
+  if ((C % 16) || C < 16 || C > 64) return p;
+  p.rpm = 16 / p.n_cg;
+  p.n_kyg = (3 + p.rpm - 1) / p.rpm;
+  if (p.n_kyg * 3 * C > 512) return p;
+  p.ksteps = ceil_div(W, 16);
+  p.P = (int)align_up((size_t)(16 * p.ksteps + 3 > W + 2 ? 16 * p.ksteps + 3 : W + 2), 8);
+  const int forced_R = wg_env_int("SNNFLOW_WG_R", 0), forced_S = wg_env_int("SNNFLOW_WG_S", 0);
+  for (int R = 2; R >= 1; --R) {
+    if (H % R) continue;
+    if (forced_R && R != forced_R) continue;
+    const int x_rows = R - 1 + p.n_kyg * p.rpm;   // rows addressed by the last tap group of the last output row
+    const size_t xb = (size_t)(x_rows > R + 2 ? x_rows : R + 2) * p.n_cg * p.P * 16;
+    const size_t gb = (size_t)R * 2 * (C / 8) * p.P * 16;
+    const size_t stage = align_up(xb + gb, 128);
+    int S = (int)(((size_t)227 * 1024 - WG_HDR) / stage);
+    if (S > WG_MAX_STAGES) S = WG_MAX_STAGES;
+    if (forced_S && S > forced_S) S = forced_S;
+    if (S < 2) continue;
+    p.R = R; p.S = S; p.x_rows = x_rows;
+    p.g_off = (uint32_t)xb;
+    p.stage_bytes = (uint32_t)stage;
+    p.ok = true;
+    break;
+  }
+  return p;
+}
+
+bool wg_supported(int C, int cin_chunks, int rec_chunks, int H, int W) { return wg_plan(C, cin_chunks, rec_chunks, H, W).ok; }
+
+int wg_grid(int n_img, int H, int W, int C, int cin_chunks, int rec_chunks) {
+  const WgPlan p = wg_plan(C, cin_chunks, rec_chunks, H, W);
+  if (!p.ok) return 0;
+  const int n_tiles = n_img * (H / p.R);
+  return n_tiles < sm_count() ? n_tiles : sm_count();
+}
+
+int launch_wgrad_planes(WgArgs a, cudaStream_t st, double bytes, double flops) {
+  const WgPlan p = wg_plan(a.C, a.x_chunks[0], a.n_xsrc > 1 ? a.x_chunks[1] : 0, a.H, a.W);
+  if (!p.ok) {
+    set_error("launch_wgrad_planes: shape not covered");
+    return SNNFLOW_EINVAL;
+  }
+  a.n_cg = p.n_cg; a.rpm = p.rpm; a.n_kyg = p.n_kyg; a.ksteps = p.ksteps; a.P = p.P; a.x_rows = p.x_rows;
+  a.R = p.R; a.S = p.S; a.stage_bytes = p.stage_bytes; a.g_off = p.g_off; a.Wp = a.W + 2;
+  const size_t smem = WG_HDR + (size_t)a.S * a.stage_bytes;
+  static size_t attr = 0;
+  if (smem > attr) {
+    SNNFLOW_CUDA(cudaFuncSetAttribute(wg_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int n_tiles = a.n_img * (a.H / a.R);
+  const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+  prof_begin("win_wgrad", st, bytes, flops);
+  wg_planes_kernel<<<grid, WG_THREADS, smem, st>>>(a);
+  return check_launch("wg_planes_kernel");
+}
+
+}  // namespace snnflow

@@ -41,6 +41,22 @@ def _bind(L):
     L.snnflow_net_backward.restype = ctypes.c_int
     L.snnflow_net_backward.argtypes = [ctypes.POINTER(NetDesc), ctypes.POINTER(LayerPtrs), P, P, ctypes.POINTER(P), P, P, P,
                                        P, P, P, ctypes.c_size_t, P]
+    L.snnflow_window_supported.restype = ctypes.c_int
+    L.snnflow_window_supported.argtypes = [ctypes.POINTER(NetDesc), ctypes.c_int]
+    L.snnflow_window_arena_bytes.restype = ctypes.c_size_t
+    L.snnflow_window_arena_bytes.argtypes = [ctypes.POINTER(NetDesc), ctypes.c_int]
+    L.snnflow_window_workspace_bytes.restype = ctypes.c_size_t
+    L.snnflow_window_workspace_bytes.argtypes = [ctypes.POINTER(NetDesc)]
+    L.snnflow_window_state_offsets.restype = ctypes.c_int
+    L.snnflow_window_state_offsets.argtypes = [ctypes.POINTER(NetDesc), ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
+    L.snnflow_window_inexact_count.restype = ctypes.c_uint
+    L.snnflow_window_inexact_count.argtypes = [ctypes.c_int]
+    L.snnflow_window_forward.restype = ctypes.c_int
+    L.snnflow_window_forward.argtypes = [ctypes.POINTER(NetDesc), ctypes.POINTER(LayerPtrs), P, P, P, ctypes.POINTER(P), P, P,
+                                         ctypes.c_int, P]
+    L.snnflow_window_backward.restype = ctypes.c_int
+    L.snnflow_window_backward.argtypes = [ctypes.POINTER(NetDesc), ctypes.POINTER(LayerPtrs), P, ctypes.POINTER(P), P, P, P,
+                                          P, P, P, ctypes.c_size_t, P]
     L._net_bound = True
 
 
@@ -144,12 +160,115 @@ class _WindowFn(torch.autograd.Function):
         grads += [d_pw, d_pb if pb is not None else None]
         return (None, None) + tuple(grads)
 
+def _make_desc(runner, cnt):
+    layers = runner.layers
+    T, B, nb, H, W = cnt.shape
+    first = layers[0]
+    flags = (_lib.HARD_RESET if first.hard_reset else 0) | (_lib.DETACH_RESET if first.detach else 0)
+    if not first.use_tensor_cores:
+        flags |= _lib.NO_TENSOR_CORES
+    mask = sum(1 << i for i, l in enumerate(layers) if l.recurrent)
+    return NetDesc(B, first.hidden_size, H, W, T, nb, mask, flags, _lib.SURROGATE_ID[first.activation], first._act_width)
+
+
+def _desc_key(d):
+    return (d.B, d.C, d.H, d.W, d.T, d.num_bins, d.recurrent_mask, d.flags, d.surrogate, d.act_width)
+
+
+class _LayerMajorWindowFn(torch.autograd.Function):
+    """The window on the layer-major engine (snnflow_window_forward / snnflow_window_backward, include/snnflow.h)."""
+
+    @staticmethod
+    def forward(ctx, runner, cnt, *params):
+        L = _lib.lib()
+        _bind(L)
+        net, layers = runner.net, runner.layers
+        T, B, nb, H, W = cnt.shape
+        dev = cnt.device
+        cnt = cnt.float().contiguous()
+        need_bwd = any(ctx.needs_input_grad)
+        desc = _make_desc(runner, cnt)
+        C = desc.C
+        lam = torch.sigmoid(torch.stack([l.leak.detach().reshape(-1) for l in layers]))      # spiking_submodules.py:136
+        theta = torch.stack([l.thresh.detach().reshape(-1) for l in layers]).clamp_min(0.01)  # :133
+        lp = (LayerPtrs * N_LAYERS)()
+        for i, l in enumerate(layers):
+            lp[i].w_ff = l.ff.weight.data_ptr()
+            lp[i].w_rec = l.rec.weight.data_ptr() if l.recurrent else None
+            lp[i].lam = lam[i].data_ptr()
+            lp[i].theta = theta[i].data_ptr()
+        arena = runner.lm_arena(desc, need_bwd, dev)
+        flow = torch.empty((T, B, 2, H, W), dtype=torch.float32, device=dev)
+        states = net._states
+        sp, keep = _state_ptrs(states)
+        pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
+        _lib.check(L.snnflow_window_forward(ctypes.byref(desc), lp, pw.data_ptr(), None if pb is None else pb.data_ptr(),
+                                            cnt.data_ptr(), sp, arena.data_ptr(), flow.data_ptr(), int(need_bwd),
+                                            _lib.stream()), "snnflow_window_forward")
+        if runner.validate_input:
+            bad = int(L.snnflow_window_inexact_count(1))
+            if bad:
+                raise _lib.SnnflowError(f"window engine: {bad} input values are not exactly representable in bfloat16 "
+                                        "(event counts above 256 or fractional values): use the per-step engine")
+        offs = (ctypes.c_size_t * N_LAYERS)()
+        _lib.check(L.snnflow_window_state_offsets(ctypes.byref(desc), int(need_bwd), offs), "snnflow_window_state_offsets")
+        nbytes = 2 * B * C * H * W * 4
+        runner.new_states = [arena[offs[i]:offs[i] + nbytes].view(torch.float32).view(2, B, C, H, W) for i in range(N_LAYERS)]
+        if need_bwd:
+            ctx.runner, ctx.desc, ctx.lam, ctx.theta = runner, desc, lam, theta
+            ctx.arena, ctx.flow, ctx.states_in = arena, flow, list(states)
+        return flow
+
+    @staticmethod
+    def backward(ctx, g_flow):
+        L = _lib.lib()
+        runner, desc, lam, theta = ctx.runner, ctx.desc, ctx.lam, ctx.theta
+        layers, net = runner.layers, runner.net
+        dev = g_flow.device
+        g_flow = g_flow.float().contiguous()
+        dlam = torch.zeros_like(lam)
+        dtheta = torch.zeros_like(theta)
+        dws = []
+        lp = (LayerPtrs * N_LAYERS)()
+        for i, l in enumerate(layers):
+            dwf = torch.zeros_like(l.ff.weight)
+            dwr = torch.zeros_like(l.rec.weight) if l.recurrent else None
+            dws.append((dwf, dwr))
+            lp[i].w_ff = l.ff.weight.data_ptr()
+            lp[i].w_rec = l.rec.weight.data_ptr() if l.recurrent else None
+            lp[i].lam = lam[i].data_ptr()
+            lp[i].theta = theta[i].data_ptr()
+            lp[i].dw_ff = dwf.data_ptr()
+            lp[i].dw_rec = None if dwr is None else dwr.data_ptr()
+            lp[i].dlam = dlam[i].data_ptr()
+            lp[i].dtheta = dtheta[i].data_ptr()
+        pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
+        d_pw = torch.zeros_like(pw)
+        d_pb = torch.zeros(2, dtype=torch.float32, device=dev)
+        ws = runner.lm_workspace(desc, dev)
+        sp, keep = _state_ptrs(ctx.states_in)
+        _lib.check(L.snnflow_window_backward(ctypes.byref(desc), lp, pw.data_ptr(), sp, ctx.arena.data_ptr(),
+                                             ctx.flow.data_ptr(), g_flow.data_ptr(), d_pw.data_ptr(), d_pb.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _lib.stream()), "snnflow_window_backward")
+        d_leak = dlam * lam * (1.0 - lam)                                           # sigmoid'
+        thr = torch.stack([l.thresh.detach().reshape(-1) for l in layers])
+        d_thresh = dtheta * (thr >= 0.01).float()                                   # clamp_min'
+        grads = []
+        for i, l in enumerate(layers):
+            grads += [dws[i][0], dws[i][1], d_leak[i].reshape(l.leak.shape), d_thresh[i].reshape(l.thresh.shape)]
+        grads += [d_pw, d_pb if pb is not None else None]
+        return (None, None) + tuple(grads)
+
 
 class WindowRunner:
     """Runs windows of T bins through a snnflow LIFFireNet / LIFFireFlowNet with one C call per direction."""
 
+    engine = "auto"          # "auto": layer-major engine when it covers the shape, else per-step; "per_step"; "layer_major"
+    validate_input = False   # check (with a host sync) that every input value was bf16-exact after each window
+
     def __init__(self, net):
         self.net = net
+        self._lm = {}
         self.layers = [net.head, net.G1, net.R1a, net.R1b, net.G2, net.R2a, net.R2b]
         self._arenas = {}
         self._flip = 0
@@ -179,6 +298,37 @@ class WindowRunner:
             self._ws = torch.empty(n, dtype=torch.uint8, device=dev)
         return self._ws
 
+    def layer_major_ok(self, cnt_window, backward):
+        L = _lib.lib()
+        _bind(L)
+        desc = _make_desc(self, cnt_window)
+        return bool(L.snnflow_window_supported(ctypes.byref(desc), int(backward)))
+
+    def lm_arena(self, desc, save, dev):
+        # zero-filled once per shape (the plane borders are never written); two arenas alternate so that the states
+        # of window k (views into arena k%2) stay valid while window k+1 is computed
+        self._flip ^= 1
+        key = ("arena", _desc_key(desc), bool(save), self._flip, str(dev))
+        buf = self._lm.get(key)
+        if buf is None:
+            n = _lib.lib().snnflow_window_arena_bytes(ctypes.byref(desc), int(save))
+            for k in [k for k in self._lm if k[0] == "arena" and k[1] != key[1]]:
+                del self._lm[k]
+            buf = torch.zeros(n, dtype=torch.uint8, device=dev)
+            self._lm[key] = buf
+        return buf
+
+    def lm_workspace(self, desc, dev):
+        key = ("ws", _desc_key(desc), str(dev))
+        buf = self._lm.get(key)
+        if buf is None:
+            n = _lib.lib().snnflow_window_workspace_bytes(ctypes.byref(desc))
+            for k in [k for k in self._lm if k[0] == "ws"]:
+                del self._lm[k]
+            buf = torch.zeros(n, dtype=torch.uint8, device=dev)
+            self._lm[key] = buf
+        return buf
+
     def __call__(self, cnt_window):
         """cnt_window [T,B,num_bins,H,W] -> flow [T,B,2,H,W]; updates net._states like T forward calls would."""
         if not cnt_window.is_cuda:
@@ -187,6 +337,11 @@ class WindowRunner:
         for l in self.layers:
             params += [l.ff.weight, l.rec.weight if l.recurrent else None, l.leak, l.thresh]
         params += [self.net.pred.conv2d.weight, self.net.pred.conv2d.bias]
-        flow = _WindowFn.apply(self, cnt_window, *params)
+        need_bwd = torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in params)
+        use_lm = self.engine != "per_step" and self.layer_major_ok(cnt_window, need_bwd)
+        if self.engine == "layer_major" and not use_lm:
+            raise _lib.SnnflowError("the layer-major window engine does not cover this shape / these options")
+        fn = _LayerMajorWindowFn if use_lm else _WindowFn
+        flow = fn.apply(self, cnt_window, *params)
         self.net._states = self.new_states
         return flow

@@ -20,6 +20,10 @@ def make_net(kind, C, seed=0):
                                       neuron_kwargs=dict(leak=(0.0, 1.0), thresh=(0.3, 0.1)))).cuda()
     with torch.no_grad():
         net.pred.conv2d.weight.mul_(20)
+    from snnflow_b200.engine import WindowRunner
+    runner = WindowRunner(net)
+    runner.engine = "per_step"   # this file pins the per-step window engine; test_gpu_window.py covers the layer-major one
+    object.__setattr__(net, "_window_runner", runner)
     return net
 
 
@@ -37,7 +41,7 @@ def test_window_equals_per_bin(kind, C, H, W):
         flows = []
         for k in range(2):   # two consecutive windows: exercises the state hand-over between arenas
             if window:
-                f = net.forward_window(cnt[k])
+                f = net.forward_window(cnt[k])   # per-step engine: same kernels as the modules => identical results
             else:
                 f = torch.stack([net(None, cnt[k, t])["flow"][0] for t in range(T)])
             (f * gout[k]).sum().backward()

@@ -1,0 +1,165 @@
+"""GPU: the layer-major window engine (snnflow_window_forward / snnflow_window_backward) against
+  * T per-bin module calls (the drop-in cells): identical spikes, membranes and flows for 2^-12-grid weights
+    (every partial sum exact), gradients equal up to fp32 accumulation order;
+  * reference-generated fixtures: the C=32 network forward and C=16 / C=32 training windows (reference autograd)."""
+import numpy as np
+import pytest
+import torch
+
+from snnflow_testutil import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def make_net(kind, C, seed=0, dyadic=True, **neuron_kwargs):
+    import snnflow_b200 as snnflow
+    from oracle.lif import dyadic as snap
+    torch.manual_seed(seed)
+    nk = dict(leak=(0.0, 1.0), thresh=(0.3, 0.1))
+    nk.update(neuron_kwargs)
+    net = getattr(snnflow, kind)(dict(num_bins=2, encoding="cnt", base_num_channels=C, kernel_size=3, neuron_kwargs=nk))
+    with torch.no_grad():
+        net.pred.conv2d.weight.mul_(20)
+        if dyadic:
+            for n, p in net.named_parameters():
+                if n.endswith("weight"):
+                    p.copy_(snap(p))
+    return net.cuda()
+
+
+def runner_of(net, engine):
+    from snnflow_b200.engine import WindowRunner
+    r = getattr(net, "_window_runner", None)
+    if r is None:
+        r = WindowRunner(net)
+        object.__setattr__(net, "_window_runner", r)
+    r.engine = engine
+    r.validate_input = True
+    return r
+
+
+CASES = [
+    ("LIFFireNet", 32, 24, 136, {}),
+    ("LIFFireFlowNet", 32, 16, 128, {}),
+    ("LIFFireNet", 16, 20, 36, {}),
+    ("LIFFireNet", 32, 6, 200, {}),
+    ("LIFFireFlowNet", 32, 6, 260, {}),
+    ("LIFFireNet", 32, 10, 40, dict(hard_reset=False, activation="superspike")),
+    ("LIFFireNet", 16, 9, 33, dict(activation="trianglespike")),
+]
+
+
+@pytest.mark.parametrize("kind,C,H,W,nk", CASES)
+def test_layer_major_equals_per_bin(kind, C, H, W, nk):
+    net = make_net(kind, C, **nk)
+    g = torch.Generator().manual_seed(5)
+    T, B = 4, 2
+    cnt = torch.poisson(torch.full((2, T, B, 2, H, W), 0.25), generator=g).cuda()
+    gout = torch.randn(2, T, B, 2, H, W, generator=g).cuda()
+
+    def run(window):
+        net.reset_states()
+        net.zero_grad(set_to_none=True)
+        flows = []
+        for k in range(2):   # two consecutive windows: exercises the state hand-over between arenas
+            if window:
+                runner_of(net, "layer_major")
+                f = net.forward_window(cnt[k])
+            else:
+                f = torch.stack([net(None, cnt[k, t])["flow"][0] for t in range(T)])
+            (f * gout[k]).sum().backward()
+            net.detach_states()
+            flows.append(f.detach().clone())
+        return flows, [s.clone() for s in net._states], {n: p.grad.clone() for n, p in net.named_parameters()}
+
+    f_a, s_a, g_a = run(False)
+    f_b, s_b, g_b = run(True)
+    for i, (a, b) in enumerate(zip(s_a, s_b)):
+        assert torch.equal(a[1], b[1]), f"layer {i}: spikes differ ({int((a[1] != b[1]).sum())})"
+        assert torch.equal(a[0], b[0]), f"layer {i}: membranes differ"
+    for a, b in zip(f_a, f_b):
+        assert torch.equal(a, b)
+    assert float(s_a[-1][1].mean()) > 0.01
+    for n in g_a:
+        scale = float(g_a[n].abs().max()) + 1e-12
+        assert torch.allclose(g_a[n], g_b[n], rtol=1e-4, atol=1e-5 * scale), (n, float((g_a[n] - g_b[n]).abs().max()), scale)
+
+
+@pytest.mark.parametrize("kind,H,W", [("LIFFireFlowNet", 16, 130), ("LIFFireNet", 12, 64)])
+def test_layer_major_eval_mode(kind, H, W):
+    net = make_net(kind, 32)
+    g = torch.Generator().manual_seed(6)
+    cnt = torch.poisson(torch.full((5, 2, 2, H, W), 0.25), generator=g).cuda()
+    with torch.no_grad():
+        net.reset_states()
+        ref = torch.stack([net(None, cnt[t])["flow"][0] for t in range(5)])
+        s_ref = [s.clone() for s in net._states]
+        net.reset_states()
+        runner_of(net, "layer_major")
+        got = torch.cat([net.forward_window(cnt[:3]), net.forward_window(cnt[3:])])
+    assert torch.equal(ref, got)
+    for a, b in zip(s_ref, net._states):
+        assert torch.equal(a, b)
+
+
+def test_layer_major_random_weights_close():
+    """Raw fp32 weights: the bf16x3 split reproduces the fp32 convolution to ~1 ulp, so only near-threshold neurons
+    may flip; after one bin from a zero state the spike maps of both engines must agree almost everywhere."""
+    net = make_net("LIFFireFlowNet", 32, dyadic=False)
+    g = torch.Generator().manual_seed(8)
+    cnt = torch.poisson(torch.full((1, 2, 2, 16, 128), 0.25), generator=g).cuda()
+    with torch.no_grad():
+        net.reset_states()
+        ref = net(None, cnt[0])["flow"][0]
+        s_ref = [s.clone() for s in net._states]
+        net.reset_states()
+        runner_of(net, "layer_major")
+        got = net.forward_window(cnt)[0]
+    for a, b in zip(s_ref, net._states):
+        assert float((a[1] != b[1]).float().mean()) < 1e-4
+    assert float((ref - got).abs().max()) < 5e-2
+
+
+def test_network_forward_fixture_c32():
+    """Reference-generated LIFFireNet C=32 fixture (oracle/make_golden.py: net_firenet_c32) through the window engine."""
+    import snnflow_b200 as snnflow
+    g = load_golden("net_firenet_c32")
+    net = snnflow.LIFFireNet(dict(num_bins=2, encoding="cnt", base_num_channels=32, kernel_size=3)).cuda()
+    net.load_state_dict({k[len("param."):]: dev(v) for k, v in g.items() if k.startswith("param.")})
+    cnt = dev(g["cnt"])
+    runner_of(net, "layer_major")
+    with torch.no_grad():
+        flow = net.forward_window(cnt)
+    np.testing.assert_allclose(flow.cpu().numpy(), g["flow"], rtol=1e-5, atol=1e-6)
+    for i, st in enumerate(net._states):
+        st = st.cpu().numpy()
+        assert np.array_equal(st[1], g[f"state{i}"][1]), f"layer {i}: spikes differ"
+        np.testing.assert_allclose(st[0], g[f"state{i}"][0], rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["train_firenet_c16", "train_fireflownet_c32"])
+def test_training_window_fixture(name):
+    """One training window (forward, contrast loss, BPTT) against the reference's own autograd."""
+    import snnflow_b200 as snnflow
+    g = load_golden(name)
+    C, B, H, W, nT, n = [int(v) for v in g["dims"]]
+    net = getattr(snnflow, str(g["kind"]))(dict(num_bins=2, encoding="cnt", base_num_channels=C, kernel_size=3)).cuda()
+    net.load_state_dict({k[len("param."):]: dev(v) for k, v in g.items() if k.startswith("param.")})
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": 0.001}, "model": {"mask_output": False}}
+    lossf = snnflow.EventWarping(cfg, torch.device("cuda"))
+    runner_of(net, "layer_major")
+    flows = net.forward_window(torch.stack([dev(g[f"cnt{t}"]) for t in range(nT)]))
+    for t in range(nT):
+        lossf.event_flow_association([flows[t]], dev(g[f"events{t}"]), dev(g[f"pol{t}"]), dev(g[f"mask{t}"]))
+    loss = lossf()
+    loss.backward()
+    np.testing.assert_allclose(float(loss.detach()), float(g["loss"]), rtol=1e-5)
+    np.testing.assert_allclose(flows.detach().cpu().numpy(), g["flow"], rtol=1e-5, atol=1e-6)
+    for k, p in net.named_parameters():   # norm-wise: see test_gpu_network.py::test_training_window on conditioning
+        ref = g["grad." + k].astype(np.float64)
+        err = np.linalg.norm(p.grad.cpu().numpy().astype(np.float64) - ref)
+        assert err <= 3e-3 * np.linalg.norm(ref) + 1e-7, (k, err, np.linalg.norm(ref))
