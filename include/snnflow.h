@@ -181,7 +181,10 @@ int snnflow_net_backward(const snnflow_net_desc* d, const snnflow_layer_ptrs* la
  * arena: snnflow_window_arena_bytes() bytes, 256-byte aligned, ZERO-FILLED ONCE by the caller when it is allocated
  *   (or when the descriptor changes): the plane borders are never written by the kernels and must read as zero.
  *   The state [2,B,C,H,W] of layer l after the window lives inside the arena at the byte offset reported by
- *   snnflow_window_state_offsets() (zero copy).  With save != 0 the arena also keeps what the backward needs.
+ *   snnflow_window_state_offsets() (zero copy).  With save != 0 the arena also keeps what the backward needs,
+ *   including a copy of state_in - so state_in[l] may be that very state block from the previous window (one arena,
+ *   fixed addresses: the whole training step can be captured in a CUDA graph).  With save == 0 the state is updated
+ *   in place when state_in[l] aliases the state block.  state_in of the backward call is only tested for NULL.
  * workspace (backward): snnflow_window_workspace_bytes() bytes, 256-byte aligned, zero-filled once as well.
  * state_in, layers, pred_*, input, flow, g_flow and the gradient accumulation semantics are those of
  * snnflow_net_forward / snnflow_net_backward (layers[l].packed is ignored: the engine packs per window).

@@ -18,7 +18,7 @@ struct WinLayout {
   bool rec[WIN_LAYERS];
   size_t off_inplanes;
   size_t off_zp[WIN_LAYERS], zp_img_stride;   // bf16 planes; recurrent layers have B leading images (initial spikes)
-  size_t off_v[WIN_LAYERS], off_cur[WIN_LAYERS];
+  size_t off_v[WIN_LAYERS], off_cur[WIN_LAYERS], off_state[WIN_LAYERS], off_init[WIN_LAYERS];
   size_t off_fwd_blob[WIN_LAYERS], off_dg_blob[WIN_LAYERS], off_rb_blob[WIN_LAYERS], off_par[WIN_LAYERS];
   uint32_t fwd_blob_bytes[WIN_LAYERS], dg_blob_bytes[WIN_LAYERS], rb_blob_bytes[WIN_LAYERS], rec_w_off[WIN_LAYERS];
   size_t total;
@@ -38,11 +38,15 @@ static WinLayout win_layout(const snnflow_net_desc* d, int save) {
     L.Cin[l] = l == 0 ? d->num_bins : C;
     L.Kin[l] = l == 0 ? 16 : C;
     L.off_zp[l] = take((size_t)(L.rec[l] ? T + 1 : T) * B * L.zp_img_stride);
+    L.off_state[l] = take((size_t)2 * L.n * sizeof(float));       // [v | z] after the window, NCHW (the caller's view)
+    // training keeps the window's INITIAL state for the backward pass: the caller may hand in the previous window's
+    // state block of this very arena, which the forward pass overwrites
+    L.off_init[l] = save ? take((size_t)2 * L.n * sizeof(float)) : 0;
     if (save) {
-      L.off_v[l] = take((size_t)(T + 1) * L.n * sizeof(float));   // v[0..T-1] then z of the last bin
-      L.off_cur[l] = take((size_t)T * L.n * sizeof(float));
+      L.off_v[l] = take((size_t)T * L.n * sizeof(float));          // membranes of all bins, c8 layout
+      L.off_cur[l] = take((size_t)T * L.n * sizeof(float));        // input currents of all bins, c8 layout
     } else {
-      L.off_v[l] = take((size_t)(L.rec[l] ? 4 : 2) * L.n * sizeof(float));   // [pp0 pp1] v_last z_last
+      L.off_v[l] = L.rec[l] ? take((size_t)2 * L.n * sizeof(float)) : 0;   // ping-pong membranes of a recurrent layer
       L.off_cur[l] = 0;
     }
     const size_t ffb = (size_t)9 * 3 * L.Kin[l] * C * 2, recb = L.rec[l] ? (size_t)9 * 3 * C * C * 2 : 0;
@@ -73,17 +77,17 @@ static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool back
   uint32_t max_fwd_rec_blob = 0;
   for (int l = 0; l < WIN_LAYERS; ++l)
     if (L.rec[l] && L.fwd_blob_bytes[l] > max_fwd_rec_blob) max_fwd_rec_blob = L.fwd_blob_bytes[l];
-  P.ok = wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 3 * C * C * 2), true, &P.R_ff, &P.S_ff, &P.sub_ff, &P.cs_ff, &P.st_ff);
-  P.ok = P.ok && wt_plan(d->H, d->W, 2, C, (uint32_t)((size_t)9 * 3 * 16 * C * 2), true, &P.R_head, &P.S_head, &P.sub_head,
+  P.ok = wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 3 * C * C * 2), true, 3, &P.R_ff, &P.S_ff, &P.sub_ff, &P.cs_ff, &P.st_ff);
+  P.ok = P.ok && wt_plan(d->H, d->W, 2, C, (uint32_t)((size_t)9 * 3 * 16 * C * 2), true, 3, &P.R_head, &P.S_head, &P.sub_head,
                          &P.cs_head, &P.st_head);
   if (any_rec)
-    P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, max_fwd_rec_blob, true, &P.R_rec, &P.S_rec, &P.sub_rec, &P.cs_rec, &P.st_rec);
+    P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, max_fwd_rec_blob, true, 3, &P.R_rec, &P.S_rec, &P.sub_rec, &P.cs_rec, &P.st_rec);
   if (!backward) return P;
   if (any_rec) {
-    P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, &P.R_rb, &P.S_rb, &P.sub_rb,
+    P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, 2, &P.R_rb, &P.S_rb, &P.sub_rb,
                            &P.cs_rb, &P.st_rb);
   }
-  P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, &P.R_dg, &P.S_dg, &P.sub_dg,
+  P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, 2, &P.R_dg, &P.S_dg, &P.sub_dg,
                          &P.cs_dg, &P.st_dg);
   return P;
 }
@@ -157,10 +161,7 @@ extern "C" unsigned int snnflow_window_inexact_count(int reset) { return win_ine
 extern "C" int snnflow_window_state_offsets(const snnflow_net_desc* d, int save, size_t* offsets_bytes) {
   SNNFLOW_REQUIRE(win_supported(d, save != 0) && offsets_bytes, "unsupported shape or null pointer");
   const WinLayout L = win_layout(d, save);
-  for (int l = 0; l < WIN_LAYERS; ++l) {
-    if (save) offsets_bytes[l] = L.off_v[l] + (size_t)(d->T - 1) * L.n * sizeof(float);
-    else offsets_bytes[l] = L.off_v[l] + (L.rec[l] ? 2 : 0) * L.n * sizeof(float);
-  }
+  for (int l = 0; l < WIN_LAYERS; ++l) offsets_bytes[l] = L.off_state[l];
   return SNNFLOW_OK;
 }
 
@@ -195,11 +196,17 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
   rc = launch_pack_input(input, A + L.off_inplanes, T * B, d->num_bins, 2, H, W, st);
   if (rc) return rc;
 
+  if (save && state_in) {
+    for (int l = 0; l < WIN_LAYERS; ++l)
+      if (state_in[l])
+        SNNFLOW_CUDA(cudaMemcpyAsync(A + L.off_init[l], state_in[l], 2 * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
   for (int l = 0; l < WIN_LAYERS; ++l) {
-    const float* v_init = (state_in && state_in[l]) ? state_in[l] : nullptr;
+    const float* v_init = (state_in && state_in[l]) ? (save ? (const float*)(A + L.off_init[l]) : state_in[l]) : nullptr;
     const float* z_init = v_init ? v_init + n : nullptr;
     float* vbase = (float*)(A + L.off_v[l]);
     float* cbase = save ? (float*)(A + L.off_cur[l]) : nullptr;
+    float* state = (float*)(A + L.off_state[l]);
     // input planes of this layer: the packed event counts, or the spikes of the layer below
     const unsigned char* xin;
     size_t x_img_stride;
@@ -221,8 +228,7 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
       a.v_init = v_init; a.z_init = z_init;
       a.v_out = save ? vbase : nullptr; a.cur_out = cbase;
       a.zp_out = A + L.off_zp[l];
-      a.v_last = save ? nullptr : vbase;
-      a.z_last = save ? vbase + (size_t)T * n : vbase + n;
+      a.v_last = state; a.z_last = state + n;
       rc = launch_wt_fwd(a, true, st, "win_fwd_seq", 4.0 * T * px * (L.Cin[l] + 4 * C + (save ? C : 0)),
                          18.0 * T * px * C * L.Cin[l]);
       if (rc) return rc;
@@ -240,15 +246,15 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
         a.src[1].planes = A + L.off_zp[l] + (size_t)t * B * L.zp_img_stride;
         a.zin_planes = a.src[1].planes; a.zin_img_stride = L.zp_img_stride;
         const bool last = t == T - 1;
+        a.v_prev_nchw = t == 0;   // the window's initial state is the caller's NCHW tensor
         if (save) {
           a.v_prev = t > 0 ? vbase + (size_t)(t - 1) * n : v_init;
           a.v_out = vbase + (size_t)t * n; a.cur_out = cbase + (size_t)t * n;
-          a.v_last = nullptr; a.z_last = last ? vbase + (size_t)T * n : nullptr;
         } else {
           a.v_prev = t > 0 ? vbase + (size_t)((t - 1) & 1) * n : v_init;
           a.v_out = vbase + (size_t)(t & 1) * n; a.cur_out = nullptr;
-          a.v_last = last ? vbase + 2 * n : nullptr; a.z_last = last ? vbase + 3 * n : nullptr;
         }
+        a.v_last = last ? state : nullptr; a.z_last = last ? state + n : nullptr;
         a.zp_out = A + L.off_zp[l] + (size_t)(t + 1) * B * L.zp_img_stride;
         rc = launch_wt_fwd(a, false, st, "win_fwd_rec", 4.0 * px * (L.Cin[l] + 4 * C + (save ? C : 0)),
                            18.0 * px * C * (L.Cin[l] + C));
@@ -299,7 +305,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
 
   for (int l = top; l >= 0; --l) {
     const snnflow_layer_ptrs& P_ = layers[l];
-    const float* v_init = (state_in && state_in[l]) ? state_in[l] : nullptr;
+    const float* v_init = (state_in && state_in[l]) ? (const float*)(A + L.off_init[l]) : nullptr;   // forward's copy
     const float* z_init = v_init ? v_init + n : nullptr;
     const float* vbase = (const float*)(A + L.off_v[l]);
     const float* cbase = (const float*)(A + L.off_cur[l]);
@@ -325,6 +331,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
         a.src[1].planes = a.src[0].planes + WS.gp_term_stride;
         a.g_out = g_out + (size_t)t * n; a.v_t = vbase + (size_t)t * n; a.cur_t = cbase + (size_t)t * n;
         a.v_in = t > 0 ? vbase + (size_t)(t - 1) * n : v_init;
+        a.v_in_nchw = t == 0;
         a.z_from_v = t > 0; a.z_init = z_init;
         a.gp_out = gp + (size_t)t * B * L.zp_img_stride;
         a.part = cpart + (size_t)t * WS.rb_grid * 2 * C;

@@ -32,8 +32,10 @@ struct WtSrc {
   const unsigned char* planes;   // image 0, term 0, chunk 0, padded row 0
   unsigned long long img_stride;   // bytes
   uint32_t n_chunks;             // K/8
-  uint32_t w_off, w_terms, w_used;   // byte offset of this source's weights in the blob ; terms stored per tap (3 forward,
-                                     // 2 gradients) ; terms multiplied with this source (gradients: hi planes x {hi, lo}, lo planes x {hi})
+  uint32_t w_off, w_terms, w_used;   // byte offset of this source's weights in the blob ; weight terms stored side by side
+                                     // along N (3 forward, 2 gradients: ONE MMA of N = terms * channels per tap and k-step,
+                                     // summed by the epilogue) ; terms multiplied with this source (gradients: hi planes x
+                                     // {hi, lo}, lo planes x {hi})
 };
 
 struct WtArgs {
@@ -50,18 +52,20 @@ struct WtArgs {
   const float* par;   // [N][4] = (lam, 1 - lam, theta, 0)
   // forward
   const float *v_init, *z_init;   // sequence mode, t == 0: [B][N][H][W] or NULL (zeros)
-  const float* v_prev;            // step mode: membrane before this step [B][N][H][W] or NULL (zeros)
+  const float* v_prev;            // step mode: membrane before this step (c8, or NCHW when v_prev_nchw) or NULL (zeros)
+  int v_prev_nchw;
   const unsigned char* zin_planes;   // step mode: spikes before this step (planes, image b) or NULL (zeros)
   unsigned long long zin_img_stride;
-  float *v_out, *cur_out;         // [images][N][H][W] or NULL
+  float *v_out, *cur_out;         // c8 layout [images][N/8][H*W][8] or NULL
   unsigned char* zp_out;          // spike planes written by this launch (image 0 = first image of the launch)
   unsigned long long zp_img_stride;
   float *v_last, *z_last;         // [B][N][H][W] or NULL: state after the last step
   // data gradient
-  float* g_x;                     // [images][N][H][W]
+  float* g_x;                     // c8 layout [images][N/8][H*W][8]
   // recurrent backward step
-  const float *g_out, *v_t, *cur_t, *v_in;   // v_in: membrane before the step or NULL ; z_init: spikes before step 0
-  float* g_v;                     // [B][N][H][W] in/out: gradient w.r.t. the membrane carried to the previous step
+  const float *g_out, *v_t, *cur_t, *v_in;   // c8 ; v_in: membrane before the step (c8, or NCHW when v_in_nchw) or NULL
+  int v_in_nchw;                  // z_init (NCHW): spikes before step 0
+  float* g_v;                     // c8 [B][N/8][H*W][8] in/out: gradient w.r.t. the membrane carried to the previous step
   unsigned char* gp_out;          // g_I planes of this step (hi ; lo at + gp_term_stride)
   unsigned long long gp_img_stride, gp_term_stride;
   float* part;                    // [grid][2][N] partial sums of dlam, dtheta
@@ -72,7 +76,7 @@ int launch_wt_fwd(const WtArgs& a, bool seq, cudaStream_t st, const char* prof_n
 int launch_wt_dgrad(const WtArgs& a, cudaStream_t st, double bytes, double flops);
 int launch_wt_recbwd(const WtArgs& a, cudaStream_t st, double bytes, double flops);
 // picks rows-per-tile / stages for the given shapes; returns false when the shape does not fit
-bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int* R, int* S,
+bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int w_terms, int* R, int* S,
              uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes);
 int wt_grid(int n_tiles);
 
@@ -106,7 +110,7 @@ struct PackLayer {
 struct PackArgs { PackLayer L[WIN_LAYERS]; };
 int launch_pack_weights(const PackArgs& p, cudaStream_t st);
 struct PwSeqArgs {
-  const float *v, *cur, *g_out;    // [T*B][C][H][W]
+  const float *v, *cur, *g_out;    // c8 layout [T*B][C/8][H*W][8]
   const float *v_init, *z_init;    // [B][C][H][W] or NULL
   const float* par;                // [C][4]
   unsigned char* gp;               // g_I planes (hi ; lo at + term_stride), image t*B + b

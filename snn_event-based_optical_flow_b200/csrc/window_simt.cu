@@ -57,8 +57,10 @@ int launch_pack_spikes(const float* z, unsigned char* planes, int n_img, int C, 
 }
 
 // ---- weights -> UMMA shared-memory images, per-channel parameters ---------------------------------------
-// forward blob : for conv in (ff[, rec]): [tap][term 0..2][K/8][C/8][8 n][8 k] bf16, value(n = co, k = ci) = w[co][ci][tap]
-// gradient blob: [tap'][term 0..1][C/8][N/8][8 n][8 k] bf16, value(n = ci, k = co) = w[co][ci][8 - tap']
+// The bf16 terms of a weight sit side by side along the MMA N dimension (column n' = term * N + n), so one MMA per tap
+// and k-step produces all partial products and the epilogue adds the column groups.
+// forward blob : for conv in (ff[, rec]): [tap][K/8][3C/8][8 n'][8 k] bf16, value(n = co, k = ci) = w[co][ci][tap]
+// gradient blob: [tap'][C/8][2N/8][8 n'][8 k] bf16, value(n = ci, k = co) = w[co][ci][8 - tap']
 __device__ __forceinline__ void split3(float v, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
   a = __float2bfloat16_rn(v);
   const float r1 = v - __bfloat162float(a);
@@ -83,10 +85,12 @@ __global__ void __launch_bounds__(256) window_pack_weights_kernel(const PackArgs
       const float v = k < Kreal ? w[((size_t)n * Kreal + k) * 9 + tap] : 0.f;
       __nv_bfloat16 t0, t1, t2;
       split3(v, t0, t1, t2);
-      const int idx = ((k >> 3) * (C >> 3) + (n >> 3)) * 64 + (n & 7) * 8 + (k & 7);
-      dst[(size_t)(tap * 3 + 0) * per_tile + idx] = t0;
-      dst[(size_t)(tap * 3 + 1) * per_tile + idx] = t1;
-      dst[(size_t)(tap * 3 + 2) * per_tile + idx] = t2;
+      const __nv_bfloat16 tt[3] = {t0, t1, t2};
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const int nc = term * C + n;
+        dst[(size_t)tap * 3 * per_tile + ((k >> 3) * (3 * C >> 3) + (nc >> 3)) * 64 + (nc & 7) * 8 + (k & 7)] = tt[term];
+      }
     }
     off += (size_t)9 * 3 * per_tile * 2;
   }
@@ -104,9 +108,12 @@ __global__ void __launch_bounds__(256) window_pack_weights_kernel(const PackArgs
       const float v = n < Nreal ? w[((size_t)k * Nreal + n) * 9 + (8 - tap)] : 0.f;
       const __nv_bfloat16 hi = __float2bfloat16_rn(v);
       const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-      const int idx = ((k >> 3) * (N >> 3) + (n >> 3)) * 64 + (n & 7) * 8 + (k & 7);
-      dst[(size_t)(tap * 2 + 0) * per_tile + idx] = hi;
-      dst[(size_t)(tap * 2 + 1) * per_tile + idx] = lo;
+      const __nv_bfloat16 tt[2] = {hi, lo};
+#pragma unroll
+      for (int term = 0; term < 2; ++term) {
+        const int nc = term * N + n;
+        dst[(size_t)tap * 2 * per_tile + ((k >> 3) * (2 * N >> 3) + (nc >> 3)) * 64 + (nc & 7) * 8 + (k & 7)] = tt[term];
+      }
     }
   }
   for (int c = tid; c < C; c += 256) {
@@ -127,6 +134,11 @@ int launch_pack_weights(const PackArgs& p, cudaStream_t st) {
 //   hard: carry = gv*lam*(1-z_in); dlam += gv*(v_in*(1-z_in) - I[t]); dtheta -= gs
 //   soft: carry = gv*lam;          dlam += gv*(v_in - I[t]);          dtheta -= gs + gv*z_in
 // with v_in = v[t-1] (the window's initial state at t = 0) and z_in = spike(v_in) (z_init at t = 0).
+__device__ __forceinline__ void ld8_c8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 __global__ void __launch_bounds__(256) pw_seq_kernel(const PwSeqArgs a) {
   const int HW = a.H * a.W, Wp = a.W + 2;
   const int p = blockIdx.x * 256 + threadIdx.x;
@@ -134,33 +146,31 @@ __global__ void __launch_bounds__(256) pw_seq_kernel(const PwSeqArgs a) {
   const bool ok = p < HW;
   const int y = ok ? p / a.W : 0, x = ok ? p - y * a.W : 0;
   const size_t plane_bytes = (size_t)(a.H + 2) * Wp * 16;
+  const int nch = a.C >> 3;
   float lam[8], oml[8], th[8], carry[8], s_lam[8], s_th[8], v_cur[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const float4 pr = __ldg(reinterpret_cast<const float4*>(a.par) + chunk * 8 + c);
     lam[c] = pr.x; oml[c] = pr.y; th[c] = pr.z;
-    carry[c] = 0.f; s_lam[c] = 0.f; s_th[c] = 0.f;
+    carry[c] = 0.f; s_lam[c] = 0.f; s_th[c] = 0.f; v_cur[c] = 0.f;
   }
-  const size_t n_img_elems = (size_t)a.C * HW;
-  const size_t ch_off = (size_t)(chunk * 8) * HW + p;
-  if (ok) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) v_cur[c] = __ldg(a.v + (size_t)((a.T - 1) * a.B + b) * n_img_elems + ch_off + (size_t)c * HW);
-  }
+  // c8 layout: [image][chunk][H*W][8]
+  const size_t img_stride = (size_t)nch * HW * 8, px_off = ((size_t)chunk * HW + (ok ? p : 0)) * 8;
+  if (ok) ld8_c8(a.v + (size_t)((a.T - 1) * a.B + b) * img_stride + px_off, v_cur);
   for (int t = a.T - 1; t >= 0; --t) {
     const size_t img = (size_t)(t * a.B + b);
-    float v_in[8], z_in[8], go[8], cu[8];
     if (ok) {
+      float v_in[8], z_in[8], go[8], cu[8];
+      ld8_c8(a.g_out + img * img_stride + px_off, go);
+      ld8_c8(a.cur + img * img_stride + px_off, cu);
+      if (t > 0) {
+        ld8_c8(a.v + (img - a.B) * img_stride + px_off, v_in);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const size_t i = img * n_img_elems + ch_off + (size_t)c * HW;
-        go[c] = __ldg(a.g_out + i);
-        cu[c] = __ldg(a.cur + i);
-        if (t > 0) {
-          v_in[c] = __ldg(a.v + (img - a.B) * n_img_elems + ch_off + (size_t)c * HW);
-          z_in[c] = (__fsub_rn(v_in[c], th[c]) > 0.f) ? 1.f : 0.f;
-        } else {
-          const size_t i0 = (size_t)b * n_img_elems + ch_off + (size_t)c * HW;
+        for (int c = 0; c < 8; ++c) z_in[c] = (__fsub_rn(v_in[c], th[c]) > 0.f) ? 1.f : 0.f;
+      } else {   // the window's initial state: NCHW tensors of the caller
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const size_t i0 = ((size_t)b * a.C + chunk * 8 + c) * HW + p;
           v_in[c] = a.v_init ? __ldg(a.v_init + i0) : 0.f;
           z_in[c] = a.z_init ? __ldg(a.z_init + i0) : 0.f;
         }
@@ -294,15 +304,20 @@ __global__ void __launch_bounds__(256) pred_bwd_planes_kernel(const unsigned cha
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned char* src = zp + (size_t)img * img_stride + ((size_t)(y + 1) * Wp + x + 1) * 16;
-  float* gxp = g_x + (size_t)img * C * HW + p;
   for (int ch = 0; ch < (C >> 3); ++ch) {
-    float f[8];
+    float f[8], gx[8];
     if (ok) unpack8(__ldg(reinterpret_cast<const uint4*>(src + ch * plane_bytes)), f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) gx[c] = g0 * sw[ch * 8 + c] + g1 * sw[C + ch * 8 + c];
+    if (ok) {   // c8 layout [image][chunk][H*W][8]
+      float4* gxp = reinterpret_cast<float4*>(g_x + (((size_t)img * (C >> 3) + ch) * HW + p) * 8);
+      gxp[0] = make_float4(gx[0], gx[1], gx[2], gx[3]);
+      gxp[1] = make_float4(gx[4], gx[5], gx[6], gx[7]);
+    }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const int co = ch * 8 + c;
       const float zv = ok ? f[c] : 0.f;
-      if (ok) gxp[(size_t)co * HW] = g0 * sw[co] + g1 * sw[C + co];
       const float s0 = warp_sum(g0 * zv), s1 = warp_sum(g1 * zv);
       if (lane == 0) { red[warp][co] = s0; red[warp][C + co] = s1; }
     }

@@ -22,6 +22,8 @@
 
 #include <stdlib.h>
 
+#include <map>
+
 namespace snnflow {
 
 constexpr int WT_EPI_WARPS = 8;
@@ -86,7 +88,7 @@ __device__ __forceinline__ ItemPos wt_item(const WtArgs& a, int k) {
 }
 
 __device__ __forceinline__ uint32_t wt_tmem_cols(const WtArgs& a) {
-  const uint32_t need = 2u * (uint32_t)(a.R * a.n_seg * a.N);
+  const uint32_t need = 2u * (uint32_t)(a.R * a.n_seg * a.N) * a.src[0].w_terms;
   uint32_t c = 32;
   while (c < need) c <<= 1;
   return c;
@@ -147,11 +149,12 @@ __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
   const int n_items = wt_n_items<SEQ>(a);
   if (n_items == 0) return;
   mbar_wait(s.wbar, 0);
-  const uint32_t idesc = make_idesc(128, a.N, /*bf16*/ 1, 0, 0);
   const int n_mt = a.R * a.n_seg;
-  const uint32_t acc_cols = (uint32_t)(n_mt * a.N);
-  const uint32_t stages_addr = smem_u32(s.stages), w_addr = smem_u32(s.w);
-  const uint32_t b_lbo = (uint32_t)(a.N >> 3) * 128;
+  const uint32_t ncat = a.src[0].w_terms * (uint32_t)a.N;       // accumulator columns per 128-pixel segment
+  const uint32_t acc_cols = (uint32_t)n_mt * ncat;
+  const uint32_t stages16 = smem_u32(s.stages) >> 4, w16 = smem_u32(s.w) >> 4;
+  const uint32_t cs16 = a.chunk_stride >> 4, b_lbo = (ncat >> 3) * 128u, blbo16 = b_lbo >> 4;
+  const uint32_t a_lo_c = ((cs16 & 0x3FFF) << 16), b_lo_c = ((blbo16 & 0x3FFF) << 16), d_hi = desc_hi(128);
   uint32_t u = 0;
   for (int k = 0; k < n_items; ++k) {
     const uint32_t ab = (uint32_t)k & 1u;
@@ -162,25 +165,26 @@ __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
       mbar_wait(&s.full[st], use & 1);
       tc_fence_after();
       const WtSrc& S = a.src[si];
-      const uint32_t base = stages_addr + st * a.stage_bytes;
-      const uint32_t w_tile = S.n_chunks * 8u * (uint32_t)a.N * 2u;
+      const uint32_t idesc = make_idesc(128, (int)(S.w_used * (uint32_t)a.N), /*bf16*/ 1, 0, 0);
+      const uint32_t base16 = stages16 + ((st * a.stage_bytes) >> 4);
+      const uint32_t tile16 = (S.n_chunks * 8u * ncat * 2u) >> 4;   // one tap of this source's weights
+      const uint32_t wsrc16 = w16 + (S.w_off >> 4);
+      const uint32_t n_kk = S.n_chunks >> 1;
+      int r = 0, seg = 0;
       for (int m = 0; m < n_mt; ++m) {
-        const int r = m / a.n_seg, seg = m - r * a.n_seg;
-        const uint32_t d = tmem_base + ab * acc_cols + (uint32_t)(m * a.N);
+        const uint32_t d = tmem_base + ab * acc_cols + (uint32_t)m * ncat;
+        const uint32_t slot0 = (uint32_t)(r * a.Wp + seg * 128);
         uint32_t accumulate = si > 0 ? 1u : 0u;
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t slot = (uint32_t)((r + tap / 3) * a.Wp + seg * 128 + tap % 3) * 16u;
-          const uint32_t wt = w_addr + S.w_off + (uint32_t)tap * S.w_terms * w_tile;
-          for (uint32_t kk = 0; kk < (S.n_chunks >> 1); ++kk) {
-            const uint32_t a0 = base + 2u * kk * a.chunk_stride + slot;
-            const uint32_t w0 = wt + 2u * kk * b_lbo;
-            const uint64_t ad0 = make_desc(a0, a.chunk_stride, 128);
-            for (uint32_t wi = 0; wi < S.w_used; ++wi) {
-              umma_f16(d, ad0, make_desc(w0 + wi * w_tile, b_lbo, 128), idesc, accumulate);
-              accumulate = 1u;
-            }
+          const uint32_t a_t = base16 + slot0 + (uint32_t)((tap / 3) * a.Wp + tap % 3);
+          const uint32_t w_t = wsrc16 + (uint32_t)tap * tile16;
+          for (uint32_t kk = 0; kk < n_kk; ++kk) {
+            umma_f16_split(d, a_lo_c | (a_t + 2u * kk * cs16), d_hi, b_lo_c | (w_t + 2u * kk * blbo16), d_hi, idesc, accumulate);
+            accumulate = 1u;
           }
         }
+        if (++seg == a.n_seg) { seg = 0; ++r; }
       }
       umma_commit(&s.empty[st]);
     }
@@ -201,9 +205,35 @@ __device__ __forceinline__ uint32_t nz16_mask(const uint4& a, const uint4& b) {
 }
 
 // =================================================================================================
+// fp32 tensors of the engine (membranes, currents, spike gradients) use the "c8" layout
+//   [image][chunk = C/8][H*W][8 channels]
+// so that the epilogue thread that owns one pixel x 16 channels moves them as 16-byte vectors.
+// =================================================================================================
+__device__ __forceinline__ size_t c8_off(int img, int n_chunks, int chunk, size_t HW, size_t pix) {
+  return (((size_t)img * n_chunks + chunk) * HW + pix) * 8;
+}
+__device__ __forceinline__ void ld16_c8(const float* base, int img, int n_chunks, int g, size_t HW, size_t pix, float (&v)[16]) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float4* p = reinterpret_cast<const float4*>(base + c8_off(img, n_chunks, g * 2 + j, HW, pix));
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    v[8 * j + 0] = a.x; v[8 * j + 1] = a.y; v[8 * j + 2] = a.z; v[8 * j + 3] = a.w;
+    v[8 * j + 4] = b.x; v[8 * j + 5] = b.y; v[8 * j + 6] = b.z; v[8 * j + 7] = b.w;
+  }
+}
+__device__ __forceinline__ void st16_c8(float* base, int img, int n_chunks, int g, size_t HW, size_t pix, const float (&v)[16]) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    float4* p = reinterpret_cast<float4*>(base + c8_off(img, n_chunks, g * 2 + j, HW, pix));
+    p[0] = make_float4(v[8 * j + 0], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]);
+    p[1] = make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]);
+  }
+}
+
+// =================================================================================================
 // Forward
 // =================================================================================================
-template <bool SEQ, int NSEG, int NG>
+template <bool SEQ, int NSEG>
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const WtSmem s = wt_smem(smem, a.wblob_bytes);
@@ -211,97 +241,124 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == WT_EPI_WARPS) {
-    if (lane == 0) wt_producer<SEQ>(a, s);
+    if (elect_one()) wt_producer<SEQ>(a, s);
     __syncwarp();
   } else if (warp == WT_EPI_WARPS + 1) {
-    if (lane == 0) wt_mma<SEQ>(a, s, tmem_base);
+    if (elect_one()) wt_mma<SEQ>(a, s, tmem_base);
     __syncwarp();
   } else {
-    const int q = warp & 3, h = warp >> 2;
+    const int q = warp & 3, g = warp >> 2;   // TMEM lane quarter ; 16-channel group of this warp
+    const bool act = g * 16 < a.N;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     const size_t HW = (size_t)a.H * a.W;
     const size_t plane_bytes = (size_t)(a.H + 2) * a.Wp * 16;
-    const uint32_t acc_cols = (uint32_t)(NSEG * a.N);
+    const int nch = a.N >> 3;
+    const uint32_t ncat = 3u * (uint32_t)a.N, acc_cols = (uint32_t)NSEG * ncat;   // three weight terms side by side
     const int n_items = wt_n_items<SEQ>(a);
-    float vst[NSEG][NG][16];
-    uint32_t zm[NSEG][NG];
+    float vst[NSEG][16];
+    uint32_t zm[NSEG];
     for (int k = 0; k < n_items; ++k) {
       const ItemPos p = wt_item<SEQ>(a, k);
       const uint32_t ab = (uint32_t)k & 1u;
       const bool load_state = SEQ ? (p.t == 0) : true;
-      if (load_state) {
-        const float* vp = SEQ ? a.v_init : a.v_prev;
+      if (load_state && act) {
 #pragma unroll
         for (int m = 0; m < NSEG; ++m) {
           const int y = p.y0 + m / a.n_seg, x = (m % a.n_seg) * 128 + q * 32 + lane;
           const bool ok = x < a.W;
+          const size_t pix = (size_t)y * a.W + x;
+          const size_t o = ((size_t)(p.b * a.N + g * 16)) * HW + pix;   // NCHW (state tensors of the caller)
+          uint32_t zmask = 0;
 #pragma unroll
-          for (int gi = 0; gi < NG; ++gi) {
-            const int g = h + 2 * gi;
-            if (g * 16 >= a.N) continue;
-            const size_t o = ((size_t)(p.b * a.N + g * 16)) * HW + (size_t)y * a.W + x;
+          for (int c = 0; c < 16; ++c) vst[m][c] = 0.f;
+          if (SEQ) {
+            if (ok && a.v_init) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) vst[m][gi][c] = (ok && vp) ? __ldg(vp + o + (size_t)c * HW) : 0.f;
-            uint32_t zmask = 0;
-            if (SEQ) {
-              if (ok && a.z_init) {
+              for (int c = 0; c < 16; ++c) vst[m][c] = __ldg(a.v_init + o + (size_t)c * HW);
+            }
+            if (ok && a.z_init) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) zmask |= (__ldg(a.z_init + o + (size_t)c * HW) != 0.f ? 1u : 0u) << c;
+              for (int c = 0; c < 16; ++c) zmask |= (__ldg(a.z_init + o + (size_t)c * HW) != 0.f ? 1u : 0u) << c;
+            }
+          } else {
+            if (ok && a.v_prev) {
+              if (a.v_prev_nchw) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) vst[m][c] = __ldg(a.v_prev + o + (size_t)c * HW);
+              } else {
+                ld16_c8(a.v_prev, p.b, nch, g, HW, pix, vst[m]);
               }
-            } else if (ok && a.zin_planes) {
+            }
+            if (ok && a.zin_planes) {
               const unsigned char* zp = a.zin_planes + (size_t)p.b * a.zin_img_stride + (size_t)(g * 2) * plane_bytes +
                                         ((size_t)(y + 1) * a.Wp + x + 1) * 16;
               const uint4 z0 = __ldg(reinterpret_cast<const uint4*>(zp));
               const uint4 z1 = __ldg(reinterpret_cast<const uint4*>(zp + plane_bytes));
               zmask = nz16_mask(z0, z1);
             }
-            zm[m][gi] = zmask;
           }
+          zm[m] = zmask;
         }
       }
-      const bool last = SEQ ? (p.t == a.T - 1) : true;
+      const bool last = (SEQ ? (p.t == a.T - 1) : true) && (a.v_last != nullptr || a.z_last != nullptr);
       mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
       tc_fence_after();
+      if (act) {
 #pragma unroll
-      for (int m = 0; m < NSEG; ++m) {
-        const int y = p.y0 + m / a.n_seg, x = (m % a.n_seg) * 128 + q * 32 + lane;
-        const bool ok = x < a.W;
+        for (int m = 0; m < NSEG; ++m) {
+          const int y = p.y0 + m / a.n_seg, x = (m % a.n_seg) * 128 + q * 32 + lane;
+          const bool ok = x < a.W;
+          const size_t pix = (size_t)y * a.W + x;
+          uint32_t u0[16], u1[16], u2[16];
+          const uint32_t tcol = tmem_base + t_lane + ab * acc_cols + (uint32_t)m * ncat + (uint32_t)(g * 16);
+          tmem_ld16_async(tcol, u0);
+          tmem_ld16_async(tcol + (uint32_t)a.N, u1);
+          tmem_ld16_async(tcol + 2u * (uint32_t)a.N, u2);
+          tmem_ld_wait();
+          float cur[16];
 #pragma unroll
-        for (int gi = 0; gi < NG; ++gi) {
-          const int g = h + 2 * gi;
-          if (g * 16 >= a.N) continue;
-          float acc[16];
-          tmem_ld16(tmem_base + t_lane + ab * acc_cols + (uint32_t)(m * a.N + g * 16), acc);
-          const size_t o = ((size_t)(p.img * a.N + g * 16)) * HW + (size_t)y * a.W + x;
-          const size_t ob = ((size_t)(p.b * a.N + g * 16)) * HW + (size_t)y * a.W + x;
-          const uint32_t zin = zm[m][gi];
+          for (int c = 0; c < 16; ++c) cur[c] = (__uint_as_float(u0[c]) + __uint_as_float(u1[c])) + __uint_as_float(u2[c]);
+          const uint32_t zin = zm[m];
           uint32_t nm = 0;
+          if (a.hard_reset) {   // ((v*lam)*(1-z)) + ((1-lam)*I)      spiking_submodules.py:144
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float4 pr = s.par[g * 16 + c];   // lam, 1 - lam, theta
-            const float v = vst[m][gi][c], z = ((zin >> c) & 1u) ? 1.f : 0.f, cur = acc[c];
-            const float t1 = __fmul_rn(v, pr.x), t3 = __fmul_rn(pr.y, cur);
-            const float vn = a.hard_reset ? __fadd_rn(__fmul_rn(t1, __fsub_rn(1.0f, z)), t3)
-                                          : __fsub_rn(__fadd_rn(t1, t3), __fmul_rn(z, pr.z));
-            const bool sp = __fsub_rn(vn, pr.z) > 0.f;
-            vst[m][gi][c] = vn;
-            nm |= (sp ? 1u : 0u) << c;
-            if (ok) {
-              if (a.v_out) a.v_out[o + (size_t)c * HW] = vn;
-              if (a.cur_out) a.cur_out[o + (size_t)c * HW] = cur;
-              if (last) {
-                if (a.v_last) a.v_last[ob + (size_t)c * HW] = vn;
-                if (a.z_last) a.z_last[ob + (size_t)c * HW] = sp ? 1.f : 0.f;
-              }
+            for (int c = 0; c < 16; ++c) {
+              const float4 pr = s.par[g * 16 + c];   // lam, 1 - lam, theta
+              const float omz = ((zin >> c) & 1u) ? 0.f : 1.f;
+              const float vn = __fadd_rn(__fmul_rn(__fmul_rn(vst[m][c], pr.x), omz), __fmul_rn(pr.y, cur[c]));
+              vst[m][c] = vn;
+              nm |= (__fsub_rn(vn, pr.z) > 0.f ? 1u : 0u) << c;
+            }
+          } else {              // ((v*lam) + ((1-lam)*I)) - (z*theta)   spiking_submodules.py:146
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const float4 pr = s.par[g * 16 + c];
+              const float zt = ((zin >> c) & 1u) ? __fmul_rn(1.0f, pr.z) : 0.f;
+              const float vn = __fsub_rn(__fadd_rn(__fmul_rn(vst[m][c], pr.x), __fmul_rn(pr.y, cur[c])), zt);
+              vst[m][c] = vn;
+              nm |= (__fsub_rn(vn, pr.z) > 0.f ? 1u : 0u) << c;
             }
           }
-          zm[m][gi] = nm;
+          zm[m] = nm;
           if (ok) {
             unsigned char* zp = a.zp_out + (size_t)p.img * a.zp_img_stride + (size_t)(g * 2) * plane_bytes +
                                 ((size_t)(y + 1) * a.Wp + x + 1) * 16;
             *reinterpret_cast<uint4*>(zp) = make_uint4(bf16_pair(nm, 0), bf16_pair(nm, 1), bf16_pair(nm, 2), bf16_pair(nm, 3));
             *reinterpret_cast<uint4*>(zp + plane_bytes) =
                 make_uint4(bf16_pair(nm, 4), bf16_pair(nm, 5), bf16_pair(nm, 6), bf16_pair(nm, 7));
+            if (a.v_out) st16_c8(a.v_out, p.img, nch, g, HW, pix, vst[m]);
+            if (a.cur_out) st16_c8(a.cur_out, p.img, nch, g, HW, pix, cur);
+            if (last) {   // the caller-visible state [2,B,C,H,W] after the window
+              const size_t o = ((size_t)(p.b * a.N + g * 16)) * HW + pix;
+              if (a.v_last) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) a.v_last[o + (size_t)c * HW] = vst[m][c];
+              }
+              if (a.z_last) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) a.z_last[o + (size_t)c * HW] = ((nm >> c) & 1u) ? 1.f : 0.f;
+              }
+            }
           }
         }
       }
@@ -315,7 +372,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
 }
 
 // =================================================================================================
-// Data gradient: g_x[img][n][y][x] = accumulator
+// Data gradient: g_x (c8 layout) = accumulator columns [0,N) + [N,2N)
 // =================================================================================================
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgrad_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -323,34 +380,38 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgrad_kernel(const __grid_co
   const uint32_t tmem_base = wt_prologue(a, s);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == WT_EPI_WARPS) {
-    if (lane == 0) wt_producer<false>(a, s);
+    if (elect_one()) wt_producer<false>(a, s);
     __syncwarp();
   } else if (warp == WT_EPI_WARPS + 1) {
-    if (lane == 0) wt_mma<false>(a, s, tmem_base);
+    if (elect_one()) wt_mma<false>(a, s, tmem_base);
     __syncwarp();
   } else {
-    const int q = warp & 3, h = warp >> 2;
+    const int q = warp & 3, g = warp >> 2;
+    const bool act = g * 16 < a.N;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     const size_t HW = (size_t)a.H * a.W;
-    const int n_mt = a.R * a.n_seg;
-    const uint32_t acc_cols = (uint32_t)(n_mt * a.N);
+    const int n_mt = a.R * a.n_seg, nch = a.N >> 3;
+    const uint32_t ncat = 2u * (uint32_t)a.N, acc_cols = (uint32_t)n_mt * ncat;   // [g*w_hi | g_hi*w_lo]
     const int n_items = wt_n_items<false>(a);
     for (int k = 0; k < n_items; ++k) {
       const ItemPos p = wt_item<false>(a, k);
       const uint32_t ab = (uint32_t)k & 1u;
       mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
       tc_fence_after();
-      for (int m = 0; m < n_mt; ++m) {
-        const int y = p.y0 + m / a.n_seg, x = (m % a.n_seg) * 128 + q * 32 + lane;
-        const bool ok = x < a.W;
-        for (int g = h; g * 16 < a.N; g += 2) {
+      if (act) {
+        int r = 0, seg = 0;
+        for (int m = 0; m < n_mt; ++m) {
+          const int y = p.y0 + r, x = seg * 128 + q * 32 + lane;
+          uint32_t u0[16], u1[16];
+          const uint32_t tcol = tmem_base + t_lane + ab * acc_cols + (uint32_t)m * ncat + (uint32_t)(g * 16);
+          tmem_ld16_async(tcol, u0);
+          tmem_ld16_async(tcol + (uint32_t)a.N, u1);
+          tmem_ld_wait();
           float acc[16];
-          tmem_ld16(tmem_base + t_lane + ab * acc_cols + (uint32_t)(m * a.N + g * 16), acc);
-          if (ok) {
-            float* o = a.g_x + ((size_t)(p.img * a.N + g * 16)) * HW + (size_t)y * a.W + x;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) o[(size_t)c * HW] = acc[c];
-          }
+          for (int c = 0; c < 16; ++c) acc[c] = __uint_as_float(u0[c]) + __uint_as_float(u1[c]);
+          if (x < a.W) st16_c8(a.g_x, p.img, nch, g, HW, (size_t)y * a.W + x, acc);
+          if (++seg == a.n_seg) { seg = 0; ++r; }
         }
       }
       tc_fence_before();
@@ -368,108 +429,120 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgrad_kernel(const __grid_co
 //   hard: g_v' = gv*lam*(1-z_in); dlam += gv*(v_in*(1-z_in) - I); dtheta -= gs
 //   soft: g_v' = gv*lam;          dlam += gv*(v_in - I);          dtheta -= gs + gv*z_in
 // =================================================================================================
-template <int NG>
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const WtSmem s = wt_smem(smem, a.wblob_bytes);
   const uint32_t tmem_base = wt_prologue(a, s);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == WT_EPI_WARPS) {
-    if (lane == 0 && a.has_gz) wt_producer<false>(a, s);
+    if (a.has_gz && elect_one()) wt_producer<false>(a, s);
     __syncwarp();
   } else if (warp == WT_EPI_WARPS + 1) {
-    if (lane == 0 && a.has_gz) wt_mma<false>(a, s, tmem_base);
+    if (a.has_gz && elect_one()) wt_mma<false>(a, s, tmem_base);
     __syncwarp();
   } else {
-    const int q = warp & 3, h = warp >> 2;
+    const int q = warp & 3, g = warp >> 2;
+    const bool act = g * 16 < a.N;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     const size_t HW = (size_t)a.H * a.W;
     const size_t plane_bytes = (size_t)(a.H + 2) * a.Wp * 16;
-    const int n_mt = a.R * a.n_seg;
-    const uint32_t acc_cols = (uint32_t)(n_mt * a.N);
+    const int n_mt = a.R * a.n_seg, nch = a.N >> 3;
+    const uint32_t ncat = 2u * (uint32_t)a.N, acc_cols = (uint32_t)n_mt * ncat;
     const int n_items = wt_n_items<false>(a);
-    float s_lam[NG][16], s_th[NG][16];
+    float s_lam[16], s_th[16];
 #pragma unroll
-    for (int gi = 0; gi < NG; ++gi)
-#pragma unroll
-      for (int c = 0; c < 16; ++c) s_lam[gi][c] = s_th[gi][c] = 0.f;
+    for (int c = 0; c < 16; ++c) s_lam[c] = s_th[c] = 0.f;
     for (int k = 0; k < n_items; ++k) {
       const ItemPos p = wt_item<false>(a, k);
       const uint32_t ab = (uint32_t)k & 1u;
       bool waited = false;
-      for (int m = 0; m < n_mt; ++m) {
-        const int y = p.y0 + m / a.n_seg, x = (m % a.n_seg) * 128 + q * 32 + lane;
+      int r = 0, seg = 0;
+      for (int m = 0; m < n_mt && act; ++m) {
+        const int y = p.y0 + r, x = seg * 128 + q * 32 + lane;
         const bool ok = x < a.W;
+        const size_t pix = (size_t)y * a.W + x;
+        const size_t o = ((size_t)(p.b * a.N + g * 16)) * HW + pix;   // NCHW (window-initial state of the caller)
 #pragma unroll
-        for (int gi = 0; gi < NG; ++gi) {
-          const int g = h + 2 * gi;
-          if (g * 16 >= a.N) continue;
-          const size_t o = ((size_t)(p.b * a.N + g * 16)) * HW + (size_t)y * a.W + x;
-          unsigned char* gp = a.gp_out + (size_t)p.b * a.gp_img_stride + (size_t)(g * 2) * plane_bytes +
-                              ((size_t)(y + 1) * a.Wp + x + 1) * 16;
+        for (int hf = 0; hf < 2; ++hf) {   // two 8-channel chunks (register pressure)
+          const int chunk = g * 2 + hf;
+          float4 go[2], vt[2], cu[2], vi[2], gv[2];
+          go[0] = go[1] = vt[0] = vt[1] = cu[0] = cu[1] = vi[0] = vi[1] = gv[0] = gv[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const size_t co = c8_off(p.b, nch, chunk, HW, pix);
+          if (ok) {
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {   // two 8-channel chunks (register pressure)
-            float go[8], vt[8], vi[8], cu[8], gv[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const size_t i = o + (size_t)(hf * 8 + c) * HW;
-              go[c] = ok ? __ldg(a.g_out + i) : 0.f;
-              vt[c] = ok ? __ldg(a.v_t + i) : 0.f;
-              cu[c] = ok ? __ldg(a.cur_t + i) : 0.f;
-              vi[c] = (ok && a.v_in) ? __ldg(a.v_in + i) : 0.f;
-              gv[c] = (ok && !a.first_step) ? a.g_v[i] : 0.f;
-            }
-            float acc[8];
-            if (a.has_gz) {
-              if (!waited) {
-                mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
-                tc_fence_after();
-                waited = true;
-              }
-              tmem_ld8(tmem_base + t_lane + ab * acc_cols + (uint32_t)(m * a.N + g * 16 + hf * 8), acc);
-              if (!ok) {   // pixels past the row end accumulate whatever the operand read found: keep them out of the sums
-#pragma unroll
-                for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-            }
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const int cc = hf * 8 + c;
-              const float4 pr = s.par[g * 16 + cc];
-              float z_in;
-              if (a.z_from_v) z_in = (__fsub_rn(vi[c], pr.z) > 0.f) ? 1.f : 0.f;
-              else z_in = (ok && a.z_init) ? __ldg(a.z_init + o + (size_t)cc * HW) : 0.f;
-              const float gz = go[c] + acc[c];
-              const float gs = gz * surrogate(vt[c] - pr.z, a.width, a.surrogate);
-              const float gvv = gv[c] + gs;
-              const float gi_ = gvv * pr.y;
-              float gvn;
-              if (a.hard_reset) {
-                gvn = gvv * pr.x * (1.0f - z_in);
-                s_lam[gi][cc] += gvv * (vi[c] * (1.0f - z_in) - cu[c]);
-                s_th[gi][cc] -= gs;
-              } else {
-                gvn = gvv * pr.x;
-                s_lam[gi][cc] += gvv * (vi[c] - cu[c]);
-                s_th[gi][cc] -= gs + gvv * z_in;
-              }
-              if (ok) a.g_v[o + (size_t)cc * HW] = gvn;
-              const __nv_bfloat16 bh = __float2bfloat16_rn(gi_);
-              const __nv_bfloat16 bl = __float2bfloat16_rn(gi_ - __bfloat162float(bh));
-              const uint32_t uh = (uint32_t)__bfloat16_as_ushort(bh), ul = (uint32_t)__bfloat16_as_ushort(bl);
-              if (c & 1) { hi[c >> 1] |= uh << 16; lo[c >> 1] |= ul << 16; }
-              else { hi[c >> 1] = uh; lo[c >> 1] = ul; }
-            }
-            if (ok) {
-              *reinterpret_cast<uint4*>(gp + (size_t)hf * plane_bytes) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(gp + a.gp_term_stride + (size_t)hf * plane_bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            for (int j = 0; j < 2; ++j) {
+              go[j] = __ldg(reinterpret_cast<const float4*>(a.g_out + co) + j);
+              vt[j] = __ldg(reinterpret_cast<const float4*>(a.v_t + co) + j);
+              cu[j] = __ldg(reinterpret_cast<const float4*>(a.cur_t + co) + j);
+              if (!a.first_step) gv[j] = reinterpret_cast<const float4*>(a.g_v + co)[j];
+              if (a.v_in && !a.v_in_nchw) vi[j] = __ldg(reinterpret_cast<const float4*>(a.v_in + co) + j);
             }
           }
+          float vin[8] = {vi[0].x, vi[0].y, vi[0].z, vi[0].w, vi[1].x, vi[1].y, vi[1].z, vi[1].w};
+          if (ok && a.v_in && a.v_in_nchw) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) vin[c] = __ldg(a.v_in + o + (size_t)(hf * 8 + c) * HW);
+          }
+          const float gof[8] = {go[0].x, go[0].y, go[0].z, go[0].w, go[1].x, go[1].y, go[1].z, go[1].w};
+          const float vtf[8] = {vt[0].x, vt[0].y, vt[0].z, vt[0].w, vt[1].x, vt[1].y, vt[1].z, vt[1].w};
+          const float cuf[8] = {cu[0].x, cu[0].y, cu[0].z, cu[0].w, cu[1].x, cu[1].y, cu[1].z, cu[1].w};
+          const float gvf[8] = {gv[0].x, gv[0].y, gv[0].z, gv[0].w, gv[1].x, gv[1].y, gv[1].z, gv[1].w};
+          float acc[8];
+          if (a.has_gz) {
+            if (!waited) {
+              mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
+              tc_fence_after();
+              waited = true;
+            }
+            float acc1[8];
+            const uint32_t tcol = tmem_base + t_lane + ab * acc_cols + (uint32_t)m * ncat + (uint32_t)(g * 16 + hf * 8);
+            tmem_ld8(tcol, acc);
+            tmem_ld8(tcol + (uint32_t)a.N, acc1);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = ok ? acc[c] + acc1[c] : 0.f;   // keep out-of-row garbage out of the sums
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+          }
+          uint32_t hi[4], lo[4];
+          float gvn[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int cc = hf * 8 + c;
+            const float4 pr = s.par[g * 16 + cc];
+            float z_in;
+            if (a.z_from_v) z_in = (__fsub_rn(vin[c], pr.z) > 0.f) ? 1.f : 0.f;
+            else z_in = (ok && a.z_init) ? __ldg(a.z_init + o + (size_t)cc * HW) : 0.f;
+            const float gz = gof[c] + acc[c];
+            const float gs = gz * surrogate(vtf[c] - pr.z, a.width, a.surrogate);
+            const float gvv = gvf[c] + gs;
+            const float gi_ = gvv * pr.y;
+            if (a.hard_reset) {
+              gvn[c] = gvv * pr.x * (1.0f - z_in);
+              s_lam[cc] += gvv * (vin[c] * (1.0f - z_in) - cuf[c]);
+              s_th[cc] -= gs;
+            } else {
+              gvn[c] = gvv * pr.x;
+              s_lam[cc] += gvv * (vin[c] - cuf[c]);
+              s_th[cc] -= gs + gvv * z_in;
+            }
+            const __nv_bfloat16 bh = __float2bfloat16_rn(gi_);
+            const __nv_bfloat16 bl = __float2bfloat16_rn(gi_ - __bfloat162float(bh));
+            const uint32_t uh = (uint32_t)__bfloat16_as_ushort(bh), ul = (uint32_t)__bfloat16_as_ushort(bl);
+            if (c & 1) { hi[c >> 1] |= uh << 16; lo[c >> 1] |= ul << 16; }
+            else { hi[c >> 1] = uh; lo[c >> 1] = ul; }
+          }
+          if (ok) {
+            float4* gvp = reinterpret_cast<float4*>(a.g_v + co);
+            gvp[0] = make_float4(gvn[0], gvn[1], gvn[2], gvn[3]);
+            gvp[1] = make_float4(gvn[4], gvn[5], gvn[6], gvn[7]);
+            unsigned char* gp = a.gp_out + (size_t)p.b * a.gp_img_stride + (size_t)chunk * plane_bytes +
+                                ((size_t)(y + 1) * a.Wp + x + 1) * 16;
+            *reinterpret_cast<uint4*>(gp) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(gp + a.gp_term_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
         }
+        if (++seg == a.n_seg) { seg = 0; ++r; }
       }
       if (a.has_gz) {
         if (!waited) mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
@@ -477,26 +550,24 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
         mbar_arrive(&s.acc_empty[ab]);
       }
     }
-    // per-warp partial sums of dlam / dtheta -> shared scratch [warp][2][16*NG]
+    // per-warp partial sums of dlam / dtheta -> shared scratch [warp][2][16]
 #pragma unroll
-    for (int gi = 0; gi < NG; ++gi)
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float l = warp_sum(s_lam[gi][c]), t = warp_sum(s_th[gi][c]);
-        if (lane == 0) {
-          s.red[(warp * 2 + 0) * (16 * NG) + gi * 16 + c] = l;
-          s.red[(warp * 2 + 1) * (16 * NG) + gi * 16 + c] = t;
-        }
+    for (int c = 0; c < 16; ++c) {
+      const float l = warp_sum(s_lam[c]), t = warp_sum(s_th[c]);
+      if (lane == 0) {
+        s.red[(warp * 2 + 0) * 16 + c] = l;
+        s.red[(warp * 2 + 1) * 16 + c] = t;
       }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (tid < 2 * a.N) {
     const int which = tid / a.N, co = tid % a.N;
-    const int g = co >> 4, hh = g & 1, gi = g >> 1, c = co & 15;
+    const int g = co >> 4, c = co & 15;
     float t = 0.f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) t += s.red[((hh * 4 + q) * 2 + which) * (16 * NG) + gi * 16 + c];
+    for (int q = 0; q < 4; ++q) t += s.red[((g * 4 + q) * 2 + which) * 16 + c];
     a.part[(size_t)blockIdx.x * 2 * a.N + tid] = t;
   }
   if (warp == 0) tmem_dealloc(tmem_base, wt_tmem_cols(a));
@@ -515,10 +586,10 @@ int wt_grid(int n_tiles) {
   return n_tiles < sms ? n_tiles : sms;
 }
 
-bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int* R_out, int* S_out,
+bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int w_terms, int* R_out, int* S_out,
              uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes) {
   const int Wp = W + 2, n_seg = ceil_div(W, 128);
-  const int NG = N > 32 ? 2 : 1;
+  if (N > 32) return false;   // one 16-channel group per epilogue warp pair
   const size_t budget = (size_t)227 * 1024 - WT_HDR - WT_TAIL - align_up(wblob_bytes, 128);
   const int forced_R = env_int("SNNFLOW_WT_R", 0), forced_S = env_int("SNNFLOW_WT_S", 0);
   int best_R = 0, best_S = 0;
@@ -526,8 +597,8 @@ bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes
     if (H % R) continue;
     if (forced_R && R != forced_R) continue;
     const int n_mt = R * n_seg;
-    if (2 * n_mt * N > 512) continue;
-    if (seq_state && n_mt * NG > 4) continue;
+    if (2 * n_mt * N * w_terms > 512) continue;
+    if (seq_state && n_mt > 4) continue;
     const size_t cs = align_up((size_t)(R + 2) * Wp * 16, 128);
     const size_t stage = cs * max_chunks_per_stage;
     int S = (int)(budget / stage);
@@ -551,39 +622,43 @@ static size_t wt_smem_bytes(const WtArgs& a) {
 }
 
 template <typename K>
-static int wt_launch(K kernel, const WtArgs& a, cudaStream_t st, const char* what) {
+static int wt_launch(K kernel, const void* key, const WtArgs& a, cudaStream_t st, const char* what) {
   const size_t smem = wt_smem_bytes(a);
   if (smem > (size_t)227 * 1024) {
     set_error("%s: shared memory %zu exceeds 227 KB", what, smem);
     return SNNFLOW_EINVAL;
   }
-  SNNFLOW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static std::map<const void*, size_t> attr;   // largest dynamic shared memory size set per kernel
+  size_t& have = attr[key];
+  if (smem > have) {
+    SNNFLOW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem;
+  }
   const int n_tiles = a.n_outer * (a.H / a.R);
   kernel<<<wt_grid(n_tiles), WT_THREADS, smem, st>>>(a);
   return check_launch(what);
 }
 
 int launch_wt_fwd(const WtArgs& a, bool seq, cudaStream_t st, const char* prof_name, double bytes, double flops) {
-  const int nseg = a.R * a.n_seg, ng = a.N > 32 ? 2 : 1;
+  const int nseg = a.R * a.n_seg;
   prof_begin(prof_name, st, bytes, flops);
-#define WT_FWD_CASE(SEQ, NS, NGV) \
-  if (seq == SEQ && nseg == NS && ng == NGV) return wt_launch(wt_fwd_kernel<SEQ, NS, NGV>, a, st, "wt_fwd_kernel");
-  WT_FWD_CASE(true, 1, 1) WT_FWD_CASE(true, 2, 1) WT_FWD_CASE(true, 3, 1) WT_FWD_CASE(true, 4, 1) WT_FWD_CASE(true, 1, 2) WT_FWD_CASE(true, 2, 2)
-  WT_FWD_CASE(false, 1, 1) WT_FWD_CASE(false, 2, 1) WT_FWD_CASE(false, 3, 1) WT_FWD_CASE(false, 4, 1) WT_FWD_CASE(false, 1, 2) WT_FWD_CASE(false, 2, 2)
+#define WT_FWD_CASE(SEQ, NS) \
+  if (seq == SEQ && nseg == NS) return wt_launch(wt_fwd_kernel<SEQ, NS>, (const void*)wt_fwd_kernel<SEQ, NS>, a, st, "wt_fwd_kernel");
+  WT_FWD_CASE(true, 1) WT_FWD_CASE(true, 2) WT_FWD_CASE(true, 3) WT_FWD_CASE(true, 4)
+  WT_FWD_CASE(false, 1) WT_FWD_CASE(false, 2) WT_FWD_CASE(false, 3) WT_FWD_CASE(false, 4)
 #undef WT_FWD_CASE
-  set_error("launch_wt_fwd: no kernel for %d accumulator tiles x %d channel groups", nseg, ng);
+  set_error("launch_wt_fwd: no kernel for %d accumulator tiles", nseg);
   return SNNFLOW_EINVAL;
 }
 
 int launch_wt_dgrad(const WtArgs& a, cudaStream_t st, double bytes, double flops) {
   prof_begin("win_dgrad", st, bytes, flops);
-  return wt_launch(wt_dgrad_kernel, a, st, "wt_dgrad_kernel");
+  return wt_launch(wt_dgrad_kernel, (const void*)wt_dgrad_kernel, a, st, "wt_dgrad_kernel");
 }
 
 int launch_wt_recbwd(const WtArgs& a, cudaStream_t st, double bytes, double flops) {
   prof_begin("win_rec_bwd", st, bytes, flops);
-  if (a.N > 32) return wt_launch(wt_recbwd_kernel<2>, a, st, "wt_recbwd_kernel");
-  return wt_launch(wt_recbwd_kernel<1>, a, st, "wt_recbwd_kernel");
+  return wt_launch(wt_recbwd_kernel, (const void*)wt_recbwd_kernel, a, st, "wt_recbwd_kernel");
 }
 
 }  // namespace snnflow

@@ -35,7 +35,7 @@ __device__ __forceinline__ int wg_n_items(const WgArgs& a) {
 }
 
 __device__ __forceinline__ uint32_t wg_tmem_cols(const WgArgs& a) {
-  const uint32_t need = (uint32_t)(a.n_kyg * 3 * a.C);
+  const uint32_t need = (uint32_t)(a.n_kyg * 3 * 2 * a.C);   // [x*g_hi | x*g_lo] per (tap group, kx)
   uint32_t c = 32;
   while (c < need) c <<= 1;
   return c;
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
   const int g_chunks = a.C >> 3;
 
   if (warp == WG_EPI_WARPS) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int k = 0; k < n_items; ++k) {
         const int tile = blockIdx.x + k * gridDim.x;
         const int img = tile / tpi, y0 = (tile - img * tpi) * a.R;
@@ -104,27 +104,30 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
     }
     __syncwarp();
   } else if (warp == WG_EPI_WARPS + 1) {
-    if (lane == 0 && n_items > 0) {
-      const uint32_t idesc = make_idesc(128, a.C, /*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1);
-      const uint32_t stages_addr = smem_u32(stages);
+    if (n_items > 0 && elect_one()) {
+      // N = 2C: the hi and lo planes of g_I are adjacent chunk groups of one row, so ONE MMA per k-step yields both
+      // partial products (columns [0,C) and [C,2C)); the read-out adds them.
+      const uint32_t idesc = make_idesc(128, 2 * a.C, /*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1);
+      const uint32_t stages16 = smem_u32(stages) >> 4, pitch16 = pitch >> 4;
+      const uint32_t lo_c = ((128u >> 4) << 16), d_hi = desc_hi(pitch);   // LBO = 128 B (k groups), SBO = pitch (chunk groups)
       for (int k = 0; k < n_items; ++k) {
         const uint32_t st = (uint32_t)k % (uint32_t)a.S, use = (uint32_t)k / (uint32_t)a.S;
         mbar_wait(&full[st], use & 1);
         tc_fence_after();
-        const uint32_t xs = stages_addr + st * a.stage_bytes, gs = xs + a.g_off;
+        const uint32_t xs16 = stages16 + ((st * a.stage_bytes) >> 4), gs16 = xs16 + (a.g_off >> 4);
         for (int r = 0; r < a.R; ++r) {
+          const uint32_t grow16 = gs16 + (uint32_t)(r * 2 * g_chunks) * pitch16 + 1u;
           for (int j = 0; j < a.n_kyg; ++j) {
-            const uint32_t arow = xs + (uint32_t)((r + j * a.rpm) * a.n_cg) * pitch;
-            for (int kx = 0; kx < 3; ++kx) {
-              const uint32_t d = tmem_base + (uint32_t)((j * 3 + kx) * a.C);
-              for (int kk = 0; kk < a.ksteps; ++kk) {
-                // g slot c (padded column) pairs with input slot c + kx - 1; the k range starts at c = 1
-                const uint64_t adesc = make_desc_mn(arow + (uint32_t)(kx + kk * 16) * 16u, 128, pitch);
+            const uint32_t arow16 = xs16 + (uint32_t)((r + j * a.rpm) * a.n_cg) * pitch16;
 #pragma unroll
-                for (int term = 0; term < 2; ++term) {
-                  const uint64_t bdesc = make_desc_mn(gs + (uint32_t)((r * 2 + term) * g_chunks) * pitch + (uint32_t)(1 + kk * 16) * 16u, 128, pitch);
-                  umma_f16(d, adesc, bdesc, idesc, (k > 0 || r > 0 || kk > 0 || term > 0) ? 1u : 0u);
-                }
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint32_t d = tmem_base + (uint32_t)((j * 3 + kx) * 2 * a.C);
+              uint32_t accumulate = (k > 0 || r > 0) ? 1u : 0u;
+              // g slot c (padded column) pairs with input slot c + kx - 1; the k range starts at c = 1
+              for (int kk = 0; kk < a.ksteps; ++kk) {
+                umma_f16_split(d, lo_c | (arow16 + (uint32_t)(kx + kk * 16)), d_hi, lo_c | (grow16 + (uint32_t)(kk * 16)), d_hi, idesc,
+                               accumulate);
+                accumulate = 1u;
               }
             }
           }
@@ -150,8 +153,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
       const bool ok = row_used && ky < 3 && ci < a.cin_real[si];
       float* dst = a.part[si] + ((size_t)blockIdx.x * 9 + (ky * 3 + kx)) * a.cin_alloc[si] * a.C + (size_t)ci * a.C;
       for (int g = 0; g < (a.C >> 4); ++g) {
-        float acc[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_id * a.C + g * 16), acc);
+        float acc[16], acc1[16];
+        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_id * 2 * a.C + g * 16);
+        tmem_ld16(tcol, acc);
+        tmem_ld16(tcol + (uint32_t)a.C, acc1);
+#pragma unroll
+        for (int v = 0; v < 16; ++v) acc[v] += acc1[v];
         if (ok) {
 #pragma unroll
           for (int v = 0; v < 4; ++v)
@@ -180,7 +187,7 @@ static WgPlan wg_plan(int C, int cin_chunks, int rec_chunks, int H, int W) {
   if ((C % 16) || C < 16 || C > 64) return p;
   p.rpm = 16 / p.n_cg;
   p.n_kyg = (3 + p.rpm - 1) / p.rpm;
-  if (p.n_kyg * 3 * C > 512) return p;
+  if (p.n_kyg * 3 * 2 * C > 512) return p;
   p.ksteps = ceil_div(W, 16);
   p.P = (int)align_up((size_t)(16 * p.ksteps + 3 > W + 2 ? 16 * p.ksteps + 3 : W + 2), 8);
   const int forced_R = wg_env_int("SNNFLOW_WG_R", 0), forced_S = wg_env_int("SNNFLOW_WG_S", 0);

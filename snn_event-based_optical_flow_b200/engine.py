@@ -32,30 +32,30 @@ def _bind(L):
         return
     P = ctypes.c_void_p
     L.snnflow_net_acts_floats.restype = ctypes.c_size_t
-    L.snnflow_net_acts_floats.argtypes = [ctypes.POINTER(NetDesc), ctypes.c_int]
+    L.snnflow_net_acts_floats.argtypes = [P, ctypes.c_int]
     L.snnflow_net_bwd_workspace_bytes.restype = ctypes.c_size_t
-    L.snnflow_net_bwd_workspace_bytes.argtypes = [ctypes.POINTER(NetDesc)]
+    L.snnflow_net_bwd_workspace_bytes.argtypes = [P]
     L.snnflow_net_forward.restype = ctypes.c_int
-    L.snnflow_net_forward.argtypes = [ctypes.POINTER(NetDesc), ctypes.POINTER(LayerPtrs), P, P, P, ctypes.POINTER(P), P, P,
+    L.snnflow_net_forward.argtypes = [P, P, P, P, P, ctypes.POINTER(P), P, P,
                                       ctypes.c_int, P]
     L.snnflow_net_backward.restype = ctypes.c_int
-    L.snnflow_net_backward.argtypes = [ctypes.POINTER(NetDesc), ctypes.POINTER(LayerPtrs), P, P, ctypes.POINTER(P), P, P, P,
+    L.snnflow_net_backward.argtypes = [P, P, P, P, ctypes.POINTER(P), P, P, P,
                                        P, P, P, ctypes.c_size_t, P]
     L.snnflow_window_supported.restype = ctypes.c_int
-    L.snnflow_window_supported.argtypes = [ctypes.POINTER(NetDesc), ctypes.c_int]
+    L.snnflow_window_supported.argtypes = [P, ctypes.c_int]
     L.snnflow_window_arena_bytes.restype = ctypes.c_size_t
-    L.snnflow_window_arena_bytes.argtypes = [ctypes.POINTER(NetDesc), ctypes.c_int]
+    L.snnflow_window_arena_bytes.argtypes = [P, ctypes.c_int]
     L.snnflow_window_workspace_bytes.restype = ctypes.c_size_t
-    L.snnflow_window_workspace_bytes.argtypes = [ctypes.POINTER(NetDesc)]
+    L.snnflow_window_workspace_bytes.argtypes = [P]
     L.snnflow_window_state_offsets.restype = ctypes.c_int
-    L.snnflow_window_state_offsets.argtypes = [ctypes.POINTER(NetDesc), ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
+    L.snnflow_window_state_offsets.argtypes = [P, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
     L.snnflow_window_inexact_count.restype = ctypes.c_uint
     L.snnflow_window_inexact_count.argtypes = [ctypes.c_int]
     L.snnflow_window_forward.restype = ctypes.c_int
-    L.snnflow_window_forward.argtypes = [ctypes.POINTER(NetDesc), ctypes.POINTER(LayerPtrs), P, P, P, ctypes.POINTER(P), P, P,
+    L.snnflow_window_forward.argtypes = [P, P, P, P, P, ctypes.POINTER(P), P, P,
                                          ctypes.c_int, P]
     L.snnflow_window_backward.restype = ctypes.c_int
-    L.snnflow_window_backward.argtypes = [ctypes.POINTER(NetDesc), ctypes.POINTER(LayerPtrs), P, ctypes.POINTER(P), P, P, P,
+    L.snnflow_window_backward.argtypes = [P, P, P, ctypes.POINTER(P), P, P, P,
                                           P, P, P, ctypes.c_size_t, P]
     L._net_bound = True
 
@@ -305,10 +305,9 @@ class WindowRunner:
         return bool(L.snnflow_window_supported(ctypes.byref(desc), int(backward)))
 
     def lm_arena(self, desc, save, dev):
-        # zero-filled once per shape (the plane borders are never written); two arenas alternate so that the states
-        # of window k (views into arena k%2) stay valid while window k+1 is computed
-        self._flip ^= 1
-        key = ("arena", _desc_key(desc), bool(save), self._flip, str(dev))
+        # zero-filled once per shape (the plane borders are never written).  ONE arena per shape: the forward call
+        # copies the incoming state before it overwrites the state block, so the addresses never change (CUDA graphs)
+        key = ("arena", _desc_key(desc), bool(save), str(dev))
         buf = self._lm.get(key)
         if buf is None:
             n = _lib.lib().snnflow_window_arena_bytes(ctypes.byref(desc), int(save))

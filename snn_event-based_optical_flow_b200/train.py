@@ -44,6 +44,42 @@ class TrainWindow:
     def __init__(self, model, loss_fn, optimizer, clip_grad=1.0, group=None):
         self.model, self.loss_fn, self.opt, self.clip = model, loss_fn, optimizer, clip_grad
         self.reducer = FlatGradAllReduce(model.parameters(), group)
+        self._graph = None
+
+    # ---- whole-step CUDA graph -----------------------------------------------------------------------------
+    def capture(self, example_batch, warmup=3):
+        """Capture one optimizer step (window forward, association, loss, BPTT, all-reduce, clip, Adam) in a CUDA graph.
+        Every buffer the step touches has a fixed address (window arena, workspace, static input copies), so
+        ``step_graphed`` only copies the new window into the static inputs and replays ~600 kernels with one launch.
+        The optimizer must be capturable (torch.optim.Adam(..., capturable=True)).  Returns the number of snnflow
+        kernel launches inside one captured step."""
+        from . import _lib
+        self._static = {k: torch.empty_like(v) for k, v in example_batch.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._load(example_batch)
+                self.step(self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        self._load(example_batch)
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self.step(self._static)
+        self.launches_per_step = _lib.launch_count() - n0
+        return self.launches_per_step
+
+    def _load(self, batch):
+        for k, v in self._static.items():
+            v.copy_(batch[k], non_blocking=True)
+
+    def step_graphed(self, batch):
+        """Same as step() after capture(): `batch` may live on the device or in pinned host memory."""
+        self._load(batch)
+        self._graph.replay()
+        return self._static_loss
 
     def step(self, batch, use_window=True):
         T = batch["event_cnt"].shape[0]

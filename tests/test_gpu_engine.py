@@ -20,7 +20,8 @@ def make_net(kind, C, seed=0):
                                       neuron_kwargs=dict(leak=(0.0, 1.0), thresh=(0.3, 0.1)))).cuda()
     with torch.no_grad():
         net.pred.conv2d.weight.mul_(20)
-    from snnflow_b200.engine import WindowRunner
+    import importlib
+    WindowRunner = importlib.import_module("snn_event-based_optical_flow_b200.engine").WindowRunner
     runner = WindowRunner(net)
     runner.engine = "per_step"   # this file pins the per-step window engine; test_gpu_window.py covers the layer-major one
     object.__setattr__(net, "_window_runner", runner)
