@@ -25,11 +25,11 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, P1;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)   // suspend-time hint (ns): a waiting warp sleeps instead of polling
       : "memory");
   return ok;
 }
@@ -115,6 +115,12 @@ __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&u)[16
         "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&u)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // warp-uniform election of one lane (the form ptxas recognises: code under it is known to run in ONE thread, so

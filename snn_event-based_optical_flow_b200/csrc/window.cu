@@ -44,7 +44,7 @@ static WinLayout win_layout(const snnflow_net_desc* d, int save) {
     L.off_init[l] = save ? take((size_t)2 * L.n * sizeof(float)) : 0;
     if (save) {
       L.off_v[l] = take((size_t)T * L.n * sizeof(float));          // membranes of all bins, c8 layout
-      L.off_cur[l] = take((size_t)T * L.n * sizeof(float));        // input currents of all bins, c8 layout
+      L.off_cur[l] = 0;   // the input currents are not stored: the backward recovers them from consecutive membranes
     } else {
       L.off_v[l] = L.rec[l] ? take((size_t)2 * L.n * sizeof(float)) : 0;   // ping-pong membranes of a recurrent layer
       L.off_cur[l] = 0;
@@ -77,17 +77,17 @@ static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool back
   uint32_t max_fwd_rec_blob = 0;
   for (int l = 0; l < WIN_LAYERS; ++l)
     if (L.rec[l] && L.fwd_blob_bytes[l] > max_fwd_rec_blob) max_fwd_rec_blob = L.fwd_blob_bytes[l];
-  P.ok = wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 3 * C * C * 2), true, 3, &P.R_ff, &P.S_ff, &P.sub_ff, &P.cs_ff, &P.st_ff);
-  P.ok = P.ok && wt_plan(d->H, d->W, 2, C, (uint32_t)((size_t)9 * 3 * 16 * C * 2), true, 3, &P.R_head, &P.S_head, &P.sub_head,
+  P.ok = wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 3 * C * C * 2), true, 3, false, &P.R_ff, &P.S_ff, &P.sub_ff, &P.cs_ff, &P.st_ff);
+  P.ok = P.ok && wt_plan(d->H, d->W, 2, C, (uint32_t)((size_t)9 * 3 * 16 * C * 2), true, 3, false, &P.R_head, &P.S_head, &P.sub_head,
                          &P.cs_head, &P.st_head);
   if (any_rec)
-    P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, max_fwd_rec_blob, true, 3, &P.R_rec, &P.S_rec, &P.sub_rec, &P.cs_rec, &P.st_rec);
+    P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, max_fwd_rec_blob, true, 3, false, &P.R_rec, &P.S_rec, &P.sub_rec, &P.cs_rec, &P.st_rec);
   if (!backward) return P;
   if (any_rec) {
-    P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, 2, &P.R_rb, &P.S_rb, &P.sub_rb,
+    P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, 2, false, &P.R_rb, &P.S_rb, &P.sub_rb,
                            &P.cs_rb, &P.st_rb);
   }
-  P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, 2, &P.R_dg, &P.S_dg, &P.sub_dg,
+  P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, 2, true, &P.R_dg, &P.S_dg, &P.sub_dg,
                          &P.cs_dg, &P.st_dg);
   return P;
 }
@@ -205,7 +205,6 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
     const float* v_init = (state_in && state_in[l]) ? (save ? (const float*)(A + L.off_init[l]) : state_in[l]) : nullptr;
     const float* z_init = v_init ? v_init + n : nullptr;
     float* vbase = (float*)(A + L.off_v[l]);
-    float* cbase = save ? (float*)(A + L.off_cur[l]) : nullptr;
     float* state = (float*)(A + L.off_state[l]);
     // input planes of this layer: the packed event counts, or the spikes of the layer below
     const unsigned char* xin;
@@ -226,10 +225,10 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
       if (l == 0) { a.R = P.R_head; a.S = P.S_head; a.sub_bytes = P.sub_head; a.chunk_stride = P.cs_head; a.stage_bytes = P.st_head; }
       else { a.R = P.R_ff; a.S = P.S_ff; a.sub_bytes = P.sub_ff; a.chunk_stride = P.cs_ff; a.stage_bytes = P.st_ff; }
       a.v_init = v_init; a.z_init = z_init;
-      a.v_out = save ? vbase : nullptr; a.cur_out = cbase;
+      a.v_out = save ? vbase : nullptr; a.cur_out = nullptr;
       a.zp_out = A + L.off_zp[l];
       a.v_last = state; a.z_last = state + n;
-      rc = launch_wt_fwd(a, true, st, "win_fwd_seq", 4.0 * T * px * (L.Cin[l] + 4 * C + (save ? C : 0)),
+      rc = launch_wt_fwd(a, true, st, "win_fwd_seq", 4.0 * T * px * (L.Cin[l] + 2 * C),   /* x in ; v, z out */
                          18.0 * T * px * C * L.Cin[l]);
       if (rc) return rc;
     } else {
@@ -249,14 +248,14 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
         a.v_prev_nchw = t == 0;   // the window's initial state is the caller's NCHW tensor
         if (save) {
           a.v_prev = t > 0 ? vbase + (size_t)(t - 1) * n : v_init;
-          a.v_out = vbase + (size_t)t * n; a.cur_out = cbase + (size_t)t * n;
+          a.v_out = vbase + (size_t)t * n; a.cur_out = nullptr;
         } else {
           a.v_prev = t > 0 ? vbase + (size_t)((t - 1) & 1) * n : v_init;
           a.v_out = vbase + (size_t)(t & 1) * n; a.cur_out = nullptr;
         }
         a.v_last = last ? state : nullptr; a.z_last = last ? state + n : nullptr;
         a.zp_out = A + L.off_zp[l] + (size_t)(t + 1) * B * L.zp_img_stride;
-        rc = launch_wt_fwd(a, false, st, "win_fwd_rec", 4.0 * px * (L.Cin[l] + 4 * C + (save ? C : 0)),
+        rc = launch_wt_fwd(a, false, st, "win_fwd_rec", 4.0 * px * (L.Cin[l] + 4 * C),   /* x, v, z in ; v, z out */
                            18.0 * px * C * (L.Cin[l] + C));
         if (rc) return rc;
       }
@@ -308,7 +307,6 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
     const float* v_init = (state_in && state_in[l]) ? (const float*)(A + L.off_init[l]) : nullptr;   // forward's copy
     const float* z_init = v_init ? v_init + n : nullptr;
     const float* vbase = (const float*)(A + L.off_v[l]);
-    const float* cbase = (const float*)(A + L.off_cur[l]);
     const float* par = (const float*)(A + L.off_par[l]);
     const float* g_out = gbuf[cur];
     int n_cpart, cpart_layout;
@@ -329,19 +327,19 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
         a.has_gz = t < T - 1; a.first_step = t == T - 1;
         a.src[0].planes = gp + (size_t)(t + 1) * B * L.zp_img_stride;
         a.src[1].planes = a.src[0].planes + WS.gp_term_stride;
-        a.g_out = g_out + (size_t)t * n; a.v_t = vbase + (size_t)t * n; a.cur_t = cbase + (size_t)t * n;
+        a.g_out = g_out + (size_t)t * n; a.v_t = vbase + (size_t)t * n;
         a.v_in = t > 0 ? vbase + (size_t)(t - 1) * n : v_init;
         a.v_in_nchw = t == 0;
         a.z_from_v = t > 0; a.z_init = z_init;
         a.gp_out = gp + (size_t)t * B * L.zp_img_stride;
         a.part = cpart + (size_t)t * WS.rb_grid * 2 * C;
-        rc = launch_wt_recbwd(a, st, 4.0 * px * C * (a.has_gz ? 8 : 7), a.has_gz ? 18.0 * px * C * C : 0.0);
+        rc = launch_wt_recbwd(a, st, 4.0 * px * C * (a.has_gz ? 7 : 6), a.has_gz ? 18.0 * px * C * C : 0.0);
         if (rc) return rc;
       }
       n_cpart = T * WS.rb_grid; cpart_layout = 1;
     } else {
       PwSeqArgs a{};
-      a.v = vbase; a.cur = cbase; a.g_out = g_out; a.v_init = v_init; a.z_init = z_init; a.par = par;
+      a.v = vbase; a.g_out = g_out; a.v_init = v_init; a.z_init = z_init; a.par = par;
       a.gp = gp; a.gp_img_stride = L.zp_img_stride; a.gp_term_stride = WS.gp_term_stride;
       a.part = cpart; a.T = T; a.B = B; a.C = C; a.H = H; a.W = W; a.hard_reset = hard; a.surrogate = d->surrogate;
       a.n_part = WS.pw_parts; a.width = d->act_width;

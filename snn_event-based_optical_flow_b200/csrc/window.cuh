@@ -49,7 +49,7 @@ struct WtArgs {
   uint32_t sub_bytes, chunk_stride, stage_bytes;
   int hard_reset, surrogate;
   float width;
-  const float* par;   // [N][4] = (lam, 1 - lam, theta, 0)
+  const float* par;   // [N][4] = (lam, 1 - lam, theta, 1 / (1 - lam))
   // forward
   const float *v_init, *z_init;   // sequence mode, t == 0: [B][N][H][W] or NULL (zeros)
   const float* v_prev;            // step mode: membrane before this step (c8, or NCHW when v_prev_nchw) or NULL (zeros)
@@ -63,20 +63,21 @@ struct WtArgs {
   // data gradient
   float* g_x;                     // c8 layout [images][N/8][H*W][8]
   // recurrent backward step
-  const float *g_out, *v_t, *cur_t, *v_in;   // c8 ; v_in: membrane before the step (c8, or NCHW when v_in_nchw) or NULL
+  const float *g_out, *v_t, *v_in;   // c8 ; v_in: membrane before the step (c8, or NCHW when v_in_nchw) or NULL
   int v_in_nchw;                  // z_init (NCHW): spikes before step 0
   float* g_v;                     // c8 [B][N/8][H*W][8] in/out: gradient w.r.t. the membrane carried to the previous step
   unsigned char* gp_out;          // g_I planes of this step (hi ; lo at + gp_term_stride)
   unsigned long long gp_img_stride, gp_term_stride;
   float* part;                    // [grid][2][N] partial sums of dlam, dtheta
   int has_gz, first_step, z_from_v;   // first_step: g_v starts at zero ; z_from_v: z_in = spike(v_in) else from z_init
+  long long* dbg;                 // optional [grid][8] cycle counters (SNNFLOW_WT_TIMING=1): where each role waits
 };
 
 int launch_wt_fwd(const WtArgs& a, bool seq, cudaStream_t st, const char* prof_name, double bytes, double flops);
 int launch_wt_dgrad(const WtArgs& a, cudaStream_t st, double bytes, double flops);
 int launch_wt_recbwd(const WtArgs& a, cudaStream_t st, double bytes, double flops);
 // picks rows-per-tile / stages for the given shapes; returns false when the shape does not fit
-bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int w_terms, int* R, int* S,
+bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int w_terms, bool tall, int* R, int* S,
              uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes);
 int wt_grid(int n_tiles);
 
@@ -110,7 +111,7 @@ struct PackLayer {
 struct PackArgs { PackLayer L[WIN_LAYERS]; };
 int launch_pack_weights(const PackArgs& p, cudaStream_t st);
 struct PwSeqArgs {
-  const float *v, *cur, *g_out;    // c8 layout [T*B][C/8][H*W][8]
+  const float *v, *g_out;          // c8 layout [T*B][C/8][H*W][8]
   const float *v_init, *z_init;    // [B][C][H][W] or NULL
   const float* par;                // [C][4]
   unsigned char* gp;               // g_I planes (hi ; lo at + term_stride), image t*B + b

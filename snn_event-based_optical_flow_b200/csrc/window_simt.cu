@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(256) window_pack_weights_kernel(const PackArgs
   }
   for (int c = tid; c < C; c += 256) {
     const float lam = L.leak_lam[c];
-    reinterpret_cast<float4*>(L.par)[c] = make_float4(lam, __fsub_rn(1.0f, lam), L.theta[c], 0.f);
+    const float oml = __fsub_rn(1.0f, lam);
+    // .w = 1 / (1 - lam) for the backward's current-free form of d loss / d lam (0 when lam == 1: sigmoid' is 0 too)
+    reinterpret_cast<float4*>(L.par)[c] = make_float4(lam, oml, L.theta[c], oml > 0.f ? 1.0f / oml : 0.f);
   }
 }
 
@@ -134,6 +136,9 @@ int launch_pack_weights(const PackArgs& p, cudaStream_t st) {
 //   hard: carry = gv*lam*(1-z_in); dlam += gv*(v_in*(1-z_in) - I[t]); dtheta -= gs
 //   soft: carry = gv*lam;          dlam += gv*(v_in - I[t]);          dtheta -= gs + gv*z_in
 // with v_in = v[t-1] (the window's initial state at t = 0) and z_in = spike(v_in) (z_init at t = 0).
+// The input current I[t] is not stored: from v[t] = lam*a + (1-lam)*I[t] (a = v_in*(1-z_in), hard reset) follows
+// a - I[t] = (a - v[t]) / (1-lam), and for the soft reset v_in - I[t] = (v_in - v[t] - z_in*theta) / (1-lam); the
+// per-channel factor 1/(1-lam) is applied once to the block sums.
 __device__ __forceinline__ void ld8_c8(const float* p, float (&v)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -147,11 +152,11 @@ __global__ void __launch_bounds__(256) pw_seq_kernel(const PwSeqArgs a) {
   const int y = ok ? p / a.W : 0, x = ok ? p - y * a.W : 0;
   const size_t plane_bytes = (size_t)(a.H + 2) * Wp * 16;
   const int nch = a.C >> 3;
-  float lam[8], oml[8], th[8], carry[8], s_lam[8], s_th[8], v_cur[8];
+  float lam[8], oml[8], th[8], inv_oml[8], carry[8], s_lam[8], s_th[8], v_cur[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const float4 pr = __ldg(reinterpret_cast<const float4*>(a.par) + chunk * 8 + c);
-    lam[c] = pr.x; oml[c] = pr.y; th[c] = pr.z;
+    lam[c] = pr.x; oml[c] = pr.y; th[c] = pr.z; inv_oml[c] = pr.w;
     carry[c] = 0.f; s_lam[c] = 0.f; s_th[c] = 0.f; v_cur[c] = 0.f;
   }
   // c8 layout: [image][chunk][H*W][8]
@@ -160,9 +165,8 @@ __global__ void __launch_bounds__(256) pw_seq_kernel(const PwSeqArgs a) {
   for (int t = a.T - 1; t >= 0; --t) {
     const size_t img = (size_t)(t * a.B + b);
     if (ok) {
-      float v_in[8], z_in[8], go[8], cu[8];
+      float v_in[8], z_in[8], go[8];
       ld8_c8(a.g_out + img * img_stride + px_off, go);
-      ld8_c8(a.cur + img * img_stride + px_off, cu);
       if (t > 0) {
         ld8_c8(a.v + (img - a.B) * img_stride + px_off, v_in);
 #pragma unroll
@@ -183,11 +187,11 @@ __global__ void __launch_bounds__(256) pw_seq_kernel(const PwSeqArgs a) {
         const float gi = gv * oml[c];
         if (a.hard_reset) {
           carry[c] = gv * lam[c] * (1.0f - z_in[c]);
-          s_lam[c] += gv * (v_in[c] * (1.0f - z_in[c]) - cu[c]);
+          s_lam[c] += gv * (v_in[c] * (1.0f - z_in[c]) - v_cur[c]);
           s_th[c] -= gs;
         } else {
           carry[c] = gv * lam[c];
-          s_lam[c] += gv * (v_in[c] - cu[c]);
+          s_lam[c] += gv * (v_in[c] - v_cur[c] - z_in[c] * th[c]);
           s_th[c] -= gs + gv * z_in[c];
         }
         const __nv_bfloat16 bh = __float2bfloat16_rn(gi);
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(256) pw_seq_kernel(const PwSeqArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const float l = warp_sum(ok ? s_lam[c] : 0.f), t = warp_sum(ok ? s_th[c] : 0.f);
+    const float l = warp_sum(ok ? s_lam[c] * inv_oml[c] : 0.f), t = warp_sum(ok ? s_th[c] : 0.f);
     if (lane == 0) { red[warp][c] = l; red[warp][8 + c] = t; }
   }
   __syncthreads();
@@ -227,7 +231,7 @@ int launch_pw_seq(const PwSeqArgs& a, cudaStream_t st) {
     set_error("launch_pw_seq: n_part mismatch");
     return SNNFLOW_EINVAL;
   }
-  prof_begin("win_pw_seq", st, (double)a.T * a.B * a.C * a.H * a.W * 16.0);
+  prof_begin("win_pw_seq", st, (double)a.T * a.B * a.C * a.H * a.W * 12.0);   // v, g_out in ; g_I out
   pw_seq_kernel<<<dim3(gx, a.C / 8, a.B), 256, 0, st>>>(a);
   return check_launch("pw_seq_kernel");
 }

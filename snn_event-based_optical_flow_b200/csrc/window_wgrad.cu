@@ -122,12 +122,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
               const uint32_t d = tmem_base + (uint32_t)((j * 3 + kx) * 2 * a.C);
-              uint32_t accumulate = (k > 0 || r > 0) ? 1u : 0u;
-              // g slot c (padded column) pairs with input slot c + kx - 1; the k range starts at c = 1
-              for (int kk = 0; kk < a.ksteps; ++kk) {
-                umma_f16_split(d, lo_c | (arow16 + (uint32_t)(kx + kk * 16)), d_hi, lo_c | (grow16 + (uint32_t)(kk * 16)), d_hi, idesc,
-                               accumulate);
-                accumulate = 1u;
+              // g slot c (padded column) pairs with input slot c + kx - 1; the k range starts at c = 1.
+              // One add per operand and MMA: a k-step advances both descriptors by 16 slots.
+              uint32_t a_lo = lo_c | (arow16 + (uint32_t)kx), b_lo = lo_c | grow16;
+              umma_f16_split(d, a_lo, d_hi, b_lo, d_hi, idesc, (k > 0 || r > 0) ? 1u : 0u);
+#pragma unroll 4
+              for (int kk = 1; kk < a.ksteps; ++kk) {
+                a_lo += 16u;
+                b_lo += 16u;
+                umma_f16_split(d, a_lo, d_hi, b_lo, d_hi, idesc, 1u);
               }
             }
           }
