@@ -25,6 +25,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) away from it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "LIFFireNet train samples/s @128x128 (batch 8/GPU, 10 bins x 1000 events, IWE loss)"
 UNIT = "samples/s"
@@ -207,6 +210,13 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def phase(msg):
+        if os.environ.get("SNNFLOW_BENCH_VERBOSE"):
+            sys.stderr.write(f"[bench rank {rank}] {msg}\n")
+            sys.stderr.flush()
+
+
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -231,6 +241,7 @@ def run_ours(a):
     dev_pool = [{k: v.to(dev) for k, v in w.items()} for w in host_pool]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_pool[0].values())
 
+    phase("pools ready")
     launches_per_step = None
     if not a.no_graph:
         # one optimizer step = one CUDA graph replay (train.TrainWindow.capture); inputs are copied into static buffers
@@ -252,9 +263,11 @@ def run_ours(a):
         return float(tw.step(w).item())          # D2H of the loss, synchronises
 
     # ---- device-resident timing ----
+    phase("warm-up")
     for i in range(a.warmup):
         step_resident(i)
     barrier()
+    phase("timed region")
     sampler = ClockSampler(local)
     sampler.start()
     l0 = _lib.launch_count()
@@ -274,6 +287,7 @@ def run_ours(a):
     ms_total = float(ms.item())
     value = a.batch * world * a.steps / (ms_total / 1e3)
 
+    phase("end-to-end")
     # ---- end-to-end timing from pinned host buffers ----
     for i in range(2):
         step_e2e(i)
@@ -289,7 +303,15 @@ def run_ours(a):
     e2e_value = a.batch * world * a.steps / (float(ms2.item()) / 1e3)
 
     # ---- per-kernel profile of two steps (live CUDA events on the launching stream) ----
+    # every rank runs the two steps (they contain the gradient all-reduce); only rank 0 records and reports
+    phase("profile")
     roofline, kernels = None, None
+    if rank == 0:
+        _lib.profile(True)
+    for i in range(2):   # the per-launch profiler needs host launches: these two steps run outside the graph
+        w = dev_pool[i % len(dev_pool)]
+        tw.step(dict(w, event_list=w["event_list"].clone()))
+    barrier()
     if rank == 0:
         peaks = {}
         try:
@@ -298,10 +320,6 @@ def run_ours(a):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        _lib.profile(True)
-        for i in range(2):   # the per-launch profiler needs host launches: these two steps run outside the graph
-            w = dev_pool[i % len(dev_pool)]
-            tw.step(dict(w, event_list=w["event_list"].clone()))
         prof = _lib.profile_summary()
         _lib.profile(False)
         tot = sum(p["ms"] for p in prof.values()) or 1.0
@@ -324,6 +342,7 @@ def run_ours(a):
                     "share_of_kernel_time": round(p["ms"] / tot, 4)}
 
     # ---- eval (LIFFireFlowNet, 256x256, batch 16: BASELINE.json configs[2]) on rank 0's GPU, every rank ----
+    phase("eval")
     eval_info = None
     if not a.no_eval:
         eval_info = run_eval(a, snnflow, dev, world, barrier)
@@ -352,7 +371,10 @@ def run_ours(a):
 
 
 def run_eval(a, snnflow, dev, world, barrier):
-    """eval frames/s: LIFFireFlowNet (feed-forward ConvLIF), 256x256, batch 16, no_grad (BASELINE configs[2])."""
+    """eval frames/s: LIFFireFlowNet (feed-forward ConvLIF), 256x256, batch 16, no_grad (BASELINE configs[2]).
+    Two ways to drive the same network: one forward() per time bin through the drop-in cells (the reference's eval
+    loop, eval_flow.py:220), and forward_window() over T bins at once (layer-major engine, membranes stay in
+    registers across the T bins of a feed-forward layer)."""
     import torch
     import torch.distributed as dist
     B, R, T = 16, 256, 10
@@ -362,22 +384,27 @@ def run_eval(a, snnflow, dev, world, barrier):
     g = torch.Generator().manual_seed(7)
     cnt = torch.poisson(torch.full((T, B, 2, R, R), 0.06), generator=g).to(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.no_grad():
-        for t in range(T):
-            net(None, cnt[t])
+
+    def timed(fn, reps):
+        fn()
         barrier()
         ev0.record()
-        for rep in range(3):
-            for t in range(T):
-                net(None, cnt[t])
+        for _ in range(reps):
+            fn()
         ev1.record()
         barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    fps = B * world * 3 * T / (float(ms.item()) / 1e3)
-    return {"metric": "LIFFireFlowNet eval frames/s @256x256, batch 16/GPU", "value": fps, "unit": "frames/s",
-            "ms_per_forward": float(ms.item()) / (3 * T)}
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / reps
+
+    with torch.no_grad():
+        ms_bin = timed(lambda: [net(None, cnt[t]) for t in range(T)], 3)
+        net.reset_states()
+        ms_win = timed(lambda: net.forward_window(cnt), 5)
+    return {"metric": "LIFFireFlowNet eval frames/s @256x256, batch 16/GPU", "value": B * world * T / (ms_win / 1e3),
+            "unit": "frames/s", "api": "forward_window (T = 10 bins per call)", "ms_per_window": ms_win,
+            "per_bin_forward": {"value": B * world * T / (ms_bin / 1e3), "unit": "frames/s", "ms_per_forward": ms_bin / T}}
 
 
 if __name__ == "__main__":

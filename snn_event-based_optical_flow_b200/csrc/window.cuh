@@ -91,6 +91,7 @@ struct WgArgs {
   float* part[2];   // per source: [grid][9][cin_alloc][C]
   int n_img, H, W, Wp, R, S, C, P, n_cg, rpm, n_kyg, ksteps, x_rows;
   uint32_t stage_bytes, g_off;
+  long long* dbg;   // optional [grid][8] cycle counters (SNNFLOW_WT_TIMING=1)
 };
 bool wg_supported(int C, int cin_chunks, int rec_chunks, int H, int W);
 int wg_grid(int n_img, int H, int W, int C, int cin_chunks, int rec_chunks);

@@ -98,6 +98,7 @@ __device__ __forceinline__ uint32_t wt_tmem_cols(const WtArgs& a) {
 // ---- common prologue: barriers, TMEM, parameters ---------------------------------------------------------
 __device__ __forceinline__ uint32_t wt_prologue(const WtArgs& a, const WtSmem& s) {
   const int tid = threadIdx.x, warp = tid >> 5;
+  const long long t_entry = clock64();
   if (tid == 0) {
     for (int i = 0; i < WT_MAX_STAGES; ++i) {
       mbar_init(&s.full[i], 1);
@@ -116,13 +117,15 @@ __device__ __forceinline__ uint32_t wt_prologue(const WtArgs& a, const WtSmem& s
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (a.dbg && tid == 0) a.dbg[blockIdx.x * 8 + 7] = clock64() - t_entry;
   return *s.tmem_slot;
 }
 
-// ---- producer: one thread ------------------------------------------------------------------------------------
+// ---- producer: one warp; lane 0 owns the barriers, lanes 0..n_chunks-1 issue one bulk copy each -------------------
 template <bool SEQ>
 __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
-  if (a.wblob_bytes) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0 && a.wblob_bytes) {
     mbar_expect_tx(s.wbar, a.wblob_bytes);
     tma_bulk_g2s(s.w, a.wblob, a.wblob_bytes, s.wbar);
   }
@@ -135,20 +138,23 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
     const ItemPos p = wt_item<SEQ>(a, k);
     for (int si = 0; si < a.n_src; ++si, ++u) {
       const uint32_t st = u % (uint32_t)a.S, use = u / (uint32_t)a.S;
-      if (use > 0) {
-        const long long t0 = clock64();
-        mbar_wait(&s.empty[st], (use - 1) & 1);
-        t_wait += clock64() - t0;
-      }
       const WtSrc& S = a.src[si];
-      unsigned char* dst = s.stages + (size_t)st * a.stage_bytes;
-      mbar_expect_tx(&s.full[st], S.n_chunks * a.sub_bytes);
-      const unsigned char* g = S.planes + (size_t)p.img * S.img_stride + (size_t)p.y0 * a.Wp * 16;
-      for (uint32_t ch = 0; ch < S.n_chunks; ++ch)
-        tma_bulk_g2s(dst + (size_t)ch * a.chunk_stride, g + ch * plane_bytes, a.sub_bytes, &s.full[st]);
+      if (lane == 0) {
+        if (use > 0) {
+          const long long t0 = clock64();
+          mbar_wait(&s.empty[st], (use - 1) & 1);
+          t_wait += clock64() - t0;
+        }
+        mbar_expect_tx(&s.full[st], S.n_chunks * a.sub_bytes);
+      }
+      __syncwarp();
+      if ((uint32_t)lane < S.n_chunks)
+        tma_bulk_g2s(s.stages + (size_t)st * a.stage_bytes + (size_t)lane * a.chunk_stride,
+                     S.planes + (size_t)p.img * S.img_stride + (size_t)p.y0 * a.Wp * 16 + (size_t)lane * plane_bytes, a.sub_bytes,
+                     &s.full[st]);
     }
   }
-  if (a.dbg) {
+  if (a.dbg && lane == 0) {
     a.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;   // producer: total
     a.dbg[blockIdx.x * 8 + 1] = t_wait;                 // producer: waiting for a free stage
   }
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == WT_EPI_WARPS) {
-    if (elect_one()) wt_producer<SEQ>(a, s);
+    wt_producer<SEQ>(a, s);
     __syncwarp();
   } else if (warp == WT_EPI_WARPS + 1) {
     if (elect_one()) wt_mma<SEQ>(a, s, tmem_base);
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgrad_kernel(const __grid_co
   const uint32_t tmem_base = wt_prologue(a, s);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == WT_EPI_WARPS) {
-    if (elect_one()) wt_producer<false>(a, s);
+    wt_producer<false>(a, s);
     __syncwarp();
   } else if (warp == WT_EPI_WARPS + 1) {
     if (elect_one()) wt_mma<false>(a, s, tmem_base);
@@ -486,7 +492,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
   const uint32_t tmem_base = wt_prologue(a, s);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == WT_EPI_WARPS) {
-    if (a.has_gz && elect_one()) wt_producer<false>(a, s);
+    if (a.has_gz) wt_producer<false>(a, s);
     __syncwarp();
   } else if (warp == WT_EPI_WARPS + 1) {
     if (a.has_gz && elect_one()) wt_mma<false>(a, s, tmem_base);
@@ -507,6 +513,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
       lam[c] = pr.x; oml[c] = pr.y; th[c] = pr.z; inv_oml[c] = pr.w;
       s_lam[c] = s_th[c] = 0.f;
     }
+    long long t_wait = 0;
+    const long long t_begin = clock64();
     for (int k = 0; k < n_items; ++k) {
       const ItemPos p = wt_item<false>(a, k);
       const uint32_t ab = (uint32_t)k & 1u;
@@ -544,7 +552,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
         float acc[8];
         if (a.has_gz) {
           if (!waited) {
+            const long long t0 = clock64();
             mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
+            t_wait += clock64() - t0;
             tc_fence_after();
             waited = true;
           }
@@ -598,6 +608,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
         tc_fence_before();
         mbar_arrive(&s.acc_empty[ab]);
       }
+    }
+    if (a.dbg && tid == 0) {
+      a.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin;
+      a.dbg[blockIdx.x * 8 + 6] = t_wait;
     }
     // per-warp partial sums of dlam / dtheta -> shared scratch [warp][2][8]
 #pragma unroll
@@ -701,8 +715,8 @@ static int wt_launch(K kernel, const void* key, const WtArgs& a, cudaStream_t st
     double avg[8] = {0};
     for (int i = 0; i < grid; ++i)
       for (int j = 0; j < 8; ++j) avg[j] += (double)h[i * 8 + j] / grid;
-    fprintf(stderr, "[wt-timing] %s R=%d S=%d n_src=%d N=%d items/CTA=%.1f | producer %.0f (wait-empty %.0f) | mma %.0f (wait-full %.0f, wait-acc %.0f) | epi %.0f (wait-acc-full %.0f)\n",
-            what, a.R, a.S, a.n_src, a.N, (double)n_tiles * (a.T > 1 ? a.T : 1) / grid, avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6]);
+    fprintf(stderr, "[wt-timing] %s R=%d S=%d n_src=%d N=%d items/CTA=%.1f | producer %.0f (wait-empty %.0f) | mma %.0f (wait-full %.0f, wait-acc %.0f) | epi %.0f (wait-acc-full %.0f) | prologue %.0f\n",
+            what, a.R, a.S, a.n_src, a.N, (double)n_tiles * (a.T > 1 ? a.T : 1) / grid, avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7]);
     return check_launch(what);
   }
   kernel<<<wt_grid(n_tiles), WT_THREADS, smem, st>>>(a);

@@ -17,6 +17,8 @@
 
 #include <stdlib.h>
 
+#include <vector>
+
 namespace snnflow {
 
 constexpr int WG_EPI_WARPS = 8;
@@ -77,31 +79,46 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
   const int g_chunks = a.C >> 3;
 
   if (warp == WG_EPI_WARPS) {
-    if (elect_one()) {
-      for (int k = 0; k < n_items; ++k) {
-        const int tile = blockIdx.x + k * gridDim.x;
-        const int img = tile / tpi, y0 = (tile - img * tpi) * a.R;
-        const uint32_t st = (uint32_t)k % (uint32_t)a.S, use = (uint32_t)k / (uint32_t)a.S;
-        if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
-        unsigned char* xs = stages + (size_t)st * a.stage_bytes;
-        unsigned char* gs = xs + a.g_off;
-        mbar_expect_tx(&full[st], (uint32_t)((a.R + 2) * a.n_cg + a.R * 2 * g_chunks) * row_bytes);
-        for (int row = 0; row < a.R + 2; ++row) {
-          int cg = 0;
-          for (int si = 0; si < a.n_xsrc; ++si) {
-            const unsigned char* src = a.xp[si] + (size_t)img * a.x_img_stride[si] + (size_t)(y0 + row) * row_bytes;
-            for (int ch = 0; ch < a.x_chunks[si]; ++ch, ++cg)
-              tma_bulk_g2s(xs + (size_t)(row * a.n_cg + cg) * pitch, src + ch * plane_bytes, row_bytes, &full[st]);
-          }
+    // Producer warp.  A tile is (R+2)*n_cg input-row pieces + R*2*C/8 gradient-row pieces of one padded row each;
+    // the lanes compute the piece addresses in parallel and each issues its own bulk copies (a single thread spends
+    // ~100 issue cycles per copy next to four busy epilogue warps - measured, profiles/), lane 0 owns the barriers.
+    const int n_xp = (a.R + 2) * a.n_cg, n_gp = a.R * 2 * g_chunks;
+    long long t_wait = 0;
+    const long long t_begin = clock64();
+    for (int k = 0; k < n_items; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      const int img = tile / tpi, y0 = (tile - img * tpi) * a.R;
+      const uint32_t st = (uint32_t)k % (uint32_t)a.S, use = (uint32_t)k / (uint32_t)a.S;
+      unsigned char* xs = stages + (size_t)st * a.stage_bytes;
+      unsigned char* gs = xs + a.g_off;
+      if (lane == 0) {
+        if (use > 0) {
+          const long long t0 = clock64();
+          mbar_wait(&empty[st], (use - 1) & 1);
+          t_wait += clock64() - t0;
         }
-        for (int r = 0; r < a.R; ++r)
-          for (int term = 0; term < 2; ++term) {
-            const unsigned char* src = a.gp + term * a.g_term_stride + (size_t)img * a.g_img_stride + (size_t)(y0 + 1 + r) * row_bytes;
-            for (int ch = 0; ch < g_chunks; ++ch)
-              tma_bulk_g2s(gs + (size_t)((r * 2 + term) * g_chunks + ch) * pitch, src + ch * plane_bytes, row_bytes, &full[st]);
-          }
+        mbar_expect_tx(&full[st], (uint32_t)(n_xp + n_gp) * row_bytes);
+      }
+      __syncwarp();
+      for (int i = lane; i < n_xp + n_gp; i += 32) {
+        const unsigned char* src;
+        unsigned char* dst;
+        if (i < n_xp) {
+          const int row = i / a.n_cg, cg = i - row * a.n_cg;
+          const int si = cg < a.x_chunks[0] ? 0 : 1, ch = si ? cg - a.x_chunks[0] : cg;
+          src = a.xp[si] + (size_t)img * a.x_img_stride[si] + (size_t)(y0 + row) * row_bytes + (size_t)ch * plane_bytes;
+          dst = xs + (size_t)i * pitch;
+        } else {
+          const int j = i - n_xp;                      // (r, term, ch)
+          const int ch = j % g_chunks, rt = j / g_chunks, term = rt & 1, r = rt >> 1;
+          src = a.gp + (size_t)term * a.g_term_stride + (size_t)img * a.g_img_stride + (size_t)(y0 + 1 + r) * row_bytes +
+                (size_t)ch * plane_bytes;
+          dst = gs + (size_t)j * pitch;
+        }
+        tma_bulk_g2s(dst, src, row_bytes, &full[st]);
       }
     }
+    if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; a.dbg[blockIdx.x * 8 + 1] = t_wait; }
     __syncwarp();
   } else if (warp == WG_EPI_WARPS + 1) {
     if (n_items > 0 && elect_one()) {
@@ -110,9 +127,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
       const uint32_t idesc = make_idesc(128, 2 * a.C, /*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1);
       const uint32_t stages16 = smem_u32(stages) >> 4, pitch16 = pitch >> 4;
       const uint32_t lo_c = ((128u >> 4) << 16), d_hi = desc_hi(pitch);   // LBO = 128 B (k groups), SBO = pitch (chunk groups)
+      long long t_wait = 0;
+      const long long t_begin = clock64();
       for (int k = 0; k < n_items; ++k) {
         const uint32_t st = (uint32_t)k % (uint32_t)a.S, use = (uint32_t)k / (uint32_t)a.S;
-        mbar_wait(&full[st], use & 1);
+        {
+          const long long t0 = clock64();
+          mbar_wait(&full[st], use & 1);
+          t_wait += clock64() - t0;
+        }
         tc_fence_after();
         const uint32_t xs16 = stages16 + ((st * a.stage_bytes) >> 4), gs16 = xs16 + (a.g_off >> 4);
         for (int r = 0; r < a.R; ++r) {
@@ -138,6 +161,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
         umma_commit(&empty[st]);
       }
       umma_commit(done);
+      if (a.dbg) { a.dbg[blockIdx.x * 8 + 2] = clock64() - t_begin; a.dbg[blockIdx.x * 8 + 3] = t_wait; }
     }
     __syncwarp();
   } else if (n_items > 0) {
@@ -240,6 +264,22 @@ int launch_wgrad_planes(WgArgs a, cudaStream_t st, double bytes, double flops) {
   const int n_tiles = a.n_img * (a.H / a.R);
   const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
   prof_begin("win_wgrad", st, bytes, flops);
+  if (wg_env_int("SNNFLOW_WT_TIMING", 0)) {   // debug: where do the producer and the MMA issuer wait? (synchronises)
+    static long long* dbg = nullptr;
+    if (!dbg) cudaMalloc(&dbg, sizeof(long long) * 8 * 1024);
+    cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * grid, st);
+    a.dbg = dbg;
+    wg_planes_kernel<<<grid, WG_THREADS, smem, st>>>(a);
+    cudaStreamSynchronize(st);
+    std::vector<long long> h(8 * grid);
+    cudaMemcpy(h.data(), dbg, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+    double avg[8] = {0};
+    for (int i = 0; i < grid; ++i)
+      for (int j = 0; j < 8; ++j) avg[j] += (double)h[i * 8 + j] / grid;
+    fprintf(stderr, "[wt-timing] wg_planes_kernel R=%d S=%d n_cg=%d items/CTA=%.1f | producer %.0f (wait-empty %.0f) | mma %.0f (wait-full %.0f)\n",
+            a.R, a.S, a.n_cg, (double)n_tiles / grid, avg[0], avg[1], avg[2], avg[3]);
+    return check_launch("wg_planes_kernel");
+  }
   wg_planes_kernel<<<grid, WG_THREADS, smem, st>>>(a);
   return check_launch("wg_planes_kernel");
 }

@@ -23,17 +23,21 @@ class FlatGradAllReduce:
             self.views.append(self.flat[o:o + p.numel()].view_as(p))
             o += p.numel()
 
-    def __call__(self):
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+    def active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def __call__(self, grads=None):
+        """SUM-reduce the gradients in place (`grads`: tensors to use instead of p.grad, e.g. graph-static ones)."""
+        if not self.active():
             return
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        if grads is None:
+            for p in self.params:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            grads = [p.grad for p in self.params]
         torch._foreach_copy_(self.views, grads)
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                p.grad = v.clone()
-            else:
-                p.grad.copy_(v)
+        torch._foreach_copy_(grads, self.views)
 
 
 class TrainWindow:
@@ -46,13 +50,40 @@ class TrainWindow:
         self.reducer = FlatGradAllReduce(model.parameters(), group)
         self._graph = None
 
+    # ---- the step in two halves (train_flow.py:232-262 and :265-279) -------------------------------------
+    def _forward_backward(self, batch, use_window=True):
+        T = batch["event_cnt"].shape[0]
+        flows = self.model.forward_window(batch["event_cnt"]) if (use_window and hasattr(self.model, "forward_window")) else None
+        for t in range(T):
+            flow = flows[t] if flows is not None else self.model(None, batch["event_cnt"][t])["flow"][0]
+            self.loss_fn.event_flow_association([flow], batch["event_list"][t], batch["event_list_pol_mask"][t],
+                                                batch["event_mask"][t])
+        loss = self.loss_fn()
+        loss.backward()
+        return loss.detach()
+
+    def _update(self):
+        if self.clip is not None:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
+        self.opt.step()
+        self.opt.zero_grad(set_to_none=True)
+        self.model.detach_states()
+        self.loss_fn.reset()
+
+    def step(self, batch, use_window=True):
+        loss = self._forward_backward(batch, use_window)
+        self.reducer()
+        self._update()
+        return loss
+
     # ---- whole-step CUDA graph -----------------------------------------------------------------------------
     def capture(self, example_batch, warmup=3):
-        """Capture one optimizer step (window forward, association, loss, BPTT, all-reduce, clip, Adam) in a CUDA graph.
-        Every buffer the step touches has a fixed address (window arena, workspace, static input copies), so
-        ``step_graphed`` only copies the new window into the static inputs and replays ~600 kernels with one launch.
-        The optimizer must be capturable (torch.optim.Adam(..., capturable=True)).  Returns the number of snnflow
-        kernel launches inside one captured step."""
+        """Capture one optimizer step in CUDA graphs.  Every buffer the step touches has a fixed address (window
+        arena, workspace, static input copies), so ``step_graphed`` only copies the new window into the static inputs
+        and replays.  Single process: ONE graph (window forward, association, loss, BPTT, clip, Adam: ~600 kernels, one
+        launch).  Data parallel: two graphs around the one eager NCCL all-reduce of the flat gradient - [forward ..
+        BPTT] | all-reduce | [clip, Adam] - so no collective is ever captured.  The optimizer must be capturable
+        (torch.optim.Adam(..., capturable=True)).  Returns the snnflow kernel launches inside one step."""
         from . import _lib
         self._static = {k: torch.empty_like(v) for k, v in example_batch.items()}
         side = torch.cuda.Stream()
@@ -63,11 +94,21 @@ class TrainWindow:
                 self.step(self._static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self._graph = torch.cuda.CUDAGraph()
         self._load(example_batch)
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self._graph):
-            self._static_loss = self.step(self._static)
+        self._graph = torch.cuda.CUDAGraph()
+        if not self.reducer.active():
+            self._graph2 = None
+            with torch.cuda.graph(self._graph):
+                self._static_loss = self.step(self._static)
+        else:
+            with torch.cuda.graph(self._graph):
+                self._static_loss = self._forward_backward(self._static)
+            self._grads = [p.grad for p in self.reducer.params]   # static addresses inside the graph's memory pool
+            self.reducer(self._grads)
+            self._graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph2, pool=self._graph.pool()):
+                self._update()
         self.launches_per_step = _lib.launch_count() - n0
         return self.launches_per_step
 
@@ -79,22 +120,7 @@ class TrainWindow:
         """Same as step() after capture(): `batch` may live on the device or in pinned host memory."""
         self._load(batch)
         self._graph.replay()
+        if self._graph2 is not None:
+            self.reducer(self._grads)
+            self._graph2.replay()
         return self._static_loss
-
-    def step(self, batch, use_window=True):
-        T = batch["event_cnt"].shape[0]
-        flows = self.model.forward_window(batch["event_cnt"]) if (use_window and hasattr(self.model, "forward_window")) else None
-        for t in range(T):
-            flow = flows[t] if flows is not None else self.model(None, batch["event_cnt"][t])["flow"][0]
-            self.loss_fn.event_flow_association([flow], batch["event_list"][t], batch["event_list_pol_mask"][t],
-                                                batch["event_mask"][t])
-        loss = self.loss_fn()
-        loss.backward()
-        self.reducer()
-        if self.clip is not None:
-            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
-        self.opt.step()
-        self.opt.zero_grad(set_to_none=True)
-        self.model.detach_states()
-        self.loss_fn.reset()
-        return loss.detach()
