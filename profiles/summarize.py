@@ -75,5 +75,33 @@ def kernels(path, out):
     print(open(out).read())
 
 
+BENCH_NAME = [("wt_fwd_kernel<1", "win_fwd_seq"), ("wt_fwd_kernel<(bool)1", "win_fwd_seq"), ("wt_fwd_kernel<0", "win_fwd_rec"),
+              ("wt_fwd_kernel<(bool)0", "win_fwd_rec"), ("wt_dgrad", "win_dgrad"), ("wt_recbwd", "win_rec_bwd"),
+              ("wg_planes", "win_wgrad"), ("pw_seq", "win_pw_seq")]
+
+
+def traffic(out, *paths):
+    """profiles/traffic.json: DRAM bytes (read + write) per launch of each window kernel, mean over the captured launches,
+    keyed by the name bench.py's per-launch profiler uses (bench.py reads it into roofline.traffic)."""
+    import json
+    acc = defaultdict(list)
+    for path in paths:
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(txt)))
+        h, units = rows[0], rows[1]
+        ir, iw, kn = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("Kernel Name")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            name = next((b for k, b in BENCH_NAME if k in r[kn]), None)
+            if name:
+                acc[name].append(float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]])
+    res = {k: round(sum(v) / len(v)) for k, v in acc.items()}
+    json.dump(res, open(out, "w"), indent=1, sort_keys=True)
+    print(res)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernels": kernels}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], *sys.argv[3:])
+    else:
+        {"launches": launches, "kernels": kernels}[sys.argv[1]](sys.argv[2], sys.argv[3])
