@@ -253,6 +253,24 @@ int snnflow_iwe_splat_bwd(const float* events, const float* ev_flow, const float
                           float* g_ev_flow, int B, int64_t N, int H, int W, float tref, float flow_scaling,
                           int n_img, int ts_mode, float ts_ref, snnflow_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Contrast-maximisation loss of one window and its gradient w.r.t. the flow maps, in one call.
+ * Replaces T calls of EventWarping.event_flow_association (loss/flow.py:58-121), EventWarping.forward (:178-303:
+ * forward- and backward-warped event images, per-pixel average timestamps, squared sums scaled by the number of
+ * pixels with events, Charbonnier smoothness over dx, dy, both diagonals and dt) and the autograd graph behind them.
+ *   flow [T,B,2,H,W] (channel 0 = x, 1 = y); events [T,B,N,4] = (ts in [0,1], y, x, p) per bin - the timestamp shift
+ *   ts += bin index of loss/flow.py:91 is applied internally, the input is not modified; pol_mask [T,B,N,2];
+ *   event_mask [T,B,1,H,W] or NULL (config model.mask_output: masks the smoothness terms)
+ *   loss [1]; g_flow [T,B,2,H,W] = d loss / d flow (overwritten); workspace: snnflow_window_loss_workspace_bytes()
+ * The per-event gradients carry the reference's autograd semantics (abs'(0) = 0, max(0,0) passes half, zero-count
+ * pixels keep the gradient path of the non-zero-pixel normaliser).  Reductions run in a fixed order; the scatter of
+ * per-event gradients onto the flow maps uses fp32 atomics.
+ * --------------------------------------------------------------------------------------------- */
+size_t snnflow_window_loss_workspace_bytes(int T, int B, int64_t N, int H, int W);
+int snnflow_window_loss(const float* flow, const float* events, const float* pol_mask, const float* event_mask, float* loss,
+                        float* g_flow, void* workspace, size_t workspace_bytes, int T, int B, int64_t N, int H, int W,
+                        float flow_scaling, float regul_weight, int loss_scaling, snnflow_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

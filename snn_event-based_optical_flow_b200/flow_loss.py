@@ -8,7 +8,36 @@ the splat (:214-301) is a handful of small torch ops on [B,4,H,W] images.
 """
 import torch
 
+from . import _lib
 from .iwe import gather_event_flow, warp_images
+from .spiking_submodules import _f32c
+
+
+class _WindowLoss(torch.autograd.Function):
+    """loss, d loss / d flow of a whole window in one C call (snnflow_window_loss, include/snnflow.h)."""
+
+    @staticmethod
+    def forward(ctx, flow, events, pol_mask, event_mask, owner):
+        L = _lib.lib()
+        flow, events, pol_mask = _f32c(flow), _f32c(events), _f32c(pol_mask)
+        T, B, N = events.shape[0], events.shape[1], events.shape[2]
+        H, W = flow.shape[-2], flow.shape[-1]
+        mask = _f32c(event_mask) if (owner.smoothing_mask and event_mask is not None) else None
+        nbytes = L.snnflow_window_loss_workspace_bytes(T, B, N, H, W)
+        ws = owner._workspace(nbytes, flow.device)
+        loss = torch.empty(1, dtype=torch.float32, device=flow.device)
+        g_flow = torch.empty_like(flow)
+        _lib.check(L.snnflow_window_loss(_lib.ptr(flow), _lib.ptr(events), _lib.ptr(pol_mask), _lib.ptr(mask), _lib.ptr(loss),
+                                         _lib.ptr(g_flow), ws.data_ptr(), ws.numel(), T, B, N, H, W, float(owner.flow_scaling),
+                                         float(owner.weight), int(bool(owner.loss_scaling)), _lib.stream()),
+                   "snnflow_window_loss")
+        ctx.save_for_backward(g_flow)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (g_flow,) = ctx.saved_tensors
+        return g_flow * g, None, None, None, None
 
 
 class EventWarping(torch.nn.Module):
@@ -24,6 +53,22 @@ class EventWarping(torch.nn.Module):
             raise NotImplementedError("snnflow EventWarping: overwrite_intermediate=True is not covered")
         self.device = device
         self.reset()
+
+    def _workspace(self, nbytes, dev):
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < nbytes or ws.device != dev:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ws = ws
+        return ws
+
+    def window_loss(self, flows, event_list, pol_mask, event_mask=None):
+        """The loss of one window from its T flow maps and event lists at once - what T calls of
+        event_flow_association followed by forward() return (loss/flow.py:58-121, :178-303) - as one fused call.
+        flows [T,B,2,H,W]; event_list [T,B,N,4] with per-bin timestamps in [0,1] (not modified); pol_mask [T,B,N,2];
+        event_mask [T,B,1,H,W] (only read when config model.mask_output is set)."""
+        if not flows.is_cuda:
+            raise _lib.SnnflowError("snnflow EventWarping.window_loss runs on CUDA tensors only (no CPU fallback)")
+        return _WindowLoss.apply(flows, event_list, pol_mask, event_mask, self)
 
     def reset(self):
         self._passes = 0

@@ -49,11 +49,17 @@ class TrainWindow:
         self.model, self.loss_fn, self.opt, self.clip = model, loss_fn, optimizer, clip_grad
         self.reducer = FlatGradAllReduce(model.parameters(), group)
         self._graph = None
+        self.fused_loss = True   # False: per-bin event_flow_association + EventWarping.forward (the reference's call pattern)
 
     # ---- the step in two halves (train_flow.py:232-262 and :265-279) -------------------------------------
     def _forward_backward(self, batch, use_window=True):
         T = batch["event_cnt"].shape[0]
         flows = self.model.forward_window(batch["event_cnt"]) if (use_window and hasattr(self.model, "forward_window")) else None
+        if flows is not None and self.fused_loss and hasattr(self.loss_fn, "window_loss"):
+            # the whole window's association + contrast loss + its gradient as one fused call (flow_loss.window_loss)
+            loss = self.loss_fn.window_loss(flows, batch["event_list"], batch["event_list_pol_mask"], batch["event_mask"])
+            loss.backward()
+            return loss.detach()
         for t in range(T):
             flow = flows[t] if flows is not None else self.model(None, batch["event_cnt"][t])["flow"][0]
             self.loss_fn.event_flow_association([flow], batch["event_list"][t], batch["event_list_pol_mask"][t],

@@ -216,3 +216,41 @@ def test_graphed_training_step_matches_eager():
         losses.append(ls)
     np.testing.assert_allclose(losses[0][0], losses[1][0], rtol=1e-5)   # same parameters, zero state
     np.testing.assert_allclose(losses[0], losses[1], rtol=2e-2)         # trajectories (near-threshold spikes may flip)
+
+
+@pytest.mark.parametrize("mask_output,zero_flow", [(False, False), (True, False), (False, True)])
+def test_fused_window_loss_matches_per_bin_loss(mask_output, zero_flow):
+    """snnflow_window_loss (one call) against the per-bin EventWarping path (event_flow_association x T + forward +
+    torch autograd), which the reference-generated training fixtures pin (test_gpu_network.py)."""
+    import snnflow_b200 as snnflow
+    T, B, N, H, W = 4, 2, 500, 24, 40
+    g = torch.Generator().manual_seed(11)
+    xs = torch.randint(0, W, (T, B, N), generator=g).float()
+    ys = torch.randint(0, H, (T, B, N), generator=g).float()
+    ts = torch.sort(torch.rand(T, B, N, generator=g), dim=2).values
+    ps = torch.randint(0, 2, (T, B, N), generator=g).float() * 2 - 1
+    events = torch.stack([ts, ys, xs, ps], dim=3).cuda()
+    pol = torch.stack([(ps > 0).float(), (ps < 0).float()], dim=3).cuda()
+    mask = (torch.rand(T, B, 1, H, W, generator=g) > 0.4).float().cuda()
+    flow0 = (torch.zeros(T, B, 2, H, W) if zero_flow else torch.tanh(0.5 * torch.randn(T, B, 2, H, W, generator=g)) * 0.05).cuda()
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": 0.01}, "model": {"mask_output": mask_output}}
+
+    fa = flow0.clone().requires_grad_(True)
+    la = snnflow.EventWarping(cfg, torch.device("cuda"))
+    for t in range(T):
+        la.event_flow_association([fa[t]], events[t].clone(), pol[t], mask[t])
+    loss_a = la()
+    loss_a.backward()
+
+    fb = flow0.clone().requires_grad_(True)
+    lb = snnflow.EventWarping(cfg, torch.device("cuda"))
+    ev_before = events.clone()
+    loss_b = lb.window_loss(fb, events, pol, mask)
+    loss_b.backward()
+    assert torch.equal(events, ev_before)   # the fused call does not shift the caller's timestamps
+    np.testing.assert_allclose(float(loss_b), float(loss_a), rtol=2e-5)
+    ga, gb = fa.grad, fb.grad
+    scale = float(ga.abs().max())
+    close = (ga - gb).abs() <= 1e-4 * ga.abs() + 1e-5 * scale
+    assert float(close.float().mean()) >= 0.995, float(close.float().mean())   # see test_gpu_network.py on conditioning
+    assert float((ga - gb).norm()) <= 3e-3 * float(ga.norm()) + 1e-7
