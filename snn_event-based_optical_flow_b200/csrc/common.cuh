@@ -73,6 +73,24 @@ __device__ __forceinline__ float surrogate(float u, float width, int kind) {
   return fmaxf(1.0f - width * fabsf(u), 0.0f);
 }
 
+// compile-time surrogate kind + fast reciprocal (MUFU.RCP, ~1 ulp): the gradient tier tolerates it (rel 1e-4)
+template <int KIND>
+__device__ __forceinline__ float surrogate_fast(float u, float width) {
+  if (KIND == SNNFLOW_SG_ARCTAN) return __fdividef(1.0f, fmaf(width * u, u, 1.0f));
+  if (KIND == SNNFLOW_SG_SUPERSPIKE) {
+    const float d = fmaf(width, fabsf(u), 1.0f);
+    return __fdividef(1.0f, d * d);
+  }
+  return fmaxf(1.0f - width * fabsf(u), 0.0f);
+}
+
+// two fp32 values -> packed bf16 hi pair + bf16 lo pair (value = hi + lo to 16 mantissa bits); even element in the low half
+__device__ __forceinline__ void split_bf16_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -66,7 +66,7 @@ static WinLayout win_layout(const snnflow_net_desc* d, int save) {
 struct WinPlan {   // tile plans of the tensor-core kernels for this shape
   int R_ff, S_ff, R_head, S_head, R_rec, S_rec, R_dg, S_dg, R_rb, S_rb;
   uint32_t sub_ff, cs_ff, st_ff, sub_head, cs_head, st_head, sub_rec, cs_rec, st_rec, sub_dg, cs_dg, st_dg, sub_rb, cs_rb, st_rb;
-  bool ok;
+  bool ok, rb_prefetch;
 };
 
 static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool backward = true) {
@@ -84,8 +84,12 @@ static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool back
     P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, max_fwd_rec_blob, true, 3, false, &P.R_rec, &P.S_rec, &P.sub_rec, &P.cs_rec, &P.st_rec);
   if (!backward) return P;
   if (any_rec) {
-    P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, 2, false, &P.R_rb, &P.S_rb, &P.sub_rb,
-                           &P.cs_rb, &P.st_rb);
+    // with the epilogue's prefetch slots if they fit next to two stages, without them otherwise
+    P.rb_prefetch = wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2 + wt_recbwd_extra_smem()), false, 2, false, &P.R_rb,
+                            &P.S_rb, &P.sub_rb, &P.cs_rb, &P.st_rb);
+    if (!P.rb_prefetch)
+      P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, 2, false, &P.R_rb, &P.S_rb, &P.sub_rb,
+                             &P.cs_rb, &P.st_rb);
   }
   P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, 2, true, &P.R_dg, &P.S_dg, &P.sub_dg,
                          &P.cs_dg, &P.st_dg);
@@ -321,7 +325,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
       a.n_outer = B; a.T = 1; a.B = B; a.H = H; a.W = W; a.Wp = W + 2; a.n_seg = ceil_div(W, 128); a.N = C;
       a.R = P.R_rb; a.S = P.S_rb; a.sub_bytes = P.sub_rb; a.chunk_stride = P.cs_rb; a.stage_bytes = P.st_rb;
       a.hard_reset = hard; a.surrogate = d->surrogate; a.width = d->act_width;
-      a.par = par;
+      a.par = par; a.prefetch = P.rb_prefetch ? 1 : 0;
       a.g_v = g_v; a.gp_img_stride = L.zp_img_stride; a.gp_term_stride = WS.gp_term_stride;
       for (int t = T - 1; t >= 0; --t) {
         a.has_gz = t < T - 1; a.first_step = t == T - 1;

@@ -69,6 +69,7 @@ struct WtArgs {
   unsigned char* gp_out;          // g_I planes of this step (hi ; lo at + gp_term_stride)
   unsigned long long gp_img_stride, gp_term_stride;
   float* part;                    // [grid][2][N] partial sums of dlam, dtheta
+  int prefetch;                   // epilogue inputs prefetched through shared memory (when the slots fit)
   int has_gz, first_step, z_from_v;   // first_step: g_v starts at zero ; z_from_v: z_in = spike(v_in) else from z_init
   long long* dbg;                 // optional [grid][8] cycle counters (SNNFLOW_WT_TIMING=1): where each role waits
 };
@@ -80,6 +81,7 @@ int launch_wt_recbwd(const WtArgs& a, cudaStream_t st, double bytes, double flop
 bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int w_terms, bool tall, int* R, int* S,
              uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes);
 int wt_grid(int n_tiles);
+size_t wt_recbwd_extra_smem();   // thread-private prefetch slots of the recurrent backward epilogue
 
 // ---- weight gradient (window_wgrad.cu) --------------------------------------------------------------
 struct WgArgs {

@@ -144,6 +144,7 @@ __device__ __forceinline__ void ld8_c8(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
+template <int SG, bool HARD>
 __global__ void __launch_bounds__(256) pw_seq_kernel(const PwSeqArgs a) {
   const int HW = a.H * a.W, Wp = a.W + 2;
   const int p = blockIdx.x * 256 + threadIdx.x;
@@ -180,27 +181,26 @@ __global__ void __launch_bounds__(256) pw_seq_kernel(const PwSeqArgs a) {
         }
       }
       uint32_t hi[4], lo[4];
+      float gI[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const float gs = go[c] * surrogate(v_cur[c] - th[c], a.width, a.surrogate);
+        const float gs = go[c] * surrogate_fast<SG>(v_cur[c] - th[c], a.width);
         const float gv = carry[c] + gs;
-        const float gi = gv * oml[c];
-        if (a.hard_reset) {
-          carry[c] = gv * lam[c] * (1.0f - z_in[c]);
-          s_lam[c] += gv * (v_in[c] * (1.0f - z_in[c]) - v_cur[c]);
+        gI[c] = gv * oml[c];
+        if (HARD) {
+          const float omz = 1.0f - z_in[c];
+          carry[c] = gv * lam[c] * omz;
+          s_lam[c] += gv * (v_in[c] * omz - v_cur[c]);
           s_th[c] -= gs;
         } else {
           carry[c] = gv * lam[c];
           s_lam[c] += gv * (v_in[c] - v_cur[c] - z_in[c] * th[c]);
           s_th[c] -= gs + gv * z_in[c];
         }
-        const __nv_bfloat16 bh = __float2bfloat16_rn(gi);
-        const __nv_bfloat16 bl = __float2bfloat16_rn(gi - __bfloat162float(bh));
-        const uint32_t uh = (uint32_t)__bfloat16_as_ushort(bh), ul = (uint32_t)__bfloat16_as_ushort(bl);
-        if (c & 1) { hi[c >> 1] |= uh << 16; lo[c >> 1] |= ul << 16; }
-        else { hi[c >> 1] = uh; lo[c >> 1] = ul; }
         v_cur[c] = v_in[c];
       }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) split_bf16_pair(gI[2 * c], gI[2 * c + 1], hi[c], lo[c]);
       unsigned char* gp = a.gp + img * a.gp_img_stride + (size_t)chunk * plane_bytes + ((size_t)(y + 1) * Wp + x + 1) * 16;
       *reinterpret_cast<uint4*>(gp) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(gp + a.gp_term_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -232,7 +232,11 @@ int launch_pw_seq(const PwSeqArgs& a, cudaStream_t st) {
     return SNNFLOW_EINVAL;
   }
   prof_begin("win_pw_seq", st, (double)a.T * a.B * a.C * a.H * a.W * 12.0);   // v, g_out in ; g_I out
-  pw_seq_kernel<<<dim3(gx, a.C / 8, a.B), 256, 0, st>>>(a);
+  const dim3 grid(gx, a.C / 8, a.B);
+#define PW_CASE(SGV, HARDV) \
+  if (a.surrogate == SGV && (a.hard_reset != 0) == HARDV) pw_seq_kernel<SGV, HARDV><<<grid, 256, 0, st>>>(a);
+  PW_CASE(0, true) PW_CASE(0, false) PW_CASE(1, true) PW_CASE(1, false) PW_CASE(2, true) PW_CASE(2, false)
+#undef PW_CASE
   return check_launch("pw_seq_kernel");
 }
 

@@ -31,7 +31,7 @@ constexpr int WT_EPI_WARPS = 16;   // 4 TMEM lane quarters x 4 eight-channel chu
 constexpr int WT_THREADS = (WT_EPI_WARPS + 2) * 32;
 constexpr int WT_MAX_STAGES = 4;
 constexpr int WT_HDR = 4096;   // barriers, TMEM slot, per-channel parameters, reduction scratch
-constexpr int WT_TAIL = 4096;  // the last 128-pixel segment of a row may address up to 128 + 2 slots past its tile: keep
+constexpr int WT_TAIL = 2304;  // the last 128-pixel segment of a row may address up to 128 + 2 slots past its tile: keep
                                // that (discarded) operand read inside the CTA's shared memory
 
 struct WtSmem {
@@ -486,6 +486,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgrad_kernel(const __grid_co
 //   soft: g_v' = gv*lam;          dlam += gv*(v_in - I);          dtheta -= gs + gv*z_in
 // (I is recovered from v_t, v_in and z_in as in pw_seq_kernel: the input current is not stored.)
 // =================================================================================================
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+constexpr int RB_PREFETCH_ARRAYS = 4;                                   // g_out, v_t, v_in, g_v
+constexpr int RB_PREFETCH_BYTES = 2 * RB_PREFETCH_ARRAYS * 2 * 16 * WT_EPI_WARPS * 32;   // 2 buffers x 128 B per thread
+
+template <int SG, bool HARD>
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const WtSmem s = wt_smem(smem, a.wblob_bytes);
@@ -506,43 +514,84 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
     const int n_mt = a.R * a.n_seg, nch = a.N >> 3;
     const uint32_t ncat = 2u * (uint32_t)a.N, acc_cols = (uint32_t)n_mt * ncat;
     const int n_items = wt_n_items<false>(a);
-    float lam[8], oml[8], th[8], inv_oml[8], s_lam[8], s_th[8];
+    const int n_sub = n_items * n_mt;   // 128-pixel segments this CTA processes, in order
+    const float4* par = s.par + (act ? ch * 8 : 0);   // (lam, 1 - lam, theta, 1 / (1 - lam)) per channel, read where used
+    float s_lam[8], s_th[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 pr = s.par[(act ? ch * 8 : 0) + c];
-      lam[c] = pr.x; oml[c] = pr.y; th[c] = pr.z; inv_oml[c] = pr.w;
-      s_lam[c] = s_th[c] = 0.f;
-    }
+    for (int c = 0; c < 8; ++c) s_lam[c] = s_th[c] = 0.f;
+    // The epilogue's own inputs (g_out, v_t, v_in, g_v: 128 B per thread and segment) are prefetched ONE SEGMENT AHEAD
+    // with cp.async into thread-private shared-memory slots, so their DRAM latency overlaps the previous segment's
+    // arithmetic instead of heading every segment (measured: the epilogue, not the MMA, bounds this kernel).
+    float4* pf = reinterpret_cast<float4*>(s.stages + (size_t)a.S * a.stage_bytes + WT_TAIL);
+    auto slot = [&](int buf, int j) { return pf + ((size_t)(buf * 2 * RB_PREFETCH_ARRAYS + j) * (WT_EPI_WARPS * 32) + tid); };
+    auto sub_pos = [&](int j, int& b, int& y, int& x, int& m) {
+      const int k = j / n_mt;
+      m = j - k * n_mt;
+      const ItemPos p = wt_item<false>(a, k);
+      b = p.b;
+      y = p.y0 + m / a.n_seg;
+      x = (m % a.n_seg) * 128 + q * 32 + lane;
+    };
+    auto prefetch = [&](int j) {
+      if (!a.prefetch) return;
+      int b, y, x, m;
+      sub_pos(j, b, y, x, m);
+      if (act && x < a.W) {
+        const size_t co = c8_off(b, nch, ch, HW, (size_t)y * a.W + x);
+        const int buf = j & 1;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          cp_async16(slot(buf, 0 + h2), a.g_out + co + 4 * h2);
+          cp_async16(slot(buf, 2 + h2), a.v_t + co + 4 * h2);
+          if (a.v_in && !a.v_in_nchw) cp_async16(slot(buf, 4 + h2), a.v_in + co + 4 * h2);
+          if (!a.first_step) cp_async16(slot(buf, 6 + h2), a.g_v + co + 4 * h2);
+        }
+      }
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    auto unpack = [&](const float4* p0, float (&v)[8]) {
+      const float4 lo = p0[0], hi = p0[WT_EPI_WARPS * 32];
+      v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    };
     long long t_wait = 0;
     const long long t_begin = clock64();
-    for (int k = 0; k < n_items; ++k) {
-      const ItemPos p = wt_item<false>(a, k);
+    if (n_sub > 0) prefetch(0);
+    for (int j = 0; j < n_sub; ++j) {
+      int b, y, x, m;
+      sub_pos(j, b, y, x, m);
+      const int k = j / n_mt;
       const uint32_t ab = (uint32_t)k & 1u;
-      bool waited = false;
-      int r = 0, seg = 0;
-      for (int m = 0; m < n_mt && act; ++m) {
-        const int y = p.y0 + r, x = seg * 128 + q * 32 + lane;
-        const bool ok = x < a.W;
-        const size_t pix = (size_t)y * a.W + x;
-        const size_t o = ((size_t)(p.b * a.N + ch * 8)) * HW + pix;   // NCHW (window-initial state of the caller)
-        const size_t co = c8_off(p.b, nch, ch, HW, pix);
-        float go[8], vt[8], vin[8], gv[8], zin[8];
+      const bool ok = x < a.W;
+      const size_t pix = (size_t)y * a.W + x;
+      const size_t o = ((size_t)(b * a.N + ch * 8)) * HW + pix;   // NCHW (window-initial state of the caller)
+      const size_t co = c8_off(b, nch, ch, HW, pix);
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+      float go[8], vt[8], vin[8], gv[8], zin[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) go[c] = vt[c] = vin[c] = gv[c] = zin[c] = 0.f;
-        if (ok) {
+      for (int c = 0; c < 8; ++c) go[c] = vt[c] = vin[c] = gv[c] = zin[c] = 0.f;
+      if (act && ok) {
+        if (a.prefetch) {
+          const int buf = j & 1;
+          unpack(slot(buf, 0), go);
+          unpack(slot(buf, 2), vt);
+          if (a.v_in && !a.v_in_nchw) unpack(slot(buf, 4), vin);
+          if (!a.first_step) unpack(slot(buf, 6), gv);
+        } else {
           ld8_c8(a.g_out + co, go);
           ld8_c8(a.v_t + co, vt);
+          if (a.v_in && !a.v_in_nchw) ld8_c8(a.v_in + co, vin);
           if (!a.first_step) {
             const float4 g0 = reinterpret_cast<const float4*>(a.g_v + co)[0], g1 = reinterpret_cast<const float4*>(a.g_v + co)[1];
             gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w; gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
           }
-          if (a.v_in) {
-            if (a.v_in_nchw) {
+        }
+      }
+      if (j + 1 < n_sub) prefetch(j + 1);
+      if (act) {
+        if (ok) {
+          if (a.v_in && a.v_in_nchw) {
 #pragma unroll
-              for (int c = 0; c < 8; ++c) vin[c] = __ldg(a.v_in + o + (size_t)c * HW);
-            } else {
-              ld8_c8(a.v_in + co, vin);
-            }
+            for (int c = 0; c < 8; ++c) vin[c] = __ldg(a.v_in + o + (size_t)c * HW);
           }
           if (!a.z_from_v && a.z_init) {
 #pragma unroll
@@ -551,12 +600,11 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
         }
         float acc[8];
         if (a.has_gz) {
-          if (!waited) {
+          if (m == 0) {
             const long long t0 = clock64();
             mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
             t_wait += clock64() - t0;
             tc_fence_after();
-            waited = true;
           }
           uint32_t u0[8], u1[8];
           const uint32_t tcol = tmem_base + t_lane + ab * acc_cols + (uint32_t)m * ncat + (uint32_t)(ch * 8);
@@ -571,40 +619,38 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
           for (int c = 0; c < 8; ++c) acc[c] = 0.f;
         }
         uint32_t hi[4], lo[4];
-        float gvn[8];
+        float gvn[8], gI[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const float z_in = a.z_from_v ? ((__fsub_rn(vin[c], th[c]) > 0.f) ? 1.f : 0.f) : zin[c];
-          const float gz = go[c] + acc[c];
-          const float gs = gz * surrogate(vt[c] - th[c], a.width, a.surrogate);
+          const float4 pr = par[c];
+          const float z_in = a.z_from_v ? ((__fsub_rn(vin[c], pr.z) > 0.f) ? 1.f : 0.f) : zin[c];
+          const float gs = (go[c] + acc[c]) * surrogate_fast<SG>(vt[c] - pr.z, a.width);
           const float gvv = gv[c] + gs;
-          const float gi_ = gvv * oml[c];
-          if (a.hard_reset) {
-            gvn[c] = gvv * lam[c] * (1.0f - z_in);
-            s_lam[c] += gvv * (vin[c] * (1.0f - z_in) - vt[c]);   // (a - I) (1 - lam), see pw_seq_kernel
+          gI[c] = gvv * pr.y;
+          if (HARD) {
+            const float omz = 1.0f - z_in;
+            gvn[c] = gvv * pr.x * omz;
+            s_lam[c] += gvv * (vin[c] * omz - vt[c]);   // (a - I) (1 - lam), see pw_seq_kernel
             s_th[c] -= gs;
           } else {
-            gvn[c] = gvv * lam[c];
-            s_lam[c] += gvv * (vin[c] - vt[c] - z_in * th[c]);
+            gvn[c] = gvv * pr.x;
+            s_lam[c] += gvv * (vin[c] - vt[c] - z_in * pr.z);
             s_th[c] -= gs + gvv * z_in;
           }
-          const __nv_bfloat16 bh = __float2bfloat16_rn(gi_);
-          const __nv_bfloat16 bl = __float2bfloat16_rn(gi_ - __bfloat162float(bh));
-          const uint32_t uh = (uint32_t)__bfloat16_as_ushort(bh), ul = (uint32_t)__bfloat16_as_ushort(bl);
-          if (c & 1) { hi[c >> 1] |= uh << 16; lo[c >> 1] |= ul << 16; }
-          else { hi[c >> 1] = uh; lo[c >> 1] = ul; }
         }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) split_bf16_pair(gI[2 * c], gI[2 * c + 1], hi[c], lo[c]);
         if (ok) {
           st8_c8(a.g_v + co, gvn);
-          unsigned char* gp = a.gp_out + (size_t)p.b * a.gp_img_stride + (size_t)ch * plane_bytes +
+          unsigned char* gp = a.gp_out + (size_t)b * a.gp_img_stride + (size_t)ch * plane_bytes +
                               ((size_t)(y + 1) * a.Wp + x + 1) * 16;
           *reinterpret_cast<uint4*>(gp) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(gp + a.gp_term_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        if (++seg == a.n_seg) { seg = 0; ++r; }
+      } else if (a.has_gz && m == 0) {
+        mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);   // idle channel groups still follow the accumulator phases
       }
-      if (a.has_gz) {
-        if (!waited) mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
+      if (a.has_gz && m == n_mt - 1) {
         tc_fence_before();
         mbar_arrive(&s.acc_empty[ab]);
       }
@@ -616,7 +662,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
     // per-warp partial sums of dlam / dtheta -> shared scratch [warp][2][8]
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const float l = warp_sum(s_lam[c] * inv_oml[c]), t = warp_sum(s_th[c]);
+      const float l = warp_sum(s_lam[c] * par[c].w), t = warp_sum(s_th[c]);
       if (lane == 0) {
         s.red[(warp * 2 + 0) * 8 + c] = l;
         s.red[(warp * 2 + 1) * 8 + c] = t;
@@ -648,6 +694,8 @@ int wt_grid(int n_tiles) {
   const int sms = sm_count();
   return n_tiles < sms ? n_tiles : sms;
 }
+
+size_t wt_recbwd_extra_smem() { return RB_PREFETCH_BYTES; }
 
 bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int w_terms, bool tall, int* R_out,
              int* S_out,
@@ -683,13 +731,13 @@ bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes
   return true;
 }
 
-static size_t wt_smem_bytes(const WtArgs& a) {
-  return (size_t)WT_HDR + align_up(a.wblob_bytes, 128) + (size_t)a.S * a.stage_bytes + WT_TAIL;
+static size_t wt_smem_bytes(const WtArgs& a, size_t extra = 0) {
+  return (size_t)WT_HDR + align_up(a.wblob_bytes, 128) + (size_t)a.S * a.stage_bytes + WT_TAIL + extra;
 }
 
 template <typename K>
-static int wt_launch(K kernel, const void* key, const WtArgs& a, cudaStream_t st, const char* what) {
-  const size_t smem = wt_smem_bytes(a);
+static int wt_launch(K kernel, const void* key, const WtArgs& a, cudaStream_t st, const char* what, size_t extra_smem = 0) {
+  const size_t smem = wt_smem_bytes(a, extra_smem);
   if (smem > (size_t)227 * 1024) {
     set_error("%s: shared memory %zu exceeds 227 KB", what, smem);
     return SNNFLOW_EINVAL;
@@ -742,7 +790,14 @@ int launch_wt_dgrad(const WtArgs& a, cudaStream_t st, double bytes, double flops
 
 int launch_wt_recbwd(const WtArgs& a, cudaStream_t st, double bytes, double flops) {
   prof_begin("win_rec_bwd", st, bytes, flops);
-  return wt_launch(wt_recbwd_kernel, (const void*)wt_recbwd_kernel, a, st, "wt_recbwd_kernel");
+  const size_t extra = a.prefetch ? RB_PREFETCH_BYTES : 0;
+#define WT_RB_CASE(SGV, HARDV) \
+  if (a.surrogate == SGV && (a.hard_reset != 0) == HARDV) \
+    return wt_launch(wt_recbwd_kernel<SGV, HARDV>, (const void*)wt_recbwd_kernel<SGV, HARDV>, a, st, "wt_recbwd_kernel", extra);
+  WT_RB_CASE(0, true) WT_RB_CASE(0, false) WT_RB_CASE(1, true) WT_RB_CASE(1, false) WT_RB_CASE(2, true) WT_RB_CASE(2, false)
+#undef WT_RB_CASE
+  set_error("launch_wt_recbwd: unknown surrogate %d", a.surrogate);
+  return SNNFLOW_EINVAL;
 }
 
 }  // namespace snnflow

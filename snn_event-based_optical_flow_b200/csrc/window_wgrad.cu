@@ -222,8 +222,13 @@ static WgPlan wg_plan(int C, int cin_chunks, int rec_chunks, int H, int W) {
     if (H % R) continue;
     if (forced_R && R != forced_R) continue;
     const int x_rows = R - 1 + p.n_kyg * p.rpm;   // rows addressed by the last tap group of the last output row
-    const size_t xb = (size_t)(x_rows > R + 2 ? x_rows : R + 2) * p.n_cg * p.P * 16;
+    // Only the R + 2 loaded rows get their own slots.  The MMA's spare vertical taps (ky >= 3) address rows past them:
+    // those reads fall into the gradient tile of the same stage (finite bf16 data) and only feed accumulator rows
+    // that the read-out ignores - this keeps a stage small enough for three of them.
     const size_t gb = (size_t)R * 2 * (C / 8) * p.P * 16;
+    const int rows_in_g = (int)(gb / ((size_t)p.n_cg * p.P * 16));   // spare rows that the gradient tile can absorb
+    const int own_rows = x_rows - rows_in_g > R + 2 ? x_rows - rows_in_g : R + 2;
+    const size_t xb = (size_t)own_rows * p.n_cg * p.P * 16;
     const size_t stage = align_up(xb + gb, 128);
     int S = (int)(((size_t)227 * 1024 - WG_HDR) / stage);
     if (S > WG_MAX_STAGES) S = WG_MAX_STAGES;
