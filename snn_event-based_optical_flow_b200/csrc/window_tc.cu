@@ -493,7 +493,29 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 constexpr int RB_PREFETCH_ARRAYS = 4;                                   // g_out, v_t, v_in, g_v
 constexpr int RB_PREFETCH_BYTES = 2 * RB_PREFETCH_ARRAYS * 2 * 16 * WT_EPI_WARPS * 32;   // 2 buffers x 128 B per thread
 
-template <int SG, bool HARD>
+// walks the 128-pixel segments of this CTA's tiles in launch order without divisions (step-mode kernels)
+struct SegIter {
+  int b, y0, r, seg, k, H, R, n_seg, step_rows;
+  __device__ __forceinline__ void init(const WtArgs& a) {
+    const int tpi = a.H / a.R;
+    b = (int)blockIdx.x / tpi;
+    y0 = ((int)blockIdx.x - b * tpi) * a.R;
+    r = seg = k = 0;
+    H = a.H; R = a.R; n_seg = a.n_seg; step_rows = (int)gridDim.x * a.R;
+  }
+  __device__ __forceinline__ void next() {
+    if (++seg < n_seg) return;
+    seg = 0;
+    if (++r < R) return;
+    r = 0;
+    ++k;
+    y0 += step_rows;
+    while (y0 >= H) { y0 -= H; ++b; }
+  }
+};
+
+// BIN0: the first bin of the window - v_in / z_in come from the caller's NCHW state tensors (or are zero)
+template <int SG, bool HARD, bool BIN0>
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const WtSmem s = wt_smem(smem, a.wblob_bytes);
@@ -507,99 +529,94 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
     __syncwarp();
   } else {
     const int q = warp & 3, ch = warp >> 2;
-    const bool act = ch * 8 < a.N;
+    // kernel parameters used per segment live in registers (re-reading them from the constant bank stalls the epilogue)
+    const int W = a.W, Wp = a.Wp, N = a.N, nch = N >> 3;
+    const bool act = ch * 8 < N, has_gz = a.has_gz != 0, first_step = a.first_step != 0, use_pf = a.prefetch != 0;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
-    const size_t HW = (size_t)a.H * a.W;
-    const size_t plane_bytes = (size_t)(a.H + 2) * a.Wp * 16;
-    const int n_mt = a.R * a.n_seg, nch = a.N >> 3;
-    const uint32_t ncat = 2u * (uint32_t)a.N, acc_cols = (uint32_t)n_mt * ncat;
-    const int n_items = wt_n_items<false>(a);
-    const int n_sub = n_items * n_mt;   // 128-pixel segments this CTA processes, in order
+    const size_t HW = (size_t)a.H * W;
+    const size_t plane_bytes = (size_t)(a.H + 2) * Wp * 16;
+    const int n_mt = a.R * a.n_seg;
+    const uint32_t ncat = 2u * (uint32_t)N, acc_cols = (uint32_t)n_mt * ncat;
+    const int n_sub = wt_n_items<false>(a) * n_mt;   // 128-pixel segments this CTA processes, in order
+    const float width = a.width;
+    const float *g_out = a.g_out, *v_t = a.v_t, *v_in = a.v_in;
+    float* g_v = a.g_v;
+    unsigned char* gp_out = a.gp_out;
+    const size_t gp_img_stride = a.gp_img_stride, gp_term_stride = a.gp_term_stride;
     const float4* par = s.par + (act ? ch * 8 : 0);   // (lam, 1 - lam, theta, 1 / (1 - lam)) per channel, read where used
     float s_lam[8], s_th[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) s_lam[c] = s_th[c] = 0.f;
     // The epilogue's own inputs (g_out, v_t, v_in, g_v: 128 B per thread and segment) are prefetched ONE SEGMENT AHEAD
-    // with cp.async into thread-private shared-memory slots, so their DRAM latency overlaps the previous segment's
-    // arithmetic instead of heading every segment (measured: the epilogue, not the MMA, bounds this kernel).
-    float4* pf = reinterpret_cast<float4*>(s.stages + (size_t)a.S * a.stage_bytes + WT_TAIL);
-    auto slot = [&](int buf, int j) { return pf + ((size_t)(buf * 2 * RB_PREFETCH_ARRAYS + j) * (WT_EPI_WARPS * 32) + tid); };
-    auto sub_pos = [&](int j, int& b, int& y, int& x, int& m) {
-      const int k = j / n_mt;
-      m = j - k * n_mt;
-      const ItemPos p = wt_item<false>(a, k);
-      b = p.b;
-      y = p.y0 + m / a.n_seg;
-      x = (m % a.n_seg) * 128 + q * 32 + lane;
-    };
-    auto prefetch = [&](int j) {
-      if (!a.prefetch) return;
-      int b, y, x, m;
-      sub_pos(j, b, y, x, m);
-      if (act && x < a.W) {
-        const size_t co = c8_off(b, nch, ch, HW, (size_t)y * a.W + x);
-        const int buf = j & 1;
+    // with cp.async into thread-private shared-memory slots, so their latency overlaps the previous segment's arithmetic.
+    float4* pf = reinterpret_cast<float4*>(s.stages + (size_t)a.S * a.stage_bytes + WT_TAIL) + tid;
+    constexpr int PF_STRIDE = WT_EPI_WARPS * 32;   // float4 elements between the slots of one thread
+    auto prefetch = [&](const SegIter& it, int buf) {
+      const int x = it.seg * 128 + q * 32 + lane;
+      if (use_pf && act && x < W) {
+        const size_t co = c8_off(it.b, nch, ch, HW, (size_t)(it.y0 + it.r) * W + x);
+        float4* d = pf + (size_t)buf * 2 * RB_PREFETCH_ARRAYS * PF_STRIDE;
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-          cp_async16(slot(buf, 0 + h2), a.g_out + co + 4 * h2);
-          cp_async16(slot(buf, 2 + h2), a.v_t + co + 4 * h2);
-          if (a.v_in && !a.v_in_nchw) cp_async16(slot(buf, 4 + h2), a.v_in + co + 4 * h2);
-          if (!a.first_step) cp_async16(slot(buf, 6 + h2), a.g_v + co + 4 * h2);
+          cp_async16(d + (0 + h2) * PF_STRIDE, g_out + co + 4 * h2);
+          cp_async16(d + (2 + h2) * PF_STRIDE, v_t + co + 4 * h2);
+          if (!BIN0) cp_async16(d + (4 + h2) * PF_STRIDE, v_in + co + 4 * h2);
+          if (!first_step) cp_async16(d + (6 + h2) * PF_STRIDE, g_v + co + 4 * h2);
         }
       }
       asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
     auto unpack = [&](const float4* p0, float (&v)[8]) {
-      const float4 lo = p0[0], hi = p0[WT_EPI_WARPS * 32];
+      const float4 lo = p0[0], hi = p0[PF_STRIDE];
       v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
     };
     long long t_wait = 0;
     const long long t_begin = clock64();
-    if (n_sub > 0) prefetch(0);
+    SegIter cur;
+    cur.init(a);
+    if (n_sub > 0) prefetch(cur, 0);
     for (int j = 0; j < n_sub; ++j) {
-      int b, y, x, m;
-      sub_pos(j, b, y, x, m);
-      const int k = j / n_mt;
+      SegIter nxt = cur;
+      nxt.next();
+      const int b = cur.b, y = cur.y0 + cur.r, x = cur.seg * 128 + q * 32 + lane, m = cur.r * cur.n_seg + cur.seg, k = cur.k;
       const uint32_t ab = (uint32_t)k & 1u;
-      const bool ok = x < a.W;
-      const size_t pix = (size_t)y * a.W + x;
-      const size_t o = ((size_t)(b * a.N + ch * 8)) * HW + pix;   // NCHW (window-initial state of the caller)
+      const bool ok = x < W;
+      const size_t pix = (size_t)y * W + x;
       const size_t co = c8_off(b, nch, ch, HW, pix);
       asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-      float go[8], vt[8], vin[8], gv[8], zin[8];
+      float go[8], vt[8], vin[8], gv[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) go[c] = vt[c] = vin[c] = gv[c] = zin[c] = 0.f;
+      for (int c = 0; c < 8; ++c) go[c] = vt[c] = vin[c] = gv[c] = 0.f;
       if (act && ok) {
-        if (a.prefetch) {
-          const int buf = j & 1;
-          unpack(slot(buf, 0), go);
-          unpack(slot(buf, 2), vt);
-          if (a.v_in && !a.v_in_nchw) unpack(slot(buf, 4), vin);
-          if (!a.first_step) unpack(slot(buf, 6), gv);
+        if (use_pf) {
+          const float4* d = pf + (size_t)(j & 1) * 2 * RB_PREFETCH_ARRAYS * PF_STRIDE;
+          unpack(d, go);
+          unpack(d + 2 * PF_STRIDE, vt);
+          if (!BIN0) unpack(d + 4 * PF_STRIDE, vin);
+          if (!first_step) unpack(d + 6 * PF_STRIDE, gv);
         } else {
-          ld8_c8(a.g_out + co, go);
-          ld8_c8(a.v_t + co, vt);
-          if (a.v_in && !a.v_in_nchw) ld8_c8(a.v_in + co, vin);
-          if (!a.first_step) {
-            const float4 g0 = reinterpret_cast<const float4*>(a.g_v + co)[0], g1 = reinterpret_cast<const float4*>(a.g_v + co)[1];
+          ld8_c8(g_out + co, go);
+          ld8_c8(v_t + co, vt);
+          if (!BIN0) ld8_c8(v_in + co, vin);
+          if (!first_step) {
+            const float4 g0 = reinterpret_cast<const float4*>(g_v + co)[0], g1 = reinterpret_cast<const float4*>(g_v + co)[1];
             gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w; gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
           }
         }
       }
-      if (j + 1 < n_sub) prefetch(j + 1);
+      if (j + 1 < n_sub) prefetch(nxt, (j + 1) & 1);
       if (act) {
-        if (ok) {
-          if (a.v_in && a.v_in_nchw) {
+        float zin[8];
+        if (BIN0) {   // window-initial state of the caller (NCHW) or zeros
+          const size_t o = ((size_t)(b * N + ch * 8)) * HW + pix;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) vin[c] = __ldg(a.v_in + o + (size_t)c * HW);
-          }
-          if (!a.z_from_v && a.z_init) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) zin[c] = __ldg(a.z_init + o + (size_t)c * HW);
+          for (int c = 0; c < 8; ++c) {
+            vin[c] = (ok && v_in) ? __ldg(v_in + o + (size_t)c * HW) : 0.f;
+            zin[c] = (ok && a.z_init) ? __ldg(a.z_init + o + (size_t)c * HW) : 0.f;
           }
         }
         float acc[8];
-        if (a.has_gz) {
+        if (has_gz) {
           if (m == 0) {
             const long long t0 = clock64();
             mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
@@ -609,7 +626,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
           uint32_t u0[8], u1[8];
           const uint32_t tcol = tmem_base + t_lane + ab * acc_cols + (uint32_t)m * ncat + (uint32_t)(ch * 8);
           tmem_ld8_async(tcol, u0);
-          tmem_ld8_async(tcol + (uint32_t)a.N, u1);
+          tmem_ld8_async(tcol + (uint32_t)N, u1);
           tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 8; ++c)   // pixels past the row end accumulate whatever the operand read found: mask them
@@ -623,8 +640,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 pr = par[c];
-          const float z_in = a.z_from_v ? ((__fsub_rn(vin[c], pr.z) > 0.f) ? 1.f : 0.f) : zin[c];
-          const float gs = (go[c] + acc[c]) * surrogate_fast<SG>(vt[c] - pr.z, a.width);
+          const float z_in = BIN0 ? zin[c] : ((__fsub_rn(vin[c], pr.z) > 0.f) ? 1.f : 0.f);
+          const float gs = (go[c] + acc[c]) * surrogate_fast<SG>(vt[c] - pr.z, width);
           const float gvv = gv[c] + gs;
           gI[c] = gvv * pr.y;
           if (HARD) {
@@ -641,19 +658,19 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
 #pragma unroll
         for (int c = 0; c < 4; ++c) split_bf16_pair(gI[2 * c], gI[2 * c + 1], hi[c], lo[c]);
         if (ok) {
-          st8_c8(a.g_v + co, gvn);
-          unsigned char* gp = a.gp_out + (size_t)b * a.gp_img_stride + (size_t)ch * plane_bytes +
-                              ((size_t)(y + 1) * a.Wp + x + 1) * 16;
+          st8_c8(g_v + co, gvn);
+          unsigned char* gp = gp_out + (size_t)b * gp_img_stride + (size_t)ch * plane_bytes + ((size_t)(y + 1) * Wp + x + 1) * 16;
           *reinterpret_cast<uint4*>(gp) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(gp + a.gp_term_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(gp + gp_term_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-      } else if (a.has_gz && m == 0) {
+      } else if (has_gz && m == 0) {
         mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);   // idle channel groups still follow the accumulator phases
       }
-      if (a.has_gz && m == n_mt - 1) {
+      if (has_gz && m == n_mt - 1) {
         tc_fence_before();
         mbar_arrive(&s.acc_empty[ab]);
       }
+      cur = nxt;
     }
     if (a.dbg && tid == 0) {
       a.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin;
@@ -791,9 +808,12 @@ int launch_wt_dgrad(const WtArgs& a, cudaStream_t st, double bytes, double flops
 int launch_wt_recbwd(const WtArgs& a, cudaStream_t st, double bytes, double flops) {
   prof_begin("win_rec_bwd", st, bytes, flops);
   const size_t extra = a.prefetch ? RB_PREFETCH_BYTES : 0;
+  const bool bin0 = !a.z_from_v;   // first bin of the window: v_in / z_in are the caller's NCHW state (or zero)
 #define WT_RB_CASE(SGV, HARDV) \
-  if (a.surrogate == SGV && (a.hard_reset != 0) == HARDV) \
-    return wt_launch(wt_recbwd_kernel<SGV, HARDV>, (const void*)wt_recbwd_kernel<SGV, HARDV>, a, st, "wt_recbwd_kernel", extra);
+  if (a.surrogate == SGV && (a.hard_reset != 0) == HARDV) { \
+    if (bin0) return wt_launch(wt_recbwd_kernel<SGV, HARDV, true>, (const void*)wt_recbwd_kernel<SGV, HARDV, true>, a, st, "wt_recbwd_kernel", extra); \
+    return wt_launch(wt_recbwd_kernel<SGV, HARDV, false>, (const void*)wt_recbwd_kernel<SGV, HARDV, false>, a, st, "wt_recbwd_kernel", extra); \
+  }
   WT_RB_CASE(0, true) WT_RB_CASE(0, false) WT_RB_CASE(1, true) WT_RB_CASE(1, false) WT_RB_CASE(2, true) WT_RB_CASE(2, false)
 #undef WT_RB_CASE
   set_error("launch_wt_recbwd: unknown surrogate %d", a.surrogate);
