@@ -88,6 +88,37 @@ __device__ __forceinline__ ItemPos wt_item(const WtArgs& a, int k) {
   return p;
 }
 
+// Walks this CTA's pipeline items in launch order without per-item divisions.
+//   sequence mode: tile (b, y0) fixed for T consecutive items (t = 0..T-1, image t*B + b), then the next tile;
+//   step mode    : one item per tile, images and row blocks advance by gridDim.x tiles.
+template <bool SEQ>
+struct ItemIter {
+  int img, b, y0, t;
+  int tile, tpi, T, B, R, H, grid, step_rows;
+  __device__ __forceinline__ void init(const WtArgs& a) {
+    tpi = a.H / a.R; T = a.T; B = a.B; R = a.R; H = a.H; grid = (int)gridDim.x; step_rows = grid * a.R;
+    tile = (int)blockIdx.x;
+    b = tile / tpi;
+    y0 = (tile - b * tpi) * R;
+    t = 0;
+    img = b;
+  }
+  __device__ __forceinline__ void next() {
+    if (SEQ) {
+      if (++t < T) { img += B; return; }
+      t = 0;
+      tile += grid;
+      b = tile / tpi;
+      y0 = (tile - b * tpi) * R;
+      img = b;
+    } else {
+      y0 += step_rows;
+      while (y0 >= H) { y0 -= H; ++b; }
+      img = b;
+    }
+  }
+};
+
 __device__ __forceinline__ uint32_t wt_tmem_cols(const WtArgs& a) {
   const uint32_t need = 2u * (uint32_t)(a.R * a.n_seg * a.N) * a.src[0].w_terms;
   uint32_t c = 32;
@@ -129,30 +160,44 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
     mbar_expect_tx(s.wbar, a.wblob_bytes);
     tma_bulk_g2s(s.w, a.wblob, a.wblob_bytes, s.wbar);
   }
-  const int n_items = wt_n_items<SEQ>(a);
-  const size_t plane_bytes = (size_t)(a.H + 2) * a.Wp * 16;
-  uint32_t u = 0;
+  const int n_items = wt_n_items<SEQ>(a), n_src = a.n_src, S = a.S;
+  const size_t plane_bytes = (size_t)(a.H + 2) * a.Wp * 16, row_bytes = (size_t)a.Wp * 16;
+  const uint32_t sub_bytes = a.sub_bytes, chunk_stride = a.chunk_stride, stage_bytes = a.stage_bytes;
+  // this lane's chunk of either source
+  const unsigned char* base[2];
+  size_t img_stride[2];
+  uint32_t n_chunks[2];
+#pragma unroll
+  for (int si = 0; si < 2; ++si) {
+    const WtSrc& Sr = a.src[si < n_src ? si : 0];
+    base[si] = Sr.planes + (size_t)lane * plane_bytes;
+    img_stride[si] = Sr.img_stride;
+    n_chunks[si] = Sr.n_chunks;
+  }
+  ItemIter<SEQ> it;
+  it.init(a);
+  uint32_t st = 0, use = 0;
   long long t_wait = 0;
   const long long t_begin = clock64();
   for (int k = 0; k < n_items; ++k) {
-    const ItemPos p = wt_item<SEQ>(a, k);
-    for (int si = 0; si < a.n_src; ++si, ++u) {
-      const uint32_t st = u % (uint32_t)a.S, use = u / (uint32_t)a.S;
-      const WtSrc& S = a.src[si];
+#pragma unroll
+    for (int si = 0; si < 2; ++si) {
+      if (si >= n_src) break;
       if (lane == 0) {
         if (use > 0) {
           const long long t0 = clock64();
           mbar_wait(&s.empty[st], (use - 1) & 1);
           t_wait += clock64() - t0;
         }
-        mbar_expect_tx(&s.full[st], S.n_chunks * a.sub_bytes);
+        mbar_expect_tx(&s.full[st], n_chunks[si] * sub_bytes);
       }
       __syncwarp();
-      if ((uint32_t)lane < S.n_chunks)
-        tma_bulk_g2s(s.stages + (size_t)st * a.stage_bytes + (size_t)lane * a.chunk_stride,
-                     S.planes + (size_t)p.img * S.img_stride + (size_t)p.y0 * a.Wp * 16 + (size_t)lane * plane_bytes, a.sub_bytes,
-                     &s.full[st]);
+      if ((uint32_t)lane < n_chunks[si])
+        tma_bulk_g2s(s.stages + (size_t)st * stage_bytes + (size_t)lane * chunk_stride,
+                     base[si] + (size_t)it.img * img_stride[si] + (size_t)it.y0 * row_bytes, sub_bytes, &s.full[st]);
+      if (++st == (uint32_t)S) { st = 0; ++use; }
     }
+    it.next();
   }
   if (a.dbg && lane == 0) {
     a.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;   // producer: total
@@ -191,7 +236,8 @@ __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) bdesc[si][tap][kk] = b_lo_c | (w16 + (S.w_off >> 4) + (uint32_t)tap * tile16 + 2u * kk * blbo16);
   }
-  uint32_t u = 0;
+  uint32_t st = 0, use = 0;
+  const uint32_t n_stages = (uint32_t)a.S;
   long long t_full = 0, t_acc = 0;
   const long long t_begin = clock64();
   for (int k = 0; k < n_items; ++k) {
@@ -205,8 +251,6 @@ __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
 #pragma unroll
     for (int si = 0; si < 2; ++si) {
       if (si >= a.n_src) break;
-      const uint32_t st = u % (uint32_t)a.S, use = u / (uint32_t)a.S;
-      ++u;
       {
         const long long t0 = clock64();
         mbar_wait(&s.full[st], use & 1);
@@ -227,6 +271,7 @@ __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
         else a_base += 128u;
       }
       umma_commit(&s.empty[st]);
+      if (++st == n_stages) { st = 0; ++use; }
     }
     umma_commit(&s.acc_full[ab]);
   }
@@ -267,7 +312,7 @@ __device__ __forceinline__ uint32_t nz8_mask(const uint4& a) {   // bit c set wh
 // =================================================================================================
 // Forward.  Epilogue warp w: TMEM lane quarter q = w & 3 (32 pixels of a segment), 8-channel chunk ch = w >> 2.
 // =================================================================================================
-template <bool SEQ, int NSEG>
+template <bool SEQ, int NSEG, bool HARD>
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const WtSmem s = wt_smem(smem, a.wblob_bytes);
@@ -282,37 +327,42 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
     __syncwarp();
   } else {
     const int q = warp & 3, ch = warp >> 2;
-    const bool act = ch * 8 < a.N;
+    // per-item parameters live in registers (re-reading the kernel parameter block per element stalls the epilogue)
+    const int W = a.W, Wp = a.Wp, N = a.N, nch = N >> 3, n_seg = a.n_seg, T = a.T;
+    const bool act = ch * 8 < N;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
-    const size_t HW = (size_t)a.H * a.W;
-    const size_t plane_bytes = (size_t)(a.H + 2) * a.Wp * 16;
-    const int nch = a.N >> 3;
-    const uint32_t ncat = 3u * (uint32_t)a.N, acc_cols = (uint32_t)NSEG * ncat;   // three weight terms side by side
+    const size_t HW = (size_t)a.H * W;
+    const size_t plane_bytes = (size_t)(a.H + 2) * Wp * 16;
+    const uint32_t ncat = 3u * (uint32_t)N, acc_cols = (uint32_t)NSEG * ncat;   // three weight terms side by side
     const int n_items = wt_n_items<SEQ>(a);
+    float* const v_out = a.v_out;
+    float* const cur_out = a.cur_out;
+    unsigned char* const zp_out = a.zp_out + (size_t)ch * plane_bytes;
+    const size_t zp_img_stride = a.zp_img_stride;
+    const bool want_last = a.v_last != nullptr || a.z_last != nullptr;
     float lam[8], oml[8], th[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const float4 pr = s.par[(act ? ch * 8 : 0) + c];
       lam[c] = pr.x; oml[c] = pr.y; th[c] = pr.z;
     }
-    float vst[NSEG][8];
-    uint32_t zm[NSEG];
+    float vst[NSEG][8], zst[NSEG][8];   // membrane and spikes of the previous bin (registers across the T bins)
     long long t_wait = 0;
     const long long t_begin = clock64();
+    ItemIter<SEQ> it;
+    it.init(a);
     for (int k = 0; k < n_items; ++k) {
-      const ItemPos p = wt_item<SEQ>(a, k);
       const uint32_t ab = (uint32_t)k & 1u;
-      const bool load_state = SEQ ? (p.t == 0) : true;
+      const bool load_state = SEQ ? (it.t == 0) : true;
       if (load_state && act) {
 #pragma unroll
         for (int m = 0; m < NSEG; ++m) {
-          const int y = p.y0 + m / a.n_seg, x = (m % a.n_seg) * 128 + q * 32 + lane;
-          const bool ok = x < a.W;
-          const size_t pix = (size_t)y * a.W + x;
-          const size_t o = ((size_t)(p.b * a.N + ch * 8)) * HW + pix;   // NCHW (state tensors of the caller)
-          uint32_t zmask = 0;
+          const int y = it.y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
+          const bool ok = x < W;
+          const size_t pix = (size_t)y * W + x;
+          const size_t o = ((size_t)(it.b * N + ch * 8)) * HW + pix;   // NCHW (state tensors of the caller)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) vst[m][c] = 0.f;
+          for (int c = 0; c < 8; ++c) vst[m][c] = zst[m][c] = 0.f;
           if (SEQ) {
             if (ok && a.v_init) {
 #pragma unroll
@@ -320,7 +370,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
             }
             if (ok && a.z_init) {
 #pragma unroll
-              for (int c = 0; c < 8; ++c) zmask |= (__ldg(a.z_init + o + (size_t)c * HW) != 0.f ? 1u : 0u) << c;
+              for (int c = 0; c < 8; ++c) zst[m][c] = __ldg(a.z_init + o + (size_t)c * HW) != 0.f ? 1.f : 0.f;
             }
           } else {
             if (ok && a.v_prev) {
@@ -328,17 +378,23 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
 #pragma unroll
                 for (int c = 0; c < 8; ++c) vst[m][c] = __ldg(a.v_prev + o + (size_t)c * HW);
               } else {
-                ld8_c8(a.v_prev + c8_off(p.b, nch, ch, HW, pix), vst[m]);
+                ld8_c8(a.v_prev + c8_off(it.b, nch, ch, HW, pix), vst[m]);
               }
             }
-            if (ok && a.zin_planes)
-              zmask = nz8_mask(__ldg(reinterpret_cast<const uint4*>(a.zin_planes + (size_t)p.b * a.zin_img_stride +
-                                                                    (size_t)ch * plane_bytes + ((size_t)(y + 1) * a.Wp + x + 1) * 16)));
+            if (ok && a.zin_planes) {
+              const uint4 zz = __ldg(reinterpret_cast<const uint4*>(a.zin_planes + (size_t)it.b * a.zin_img_stride + (size_t)ch * plane_bytes +
+                                                                   ((size_t)(y + 1) * Wp + x + 1) * 16));
+              const uint32_t w4[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                zst[m][2 * i] = (w4[i] & 0xFFFFu) ? 1.f : 0.f;
+                zst[m][2 * i + 1] = (w4[i] >> 16) ? 1.f : 0.f;
+              }
+            }
           }
-          zm[m] = zmask;
         }
       }
-      const bool last = (SEQ ? (p.t == a.T - 1) : true) && (a.v_last != nullptr || a.z_last != nullptr);
+      const bool last = (SEQ ? (it.t == T - 1) : true) && want_last;
       {
         const long long t0 = clock64();
         mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
@@ -351,54 +407,44 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
         for (int m = 0; m < NSEG; ++m) {
           const uint32_t tcol = tmem_base + t_lane + ab * acc_cols + (uint32_t)m * ncat + (uint32_t)(ch * 8);
           tmem_ld8_async(tcol, u0[m]);
-          tmem_ld8_async(tcol + (uint32_t)a.N, u1[m]);
-          tmem_ld8_async(tcol + 2u * (uint32_t)a.N, u2[m]);
+          tmem_ld8_async(tcol + (uint32_t)N, u1[m]);
+          tmem_ld8_async(tcol + 2u * (uint32_t)N, u2[m]);
         }
         tmem_ld_wait();
 #pragma unroll
         for (int m = 0; m < NSEG; ++m) {
-          const int y = p.y0 + m / a.n_seg, x = (m % a.n_seg) * 128 + q * 32 + lane;
-          const bool ok = x < a.W;
-          const size_t pix = (size_t)y * a.W + x;
+          const int y = it.y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
+          const bool ok = x < W;
+          const size_t pix = (size_t)y * W + x;
           float cur[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
+          for (int c = 0; c < 8; ++c) {
             cur[c] = (__uint_as_float(u0[m][c]) + __uint_as_float(u1[m][c])) + __uint_as_float(u2[m][c]);   // hi + mid + lo terms
-          const uint32_t zin = zm[m];
-          uint32_t nm = 0;
-          if (a.hard_reset) {   // ((v*lam)*(1-z)) + ((1-lam)*I)      spiking_submodules.py:144
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float omz = ((zin >> c) & 1u) ? 0.f : 1.f;
-              const float vn = __fadd_rn(__fmul_rn(__fmul_rn(vst[m][c], lam[c]), omz), __fmul_rn(oml[c], cur[c]));
-              vst[m][c] = vn;
-              nm |= (__fsub_rn(vn, th[c]) > 0.f ? 1u : 0u) << c;
-            }
-          } else {              // ((v*lam) + ((1-lam)*I)) - (z*theta)   spiking_submodules.py:146
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float zt = ((zin >> c) & 1u) ? th[c] : 0.f;
-              const float vn = __fsub_rn(__fadd_rn(__fmul_rn(vst[m][c], lam[c]), __fmul_rn(oml[c], cur[c])), zt);
-              vst[m][c] = vn;
-              nm |= (__fsub_rn(vn, th[c]) > 0.f ? 1u : 0u) << c;
-            }
+            const float t1 = __fmul_rn(vst[m][c], lam[c]), t3 = __fmul_rn(oml[c], cur[c]);
+            float vn;
+            if (HARD) vn = __fadd_rn(__fmul_rn(t1, __fsub_rn(1.0f, zst[m][c])), t3);    // spiking_submodules.py:144
+            else vn = __fsub_rn(__fadd_rn(t1, t3), __fmul_rn(zst[m][c], th[c]));         // spiking_submodules.py:146
+            vst[m][c] = vn;
+            zst[m][c] = __fsub_rn(vn, th[c]) > 0.f ? 1.f : 0.f;                          // spiking_util.py:21
           }
-          zm[m] = nm;
           if (ok) {
-            *reinterpret_cast<uint4*>(a.zp_out + (size_t)p.img * a.zp_img_stride + (size_t)ch * plane_bytes +
-                                      ((size_t)(y + 1) * a.Wp + x + 1) * 16) =
-                make_uint4(bf16_pair(nm, 0), bf16_pair(nm, 1), bf16_pair(nm, 2), bf16_pair(nm, 3));
-            if (a.v_out) st8_c8(a.v_out + c8_off(p.img, nch, ch, HW, pix), vst[m]);
-            if (a.cur_out) st8_c8(a.cur_out + c8_off(p.img, nch, ch, HW, pix), cur);
+            uint4 zz;   // {0, 1} are exact in bf16: one packed convert per channel pair
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz.x) : "f"(zst[m][1]), "f"(zst[m][0]));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz.y) : "f"(zst[m][3]), "f"(zst[m][2]));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz.z) : "f"(zst[m][5]), "f"(zst[m][4]));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz.w) : "f"(zst[m][7]), "f"(zst[m][6]));
+            *reinterpret_cast<uint4*>(zp_out + (size_t)it.img * zp_img_stride + ((size_t)(y + 1) * Wp + x + 1) * 16) = zz;
+            if (v_out) st8_c8(v_out + c8_off(it.img, nch, ch, HW, pix), vst[m]);
+            if (cur_out) st8_c8(cur_out + c8_off(it.img, nch, ch, HW, pix), cur);
             if (last) {   // the caller-visible state [2,B,C,H,W] after the window
-              const size_t o = ((size_t)(p.b * a.N + ch * 8)) * HW + pix;
+              const size_t o = ((size_t)(it.b * N + ch * 8)) * HW + pix;
               if (a.v_last) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) a.v_last[o + (size_t)c * HW] = vst[m][c];
               }
               if (a.z_last) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) a.z_last[o + (size_t)c * HW] = ((nm >> c) & 1u) ? 1.f : 0.f;
+                for (int c = 0; c < 8; ++c) a.z_last[o + (size_t)c * HW] = zst[m][c];
               }
             }
           }
@@ -406,6 +452,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
       }
       tc_fence_before();
       mbar_arrive(&s.acc_empty[ab]);
+      it.next();
     }
     if (a.dbg && tid == 0) {
       a.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin;   // epilogue warp 0: total
@@ -439,10 +486,13 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgrad_kernel(const __grid_co
     const int n_mt = a.R * a.n_seg, nch = a.N >> 3;
     const uint32_t ncat = 2u * (uint32_t)a.N, acc_cols = (uint32_t)n_mt * ncat;   // [g*w_hi | g_hi*w_lo]
     const int n_items = wt_n_items<false>(a);
+    const int W = a.W, N = a.N, n_seg = a.n_seg;
+    float* const g_x = a.g_x;
     long long t_wait = 0;
     const long long t_begin = clock64();
-    for (int k = 0; k < n_items; ++k) {
-      const ItemPos p = wt_item<false>(a, k);
+    ItemIter<false> p;
+    p.init(a);
+    for (int k = 0; k < n_items; ++k, p.next()) {
       const uint32_t ab = (uint32_t)k & 1u;
       {
         const long long t0 = clock64();
@@ -457,13 +507,13 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgrad_kernel(const __grid_co
           uint32_t u0[8], u1[8];
           const uint32_t tcol = tmem_base + t_lane + ab * acc_cols + (uint32_t)m * ncat + (uint32_t)(ch * 8);
           tmem_ld8_async(tcol, u0);
-          tmem_ld8_async(tcol + (uint32_t)a.N, u1);
+          tmem_ld8_async(tcol + (uint32_t)N, u1);
           tmem_ld_wait();
           float acc[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) acc[c] = __uint_as_float(u0[c]) + __uint_as_float(u1[c]);
-          if (x < a.W) st8_c8(a.g_x + c8_off(p.img, nch, ch, HW, (size_t)y * a.W + x), acc);
-          if (++seg == a.n_seg) { seg = 0; ++r; }
+          if (x < W) st8_c8(g_x + c8_off(p.img, nch, ch, HW, (size_t)y * W + x), acc);
+          if (++seg == n_seg) { seg = 0; ++r; }
         }
       }
       tc_fence_before();
@@ -791,8 +841,12 @@ static int wt_launch(K kernel, const void* key, const WtArgs& a, cudaStream_t st
 int launch_wt_fwd(const WtArgs& a, bool seq, cudaStream_t st, const char* prof_name, double bytes, double flops) {
   const int nseg = a.R * a.n_seg;
   prof_begin(prof_name, st, bytes, flops);
+  const bool hard = a.hard_reset != 0;
 #define WT_FWD_CASE(SEQ, NS) \
-  if (seq == SEQ && nseg == NS) return wt_launch(wt_fwd_kernel<SEQ, NS>, (const void*)wt_fwd_kernel<SEQ, NS>, a, st, "wt_fwd_kernel");
+  if (seq == SEQ && nseg == NS) { \
+    if (hard) return wt_launch(wt_fwd_kernel<SEQ, NS, true>, (const void*)wt_fwd_kernel<SEQ, NS, true>, a, st, "wt_fwd_kernel"); \
+    return wt_launch(wt_fwd_kernel<SEQ, NS, false>, (const void*)wt_fwd_kernel<SEQ, NS, false>, a, st, "wt_fwd_kernel"); \
+  }
   WT_FWD_CASE(true, 1) WT_FWD_CASE(true, 2) WT_FWD_CASE(true, 3) WT_FWD_CASE(true, 4)
   WT_FWD_CASE(false, 1) WT_FWD_CASE(false, 2) WT_FWD_CASE(false, 3) WT_FWD_CASE(false, 4)
 #undef WT_FWD_CASE
