@@ -18,6 +18,7 @@ ap.add_argument("--res", type=int, default=128)
 ap.add_argument("--bins", type=int, default=10)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--kind", default="LIFFireNet")
+ap.add_argument("--eval", action="store_true", help="forward only, no_grad (eval path)")
 a = ap.parse_args()
 snnflow = importlib.import_module("snn_event-based_optical_flow_b200")
 torch.manual_seed(0)
@@ -29,6 +30,10 @@ g = torch.Generator().manual_seed(1)
 cnt = torch.poisson(torch.full((a.bins, a.batch, 2, a.res, a.res), 0.06), generator=g).cuda()
 gout = torch.randn(a.bins, a.batch, 2, a.res, a.res, generator=g).cuda()
 for rep in range(a.reps):
+    if a.eval:
+        with torch.no_grad():
+            flow = net.forward_window(cnt)
+        continue
     net.zero_grad(set_to_none=True)
     flow = net.forward_window(cnt)
     (flow * gout).sum().backward()

@@ -1,5 +1,6 @@
 // Library-level plumbing: thread-local error string, launch counter, device queries.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <map>
@@ -68,6 +69,15 @@ int sm_count() {
       n = 148;  // B200
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* v = getenv("SNNFLOW_PDL");
+    on = (v && v[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 }  // namespace snnflow

@@ -50,6 +50,32 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // number of SMs of the current device (cached)
 int sm_count();
+// programmatic dependent launch on (default) / off (SNNFLOW_PDL=0)
+bool pdl_enabled();
+
+// ---- programmatic dependent launch -----------------------------------------------------------------
+// Consecutive launches of a window run back to back on one stream; each is short (20 - 100 us), so the drain of one grid
+// and the ramp-up of the next (launch latency, barrier / TMEM set-up, weight staging) are a visible fraction of a step.
+// Kernels launched through launch_pdl() may begin while the previous grid is still retiring; they call pdl_wait()
+// before their first access to global memory the previous launches wrote (it returns once those grids have completed and
+// flushed), and pdl_launch_dependents() as early as possible.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 // ---- device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, bool valid) {

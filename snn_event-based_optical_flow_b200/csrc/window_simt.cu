@@ -146,6 +146,8 @@ __device__ __forceinline__ void ld8_c8(const float* p, float (&v)[8]) {
 
 template <int SG, bool HARD>
 __global__ void __launch_bounds__(256) pw_seq_kernel(const PwSeqArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int HW = a.H * a.W, Wp = a.W + 2;
   const int p = blockIdx.x * 256 + threadIdx.x;
   const int chunk = blockIdx.y, b = blockIdx.z;
@@ -234,7 +236,7 @@ int launch_pw_seq(const PwSeqArgs& a, cudaStream_t st) {
   prof_begin("win_pw_seq", st, (double)a.T * a.B * a.C * a.H * a.W * 12.0);   // v, g_out in ; g_I out
   const dim3 grid(gx, a.C / 8, a.B);
 #define PW_CASE(SGV, HARDV) \
-  if (a.surrogate == SGV && (a.hard_reset != 0) == HARDV) pw_seq_kernel<SGV, HARDV><<<grid, 256, 0, st>>>(a);
+  if (a.surrogate == SGV && (a.hard_reset != 0) == HARDV) launch_pdl(pw_seq_kernel<SGV, HARDV>, grid, dim3(256), 0, st, a);
   PW_CASE(0, true) PW_CASE(0, false) PW_CASE(1, true) PW_CASE(1, false) PW_CASE(2, true) PW_CASE(2, false)
 #undef PW_CASE
   return check_launch("pw_seq_kernel");
@@ -381,6 +383,8 @@ int launch_pred_reduce_planes(const float* part, float* dw, float* db, int C, in
 //   blockIdx.y 0/1: dW_ff / dW_rec[co][ci][tap] += sum_p part[p][tap][ci][co]
 //   blockIdx.y 2  : dlam / dtheta[c] += sum_j cpart
 __global__ void __launch_bounds__(256) win_reduce_kernel(const WinReduceArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, stripe = threadIdx.x >> 5;
   const int job = blockIdx.y;
@@ -433,7 +437,7 @@ int launch_win_reduce(const WinReduceArgs& a, cudaStream_t st) {
   int gx = ceil_div(a.C * cmax * 9, 32);
   if (gx > 4 * sm_count()) gx = 4 * sm_count();
   prof_begin("win_reduce", st, 4.0 * a.n_wpart * 9.0 * a.C * (a.cin_alloc[0] + (a.wdst[1] ? a.cin_alloc[1] : 0)) + 8.0 * a.C * a.n_cpart);
-  win_reduce_kernel<<<dim3(gx, 3), 256, 0, st>>>(a);
+  launch_pdl(win_reduce_kernel, dim3(gx, 3), dim3(256), 0, st, a);
   return check_launch("win_reduce_kernel");
 }
 

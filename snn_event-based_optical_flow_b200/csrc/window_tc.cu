@@ -130,6 +130,7 @@ __device__ __forceinline__ uint32_t wt_tmem_cols(const WtArgs& a) {
 __device__ __forceinline__ uint32_t wt_prologue(const WtArgs& a, const WtSmem& s) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const long long t_entry = clock64();
+  pdl_launch_dependents();   // the next launch may start its own prologue as soon as this grid's CTAs retire
   if (tid == 0) {
     for (int i = 0; i < WT_MAX_STAGES; ++i) {
       mbar_init(&s.full[i], 1);
@@ -160,6 +161,7 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
     mbar_expect_tx(s.wbar, a.wblob_bytes);
     tma_bulk_g2s(s.w, a.wblob, a.wblob_bytes, s.wbar);
   }
+  pdl_wait();   // the planes are written by the preceding launches (the weights were packed at the start of the pass)
   const int n_items = wt_n_items<SEQ>(a), n_src = a.n_src, S = a.S;
   const size_t plane_bytes = (size_t)(a.H + 2) * a.Wp * 16, row_bytes = (size_t)a.Wp * 16;
   const uint32_t sub_bytes = a.sub_bytes, chunk_stride = a.chunk_stride, stage_bytes = a.stage_bytes;
@@ -326,6 +328,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
     if (elect_one()) wt_mma<SEQ>(a, s, tmem_base);
     __syncwarp();
   } else {
+    pdl_wait();
     const int q = warp & 3, ch = warp >> 2;
     // per-item parameters live in registers (re-reading the kernel parameter block per element stalls the epilogue)
     const int W = a.W, Wp = a.Wp, N = a.N, nch = N >> 3, n_seg = a.n_seg, T = a.T;
@@ -479,6 +482,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgrad_kernel(const __grid_co
     if (elect_one()) wt_mma<false>(a, s, tmem_base);
     __syncwarp();
   } else {
+    pdl_wait();
     const int q = warp & 3, ch = warp >> 2;
     const bool act = ch * 8 < a.N;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
@@ -578,6 +582,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
     if (a.has_gz && elect_one()) wt_mma<false>(a, s, tmem_base);
     __syncwarp();
   } else {
+    pdl_wait();
     const int q = warp & 3, ch = warp >> 2;
     // kernel parameters used per segment live in registers (re-reading them from the constant bank stalls the epilogue)
     const int W = a.W, Wp = a.Wp, N = a.N, nch = N >> 3;
@@ -834,7 +839,7 @@ static int wt_launch(K kernel, const void* key, const WtArgs& a, cudaStream_t st
             what, a.R, a.S, a.n_src, a.N, (double)n_tiles * (a.T > 1 ? a.T : 1) / grid, avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7]);
     return check_launch(what);
   }
-  kernel<<<wt_grid(n_tiles), WT_THREADS, smem, st>>>(a);
+  SNNFLOW_CUDA(launch_pdl(kernel, dim3(wt_grid(n_tiles)), dim3(WT_THREADS), smem, st, a));
   return check_launch(what);
 }
 

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
   unsigned char* stages = smem + WG_HDR;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < WG_MAX_STAGES; ++i) {
       mbar_init(&full[i], 1);
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
     // Producer warp.  A tile is (R+2)*n_cg input-row pieces + R*2*C/8 gradient-row pieces of one padded row each;
     // the lanes compute the piece addresses in parallel and each issues its own bulk copies (a single thread spends
     // ~100 issue cycles per copy next to four busy epilogue warps - measured, profiles/), lane 0 owns the barriers.
+    pdl_wait();   // planes and gradient planes come from the preceding launches
     const int n_xp = (a.R + 2) * a.n_cg, n_gp = a.R * 2 * g_chunks;
     long long t_wait = 0;
     const long long t_begin = clock64();
@@ -166,6 +168,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
     __syncwarp();
   } else if (n_items > 0) {
     // ---- read-out: D[(j, kx)] row M = (ky - j*rpm) * n_cg*8 + cg*8 + c  ->  part[tap][ci][co] ----
+    pdl_wait();   // the partial buffers are read by the preceding layer's reduction
     mbar_wait(done, 0);
     tc_fence_after();
     const int q = warp & 3, par = warp >> 2;
@@ -274,7 +277,7 @@ int launch_wgrad_planes(WgArgs a, cudaStream_t st, double bytes, double flops) {
     if (!dbg) cudaMalloc(&dbg, sizeof(long long) * 8 * 1024);
     cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * grid, st);
     a.dbg = dbg;
-    wg_planes_kernel<<<grid, WG_THREADS, smem, st>>>(a);
+    launch_pdl(wg_planes_kernel, dim3(grid), dim3(WG_THREADS), smem, st, a);
     cudaStreamSynchronize(st);
     std::vector<long long> h(8 * grid);
     cudaMemcpy(h.data(), dbg, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
@@ -285,7 +288,7 @@ int launch_wgrad_planes(WgArgs a, cudaStream_t st, double bytes, double flops) {
             a.R, a.S, a.n_cg, (double)n_tiles / grid, avg[0], avg[1], avg[2], avg[3]);
     return check_launch("wg_planes_kernel");
   }
-  wg_planes_kernel<<<grid, WG_THREADS, smem, st>>>(a);
+  SNNFLOW_CUDA(launch_pdl(wg_planes_kernel, dim3(grid), dim3(WG_THREADS), smem, st, a));
   return check_launch("wg_planes_kernel");
 }
 
