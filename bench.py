@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--events", type=int, default=1000, help="events per sample per bin")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="N > 1: NCCL all-reduce between two graphs instead of the peer-memory kernel inside one graph")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -235,7 +236,7 @@ def run_ours(a):
     cfg = {"loader": {"resolution": [a.res, a.res]}, "loss": {"flow_regul_weight": 0.001}, "model": {"mask_output": False}}
     lossf = snnflow.EventWarping(cfg, dev)
     opt = torch.optim.Adam(net.parameters(), lr=2e-4, capturable=not a.no_graph)
-    tw = TrainWindow(net, lossf, opt, clip_grad=1.0)
+    tw = TrainWindow(net, lossf, opt, clip_grad=1.0, peer_allreduce=not a.nccl_allreduce)
 
     host_pool = [{k: v.pin_memory() for k, v in make_window(a, 1000 * rank + i).items()} for i in range(4)]
     dev_pool = [{k: v.to(dev) for k, v in w.items()} for w in host_pool]
@@ -408,6 +409,12 @@ def run_eval(a, snnflow, dev, world, barrier):
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE JSON line: native libraries (NCCL's version banner) write to file descriptor 1 directly,
+    # so fd 1 points at stderr while the benchmark runs and the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     args = parse()
     if args.impl == "reference":
         run_reference(args)

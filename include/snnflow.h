@@ -271,6 +271,21 @@ int snnflow_window_loss(const float* flow, const float* events, const float* pol
                         float* g_flow, void* workspace, size_t workspace_bytes, int T, int B, int64_t N, int H, int W,
                         float flow_scaling, float regul_weight, int loss_scaling, snnflow_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange (the reference has no distributed code): SUM all-reduce
+ * of a flat fp32 buffer across the ranks of one NVLink domain as ONE kernel per rank, replayable inside a CUDA graph.
+ *   peer_bufs  device array of `world` pointers: every rank's symmetric buffer (n floats) mapped into this process
+ *   peer_pads  device array of `world` pointers: every rank's symmetric signal pad, >= 256 + ctas * world uint32, zero
+ *              beyond slot 256 (the first 256 slots are left to the pad's owner, e.g. torch's own barriers)
+ *   out        local result, n floats (must not alias a symmetric buffer that peers read)
+ *   counter    snnflow_dp_allreduce_ctas() uint32 in local device memory, zeroed once; counts launches
+ * All ranks must launch the kernel the same number of times.  The terms are added in rank order (deterministic,
+ * identical on every rank).  A peer that never arrives traps the kernel instead of hanging it.
+ * --------------------------------------------------------------------------------------------- */
+int snnflow_dp_allreduce_ctas(void);
+int snnflow_dp_allreduce_sum(const void* peer_bufs, const void* peer_pads, float* out, unsigned int* counter, int rank, int world,
+                             size_t n, snnflow_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,14 +40,75 @@ class FlatGradAllReduce:
         torch._foreach_copy_(grads, self.views)
 
 
+class PeerGradAllReduce:
+    """The same SUM all-reduce as one peer-memory kernel per rank (snnflow_dp_allreduce_sum): every rank reads every
+    peer's gradient buffer over NVLink between two flag barriers.  No NCCL call, no stream hand-over: it is captured
+    inside the step's CUDA graph.  Needs torch symmetric memory (one NVLink domain); `available()` tells."""
+
+    graph_safe = True
+
+    def __init__(self, params, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib = _lib
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.n = n
+        self.sym = symm_mem.empty(n, dtype=torch.float32, device=dev)     # this rank's contribution, readable by peers
+        self.hdl = symm_mem.rendezvous(self.sym, self.group)
+        self.out = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views_in, self.views_out, o = [], [], 0
+        for p in self.params:
+            self.views_in.append(self.sym[o:o + p.numel()].view_as(p))
+            self.views_out.append(self.out[o:o + p.numel()].view_as(p))
+            o += p.numel()
+        self.bufs = torch.tensor([int(x) for x in self.hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.pads = torch.tensor([int(x) for x in self.hdl.signal_pad_ptrs], dtype=torch.int64, device=dev)
+        self.counter = torch.zeros(_lib.lib().snnflow_dp_allreduce_ctas(), dtype=torch.int32, device=dev)
+        self.hdl.barrier()
+
+    @staticmethod
+    def available():
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+            return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl"
+        except Exception:  # noqa: BLE001
+            return False
+
+    def active(self):
+        return True
+
+    def __call__(self, grads=None):
+        if grads is None:
+            for p in self.params:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            grads = [p.grad for p in self.params]
+        L = self._lib
+        torch._foreach_copy_(self.views_in, grads)
+        L.check(L.lib().snnflow_dp_allreduce_sum(self.bufs.data_ptr(), self.pads.data_ptr(), self.out.data_ptr(),
+                                                 self.counter.data_ptr(), self.rank, self.world, self.n, L.stream()),
+                "snnflow_dp_allreduce_sum")
+        torch._foreach_copy_(grads, self.views_out)
+
+
 class TrainWindow:
     """Runs optimizer steps on windows of T bins.  `batch` is the loader dict of the reference
     (dataloader/base.py:261-278) stacked over the T bins of the window:
         event_cnt [T,B,2,H,W], event_list [T,B,N,4], event_list_pol_mask [T,B,N,2], event_mask [T,B,1,H,W]."""
 
-    def __init__(self, model, loss_fn, optimizer, clip_grad=1.0, group=None):
+    def __init__(self, model, loss_fn, optimizer, clip_grad=1.0, group=None, peer_allreduce=False):
         self.model, self.loss_fn, self.opt, self.clip = model, loss_fn, optimizer, clip_grad
         self.reducer = FlatGradAllReduce(model.parameters(), group)
+        if peer_allreduce and PeerGradAllReduce.available():
+            try:   # NVLink peer memory: the exchange becomes one kernel inside the step graph
+                self.reducer = PeerGradAllReduce(model.parameters(), group)
+            except Exception as e:  # noqa: BLE001 - no symmetric memory on this system: keep the NCCL all-reduce
+                import warnings
+                warnings.warn(f"peer-memory all-reduce unavailable ({e}); using the NCCL all-reduce")
         self._graph = None
         self.fused_loss = True   # False: per-bin event_flow_association + EventWarping.forward (the reference's call pattern)
 
@@ -103,7 +164,7 @@ class TrainWindow:
         self._load(example_batch)
         n0 = _lib.launch_count()
         self._graph = torch.cuda.CUDAGraph()
-        if not self.reducer.active():
+        if not self.reducer.active() or getattr(self.reducer, "graph_safe", False):
             self._graph2 = None
             with torch.cuda.graph(self._graph):
                 self._static_loss = self.step(self._static)
