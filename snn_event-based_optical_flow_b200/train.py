@@ -183,9 +183,32 @@ class TrainWindow:
         for k, v in self._static.items():
             v.copy_(batch[k], non_blocking=True)
 
+    def prefetch(self, batch):
+        """Start copying the NEXT window (pinned host memory or device) into a staging buffer on a side stream; the copy
+        overlaps the step that is running.  `step_graphed(batch)` with the same object then only moves it device to device."""
+        if getattr(self, "_staging", None) is None:
+            self._staging = {k: torch.empty_like(v) for k, v in self._static.items()}
+            self._copy_stream = torch.cuda.Stream()
+            self._staging_free = None
+        cs = self._copy_stream
+        if self._staging_free is not None:
+            cs.wait_event(self._staging_free)          # the previous window has left the staging buffer
+        with torch.cuda.stream(cs):
+            for k, v in self._staging.items():
+                v.copy_(batch[k], non_blocking=True)
+            self._staged = (batch, cs.record_event())
+
     def step_graphed(self, batch):
         """Same as step() after capture(): `batch` may live on the device or in pinned host memory."""
-        self._load(batch)
+        staged = getattr(self, "_staged", None)
+        if staged is not None and staged[0] is batch:
+            torch.cuda.current_stream().wait_event(staged[1])
+            for k, v in self._static.items():
+                v.copy_(self._staging[k], non_blocking=True)
+            self._staging_free = torch.cuda.current_stream().record_event()
+            self._staged = None
+        else:
+            self._load(batch)
         self._graph.replay()
         if self._graph2 is not None:
             self.reducer(self._grads)
