@@ -210,6 +210,16 @@ class TrainWindow:
         else:
             self._load(batch)
         self._graph.replay()
+        self._replays = getattr(self, "_replays", 0) + 1
+        if self._replays % 64 == 0:   # graph replays bypass the engine's Python-side input check: poll the device counter
+            from . import _lib
+            from . import engine
+            L = _lib.lib()
+            engine._bind(L)
+            bad = int(L.snnflow_window_inexact_count(1))
+            if bad:
+                raise _lib.SnnflowError(f"window engine: {bad} input values were not exactly representable in bfloat16 "
+                                        "(event counts above 256 or fractional values): use the per-step engine")
         if self._graph2 is not None:
             self.reducer(self._grads)
             self._graph2.replay()
