@@ -84,12 +84,21 @@ static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool back
     P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, max_fwd_rec_blob, true, 3, false, &P.R_rec, &P.S_rec, &P.sub_rec, &P.cs_rec, &P.st_rec);
   if (!backward) return P;
   if (any_rec) {
-    // with the epilogue's prefetch slots if they fit next to two stages, without them otherwise
-    P.rb_prefetch = wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2 + wt_recbwd_extra_smem()), false, 2, false, &P.R_rb,
-                            &P.S_rb, &P.sub_rb, &P.cs_rb, &P.st_rb);
-    if (!P.rb_prefetch)
-      P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, 2, false, &P.R_rb, &P.S_rb, &P.sub_rb,
-                             &P.cs_rb, &P.st_rb);
+    // Measured (B200, 128x128): two-row tiles without the epilogue prefetch beat one-row tiles with it (35 vs 38 us per
+    // bin); the prefetch slots are used when only one-row tiles are possible.  SNNFLOW_RB_R / SNNFLOW_RB_PF override.
+    const int rb_R = wt_env_int("SNNFLOW_RB_R", 0), rb_pf = wt_env_int("SNNFLOW_RB_PF", -1);
+    const uint32_t rb_blob = (uint32_t)((size_t)9 * 2 * C * C * 2);
+    bool have = false;
+    P.rb_prefetch = false;
+    if (rb_pf != 1 && (rb_R == 0 || rb_R == 2))
+      have = wt_plan(d->H, d->W, C / 8, C, rb_blob, false, 2, false, &P.R_rb, &P.S_rb, &P.sub_rb, &P.cs_rb, &P.st_rb, 2);
+    if (!have && rb_pf != 0) {
+      have = wt_plan(d->H, d->W, C / 8, C, rb_blob + (uint32_t)wt_recbwd_extra_smem(), false, 2, false, &P.R_rb, &P.S_rb, &P.sub_rb,
+                     &P.cs_rb, &P.st_rb, rb_R);
+      P.rb_prefetch = have;
+    }
+    if (!have) have = wt_plan(d->H, d->W, C / 8, C, rb_blob, false, 2, false, &P.R_rb, &P.S_rb, &P.sub_rb, &P.cs_rb, &P.st_rb, rb_R);
+    P.ok = P.ok && have;
   }
   P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, 2, true, &P.R_dg, &P.S_dg, &P.sub_dg,
                          &P.cs_dg, &P.st_dg);

@@ -79,7 +79,8 @@ int launch_wt_dgrad(const WtArgs& a, cudaStream_t st, double bytes, double flops
 int launch_wt_recbwd(const WtArgs& a, cudaStream_t st, double bytes, double flops);
 // picks rows-per-tile / stages for the given shapes; returns false when the shape does not fit
 bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int w_terms, bool tall, int* R, int* S,
-             uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes);
+             uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes, int only_R = 0);
+int wt_env_int(const char* name, int dflt);
 int wt_grid(int n_tiles);
 size_t wt_recbwd_extra_smem();   // thread-private prefetch slots of the recurrent backward epilogue
 

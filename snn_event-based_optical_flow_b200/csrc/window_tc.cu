@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
             }
             if (ok && a.z_init) {
 #pragma unroll
-              for (int c = 0; c < 8; ++c) zst[m][c] = __ldg(a.z_init + o + (size_t)c * HW) != 0.f ? 1.f : 0.f;
+              for (int c = 0; c < 8; ++c) zst[m][c] = __ldg(a.z_init + o + (size_t)c * HW);   // {0, 1}: no dependent op before the wait
             }
           } else {
             if (ok && a.v_prev) {
@@ -769,13 +769,18 @@ int wt_grid(int n_tiles) {
 
 size_t wt_recbwd_extra_smem() { return RB_PREFETCH_BYTES; }
 
+int wt_env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
 bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int w_terms, bool tall, int* R_out,
              int* S_out,
-             uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes) {
+             uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes, int only_R) {
   const int Wp = W + 2, n_seg = ceil_div(W, 128);
   if (N > 32) return false;   // one 16-channel group per epilogue warp pair
   const size_t budget = (size_t)227 * 1024 - WT_HDR - WT_TAIL - align_up(wblob_bytes, 128);
-  const int forced_R = env_int("SNNFLOW_WT_R", 0), forced_S = env_int("SNNFLOW_WT_S", 0);
+  const int forced_R = only_R ? only_R : env_int("SNNFLOW_WT_R", 0), forced_S = env_int("SNNFLOW_WT_S", 0);
   // measured on B200 (profiles/): the LIF epilogues run best on one-row tiles (more, shorter pipeline items per CTA),
   // the data gradient (cheap epilogue, MMA-bound) on the tallest tile that still leaves three stages
   int best_R = 0, best_S = 0;
