@@ -358,6 +358,11 @@ def run_ours(a):
     if not a.no_eval:
         eval_info = run_eval(a, snnflow, dev, world, barrier)
 
+    micro = None
+    if rank == 0 and not a.no_eval:
+        phase("microbench")
+        micro = run_micro(snnflow, dev)
+
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -375,6 +380,7 @@ def run_ours(a):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "eval": eval_info,
+            "encode_iwe_microbench": micro,
             "loss": last_loss,
         }))
     if world > 1:
@@ -416,6 +422,46 @@ def run_eval(a, snnflow, dev, world, barrier):
     return {"metric": "LIFFireFlowNet eval frames/s @256x256, batch 16/GPU", "value": B * world * T / (ms_win / 1e3),
             "unit": "frames/s", "api": "forward_window (T = 10 bins per call)", "ms_per_window": ms_win,
             "per_bin_forward": {"value": B * world * T / (ms_bin / 1e3), "unit": "frames/s", "ms_per_forward": ms_bin / T}}
+
+
+def run_micro(snnflow, dev):
+    """BASELINE.json configs[4]: 10 M synthetic events into 256x256 count / voxel grids and the warp-splat (one GPU).
+    Mev/s and GB/s on the algorithmic bytes of SURVEY.md section 8(d) (12 B/event counts, 16 B/event voxel, 32 B/event
+    splat, plus the output images)."""
+    import torch
+    N, H, W = 10_000_000, 256, 256
+    g = torch.Generator().manual_seed(3)
+    xs = torch.randint(0, W, (N,), generator=g).float().to(dev)
+    ys = torch.randint(0, H, (N,), generator=g).float().to(dev)
+    ts = torch.sort(torch.rand(N, generator=g)).values.to(dev)
+    ps = (torch.randint(0, 2, (N,), generator=g).float() * 2 - 1).to(dev)
+    flow = torch.tanh(0.5 * torch.randn(1, 2, H, W, generator=g)).to(dev)
+    events = torch.stack([ts, ys, xs, ps], dim=1).unsqueeze(0).contiguous()
+    pos, neg = (ps > 0).float().reshape(1, N, 1), (ps < 0).float().reshape(1, N, 1)
+    enc, iwe = snnflow.encodings, snnflow.iwe
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, nbytes):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(5):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / 5
+        return {"ms": round(ms, 4), "Mev_s": round(N / ms / 1e3, 1), "GBps": round(nbytes / ms / 1e6, 1)}
+
+    with torch.no_grad():
+        return {
+            "events": N, "resolution": [H, W],
+            "events_to_channels": timed(lambda: enc.events_to_channels(xs, ys, ps, (H, W)), 12.0 * N + 8.0 * H * W),
+            "events_to_voxel_5": timed(lambda: enc.events_to_voxel(xs, ys, ts, ps, 5, (H, W)), 16.0 * N + 20.0 * H * W),
+            "events_to_image_mask": timed(lambda: enc.events_to_image(xs, ys, ps.abs(), (H, W), accumulate=False), 12.0 * N + 4.0 * H * W),
+            "compute_pol_iwe_round": timed(lambda: iwe.compute_pol_iwe(flow, events, (H, W), pos, neg, 128, True), 32.0 * N + 8.0 * H * W),
+            "compute_pol_iwe_bilinear": timed(lambda: iwe.compute_pol_iwe(flow, events, (H, W), pos, neg, 128, False), 32.0 * N + 8.0 * H * W),
+        }
 
 
 if __name__ == "__main__":
