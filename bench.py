@@ -182,7 +182,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.004)   # a step is ~4 ms: sample several times inside even a short timed region
 
     def start(self):
         if self.nv:
