@@ -148,7 +148,8 @@ static WinWorkspace win_workspace(const snnflow_net_desc* d, const WinLayout& L,
   const size_t c1 = (size_t)2 * C * W.pw_parts, c2 = (size_t)T * W.rb_grid * 2 * C;
   W.off_cpart = take((c1 > c2 ? c1 : c2) * sizeof(float));
   W.pred_parts = pred_planes_parts(T * B, d->H, d->W);
-  W.off_ppart = take((size_t)W.pred_parts * (2 * C + 2) * sizeof(float));
+  const int pp = W.pred_parts > W.pw_parts ? W.pred_parts : W.pw_parts;
+  W.off_ppart = take((size_t)pp * (2 * C + 2) * sizeof(float));
   W.total = o;
   return W;
 }
@@ -309,11 +310,17 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
 
   const int top = WIN_LAYERS - 1;
   int cur = 0;
-  int rc = launch_pred_bwd_planes(A + L.off_zp[top] + (L.rec[top] ? (size_t)B * L.zp_img_stride : 0), L.zp_img_stride, pred_w,
-                                  flow, g_flow, gbuf[cur], ppart, T * B, C, H, W, st);
-  if (rc) return rc;
-  rc = launch_pred_reduce_planes(ppart, d_pred_w, d_pred_b, C, WS.pred_parts, st);
-  if (rc) return rc;
+  int rc = SNNFLOW_OK;
+  // A feed-forward top layer takes its spike gradient straight from the flow head inside its time-fused pointwise
+  // kernel (no [T*B,C,H,W] gradient tensor is written or read); a recurrent top layer goes through the head's own kernel.
+  const bool fuse_head = !L.rec[top];
+  if (!fuse_head) {
+    rc = launch_pred_bwd_planes(A + L.off_zp[top] + (size_t)B * L.zp_img_stride, L.zp_img_stride, pred_w, flow, g_flow, gbuf[cur], ppart,
+                                T * B, C, H, W, st);
+    if (rc) return rc;
+    rc = launch_pred_reduce_planes(ppart, d_pred_w, d_pred_b, C, WS.pred_parts, st);
+    if (rc) return rc;
+  }
 
   for (int l = top; l >= 0; --l) {
     const snnflow_layer_ptrs& P_ = layers[l];
@@ -352,12 +359,17 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
       n_cpart = T * WS.rb_grid; cpart_layout = 1;
     } else {
       PwSeqArgs a{};
-      a.v = vbase; a.g_out = g_out; a.v_init = v_init; a.z_init = z_init; a.par = par;
+      a.v = vbase; a.g_out = (l == top && fuse_head) ? nullptr : g_out; a.v_init = v_init; a.z_init = z_init; a.par = par;
+      a.flow = flow; a.g_flow = g_flow; a.pred_w = pred_w; a.pred_part = ppart;
       a.gp = gp; a.gp_img_stride = L.zp_img_stride; a.gp_term_stride = WS.gp_term_stride;
       a.part = cpart; a.T = T; a.B = B; a.C = C; a.H = H; a.W = W; a.hard_reset = hard; a.surrogate = d->surrogate;
       a.n_part = WS.pw_parts; a.width = d->act_width;
       rc = launch_pw_seq(a, st);
       if (rc) return rc;
+      if (l == top && fuse_head) {
+        rc = launch_pred_reduce_rows(ppart, d_pred_w, d_pred_b, C, WS.pw_parts, st);
+        if (rc) return rc;
+      }
       n_cpart = WS.pw_parts; cpart_layout = 0;
     }
     // data gradient through W_ff: the spike gradient of the layer below, all T*B images at once

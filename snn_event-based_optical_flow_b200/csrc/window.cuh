@@ -123,6 +123,11 @@ struct PwSeqArgs {
   float* part;                     // [2][C][n_part]
   int T, B, C, H, W, hard_reset, surrogate, n_part;
   float width;
+  // top layer only (g_out == NULL): the spike gradient comes straight from the flow head,
+  //   g_out[c] = g_pre_x * w[0][c] + g_pre_y * w[1][c],  g_pre = g_flow * (1 - flow^2)      (models/submodules.py:96-113)
+  // and the head's own gradients dw [2][C], db [2] are accumulated as per-block partials pred_part [2C + 2][n_part]
+  const float *flow, *g_flow, *pred_w;   // [T*B][2][H*W], [T*B][2][H*W], [2][C]
+  float* pred_part;
 };
 int launch_pw_seq(const PwSeqArgs& a, cudaStream_t st);
 int launch_pred_fwd_planes(const unsigned char* zp, unsigned long long img_stride, const float* w, const float* b,
@@ -142,5 +147,6 @@ struct WinReduceArgs {
 };
 int launch_win_reduce(const WinReduceArgs& a, cudaStream_t st);
 int launch_pred_reduce_planes(const float* part, float* dw, float* db, int C, int n_part, cudaStream_t st);
+int launch_pred_reduce_rows(const float* part, float* dw, float* db, int C, int n_part, cudaStream_t st);
 
 }  // namespace snnflow

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) window_pack_weights_kernel(const PackArgs
     const int K = conv == 0 ? L.Kin : C, Kreal = conv == 0 ? L.Cin : C;
     const int per_tile = K * C;
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(L.fwd_blob + off);
-    for (int i = tid; i < 9 * per_tile; i += 256) {
+    for (int i = blockIdx.y * 256 + tid; i < 9 * per_tile; i += gridDim.y * 256) {
       const int tap = i / per_tile, r = i - tap * per_tile;
       const int n = r / K, k = r - n * K;
       const float v = k < Kreal ? w[((size_t)n * Kreal + k) * 9 + tap] : 0.f;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) window_pack_weights_kernel(const PackArgs
     const int N = which == 0 ? L.Kin : C, Nreal = which == 0 ? L.Cin : C;
     const int per_tile = N * C;
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(blob);
-    for (int i = tid; i < 9 * per_tile; i += 256) {
+    for (int i = blockIdx.y * 256 + tid; i < 9 * per_tile; i += gridDim.y * 256) {
       const int tap = i / per_tile, r = i - tap * per_tile;
       const int n = r / C, k = r - n * C;
       const float v = n < Nreal ? w[((size_t)k * Nreal + n) * 9 + (8 - tap)] : 0.f;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) window_pack_weights_kernel(const PackArgs
       }
     }
   }
-  for (int c = tid; c < C; c += 256) {
+  for (int c = tid; c < C && blockIdx.y == 0; c += 256) {
     const float lam = L.leak_lam[c];
     const float oml = __fsub_rn(1.0f, lam);
     // .w = 1 / (1 - lam) for the backward's current-free form of d loss / d lam (0 when lam == 1: sigmoid' is 0 too)
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) window_pack_weights_kernel(const PackArgs
 
 int launch_pack_weights(const PackArgs& p, cudaStream_t st) {
   prof_begin("win_pack_weights", st, 0.0);
-  window_pack_weights_kernel<<<WIN_LAYERS, 256, 0, st>>>(p);
+  window_pack_weights_kernel<<<dim3(WIN_LAYERS, 16), 256, 0, st>>>(p);
   return check_launch("window_pack_weights_kernel");
 }
 
@@ -144,8 +144,8 @@ __device__ __forceinline__ void ld8_c8(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-template <int SG, bool HARD>
-__global__ void __launch_bounds__(256) pw_seq_kernel(const PwSeqArgs a) {
+template <int SG, bool HARD, bool TOP>
+__global__ void __launch_bounds__(256, 2) pw_seq_kernel(const PwSeqArgs a) {
   pdl_launch_dependents();
   pdl_wait();
   const int HW = a.H * a.W, Wp = a.W + 2;
@@ -165,11 +165,34 @@ __global__ void __launch_bounds__(256) pw_seq_kernel(const PwSeqArgs a) {
   // c8 layout: [image][chunk][H*W][8]
   const size_t img_stride = (size_t)nch * HW * 8, px_off = ((size_t)chunk * HW + (ok ? p : 0)) * 8;
   if (ok) ld8_c8(a.v + (size_t)((a.T - 1) * a.B + b) * img_stride + px_off, v_cur);
+  float w0[8], w1[8], dw0[8], dw1[8], db0 = 0.f, db1 = 0.f;   // flow head (TOP): weights of this chunk, gradient partials
+  if (TOP) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      w0[c] = __ldg(a.pred_w + chunk * 8 + c);
+      w1[c] = __ldg(a.pred_w + a.C + chunk * 8 + c);
+      dw0[c] = dw1[c] = 0.f;
+    }
+  }
   for (int t = a.T - 1; t >= 0; --t) {
     const size_t img = (size_t)(t * a.B + b);
     if (ok) {
       float v_in[8], z_in[8], go[8];
-      ld8_c8(a.g_out + img * img_stride + px_off, go);
+      if (TOP) {
+        const size_t fo = img * 2 * HW + p;
+        const float f0 = __ldg(a.flow + fo), f1 = __ldg(a.flow + fo + HW);
+        const float g0 = __ldg(a.g_flow + fo) * (1.0f - f0 * f0), g1 = __ldg(a.g_flow + fo + HW) * (1.0f - f1 * f1);
+        db0 += g0; db1 += g1;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          go[c] = g0 * w0[c] + g1 * w1[c];
+          const float z = (__fsub_rn(v_cur[c], th[c]) > 0.f) ? 1.f : 0.f;   // this bin's spikes: the head's input
+          dw0[c] = fmaf(g0, z, dw0[c]);
+          dw1[c] = fmaf(g1, z, dw1[c]);
+        }
+      } else {
+        ld8_c8(a.g_out + img * img_stride + px_off, go);
+      }
       if (t > 0) {
         ld8_c8(a.v + (img - a.B) * img_stride + px_off, v_in);
 #pragma unroll
@@ -225,6 +248,30 @@ __global__ void __launch_bounds__(256) pw_seq_kernel(const PwSeqArgs a) {
     const int j = b * gridDim.x + blockIdx.x;
     a.part[((size_t)which * a.C + chunk * 8 + c) * a.n_part + j] = t;
   }
+  if (TOP) {   // flow-head gradients: same fixed-order block reduction, rows [dw0 | dw1 | db] of pred_part
+    __syncthreads();
+    __shared__ float pred[8][18];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float l = warp_sum(ok ? dw0[c] : 0.f), t = warp_sum(ok ? dw1[c] : 0.f);
+      if (lane == 0) { pred[warp][c] = l; pred[warp][8 + c] = t; }
+    }
+    const float e0 = warp_sum(ok ? db0 : 0.f), e1 = warp_sum(ok ? db1 : 0.f);
+    if (lane == 0) { pred[warp][16] = e0; pred[warp][17] = e1; }
+    __syncthreads();
+    if (threadIdx.x < 18) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += pred[w][threadIdx.x];
+      const int j = b * gridDim.x + blockIdx.x;
+      if (threadIdx.x < 16) {
+        const int which = threadIdx.x >> 3, c = threadIdx.x & 7;
+        a.pred_part[((size_t)which * a.C + chunk * 8 + c) * a.n_part + j] = t;
+      } else if (chunk == 0) {   // every chunk sees the same g_pre: count the bias gradient once
+        a.pred_part[((size_t)2 * a.C + (threadIdx.x - 16)) * a.n_part + j] = t;
+      }
+    }
+  }
 }
 
 int launch_pw_seq(const PwSeqArgs& a, cudaStream_t st) {
@@ -235,8 +282,12 @@ int launch_pw_seq(const PwSeqArgs& a, cudaStream_t st) {
   }
   prof_begin("win_pw_seq", st, (double)a.T * a.B * a.C * a.H * a.W * 12.0);   // v, g_out in ; g_I out
   const dim3 grid(gx, a.C / 8, a.B);
+  const bool top = a.g_out == nullptr;
 #define PW_CASE(SGV, HARDV) \
-  if (a.surrogate == SGV && (a.hard_reset != 0) == HARDV) launch_pdl(pw_seq_kernel<SGV, HARDV>, grid, dim3(256), 0, st, a);
+  if (a.surrogate == SGV && (a.hard_reset != 0) == HARDV) { \
+    if (top) launch_pdl(pw_seq_kernel<SGV, HARDV, true>, grid, dim3(256), 0, st, a); \
+    else launch_pdl(pw_seq_kernel<SGV, HARDV, false>, grid, dim3(256), 0, st, a); \
+  }
   PW_CASE(0, true) PW_CASE(0, false) PW_CASE(1, true) PW_CASE(1, false) PW_CASE(2, true) PW_CASE(2, false)
 #undef PW_CASE
   return check_launch("pw_seq_kernel");
@@ -292,47 +343,58 @@ int launch_pred_fwd_planes(const unsigned char* zp, unsigned long long img_strid
   return check_launch("pred_fwd_planes_kernel");
 }
 
-// g_pre = g_flow * (1 - flow^2); g_x[c] = g_pre0*w[0][c] + g_pre1*w[1][c]; per-CTA partials of dw [2][C], db [2]
+// g_pre = g_flow * (1 - flow^2); g_x[c] = g_pre0*w[0][c] + g_pre1*w[1][c]; per-CTA partials of dw [2][C], db [2].
+// Every thread walks PB_PX pixels (256 apart: coalesced) and keeps its 2C + 2 partial sums in registers, so the block
+// reduction (66 warp reductions) is paid once per 2048 pixels instead of once per 256.
+constexpr int PB_PX = 2;
+constexpr int PB_MAX_C = 32;
+
 __global__ void __launch_bounds__(256) pred_bwd_planes_kernel(const unsigned char* __restrict__ zp, unsigned long long img_stride,
                                                               const float* __restrict__ w, const float* __restrict__ flow,
                                                               const float* __restrict__ g_flow, float* __restrict__ g_x,
                                                               float* __restrict__ part, int C, int H, int W) {
-  __shared__ float sw[2 * PP_MAX_C];
-  __shared__ float red[8][2 * PP_MAX_C + 2];
+  __shared__ float sw[2 * PB_MAX_C];
+  __shared__ float red[8][2 * PB_MAX_C + 2];
   for (int i = threadIdx.x; i < 2 * C; i += 256) sw[i] = w[i];
   __syncthreads();
-  const int HW = H * W, Wp = W + 2;
-  const int p = blockIdx.x * 256 + threadIdx.x, img = blockIdx.y;
-  const bool ok = p < HW;
-  const int y = ok ? p / W : 0, x = ok ? p - y * W : 0;
+  const int HW = H * W, Wp = W + 2, img = blockIdx.y, nch = C >> 3;
   const size_t plane_bytes = (size_t)(H + 2) * Wp * 16;
-  float g0 = 0.f, g1 = 0.f;
-  if (ok) {
-    const float f0 = flow[((size_t)img * 2 + 0) * HW + p], f1 = flow[((size_t)img * 2 + 1) * HW + p];
-    g0 = g_flow[((size_t)img * 2 + 0) * HW + p] * (1.0f - f0 * f0);
-    g1 = g_flow[((size_t)img * 2 + 1) * HW + p] * (1.0f - f1 * f1);
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned char* src = zp + (size_t)img * img_stride + ((size_t)(y + 1) * Wp + x + 1) * 16;
-  for (int ch = 0; ch < (C >> 3); ++ch) {
-    float f[8], gx[8];
-    if (ok) unpack8(__ldg(reinterpret_cast<const uint4*>(src + ch * plane_bytes)), f);
+  float a0[PB_MAX_C], a1[PB_MAX_C], b0 = 0.f, b1 = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) gx[c] = g0 * sw[ch * 8 + c] + g1 * sw[C + ch * 8 + c];
-    if (ok) {   // c8 layout [image][chunk][H*W][8]
-      float4* gxp = reinterpret_cast<float4*>(g_x + (((size_t)img * (C >> 3) + ch) * HW + p) * 8);
+  for (int c = 0; c < PB_MAX_C; ++c) a0[c] = a1[c] = 0.f;
+  for (int j = 0; j < PB_PX; ++j) {
+    const int p = (blockIdx.x * PB_PX + j) * 256 + threadIdx.x;
+    if (p >= HW) break;
+    const int y = p / W, x = p - y * W;
+    const float f0 = flow[((size_t)img * 2 + 0) * HW + p], f1 = flow[((size_t)img * 2 + 1) * HW + p];
+    const float g0 = g_flow[((size_t)img * 2 + 0) * HW + p] * (1.0f - f0 * f0);
+    const float g1 = g_flow[((size_t)img * 2 + 1) * HW + p] * (1.0f - f1 * f1);
+    b0 += g0; b1 += g1;
+    const unsigned char* src = zp + (size_t)img * img_stride + ((size_t)(y + 1) * Wp + x + 1) * 16;
+#pragma unroll
+    for (int ch = 0; ch < PB_MAX_C / 8; ++ch) {
+      if (ch >= nch) break;
+      float f[8], gx[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(src + ch * plane_bytes)), f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        gx[c] = g0 * sw[ch * 8 + c] + g1 * sw[C + ch * 8 + c];
+        a0[ch * 8 + c] = fmaf(g0, f[c], a0[ch * 8 + c]);
+        a1[ch * 8 + c] = fmaf(g1, f[c], a1[ch * 8 + c]);
+      }
+      float4* gxp = reinterpret_cast<float4*>(g_x + (((size_t)img * nch + ch) * HW + p) * 8);   // c8 layout
       gxp[0] = make_float4(gx[0], gx[1], gx[2], gx[3]);
       gxp[1] = make_float4(gx[4], gx[5], gx[6], gx[7]);
     }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int co = ch * 8 + c;
-      const float zv = ok ? f[c] : 0.f;
-      const float s0 = warp_sum(g0 * zv), s1 = warp_sum(g1 * zv);
-      if (lane == 0) { red[warp][co] = s0; red[warp][C + co] = s1; }
-    }
   }
-  const float s0 = warp_sum(g0), s1 = warp_sum(g1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < PB_MAX_C; ++c) {
+    if (c >= C) break;
+    const float s0 = warp_sum(a0[c]), s1 = warp_sum(a1[c]);
+    if (lane == 0) { red[warp][c] = s0; red[warp][C + c] = s1; }
+  }
+  const float s0 = warp_sum(b0), s1 = warp_sum(b1);
   if (lane == 0) { red[warp][2 * C] = s0; red[warp][2 * C + 1] = s1; }
   __syncthreads();
   float* mypart = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (2 * C + 2);
@@ -344,17 +406,17 @@ __global__ void __launch_bounds__(256) pred_bwd_planes_kernel(const unsigned cha
   }
 }
 
-int pred_planes_parts(int n_img, int H, int W) { return n_img * ceil_div(H * W, 256); }
+int pred_planes_parts(int n_img, int H, int W) { return n_img * ceil_div(H * W, 256 * PB_PX); }
 
 int launch_pred_bwd_planes(const unsigned char* zp, unsigned long long img_stride, const float* w, const float* flow,
                            const float* g_flow, float* g_x, float* part, int n_img, int C, int H, int W,
                            cudaStream_t st) {
-  if (C > PP_MAX_C) {
-    set_error("pred planes: C <= 64");
+  if (C > PB_MAX_C) {
+    set_error("pred planes: C <= 32");
     return SNNFLOW_EINVAL;
   }
   prof_begin("win_pred_bwd", st, (double)n_img * H * W * (2.0 * C + 4.0 * C + 16.0), 8.0 * n_img * H * W * C);
-  pred_bwd_planes_kernel<<<dim3(ceil_div(H * W, 256), n_img), 256, 0, st>>>(zp, img_stride, w, flow, g_flow, g_x, part, C, H, W);
+  pred_bwd_planes_kernel<<<dim3(ceil_div(H * W, 256 * PB_PX), n_img), 256, 0, st>>>(zp, img_stride, w, flow, g_flow, g_x, part, C, H, W);
   return check_launch("pred_bwd_planes_kernel");
 }
 
@@ -371,6 +433,26 @@ __global__ void __launch_bounds__(256) pred_reduce_planes_kernel(const float* __
     if (wid < 2 * C) { if (dw) dw[wid] += s; }
     else if (db) db[wid - 2 * C] += s;
   }
+}
+
+// same for the row-major partials [2C + 2][n_part] written by the fused top-layer pointwise kernel
+__global__ void __launch_bounds__(256) pred_reduce_rows_kernel(const float* __restrict__ part, float* dw, float* db, int C, int n_part) {
+  const int n = 2 * C + 2;
+  const int wid = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= n) return;
+  float s = 0.f;
+  for (int p = lane; p < n_part; p += 32) s += part[(size_t)wid * n_part + p];
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (wid < 2 * C) { if (dw) dw[wid] += s; }
+    else if (db) db[wid - 2 * C] += s;
+  }
+}
+
+int launch_pred_reduce_rows(const float* part, float* dw, float* db, int C, int n_part, cudaStream_t st) {
+  prof_begin("win_pred_reduce", st, 4.0 * n_part * (2 * C + 2));
+  pred_reduce_rows_kernel<<<ceil_div((2 * C + 2) * 32, 256), 256, 0, st>>>(part, dw, db, C, n_part);
+  return check_launch("pred_reduce_rows_kernel");
 }
 
 int launch_pred_reduce_planes(const float* part, float* dw, float* db, int C, int n_part, cudaStream_t st) {
