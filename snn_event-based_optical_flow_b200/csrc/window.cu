@@ -64,8 +64,8 @@ static WinLayout win_layout(const snnflow_net_desc* d, int save) {
 }
 
 struct WinPlan {   // tile plans of the tensor-core kernels for this shape
-  int R_ff, S_ff, R_head, S_head, R_rec, S_rec, R_dg, S_dg, R_rb, S_rb;
-  uint32_t sub_ff, cs_ff, st_ff, sub_head, cs_head, st_head, sub_rec, cs_rec, st_rec, sub_dg, cs_dg, st_dg, sub_rb, cs_rb, st_rb;
+  int R_ff, S_ff, R_head, S_head, R_rec, S_rec, R_dg, S_dg, R_rb, S_rb, R_dp, S_dp;
+  uint32_t sub_ff, cs_ff, st_ff, sub_head, cs_head, st_head, sub_rec, cs_rec, st_rec, sub_dg, cs_dg, st_dg, sub_rb, cs_rb, st_rb, sub_dp, cs_dp, st_dp;
   bool ok, rb_prefetch;
 };
 
@@ -102,6 +102,10 @@ static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool back
   }
   P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, 2, true, &P.R_dg, &P.S_dg, &P.sub_dg,
                          &P.cs_dg, &P.st_dg);
+  // data gradient fused with the time-fused pointwise chain of the layer below (state in registers: short tiles)
+  P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), true, 2, false, &P.R_dp, &P.S_dp, &P.sub_dp,
+                         &P.cs_dp, &P.st_dp, wt_env_int("SNNFLOW_DP_R", 0));
+  if (P.ok && P.R_dp * ceil_div(d->W, 128) > 2) P.ok = false;   // the fused kernel is instantiated for 1 or 2 segments per item
   return P;
 }
 
@@ -122,8 +126,8 @@ static bool win_supported(const snnflow_net_desc* d, bool backward = true) {
 }
 
 struct WinWorkspace {
-  size_t off_g[2], off_gp, gp_term_stride, off_gv, off_wpart[2], off_cpart, off_ppart, total;
-  int wg_grid_max, rb_grid, pw_parts, pred_parts;
+  size_t off_g[2], off_gp[2], gp_term_stride, off_gv, off_wpart[2], off_cpart, off_ppart, total;
+  int wg_grid_max, rb_grid, dp_grid, pw_parts, pred_parts;
 };
 
 static WinWorkspace win_workspace(const snnflow_net_desc* d, const WinLayout& L, const WinPlan& P) {
@@ -134,7 +138,8 @@ static WinWorkspace win_workspace(const snnflow_net_desc* d, const WinLayout& L,
   W.off_g[0] = take((size_t)T * L.n * sizeof(float));
   W.off_g[1] = take((size_t)T * L.n * sizeof(float));
   W.gp_term_stride = align_up((size_t)T * B * L.zp_img_stride, 256);
-  W.off_gp = take(2 * W.gp_term_stride);
+  W.off_gp[0] = take(2 * W.gp_term_stride);   // g_I planes (hi | lo) of even layers ...
+  W.off_gp[1] = take(2 * W.gp_term_stride);   // ... and of odd layers: a layer's planes are read while the next ones are written
   W.off_gv = take(L.n * sizeof(float));
   W.wg_grid_max = 0;
   for (int l = 0; l < WIN_LAYERS; ++l) {
@@ -145,8 +150,11 @@ static WinWorkspace win_workspace(const snnflow_net_desc* d, const WinLayout& L,
   W.off_wpart[1] = take((size_t)W.wg_grid_max * 9 * C * C * sizeof(float));
   W.rb_grid = P.R_rb ? wt_grid(B * (d->H / P.R_rb)) : 0;
   W.pw_parts = B * ceil_div(d->H * d->W, 256);
-  const size_t c1 = (size_t)2 * C * W.pw_parts, c2 = (size_t)T * W.rb_grid * 2 * C;
-  W.off_cpart = take((c1 > c2 ? c1 : c2) * sizeof(float));
+  W.dp_grid = wt_grid(B * (d->H / P.R_dp));
+  size_t c1 = (size_t)2 * C * W.pw_parts;
+  const size_t c2 = (size_t)T * W.rb_grid * 2 * C, c3 = (size_t)W.dp_grid * 2 * C;
+  c1 = c1 > c2 ? c1 : c2;
+  W.off_cpart = take((c1 > c3 ? c1 : c3) * sizeof(float));
   W.pred_parts = pred_planes_parts(T * B, d->H, d->W);
   const int pp = W.pred_parts > W.pw_parts ? W.pred_parts : W.pw_parts;
   W.off_ppart = take((size_t)pp * (2 * C + 2) * sizeof(float));
@@ -300,36 +308,37 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
   const int C = d->C, T = d->T, B = d->B, H = d->H, W = d->W;
   const size_t n = L.n;
   const double px = (double)B * H * W;
-  float* gbuf[2] = {(float*)(Wk + WS.off_g[0]), (float*)(Wk + WS.off_g[1])};
-  unsigned char* gp = Wk + WS.off_gp;
+  float* gbuf = (float*)(Wk + WS.off_g[0]);   // spike gradient of a recurrent layer (from the layer above), c8
+  unsigned char* gplanes[2] = {Wk + WS.off_gp[0], Wk + WS.off_gp[1]};   // g_I planes of layer l live in gplanes[l & 1]
   float* g_v = (float*)(Wk + WS.off_gv);
   float* wpart[2] = {(float*)(Wk + WS.off_wpart[0]), (float*)(Wk + WS.off_wpart[1])};
   float* cpart = (float*)(Wk + WS.off_cpart);
   float* ppart = (float*)(Wk + WS.off_ppart);
   const int hard = (d->flags & SNNFLOW_HARD_RESET) ? 1 : 0;
-
   const int top = WIN_LAYERS - 1;
-  int cur = 0;
   int rc = SNNFLOW_OK;
   // A feed-forward top layer takes its spike gradient straight from the flow head inside its time-fused pointwise
   // kernel (no [T*B,C,H,W] gradient tensor is written or read); a recurrent top layer goes through the head's own kernel.
   const bool fuse_head = !L.rec[top];
   if (!fuse_head) {
-    rc = launch_pred_bwd_planes(A + L.off_zp[top] + (size_t)B * L.zp_img_stride, L.zp_img_stride, pred_w, flow, g_flow, gbuf[cur], ppart,
-                                T * B, C, H, W, st);
+    rc = launch_pred_bwd_planes(A + L.off_zp[top] + (size_t)B * L.zp_img_stride, L.zp_img_stride, pred_w, flow, g_flow, gbuf, ppart, T * B,
+                                C, H, W, st);
     if (rc) return rc;
     rc = launch_pred_reduce_planes(ppart, d_pred_w, d_pred_b, C, WS.pred_parts, st);
     if (rc) return rc;
   }
-
+  // Per layer, top down:  (1) its g_I planes - recurrent: one fused conv^T(W_rec) + pointwise launch per bin; feed-forward:
+  // already produced by step (3) of the layer above (top layer: its own time-fused pointwise kernel);  (2) weight gradient
+  // over all T*B images + reductions;  (3) data gradient through W_ff for the layer below - fused with that layer's
+  // time-fused pointwise chain when it is feed-forward, a plain launch into the c8 gradient buffer when it is recurrent.
+  int n_cpart = 0, cpart_layout = 0;   // d lam / d theta partials of the CURRENT layer
   for (int l = top; l >= 0; --l) {
     const snnflow_layer_ptrs& P_ = layers[l];
     const float* v_init = (state_in && state_in[l]) ? (const float*)(A + L.off_init[l]) : nullptr;   // forward's copy
     const float* z_init = v_init ? v_init + n : nullptr;
     const float* vbase = (const float*)(A + L.off_v[l]);
     const float* par = (const float*)(A + L.off_par[l]);
-    const float* g_out = gbuf[cur];
-    int n_cpart, cpart_layout;
+    unsigned char* gp = gplanes[l & 1];
     if (L.rec[l]) {
       WtArgs a{};
       // hi planes x (w_hi, w_lo), then lo planes x w_hi: two pipeline units per tile
@@ -347,7 +356,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
         a.has_gz = t < T - 1; a.first_step = t == T - 1;
         a.src[0].planes = gp + (size_t)(t + 1) * B * L.zp_img_stride;
         a.src[1].planes = a.src[0].planes + WS.gp_term_stride;
-        a.g_out = g_out + (size_t)t * n; a.v_t = vbase + (size_t)t * n;
+        a.g_out = gbuf + (size_t)t * n; a.v_t = vbase + (size_t)t * n;
         a.v_in = t > 0 ? vbase + (size_t)(t - 1) * n : v_init;
         a.v_in_nchw = t == 0;
         a.z_from_v = t > 0; a.z_init = z_init;
@@ -357,36 +366,23 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
         if (rc) return rc;
       }
       n_cpart = T * WS.rb_grid; cpart_layout = 1;
-    } else {
+    } else if (l == top) {
       PwSeqArgs a{};
-      a.v = vbase; a.g_out = (l == top && fuse_head) ? nullptr : g_out; a.v_init = v_init; a.z_init = z_init; a.par = par;
+      a.v = vbase; a.g_out = fuse_head ? nullptr : gbuf; a.v_init = v_init; a.z_init = z_init; a.par = par;
       a.flow = flow; a.g_flow = g_flow; a.pred_w = pred_w; a.pred_part = ppart;
       a.gp = gp; a.gp_img_stride = L.zp_img_stride; a.gp_term_stride = WS.gp_term_stride;
       a.part = cpart; a.T = T; a.B = B; a.C = C; a.H = H; a.W = W; a.hard_reset = hard; a.surrogate = d->surrogate;
       a.n_part = WS.pw_parts; a.width = d->act_width;
       rc = launch_pw_seq(a, st);
       if (rc) return rc;
-      if (l == top && fuse_head) {
+      if (fuse_head) {
         rc = launch_pred_reduce_rows(ppart, d_pred_w, d_pred_b, C, WS.pw_parts, st);
         if (rc) return rc;
       }
       n_cpart = WS.pw_parts; cpart_layout = 0;
-    }
-    // data gradient through W_ff: the spike gradient of the layer below, all T*B images at once
-    if (l > 0) {
-      WtArgs a{};
-      a.src[0].planes = gp; a.src[0].img_stride = L.zp_img_stride; a.src[0].n_chunks = (uint32_t)(C / 8);
-      a.src[0].w_off = 0; a.src[0].w_terms = 2; a.src[0].w_used = 2;
-      a.src[1] = a.src[0]; a.src[1].planes = gp + WS.gp_term_stride; a.src[1].w_used = 1;
-      a.n_src = 2;
-      a.wblob = A + L.off_dg_blob[l]; a.wblob_bytes = L.dg_blob_bytes[l];
-      a.n_outer = T * B; a.T = 1; a.B = B; a.H = H; a.W = W; a.Wp = W + 2; a.n_seg = ceil_div(W, 128); a.N = L.Kin[l];
-      a.R = P.R_dg; a.S = P.S_dg; a.sub_bytes = P.sub_dg; a.chunk_stride = P.cs_dg; a.stage_bytes = P.st_dg;
-      a.g_x = gbuf[cur ^ 1];
-      rc = launch_wt_dgrad(a, st, 4.0 * T * px * (C + L.Kin[l]), 18.0 * T * px * C * L.Kin[l]);
-      if (rc) return rc;
-    }
-    // weight gradients over all T*B images, then the fixed-order reduction into the caller's accumulators
+    }   // else: planes and partials of this feed-forward layer were produced by step (3) of layer l + 1
+
+    // (2) weight gradients over all T*B images, then the fixed-order reduction into the caller's accumulators
     {
       WgArgs a{};
       if (l == 0) { a.xp[0] = A + L.off_inplanes; a.x_img_stride[0] = 2 * L.g.plane_bytes; }
@@ -413,7 +409,38 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
       rc = launch_win_reduce(r, st);
       if (rc) return rc;
     }
-    if (l > 0) cur ^= 1;
+
+    // (3) data gradient through W_ff: the spike gradient of the layer below
+    if (l > 0) {
+      WtArgs a{};
+      a.src[0].planes = gp; a.src[0].img_stride = L.zp_img_stride; a.src[0].n_chunks = (uint32_t)(C / 8);
+      a.src[0].w_off = 0; a.src[0].w_terms = 2; a.src[0].w_used = 2;
+      a.src[1] = a.src[0]; a.src[1].planes = gp + WS.gp_term_stride; a.src[1].w_used = 1;
+      a.n_src = 2;
+      a.wblob = A + L.off_dg_blob[l]; a.wblob_bytes = L.dg_blob_bytes[l];
+      a.B = B; a.H = H; a.W = W; a.Wp = W + 2; a.n_seg = ceil_div(W, 128); a.N = L.Kin[l];
+      if (!L.rec[l - 1]) {
+        // ... fused with the time-fused pointwise chain of the feed-forward layer below (writes ITS g_I planes and partials)
+        const float* v_init_b = (state_in && state_in[l - 1]) ? (const float*)(A + L.off_init[l - 1]) : nullptr;
+        a.n_outer = B; a.T = T; a.t_reverse = 1;
+        a.R = P.R_dp; a.S = P.S_dp; a.sub_bytes = P.sub_dp; a.chunk_stride = P.cs_dp; a.stage_bytes = P.st_dp;
+        a.hard_reset = hard; a.surrogate = d->surrogate; a.width = d->act_width;
+        a.par = (const float*)(A + L.off_par[l - 1]);
+        a.v_t = (const float*)(A + L.off_v[l - 1]);
+        a.v_init = v_init_b; a.z_init = v_init_b ? v_init_b + n : nullptr;
+        a.gp_out = gplanes[(l - 1) & 1]; a.gp_img_stride = L.zp_img_stride; a.gp_term_stride = WS.gp_term_stride;
+        a.part = cpart;
+        rc = launch_wt_dgpw(a, st, 4.0 * T * px * (C + 3 * L.Kin[l]) /* g_I in ; v (x2), g_I out */, 18.0 * T * px * C * L.Kin[l]);
+        if (rc) return rc;
+        n_cpart = WS.dp_grid; cpart_layout = 1;
+      } else {
+        a.n_outer = T * B; a.T = 1;
+        a.R = P.R_dg; a.S = P.S_dg; a.sub_bytes = P.sub_dg; a.chunk_stride = P.cs_dg; a.stage_bytes = P.st_dg;
+        a.g_x = gbuf;
+        rc = launch_wt_dgrad(a, st, 4.0 * T * px * (C + L.Kin[l]), 18.0 * T * px * C * L.Kin[l]);
+        if (rc) return rc;
+      }
+    }
   }
   return SNNFLOW_OK;
 }

@@ -69,6 +69,7 @@ struct WtArgs {
   unsigned char* gp_out;          // g_I planes of this step (hi ; lo at + gp_term_stride)
   unsigned long long gp_img_stride, gp_term_stride;
   float* part;                    // [grid][2][N] partial sums of dlam, dtheta
+  int t_reverse;                  // sequence mode: walk the bins backwards (t = T-1 .. 0)
   int prefetch;                   // epilogue inputs prefetched through shared memory (when the slots fit)
   int has_gz, first_step, z_from_v;   // first_step: g_v starts at zero ; z_from_v: z_in = spike(v_in) else from z_init
   long long* dbg;                 // optional [grid][8] cycle counters (SNNFLOW_WT_TIMING=1): where each role waits
@@ -77,6 +78,8 @@ struct WtArgs {
 int launch_wt_fwd(const WtArgs& a, bool seq, cudaStream_t st, const char* prof_name, double bytes, double flops);
 int launch_wt_dgrad(const WtArgs& a, cudaStream_t st, double bytes, double flops);
 int launch_wt_recbwd(const WtArgs& a, cudaStream_t st, double bytes, double flops);
+// data gradient of layer l+1 fused with the time-fused pointwise BPTT of the feed-forward layer l below it
+int launch_wt_dgpw(const WtArgs& a, cudaStream_t st, double bytes, double flops);
 // picks rows-per-tile / stages for the given shapes; returns false when the shape does not fit
 bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int w_terms, bool tall, int* R, int* S,
              uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes, int only_R = 0);

@@ -165,6 +165,7 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
   const int n_items = wt_n_items<SEQ>(a), n_src = a.n_src, S = a.S;
   const size_t plane_bytes = (size_t)(a.H + 2) * a.Wp * 16, row_bytes = (size_t)a.Wp * 16;
   const uint32_t sub_bytes = a.sub_bytes, chunk_stride = a.chunk_stride, stage_bytes = a.stage_bytes;
+  const bool t_rev = a.t_reverse != 0;
   // this lane's chunk of either source
   const unsigned char* base[2];
   size_t img_stride[2];
@@ -194,9 +195,11 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
         mbar_expect_tx(&s.full[st], n_chunks[si] * sub_bytes);
       }
       __syncwarp();
-      if ((uint32_t)lane < n_chunks[si])
+      if ((uint32_t)lane < n_chunks[si]) {
+        const int img = (SEQ && t_rev) ? (it.T - 1 - it.t) * it.B + it.b : it.img;
         tma_bulk_g2s(s.stages + (size_t)st * stage_bytes + (size_t)lane * chunk_stride,
-                     base[si] + (size_t)it.img * img_stride[si] + (size_t)it.y0 * row_bytes, sub_bytes, &s.full[st]);
+                     base[si] + (size_t)img * img_stride[si] + (size_t)it.y0 * row_bytes, sub_bytes, &s.full[st]);
+      }
       if (++st == (uint32_t)S) { st = 0; ++use; }
     }
     it.next();
@@ -755,6 +758,149 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
 }
 
 // =================================================================================================
+// Data gradient of layer l+1 fused with the time-fused pointwise BPTT of the feed-forward layer l below it.
+// A CTA owns a row tile for ALL T bins and walks them backwards (t = T-1 .. 0):
+//   MMA      : g_out[t] = conv^T(g_I^{l+1}[t], W_ff^{l+1})                     (hi planes x [w_hi | w_lo], lo planes x w_hi)
+//   epilogue : gs = g_out * sg(v[t] - theta);  gv = carry + gs;  g_I^{l}[t] = gv * (1 - lam)  -> bf16 hi/lo planes
+//              carry = gv * lam * (1 - z_in)  (hard reset) / gv * lam  (soft)  stays in registers across the bins,
+//              d lam / d theta partial sums as in pw_seq_kernel.
+// The spike gradient g_out of layer l ([T*B,C,H,W] fp32) is never written to or read from memory.
+// =================================================================================================
+template <int SG, bool HARD, int NSEG>
+__global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_constant__ WtArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const WtSmem s = wt_smem(smem, a.wblob_bytes);
+  const uint32_t tmem_base = wt_prologue(a, s);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == WT_EPI_WARPS) {
+    wt_producer<true>(a, s);
+    __syncwarp();
+  } else if (warp == WT_EPI_WARPS + 1) {
+    if (elect_one()) wt_mma<true>(a, s, tmem_base);
+    __syncwarp();
+  } else {
+    pdl_wait();
+    const int q = warp & 3, ch = warp >> 2;
+    const int W = a.W, Wp = a.Wp, N = a.N, nch = N >> 3, n_seg = a.n_seg, T = a.T, B = a.B;
+    const bool act = ch * 8 < N;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    const size_t HW = (size_t)a.H * W;
+    const size_t plane_bytes = (size_t)(a.H + 2) * Wp * 16;
+    const uint32_t ncat = 2u * (uint32_t)N, acc_cols = (uint32_t)NSEG * ncat;
+    const int n_items = wt_n_items<true>(a);
+    const float width = a.width;
+    const float* const v = a.v_t;          // membranes of layer l, all bins (c8)
+    unsigned char* const gp_out = a.gp_out + (size_t)ch * plane_bytes;
+    const size_t gp_img_stride = a.gp_img_stride, gp_term_stride = a.gp_term_stride;
+    const float4* par = s.par + (act ? ch * 8 : 0);
+    float s_lam[8], s_th[8], carry[NSEG][8], v_cur[NSEG][8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s_lam[c] = s_th[c] = 0.f;
+    ItemIter<true> it;
+    it.init(a);
+    for (int k = 0; k < n_items; ++k, it.next()) {
+      const uint32_t ab = (uint32_t)k & 1u;
+      const int t = T - 1 - it.t;            // bins are walked backwards
+      const int img = t * B + it.b;
+      // this bin's inputs of the epilogue: v[t-1] (or the window-initial state); v[t] is carried from the previous item
+      float vin[NSEG][8], zin[NSEG][8];
+#pragma unroll
+      for (int m = 0; m < NSEG; ++m) {
+        const int y = it.y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
+        const bool ok = act && x < W;
+        const size_t pix = (size_t)y * W + x;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) vin[m][c] = zin[m][c] = 0.f;
+        if (it.t == 0) {   // first item of a tile: last bin of the window
+#pragma unroll
+          for (int c = 0; c < 8; ++c) carry[m][c] = v_cur[m][c] = 0.f;
+          if (ok) ld8_c8(v + c8_off(img, nch, ch, HW, pix), v_cur[m]);
+        }
+        if (ok) {
+          if (t > 0) {
+            ld8_c8(v + c8_off(img - B, nch, ch, HW, pix), vin[m]);
+          } else {
+            const size_t o = ((size_t)(it.b * N + ch * 8)) * HW + pix;   // NCHW state tensors of the caller
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              vin[m][c] = a.v_init ? __ldg(a.v_init + o + (size_t)c * HW) : 0.f;
+              zin[m][c] = a.z_init ? __ldg(a.z_init + o + (size_t)c * HW) : 0.f;
+            }
+          }
+        }
+      }
+      mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
+      tc_fence_after();
+      if (act) {
+        uint32_t u0[NSEG][8], u1[NSEG][8];
+#pragma unroll
+        for (int m = 0; m < NSEG; ++m) {
+          const uint32_t tcol = tmem_base + t_lane + ab * acc_cols + (uint32_t)m * ncat + (uint32_t)(ch * 8);
+          tmem_ld8_async(tcol, u0[m]);
+          tmem_ld8_async(tcol + (uint32_t)N, u1[m]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int m = 0; m < NSEG; ++m) {
+          const int y = it.y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
+          const bool ok = x < W;
+          uint32_t hi[4], lo[4];
+          float gI[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 pr = par[c];
+            const float go = ok ? __uint_as_float(u0[m][c]) + __uint_as_float(u1[m][c]) : 0.f;   // mask out-of-row garbage
+            const float z_in = t > 0 ? ((__fsub_rn(vin[m][c], pr.z) > 0.f) ? 1.f : 0.f) : zin[m][c];
+            const float gs = go * surrogate_fast<SG>(v_cur[m][c] - pr.z, width);
+            const float gv = carry[m][c] + gs;
+            gI[c] = gv * pr.y;
+            if (HARD) {
+              const float omz = 1.0f - z_in;
+              carry[m][c] = gv * pr.x * omz;
+              s_lam[c] += gv * (vin[m][c] * omz - v_cur[m][c]);
+              s_th[c] -= gs;
+            } else {
+              carry[m][c] = gv * pr.x;
+              s_lam[c] += gv * (vin[m][c] - v_cur[m][c] - z_in * pr.z);
+              s_th[c] -= gs + gv * z_in;
+            }
+            v_cur[m][c] = vin[m][c];
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) split_bf16_pair(gI[2 * c], gI[2 * c + 1], hi[c], lo[c]);
+          if (ok) {
+            unsigned char* gp = gp_out + (size_t)img * gp_img_stride + ((size_t)(y + 1) * Wp + x + 1) * 16;
+            *reinterpret_cast<uint4*>(gp) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(gp + gp_term_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&s.acc_empty[ab]);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float l = warp_sum(s_lam[c] * par[c].w), t = warp_sum(s_th[c]);
+      if (lane == 0) {
+        s.red[(warp * 2 + 0) * 8 + c] = l;
+        s.red[(warp * 2 + 1) * 8 + c] = t;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 2 * a.N) {
+    const int which = tid / a.N, co = tid % a.N;
+    const int ch = co >> 3, c = co & 7;
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) t += s.red[((ch * 4 + q) * 2 + which) * 8 + c];
+    a.part[(size_t)blockIdx.x * 2 * a.N + tid] = t;
+  }
+  if (warp == 0) tmem_dealloc(tmem_base, wt_tmem_cols(a));
+}
+
+// =================================================================================================
 // host side
 // =================================================================================================
 static int env_int(const char* name, int dflt) {
@@ -867,6 +1013,19 @@ int launch_wt_fwd(const WtArgs& a, bool seq, cudaStream_t st, const char* prof_n
 int launch_wt_dgrad(const WtArgs& a, cudaStream_t st, double bytes, double flops) {
   prof_begin("win_dgrad", st, bytes, flops);
   return wt_launch(wt_dgrad_kernel, (const void*)wt_dgrad_kernel, a, st, "wt_dgrad_kernel");
+}
+
+int launch_wt_dgpw(const WtArgs& a, cudaStream_t st, double bytes, double flops) {
+  prof_begin("win_dgrad_pw", st, bytes, flops);
+  const int nseg = a.R * a.n_seg;
+#define WT_DP_CASE(SGV, HARDV, NS) \
+  if (a.surrogate == SGV && (a.hard_reset != 0) == HARDV && nseg == NS) \
+    return wt_launch(wt_dgpw_kernel<SGV, HARDV, NS>, (const void*)wt_dgpw_kernel<SGV, HARDV, NS>, a, st, "wt_dgpw_kernel");
+  WT_DP_CASE(0, true, 1) WT_DP_CASE(0, false, 1) WT_DP_CASE(1, true, 1) WT_DP_CASE(1, false, 1) WT_DP_CASE(2, true, 1) WT_DP_CASE(2, false, 1)
+  WT_DP_CASE(0, true, 2) WT_DP_CASE(0, false, 2) WT_DP_CASE(1, true, 2) WT_DP_CASE(1, false, 2) WT_DP_CASE(2, true, 2) WT_DP_CASE(2, false, 2)
+#undef WT_DP_CASE
+  set_error("launch_wt_dgpw: no kernel for surrogate %d / %d accumulator tiles", a.surrogate, nseg);
+  return SNNFLOW_EINVAL;
 }
 
 int launch_wt_recbwd(const WtArgs& a, cudaStream_t st, double bytes, double flops) {
