@@ -292,26 +292,35 @@ def run_ours(a):
     # ---- end-to-end timing from pinned host buffers ----
     # every step's window is copied from pinned host memory inside the timed region; with the graph the copy of window
     # i+1 is issued on a side stream before the loss of window i is read back, so it overlaps window i's compute
-    for i in range(2):
-        step_e2e(i)
-    barrier()
-    ev0.record()
-    if not a.no_graph:
-        tw.prefetch(host_pool[0])
-        for i in range(a.steps):
-            loss_t = tw.step_graphed(host_pool[i % len(host_pool)])
-            if i + 1 < a.steps:
-                tw.prefetch(host_pool[(i + 1) % len(host_pool)])
-            last_loss = float(loss_t.item())         # D2H of the loss, synchronises
-    else:
-        for i in range(a.steps):
-            last_loss = step_e2e(i)
-    ev1.record()
-    barrier()
-    ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = a.batch * world * a.steps / (float(ms2.item()) / 1e3)
+    def e2e_pass(n_steps):
+        last = None
+        if not a.no_graph:
+            tw.prefetch(host_pool[0])
+            for i in range(n_steps):
+                loss_t = tw.step_graphed(host_pool[i % len(host_pool)])
+                if i + 1 < n_steps:
+                    tw.prefetch(host_pool[(i + 1) % len(host_pool)])
+                last = float(loss_t.item())         # D2H of the loss, synchronises
+        else:
+            for i in range(n_steps):
+                last = step_e2e(i)
+        return last
+
+    e2e_pass(3)   # warm the same path (side stream, pinned staging) outside the timed region
+    # The host drives every step here (copy, replay, read-back), so one descheduling of the Python thread shows up as
+    # a 2x outlier over K short steps: the K-step region is timed three times and the MEDIAN is reported (all three listed).
+    e2e_runs = []
+    for rep in range(3):
+        barrier()
+        ev0.record()
+        last_loss = e2e_pass(a.steps)
+        ev1.record()
+        barrier()
+        ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        e2e_runs.append(a.batch * world * a.steps / (float(ms2.item()) / 1e3))
+    e2e_value = sorted(e2e_runs)[1]
 
     # ---- per-kernel profile of two steps (live CUDA events on the launching stream) ----
     # every rank runs the two steps (they contain the gradient all-reduce); only rank 0 records and reports
@@ -377,7 +386,8 @@ def run_ours(a):
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "runs": [round(v, 1) for v in e2e_runs], "stat": "median of 3 timed K-step regions"},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "eval": eval_info,
             "encode_iwe_microbench": micro,

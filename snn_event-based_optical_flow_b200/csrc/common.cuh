@@ -59,6 +59,19 @@ bool pdl_enabled();
 // Kernels launched through launch_pdl() may begin while the previous grid is still retiring; they call pdl_wait()
 // before their first access to global memory the previous launches wrote (it returns once those grids have completed and
 // flushed), and pdl_launch_dependents() as early as possible.  Both are no-ops for a normal launch.
+// 256-bit global loads / stores (sm_100): eight fp32 of one pixel in the c8 layout = one 32-byte sector per lane.
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void stg256(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+               :: "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(p)
+               : "memory");
+}
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 
@@ -75,6 +88,54 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// Cooperative launch: every CTA of the grid is resident at once (the launch fails otherwise), which is what the grid
+// barrier of the persistent multi-bin kernels relies on.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_coop(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// ---- grid barrier of the persistent multi-bin kernels (one counter, zeroed by the launcher) --------------------------
+// arrive: called by ONE thread of a CTA after a CTA-level barrier over the threads whose global writes must be published.
+__device__ __forceinline__ void grid_bar_arrive(unsigned int* bar) {
+  __threadfence();
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+}
+// wait until `target` arrivals; traps instead of hanging the device if a CTA never arrives
+__device__ __forceinline__ void grid_bar_wait(const unsigned int* bar, unsigned int target) {
+  const long long t0 = clock64();
+  while (true) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    if (v >= target) break;
+    __nanosleep(40);
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// coherent 256-bit load (data written earlier by this same launch)
+__device__ __forceinline__ void ldg256_coherent(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p) : "memory");
+}
+
+__device__ __forceinline__ uint4 ldg128_coherent(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
 }
 
 // ---- device helpers -------------------------------------------------------------------------

@@ -47,9 +47,9 @@ __device__ __forceinline__ WtSmem wt_smem(unsigned char* smem, uint32_t wblob_by
   s.full = reinterpret_cast<uint64_t*>(smem);
   s.empty = s.full + WT_MAX_STAGES;
   s.acc_full = s.empty + WT_MAX_STAGES;
-  s.acc_empty = s.acc_full + 2;
-  s.wbar = s.acc_empty + 2;
-  s.tmem_slot = reinterpret_cast<uint32_t*>(smem + 128);
+  s.acc_empty = s.acc_full + 4;
+  s.wbar = s.acc_empty + 4;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(smem + 192);
   s.par = reinterpret_cast<float4*>(smem + 256);
   s.red = reinterpret_cast<float*>(smem + 1280);
   s.w = smem + WT_HDR;
@@ -120,7 +120,7 @@ struct ItemIter {
 };
 
 __device__ __forceinline__ uint32_t wt_tmem_cols(const WtArgs& a) {
-  const uint32_t need = 2u * (uint32_t)(a.R * a.n_seg * a.N) * a.src[0].w_terms;
+  const uint32_t need = ((uint32_t)(a.R * a.n_seg * a.N) * a.src[0].w_terms) << a.acc_lg;
   uint32_t c = 32;
   while (c < need) c <<= 1;
   return c;
@@ -136,7 +136,7 @@ __device__ __forceinline__ uint32_t wt_prologue(const WtArgs& a, const WtSmem& s
       mbar_init(&s.full[i], 1);
       mbar_init(&s.empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&s.acc_full[i], 1);
       mbar_init(&s.acc_empty[i], WT_EPI_WARPS * 32);
     }
@@ -178,31 +178,42 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
     n_chunks[si] = Sr.n_chunks;
   }
   ItemIter<SEQ> it;
-  it.init(a);
   uint32_t st = 0, use = 0;
   long long t_wait = 0;
   const long long t_begin = clock64();
-  for (int k = 0; k < n_items; ++k) {
+  const int n_bins = (!SEQ && a.n_bins > 1) ? a.n_bins : 1, dep_mask = a.bin_dep_mask;
+  for (int bin = 0; bin < n_bins; ++bin) {
+    it.init(a);
+    bool synced = bin == 0;
+    for (int k = 0; k < n_items; ++k) {
 #pragma unroll
-    for (int si = 0; si < 2; ++si) {
-      if (si >= n_src) break;
-      if (lane == 0) {
-        if (use > 0) {
-          const long long t0 = clock64();
-          mbar_wait(&s.empty[st], (use - 1) & 1);
-          t_wait += clock64() - t0;
+      for (int si = 0; si < 2; ++si) {
+        if (si >= n_src) break;
+        if (!synced && ((dep_mask >> si) & 1)) {   // planes written by every CTA's epilogue of the previous bin
+          if (lane == 0) grid_bar_wait(a.grid_bar, (unsigned int)bin * gridDim.x);
+          __syncwarp();
+          fence_proxy_async_global();
+          synced = true;
         }
-        mbar_expect_tx(&s.full[st], n_chunks[si] * sub_bytes);
+        if (lane == 0) {
+          if (use > 0) {
+            const long long t0 = clock64();
+            mbar_wait(&s.empty[st], (use - 1) & 1);
+            t_wait += clock64() - t0;
+          }
+          mbar_expect_tx(&s.full[st], n_chunks[si] * sub_bytes);
+        }
+        __syncwarp();
+        if ((uint32_t)lane < n_chunks[si]) {
+          const int img = (SEQ && t_rev) ? (it.T - 1 - it.t) * it.B + it.b : it.img;
+          tma_bulk_g2s(s.stages + (size_t)st * stage_bytes + (size_t)lane * chunk_stride,
+                       base[si] + (long long)bin * a.bin_src_stride[si] + (size_t)img * img_stride[si] + (size_t)it.y0 * row_bytes,
+                       sub_bytes, &s.full[st]);
+        }
+        if (++st == (uint32_t)S) { st = 0; ++use; }
       }
-      __syncwarp();
-      if ((uint32_t)lane < n_chunks[si]) {
-        const int img = (SEQ && t_rev) ? (it.T - 1 - it.t) * it.B + it.b : it.img;
-        tma_bulk_g2s(s.stages + (size_t)st * stage_bytes + (size_t)lane * chunk_stride,
-                     base[si] + (size_t)img * img_stride[si] + (size_t)it.y0 * row_bytes, sub_bytes, &s.full[st]);
-      }
-      if (++st == (uint32_t)S) { st = 0; ++use; }
+      it.next();
     }
-    it.next();
   }
   if (a.dbg && lane == 0) {
     a.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;   // producer: total
@@ -213,7 +224,7 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
 // ---- MMA issuer: one thread ----------------------------------------------------------------------------------
 template <bool SEQ>
 __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
-  const int n_items = wt_n_items<SEQ>(a);
+  const int n_items = wt_n_items<SEQ>(a) * ((!SEQ && a.n_bins > 1) ? a.n_bins : 1);
   if (n_items == 0) return;
   mbar_wait(s.wbar, 0);
   const int n_mt = a.R * a.n_seg;
@@ -242,14 +253,14 @@ __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
       for (int kk = 0; kk < 2; ++kk) bdesc[si][tap][kk] = b_lo_c | (w16 + (S.w_off >> 4) + (uint32_t)tap * tile16 + 2u * kk * blbo16);
   }
   uint32_t st = 0, use = 0;
-  const uint32_t n_stages = (uint32_t)a.S;
+  const uint32_t n_stages = (uint32_t)a.S, acc_lg = a.acc_lg, acc_mask = (1u << acc_lg) - 1u;
   long long t_full = 0, t_acc = 0;
   const long long t_begin = clock64();
   for (int k = 0; k < n_items; ++k) {
-    const uint32_t ab = (uint32_t)k & 1u;
-    if (k >= 2) {
+    const uint32_t ab = (uint32_t)k & acc_mask;
+    if (k > (int)acc_mask) {
       const long long t0 = clock64();
-      mbar_wait(&s.acc_empty[ab], (uint32_t)((k >> 1) - 1) & 1u);
+      mbar_wait(&s.acc_empty[ab], (uint32_t)((k >> acc_lg) - 1) & 1u);
       t_acc += clock64() - t0;
     }
     tc_fence_after();
@@ -299,12 +310,10 @@ __device__ __forceinline__ size_t c8_off(int img, int n_chunks, int chunk, size_
   return (((size_t)img * n_chunks + chunk) * HW + pix) * 8;
 }
 __device__ __forceinline__ void ld8_c8(const float* p, float (&v)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  ldg256(p, v);   // one 32-byte sector per lane, one instruction
 }
 __device__ __forceinline__ void st8_c8(float* p, const float (&v)[8]) {
-  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  stg256(p, v);
 }
 __device__ __forceinline__ uint32_t nz8_mask(const uint4& a) {   // bit c set when the c-th bf16 is non-zero
   uint32_t m = 0;
@@ -341,11 +350,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
     const size_t plane_bytes = (size_t)(a.H + 2) * Wp * 16;
     const uint32_t ncat = 3u * (uint32_t)N, acc_cols = (uint32_t)NSEG * ncat;   // three weight terms side by side
     const int n_items = wt_n_items<SEQ>(a);
-    float* const v_out = a.v_out;
     float* const cur_out = a.cur_out;
-    unsigned char* const zp_out = a.zp_out + (size_t)ch * plane_bytes;
     const size_t zp_img_stride = a.zp_img_stride;
-    const bool want_last = a.v_last != nullptr || a.z_last != nullptr;
     float lam[8], oml[8], th[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -355,10 +361,22 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
     float vst[NSEG][8], zst[NSEG][8];   // membrane and spikes of the previous bin (registers across the T bins)
     long long t_wait = 0;
     const long long t_begin = clock64();
+    const uint32_t acc_lg = a.acc_lg, acc_mask = (1u << acc_lg) - 1u;
     ItemIter<SEQ> it;
+    const int n_bins = (!SEQ && a.n_bins > 1) ? a.n_bins : 1;
+    const bool multi = n_bins > 1;
+    for (int bin = 0; bin < n_bins; ++bin) {
+    // per-bin views of the planes / membrane arena (bin 0 = the launch arguments)
+    float* const v_out = a.v_out ? a.v_out + (size_t)(bin & a.bin_v_mask) * a.bin_v_stride : nullptr;
+    const float* const v_prev = bin == 0 ? a.v_prev : a.v_out + (size_t)((bin - 1) & a.bin_v_mask) * a.bin_v_stride;
+    const bool v_prev_nchw = bin == 0 && a.v_prev_nchw;
+    unsigned char* const zp_out = a.zp_out + (long long)bin * a.bin_zp_stride + (size_t)ch * plane_bytes;
+    const unsigned char* const zin_planes = a.zin_planes ? a.zin_planes + (long long)bin * a.bin_zp_stride : nullptr;
+    const bool want_last = bin == n_bins - 1 && (a.v_last != nullptr || a.z_last != nullptr);
     it.init(a);
     for (int k = 0; k < n_items; ++k) {
-      const uint32_t ab = (uint32_t)k & 1u;
+      const int kg = bin * n_items + k;
+      const uint32_t ab = (uint32_t)kg & acc_mask;
       const bool load_state = SEQ ? (it.t == 0) : true;
       if (load_state && act) {
 #pragma unroll
@@ -379,17 +397,20 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
               for (int c = 0; c < 8; ++c) zst[m][c] = __ldg(a.z_init + o + (size_t)c * HW);   // {0, 1}: no dependent op before the wait
             }
           } else {
-            if (ok && a.v_prev) {
-              if (a.v_prev_nchw) {
+            if (ok && v_prev) {
+              if (v_prev_nchw) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) vst[m][c] = __ldg(a.v_prev + o + (size_t)c * HW);
+                for (int c = 0; c < 8; ++c) vst[m][c] = __ldg(v_prev + o + (size_t)c * HW);
+              } else if (multi) {
+                ldg256_coherent(v_prev + c8_off(it.b, nch, ch, HW, pix), vst[m]);   // written by this thread one bin ago
               } else {
-                ld8_c8(a.v_prev + c8_off(it.b, nch, ch, HW, pix), vst[m]);
+                ld8_c8(v_prev + c8_off(it.b, nch, ch, HW, pix), vst[m]);
               }
             }
-            if (ok && a.zin_planes) {
-              const uint4 zz = __ldg(reinterpret_cast<const uint4*>(a.zin_planes + (size_t)it.b * a.zin_img_stride + (size_t)ch * plane_bytes +
-                                                                   ((size_t)(y + 1) * Wp + x + 1) * 16));
+            if (ok && zin_planes) {
+              const uint4* zsrc = reinterpret_cast<const uint4*>(zin_planes + (size_t)it.b * a.zin_img_stride + (size_t)ch * plane_bytes +
+                                                                 ((size_t)(y + 1) * Wp + x + 1) * 16);
+              const uint4 zz = multi ? ldg128_coherent(zsrc) : __ldg(zsrc);
               const uint32_t w4[4] = {zz.x, zz.y, zz.z, zz.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -403,7 +424,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
       const bool last = (SEQ ? (it.t == T - 1) : true) && want_last;
       {
         const long long t0 = clock64();
-        mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
+        mbar_wait(&s.acc_full[ab], (uint32_t)(kg >> acc_lg) & 1u);
         t_wait += clock64() - t0;
       }
       tc_fence_after();
@@ -460,6 +481,12 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
       mbar_arrive(&s.acc_empty[ab]);
       it.next();
     }
+    if (bin + 1 < n_bins) {   // publish this CTA's spike planes of the bin to the other CTAs' producers
+      fence_proxy_async_global();
+      asm volatile("bar.sync 1, %0;" ::"n"(WT_EPI_WARPS * 32) : "memory");
+      if (tid == 0) grid_bar_arrive(a.grid_bar);
+    }
+    }
     if (a.dbg && tid == 0) {
       a.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin;   // epilogue warp 0: total
       a.dbg[blockIdx.x * 8 + 6] = t_wait;                 // ... waiting for the accumulator
@@ -497,13 +524,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgrad_kernel(const __grid_co
     float* const g_x = a.g_x;
     long long t_wait = 0;
     const long long t_begin = clock64();
+    const uint32_t acc_lg = a.acc_lg, acc_mask = (1u << acc_lg) - 1u;
     ItemIter<false> p;
     p.init(a);
     for (int k = 0; k < n_items; ++k, p.next()) {
-      const uint32_t ab = (uint32_t)k & 1u;
+      const uint32_t ab = (uint32_t)k & acc_mask;
       {
         const long long t0 = clock64();
-        mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
+        mbar_wait(&s.acc_full[ab], (uint32_t)(k >> acc_lg) & 1u);
         t_wait += clock64() - t0;
       }
       tc_fence_after();
@@ -630,6 +658,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
     };
     long long t_wait = 0;
     const long long t_begin = clock64();
+    const uint32_t acc_lg = a.acc_lg, acc_mask = (1u << acc_lg) - 1u;
     SegIter cur;
     cur.init(a);
     if (n_sub > 0) prefetch(cur, 0);
@@ -637,7 +666,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
       SegIter nxt = cur;
       nxt.next();
       const int b = cur.b, y = cur.y0 + cur.r, x = cur.seg * 128 + q * 32 + lane, m = cur.r * cur.n_seg + cur.seg, k = cur.k;
-      const uint32_t ab = (uint32_t)k & 1u;
+      const uint32_t ab = (uint32_t)k & acc_mask;
       const bool ok = x < W;
       const size_t pix = (size_t)y * W + x;
       const size_t co = c8_off(b, nch, ch, HW, pix);
@@ -677,7 +706,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
         if (has_gz) {
           if (m == 0) {
             const long long t0 = clock64();
-            mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
+            mbar_wait(&s.acc_full[ab], (uint32_t)(k >> acc_lg) & 1u);
             t_wait += clock64() - t0;
             tc_fence_after();
           }
@@ -722,7 +751,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
           *reinterpret_cast<uint4*>(gp + gp_term_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       } else if (has_gz && m == 0) {
-        mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);   // idle channel groups still follow the accumulator phases
+        mbar_wait(&s.acc_full[ab], (uint32_t)(k >> acc_lg) & 1u);   // idle channel groups still follow the accumulator phases
       }
       if (has_gz && m == n_mt - 1) {
         tc_fence_before();
@@ -793,16 +822,28 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
     unsigned char* const gp_out = a.gp_out + (size_t)ch * plane_bytes;
     const size_t gp_img_stride = a.gp_img_stride, gp_term_stride = a.gp_term_stride;
     const float4* par = s.par + (act ? ch * 8 : 0);
-    float s_lam[8], s_th[8], carry[NSEG][8], v_cur[NSEG][8];
+    float s_lam[8], s_th[8], carry[NSEG][8], v_cur[NSEG][8], vin_n[NSEG][8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) s_lam[c] = s_th[c] = 0.f;
+    long long t_wait = 0;
+    const long long t_begin = a.dbg ? clock64() : 0;
+    const uint32_t acc_lg = a.acc_lg, acc_mask = (1u << acc_lg) - 1u;
     ItemIter<true> it;
     it.init(a);
+#pragma unroll
+    for (int m = 0; m < NSEG; ++m) {   // v[T-2] of the first tile
+      const int y = it.y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) vin_n[m][c] = 0.f;
+      if (n_items > 0 && act && x < W && T > 1) ld8_c8(v + c8_off((T - 2) * B + it.b, nch, ch, HW, (size_t)y * W + x), vin_n[m]);
+    }
     for (int k = 0; k < n_items; ++k, it.next()) {
-      const uint32_t ab = (uint32_t)k & 1u;
+      const uint32_t ab = (uint32_t)k & acc_mask;
       const int t = T - 1 - it.t;            // bins are walked backwards
       const int img = t * B + it.b;
-      // this bin's inputs of the epilogue: v[t-1] (or the window-initial state); v[t] is carried from the previous item
+      // Inputs of this bin's epilogue: v[t-1] was requested while the previous item was in flight (vin_n); v[t] is carried
+      // from the previous item.  The rare loads (first item of a tile: v[T-1]; bin 0: the caller's NCHW state) were
+      // announced to L2 one item ahead.
       float vin[NSEG][8], zin[NSEG][8];
 #pragma unroll
       for (int m = 0; m < NSEG; ++m) {
@@ -810,26 +851,48 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
         const bool ok = act && x < W;
         const size_t pix = (size_t)y * W + x;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) vin[m][c] = zin[m][c] = 0.f;
+        for (int c = 0; c < 8; ++c) { vin[m][c] = vin_n[m][c]; zin[m][c] = 0.f; }
         if (it.t == 0) {   // first item of a tile: last bin of the window
 #pragma unroll
           for (int c = 0; c < 8; ++c) carry[m][c] = v_cur[m][c] = 0.f;
           if (ok) ld8_c8(v + c8_off(img, nch, ch, HW, pix), v_cur[m]);
         }
-        if (ok) {
-          if (t > 0) {
-            ld8_c8(v + c8_off(img - B, nch, ch, HW, pix), vin[m]);
-          } else {
-            const size_t o = ((size_t)(it.b * N + ch * 8)) * HW + pix;   // NCHW state tensors of the caller
+        if (ok && t == 0) {
+          const size_t o = ((size_t)(it.b * N + ch * 8)) * HW + pix;   // NCHW state tensors of the caller
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              vin[m][c] = a.v_init ? __ldg(a.v_init + o + (size_t)c * HW) : 0.f;
-              zin[m][c] = a.z_init ? __ldg(a.z_init + o + (size_t)c * HW) : 0.f;
+          for (int c = 0; c < 8; ++c) {
+            vin[m][c] = a.v_init ? __ldg(a.v_init + o + (size_t)c * HW) : 0.f;
+            zin[m][c] = a.z_init ? __ldg(a.z_init + o + (size_t)c * HW) : 0.f;
+          }
+        }
+      }
+      if (k + 1 < n_items) {   // request the next item's v[t-1] now: it lands while this item's epilogue runs
+        ItemIter<true> nx = it;
+        nx.next();
+        const int tn = T - 1 - nx.t;
+#pragma unroll
+        for (int m = 0; m < NSEG; ++m) {
+          const int y = nx.y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
+          const size_t pix = (size_t)y * W + x;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) vin_n[m][c] = 0.f;
+          if (act && x < W) {
+            if (tn > 0) ld8_c8(v + c8_off((tn - 1) * B + nx.b, nch, ch, HW, pix), vin_n[m]);
+            if (nx.t == 0) prefetch_l2(v + c8_off(tn * B + nx.b, nch, ch, HW, pix));
+            if (tn == 0 && a.v_init) {
+              const size_t o = ((size_t)(nx.b * N + ch * 8)) * HW + pix;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                prefetch_l2(a.v_init + o + (size_t)c * HW);
+                prefetch_l2(a.z_init + o + (size_t)c * HW);
+              }
             }
           }
         }
       }
-      mbar_wait(&s.acc_full[ab], (uint32_t)(k >> 1) & 1u);
+      const long long tw0 = a.dbg ? clock64() : 0;
+      mbar_wait(&s.acc_full[ab], (uint32_t)(k >> acc_lg) & 1u);
+      if (a.dbg) t_wait += clock64() - tw0;
       tc_fence_after();
       if (act) {
         uint32_t u0[NSEG][8], u1[NSEG][8];
@@ -877,6 +940,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
       }
       tc_fence_before();
       mbar_arrive(&s.acc_empty[ab]);
+    }
+    if (a.dbg && tid == 0) {
+      a.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin;
+      a.dbg[blockIdx.x * 8 + 6] = t_wait;
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -959,8 +1026,8 @@ static size_t wt_smem_bytes(const WtArgs& a, size_t extra = 0) {
 }
 
 template <typename K>
-static int wt_launch(K kernel, const void* key, const WtArgs& a, cudaStream_t st, const char* what, size_t extra_smem = 0) {
-  const size_t smem = wt_smem_bytes(a, extra_smem);
+static int wt_launch(K kernel, const void* key, const WtArgs& a_in, cudaStream_t st, const char* what, size_t extra_smem = 0) {
+  const size_t smem = wt_smem_bytes(a_in, extra_smem);
   if (smem > (size_t)227 * 1024) {
     set_error("%s: shared memory %zu exceeds 227 KB", what, smem);
     return SNNFLOW_EINVAL;
@@ -971,7 +1038,13 @@ static int wt_launch(K kernel, const void* key, const WtArgs& a, cudaStream_t st
     SNNFLOW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     have = smem;
   }
+  WtArgs a = a_in;
   const int n_tiles = a.n_outer * (a.H / a.R);
+  {   // accumulator ring: as many buffers (2 or 4) as the 512 TMEM columns hold
+    const uint32_t acc_cols = (uint32_t)(a.R * a.n_seg * a.N) * a.src[0].w_terms;
+    static const int max_lg = env_int("SNNFLOW_WT_ACC_LG", 2);
+    a.acc_lg = (max_lg >= 2 && 4u * acc_cols <= 512u) ? 2u : 1u;
+  }
   if (env_int("SNNFLOW_WT_TIMING", 0)) {   // debug: where does each role of the pipeline wait? (synchronises)
     static long long* dbg = nullptr;
     const int grid = wt_grid(n_tiles);
@@ -988,6 +1061,14 @@ static int wt_launch(K kernel, const void* key, const WtArgs& a, cudaStream_t st
       for (int j = 0; j < 8; ++j) avg[j] += (double)h[i * 8 + j] / grid;
     fprintf(stderr, "[wt-timing] %s R=%d S=%d n_src=%d N=%d items/CTA=%.1f | producer %.0f (wait-empty %.0f) | mma %.0f (wait-full %.0f, wait-acc %.0f) | epi %.0f (wait-acc-full %.0f) | prologue %.0f\n",
             what, a.R, a.S, a.n_src, a.N, (double)n_tiles * (a.T > 1 ? a.T : 1) / grid, avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7]);
+    return check_launch(what);
+  }
+  if (a.n_bins > 1) {   // persistent over the bins: every CTA must be resident (grid barrier between bins)
+    SNNFLOW_REQUIRE(a.grid_bar != nullptr, "multi-bin launch without a grid barrier counter");
+    SNNFLOW_CUDA(cudaMemsetAsync(a.grid_bar, 0, sizeof(unsigned int), st));
+    static const int coop = env_int("SNNFLOW_COOP", 1);
+    if (coop) SNNFLOW_CUDA(launch_coop(kernel, dim3(wt_grid(n_tiles)), dim3(WT_THREADS), smem, st, a));
+    else SNNFLOW_CUDA(launch_pdl(kernel, dim3(wt_grid(n_tiles)), dim3(WT_THREADS), smem, st, a));
     return check_launch(what);
   }
   SNNFLOW_CUDA(launch_pdl(kernel, dim3(wt_grid(n_tiles)), dim3(WT_THREADS), smem, st, a));
