@@ -161,12 +161,17 @@ __device__ __forceinline__ float surrogate(float u, float width, int kind) {
 }
 
 // compile-time surrogate kind + fast reciprocal (MUFU.RCP, ~1 ulp): the gradient tier tolerates it (rel 1e-4)
+__device__ __forceinline__ float fast_rcp(float x) {   // one MUFU.RCP; the arguments here are >= 1 and finite
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 template <int KIND>
 __device__ __forceinline__ float surrogate_fast(float u, float width) {
-  if (KIND == SNNFLOW_SG_ARCTAN) return __fdividef(1.0f, fmaf(width * u, u, 1.0f));
+  if (KIND == SNNFLOW_SG_ARCTAN) return fast_rcp(fmaf(width * u, u, 1.0f));
   if (KIND == SNNFLOW_SG_SUPERSPIKE) {
     const float d = fmaf(width, fabsf(u), 1.0f);
-    return __fdividef(1.0f, d * d);
+    return fast_rcp(d * d);
   }
   return fmaxf(1.0f - width * fabsf(u), 0.0f);
 }

@@ -20,8 +20,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef SNNFLOW_MBAR_HINT_NS
+#define SNNFLOW_MBAR_HINT_NS 20000   // suspend-time hint of try_wait; 0 = no hint operand (hardware default)
+#endif
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if SNNFLOW_MBAR_HINT_NS > 0
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -29,8 +33,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       "selp.u32 %0, 1, 0, P1;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)   // suspend-time hint (ns): a waiting warp sleeps instead of polling
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SNNFLOW_MBAR_HINT_NS)   // a waiting warp sleeps instead of polling
       : "memory");
+#else
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#endif
   return ok;
 }
 // try_wait suspends in hardware up to a system time limit per attempt; the attempt counter is a watchdog that turns

@@ -358,10 +358,102 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
       const float4 pr = s.par[(act ? ch * 8 : 0) + c];
       lam[c] = pr.x; oml[c] = pr.y; th[c] = pr.z;
     }
-    float vst[NSEG][8], zst[NSEG][8];   // membrane and spikes of the previous bin (registers across the T bins)
     long long t_wait = 0;
     const long long t_begin = clock64();
     const uint32_t acc_lg = a.acc_lg, acc_mask = (1u << acc_lg) - 1u;
+    if constexpr (SEQ) {
+      // Time-fused feed-forward layer: a tile (b, y0) is walked through its T bins with the membrane and the previous
+      // spikes in registers and RUNNING output pointers - one bin ahead is a constant step, nothing is re-derived per item.
+      const int tpi = a.H / a.R, n_tiles = a.n_outer * tpi, B = a.B;
+      const long long v_bin = (long long)B * nch * (long long)HW * 8;          // floats between bins (c8 membranes)
+      const long long zp_bin = (long long)B * (long long)zp_img_stride;        // bytes between bins (spike planes)
+      const bool have_v = a.v_out != nullptr, want_last = a.v_last != nullptr || a.z_last != nullptr;
+      uint32_t k = 0;
+      for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
+        const int b = tile / tpi, y0 = (tile - b * tpi) * a.R;
+        float* vp[NSEG];
+        unsigned char* zp[NSEG];
+        size_t o_state[NSEG];
+        bool okm[NSEG];
+        float vst[NSEG][8], zst[NSEG][8];
+#pragma unroll
+        for (int m = 0; m < NSEG; ++m) {
+          const int y = y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
+          const size_t pix = (size_t)y * W + x;
+          okm[m] = act && x < W;
+          vp[m] = have_v ? a.v_out + c8_off(b, nch, ch, HW, pix) : nullptr;
+          zp[m] = a.zp_out + (size_t)ch * plane_bytes + (size_t)b * zp_img_stride + ((size_t)(y + 1) * Wp + x + 1) * 16;
+          o_state[m] = ((size_t)(b * N + ch * 8)) * HW + pix;   // NCHW (state tensors of the caller)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) vst[m][c] = zst[m][c] = 0.f;
+          if (okm[m] && a.v_init) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) vst[m][c] = __ldg(a.v_init + o_state[m] + (size_t)c * HW);
+          }
+          if (okm[m] && a.z_init) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) zst[m][c] = __ldg(a.z_init + o_state[m] + (size_t)c * HW);
+          }
+        }
+        for (int t = 0; t < T; ++t, ++k) {
+          const uint32_t ab = k & acc_mask;
+          {
+            const long long t0 = a.dbg ? clock64() : 0;
+            mbar_wait(&s.acc_full[ab], (k >> acc_lg) & 1u);
+            if (a.dbg) t_wait += clock64() - t0;
+          }
+          tc_fence_after();
+          if (act) {
+            uint32_t u0[NSEG][8], u1[NSEG][8], u2[NSEG][8];
+#pragma unroll
+            for (int m = 0; m < NSEG; ++m) {
+              const uint32_t tcol = tmem_base + t_lane + ab * acc_cols + (uint32_t)m * ncat + (uint32_t)(ch * 8);
+              tmem_ld8_async(tcol, u0[m]);
+              tmem_ld8_async(tcol + (uint32_t)N, u1[m]);
+              tmem_ld8_async(tcol + 2u * (uint32_t)N, u2[m]);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int m = 0; m < NSEG; ++m) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float cur = (__uint_as_float(u0[m][c]) + __uint_as_float(u1[m][c])) + __uint_as_float(u2[m][c]);   // hi + mid + lo terms
+                const float t1 = __fmul_rn(vst[m][c], lam[c]), t3 = __fmul_rn(oml[c], cur);
+                float vn;
+                if (HARD) vn = __fadd_rn(__fmul_rn(t1, __fsub_rn(1.0f, zst[m][c])), t3);    // spiking_submodules.py:144
+                else vn = __fsub_rn(__fadd_rn(t1, t3), __fmul_rn(zst[m][c], th[c]));         // spiking_submodules.py:146
+                vst[m][c] = vn;
+                zst[m][c] = __fsub_rn(vn, th[c]) > 0.f ? 1.f : 0.f;                          // spiking_util.py:21
+              }
+              if (okm[m]) {
+                uint4 zz;   // {0, 1} are exact in bf16: one packed convert per channel pair
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz.x) : "f"(zst[m][1]), "f"(zst[m][0]));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz.y) : "f"(zst[m][3]), "f"(zst[m][2]));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz.z) : "f"(zst[m][5]), "f"(zst[m][4]));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz.w) : "f"(zst[m][7]), "f"(zst[m][6]));
+                *reinterpret_cast<uint4*>(zp[m]) = zz;
+                if (have_v) st8_c8(vp[m], vst[m]);
+                if (t == T - 1 && want_last) {   // the caller-visible state [2,B,C,H,W] after the window
+                  if (a.v_last) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) a.v_last[o_state[m] + (size_t)c * HW] = vst[m][c];
+                  }
+                  if (a.z_last) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) a.z_last[o_state[m] + (size_t)c * HW] = zst[m][c];
+                  }
+                }
+              }
+              zp[m] += zp_bin;
+              if (have_v) vp[m] += v_bin;
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&s.acc_empty[ab]);
+        }
+      }
+    } else {
+    float vst[NSEG][8], zst[NSEG][8];   // membrane and spikes entering the bin
     ItemIter<SEQ> it;
     const int n_bins = (!SEQ && a.n_bins > 1) ? a.n_bins : 1;
     const bool multi = n_bins > 1;
@@ -485,6 +577,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
       fence_proxy_async_global();
       asm volatile("bar.sync 1, %0;" ::"n"(WT_EPI_WARPS * 32) : "memory");
       if (tid == 0) grid_bar_arrive(a.grid_bar);
+    }
     }
     }
     if (a.dbg && tid == 0) {
@@ -794,6 +887,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
 //              carry = gv * lam * (1 - z_in)  (hard reset) / gv * lam  (soft)  stays in registers across the bins,
 //              d lam / d theta partial sums as in pw_seq_kernel.
 // The spike gradient g_out of layer l ([T*B,C,H,W] fp32) is never written to or read from memory.
+// Measured (B200, C=32, 128x128, B=8, T=10): this plain epilogue (v[t-1] loaded at the top of the item, one division-free
+// iterator) runs in 141 us; a variant with running pointers and a register prefetch of v[t-2] executed 26 % fewer
+// instructions but spilled 180 B per thread and took 161 us - the epilogue is latency bound, not issue bound.
 // =================================================================================================
 template <int SG, bool HARD, int NSEG>
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_constant__ WtArgs a) {
@@ -809,6 +905,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
     __syncwarp();
   } else {
     pdl_wait();
+
     const int q = warp & 3, ch = warp >> 2;
     const int W = a.W, Wp = a.Wp, N = a.N, nch = N >> 3, n_seg = a.n_seg, T = a.T, B = a.B;
     const bool act = ch * 8 < N;
@@ -822,28 +919,17 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
     unsigned char* const gp_out = a.gp_out + (size_t)ch * plane_bytes;
     const size_t gp_img_stride = a.gp_img_stride, gp_term_stride = a.gp_term_stride;
     const float4* par = s.par + (act ? ch * 8 : 0);
-    float s_lam[8], s_th[8], carry[NSEG][8], v_cur[NSEG][8], vin_n[NSEG][8];
+    float s_lam[8], s_th[8], carry[NSEG][8], v_cur[NSEG][8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) s_lam[c] = s_th[c] = 0.f;
-    long long t_wait = 0;
-    const long long t_begin = a.dbg ? clock64() : 0;
     const uint32_t acc_lg = a.acc_lg, acc_mask = (1u << acc_lg) - 1u;
     ItemIter<true> it;
     it.init(a);
-#pragma unroll
-    for (int m = 0; m < NSEG; ++m) {   // v[T-2] of the first tile
-      const int y = it.y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) vin_n[m][c] = 0.f;
-      if (n_items > 0 && act && x < W && T > 1) ld8_c8(v + c8_off((T - 2) * B + it.b, nch, ch, HW, (size_t)y * W + x), vin_n[m]);
-    }
     for (int k = 0; k < n_items; ++k, it.next()) {
       const uint32_t ab = (uint32_t)k & acc_mask;
       const int t = T - 1 - it.t;            // bins are walked backwards
       const int img = t * B + it.b;
-      // Inputs of this bin's epilogue: v[t-1] was requested while the previous item was in flight (vin_n); v[t] is carried
-      // from the previous item.  The rare loads (first item of a tile: v[T-1]; bin 0: the caller's NCHW state) were
-      // announced to L2 one item ahead.
+      // this bin's inputs of the epilogue: v[t-1] (or the window-initial state); v[t] is carried from the previous item
       float vin[NSEG][8], zin[NSEG][8];
 #pragma unroll
       for (int m = 0; m < NSEG; ++m) {
@@ -851,48 +937,26 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
         const bool ok = act && x < W;
         const size_t pix = (size_t)y * W + x;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { vin[m][c] = vin_n[m][c]; zin[m][c] = 0.f; }
+        for (int c = 0; c < 8; ++c) vin[m][c] = zin[m][c] = 0.f;
         if (it.t == 0) {   // first item of a tile: last bin of the window
 #pragma unroll
           for (int c = 0; c < 8; ++c) carry[m][c] = v_cur[m][c] = 0.f;
           if (ok) ld8_c8(v + c8_off(img, nch, ch, HW, pix), v_cur[m]);
         }
-        if (ok && t == 0) {
-          const size_t o = ((size_t)(it.b * N + ch * 8)) * HW + pix;   // NCHW state tensors of the caller
+        if (ok) {
+          if (t > 0) {
+            ld8_c8(v + c8_off(img - B, nch, ch, HW, pix), vin[m]);
+          } else {
+            const size_t o = ((size_t)(it.b * N + ch * 8)) * HW + pix;   // NCHW state tensors of the caller
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            vin[m][c] = a.v_init ? __ldg(a.v_init + o + (size_t)c * HW) : 0.f;
-            zin[m][c] = a.z_init ? __ldg(a.z_init + o + (size_t)c * HW) : 0.f;
-          }
-        }
-      }
-      if (k + 1 < n_items) {   // request the next item's v[t-1] now: it lands while this item's epilogue runs
-        ItemIter<true> nx = it;
-        nx.next();
-        const int tn = T - 1 - nx.t;
-#pragma unroll
-        for (int m = 0; m < NSEG; ++m) {
-          const int y = nx.y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
-          const size_t pix = (size_t)y * W + x;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) vin_n[m][c] = 0.f;
-          if (act && x < W) {
-            if (tn > 0) ld8_c8(v + c8_off((tn - 1) * B + nx.b, nch, ch, HW, pix), vin_n[m]);
-            if (nx.t == 0) prefetch_l2(v + c8_off(tn * B + nx.b, nch, ch, HW, pix));
-            if (tn == 0 && a.v_init) {
-              const size_t o = ((size_t)(nx.b * N + ch * 8)) * HW + pix;
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                prefetch_l2(a.v_init + o + (size_t)c * HW);
-                prefetch_l2(a.z_init + o + (size_t)c * HW);
-              }
+            for (int c = 0; c < 8; ++c) {
+              vin[m][c] = a.v_init ? __ldg(a.v_init + o + (size_t)c * HW) : 0.f;
+              zin[m][c] = a.z_init ? __ldg(a.z_init + o + (size_t)c * HW) : 0.f;
             }
           }
         }
       }
-      const long long tw0 = a.dbg ? clock64() : 0;
       mbar_wait(&s.acc_full[ab], (uint32_t)(k >> acc_lg) & 1u);
-      if (a.dbg) t_wait += clock64() - tw0;
       tc_fence_after();
       if (act) {
         uint32_t u0[NSEG][8], u1[NSEG][8];
@@ -940,10 +1004,6 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
       }
       tc_fence_before();
       mbar_arrive(&s.acc_empty[ab]);
-    }
-    if (a.dbg && tid == 0) {
-      a.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin;
-      a.dbg[blockIdx.x * 8 + 6] = t_wait;
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -1052,15 +1112,25 @@ static int wt_launch(K kernel, const void* key, const WtArgs& a_in, cudaStream_t
     cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * grid, st);
     WtArgs b = a;
     b.dbg = dbg;
+    if (b.n_bins > 1) cudaMemsetAsync(b.grid_bar, 0, sizeof(unsigned int), st);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
     kernel<<<grid, WT_THREADS, smem, st>>>(b);
+    cudaEventRecord(e1, st);
     cudaStreamSynchronize(st);
+    float ev_ms = 0.f;
+    cudaEventElapsedTime(&ev_ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     std::vector<long long> h(8 * grid);
     cudaMemcpy(h.data(), dbg, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
     double avg[8] = {0};
     for (int i = 0; i < grid; ++i)
       for (int j = 0; j < 8; ++j) avg[j] += (double)h[i * 8 + j] / grid;
-    fprintf(stderr, "[wt-timing] %s R=%d S=%d n_src=%d N=%d items/CTA=%.1f | producer %.0f (wait-empty %.0f) | mma %.0f (wait-full %.0f, wait-acc %.0f) | epi %.0f (wait-acc-full %.0f) | prologue %.0f\n",
-            what, a.R, a.S, a.n_src, a.N, (double)n_tiles * (a.T > 1 ? a.T : 1) / grid, avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7]);
+    fprintf(stderr, "[wt-timing] %s R=%d S=%d n_src=%d N=%d items/CTA=%.1f | producer %.0f (wait-empty %.0f) | mma %.0f (wait-full %.0f, wait-acc %.0f) | epi %.0f (wait-acc-full %.0f) | prologue %.0f | %.1f us\n",
+            what, a.R, a.S, a.n_src, a.N, (double)n_tiles * (a.T > 1 ? a.T : 1) / grid, avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7], ev_ms * 1e3);
     return check_launch(what);
   }
   if (a.n_bins > 1) {   // persistent over the bins: every CTA must be resident (grid barrier between bins)
