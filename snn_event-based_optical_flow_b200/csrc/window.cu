@@ -67,7 +67,7 @@ static WinLayout win_layout(const snnflow_net_desc* d, int save) {
 struct WinPlan {   // tile plans of the tensor-core kernels for this shape
   int R_ff, S_ff, R_head, S_head, R_rec, S_rec, R_dg, S_dg, R_rb, S_rb, R_dp, S_dp;
   uint32_t sub_ff, cs_ff, st_ff, sub_head, cs_head, st_head, sub_rec, cs_rec, st_rec, sub_dg, cs_dg, st_dg, sub_rb, cs_rb, st_rb, sub_dp, cs_dp, st_dp;
-  bool ok, rb_prefetch;
+  bool ok;
 };
 
 static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool backward = true) {
@@ -85,19 +85,12 @@ static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool back
     P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, max_fwd_rec_blob, true, 3, false, &P.R_rec, &P.S_rec, &P.sub_rec, &P.cs_rec, &P.st_rec);
   if (!backward) return P;
   if (any_rec) {
-    // Measured (B200, 128x128): two-row tiles without the epilogue prefetch beat one-row tiles with it (35 vs 38 us per
-    // bin); the prefetch slots are used when only one-row tiles are possible.  SNNFLOW_RB_R / SNNFLOW_RB_PF override.
-    const int rb_R = wt_env_int("SNNFLOW_RB_R", 0), rb_pf = wt_env_int("SNNFLOW_RB_PF", -1);
+    // two-row tiles when they fit (measured faster than one-row tiles at 128x128); SNNFLOW_RB_R overrides
+    const int rb_R = wt_env_int("SNNFLOW_RB_R", 0);
     const uint32_t rb_blob = (uint32_t)((size_t)9 * 2 * C * C * 2);
     bool have = false;
-    P.rb_prefetch = false;
-    if (rb_pf != 1 && (rb_R == 0 || rb_R == 2))
+    if (rb_R == 0 || rb_R == 2)
       have = wt_plan(d->H, d->W, C / 8, C, rb_blob, false, 2, false, &P.R_rb, &P.S_rb, &P.sub_rb, &P.cs_rb, &P.st_rb, 2);
-    if (!have && rb_pf != 0) {
-      have = wt_plan(d->H, d->W, C / 8, C, rb_blob + (uint32_t)wt_recbwd_extra_smem(), false, 2, false, &P.R_rb, &P.S_rb, &P.sub_rb,
-                     &P.cs_rb, &P.st_rb, rb_R);
-      P.rb_prefetch = have;
-    }
     if (!have) have = wt_plan(d->H, d->W, C / 8, C, rb_blob, false, 2, false, &P.R_rb, &P.S_rb, &P.sub_rb, &P.cs_rb, &P.st_rb, rb_R);
     P.ok = P.ok && have;
   }
@@ -375,7 +368,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
       a.n_outer = B; a.T = 1; a.B = B; a.H = H; a.W = W; a.Wp = W + 2; a.n_seg = ceil_div(W, 128); a.N = C;
       a.R = P.R_rb; a.S = P.S_rb; a.sub_bytes = P.sub_rb; a.chunk_stride = P.cs_rb; a.stage_bytes = P.st_rb;
       a.hard_reset = hard; a.surrogate = d->surrogate; a.width = d->act_width;
-      a.par = par; a.prefetch = P.rb_prefetch ? 1 : 0;
+      a.par = par;
       a.g_v = g_v; a.gp_img_stride = L.zp_img_stride; a.gp_term_stride = WS.gp_term_stride;
       for (int t = T - 1; t >= 0; --t) {
         a.has_gz = t < T - 1; a.first_step = t == T - 1;

@@ -81,7 +81,6 @@ struct WtArgs {
   long long bin_v_stride;         // floats per bin for the membrane arena (v_out; v_prev of bin j is v_out of bin j-1)
   int bin_v_mask;                 // membrane slot of bin j = j & bin_v_mask (eval keeps two slots, training all bins)
   unsigned int* grid_bar;         // zeroed by the launcher
-  int prefetch;                   // epilogue inputs prefetched through shared memory (when the slots fit)
   int has_gz, first_step, z_from_v;   // first_step: g_v starts at zero ; z_from_v: z_in = spike(v_in) else from z_init
   long long* dbg;                 // optional [grid][8] cycle counters (SNNFLOW_WT_TIMING=1): where each role waits
 };
@@ -96,7 +95,6 @@ bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes
              uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes, int only_R = 0);
 int wt_env_int(const char* name, int dflt);
 int wt_grid(int n_tiles);
-size_t wt_recbwd_extra_smem();   // thread-private prefetch slots of the recurrent backward epilogue
 
 // ---- weight gradient (window_wgrad.cu) --------------------------------------------------------------
 struct WgArgs {
