@@ -160,7 +160,27 @@ class _WindowFn(torch.autograd.Function):
         grads += [d_pw, d_pb if pb is not None else None]
         return (None, None) + tuple(grads)
 
-def _make_desc(runner, cnt):
+_LM_WIDTHS = (16, 32, 64)   # channel counts the layer-major engine is built for
+
+
+def _lm_channels(c):
+    """Width the layer-major engine runs a C-channel network at: narrower networks (the shipped configs use
+    base_num_channels = 8, configs/train_SNN.yml:19) are zero-padded - padded neurons have zero weights, never spike and
+    get zero gradients, so the real channels are bit-identical to an unpadded run."""
+    for w in _LM_WIDTHS:
+        if c <= w:
+            return w
+    return c
+
+
+def _pad_dim(t, dim, n, value=0.0):
+    if t is None or t.shape[dim] == n:
+        return t
+    pad = [0, 0] * (t.dim() - 1 - dim) + [0, n - t.shape[dim]]
+    return torch.nn.functional.pad(t, pad, value=value).contiguous()
+
+
+def _make_desc(runner, cnt, channels=None):
     layers = runner.layers
     T, B, nb, H, W = cnt.shape
     first = layers[0]
@@ -168,7 +188,7 @@ def _make_desc(runner, cnt):
     if not first.use_tensor_cores:
         flags |= _lib.NO_TENSOR_CORES
     mask = sum(1 << i for i, l in enumerate(layers) if l.recurrent)
-    return NetDesc(B, first.hidden_size, H, W, T, nb, mask, flags, _lib.SURROGATE_ID[first.activation], first._act_width)
+    return NetDesc(B, channels or first.hidden_size, H, W, T, nb, mask, flags, _lib.SURROGATE_ID[first.activation], first._act_width)
 
 
 def _desc_key(d):
@@ -187,22 +207,32 @@ class _LayerMajorWindowFn(torch.autograd.Function):
         dev = cnt.device
         cnt = cnt.float().contiguous()
         need_bwd = any(ctx.needs_input_grad)
-        desc = _make_desc(runner, cnt)
-        C = desc.C
+        Cr = layers[0].hidden_size                 # the network's width ...
+        C = _lm_channels(Cr)                       # ... and the (zero-padded) width the engine runs it at
+        desc = _make_desc(runner, cnt, C)
         lam = torch.sigmoid(torch.stack([l.leak.detach().reshape(-1) for l in layers]))      # spiking_submodules.py:136
         theta = torch.stack([l.thresh.detach().reshape(-1) for l in layers]).clamp_min(0.01)  # :133
+        lam_e, theta_e = _pad_dim(lam, 1, C, 0.5), _pad_dim(theta, 1, C, 1.0)
+        w_e = []
+        for i, l in enumerate(layers):
+            wf = _pad_dim(l.ff.weight.detach(), 0, C)
+            if i > 0:
+                wf = _pad_dim(wf, 1, C)
+            wr = _pad_dim(_pad_dim(l.rec.weight.detach(), 0, C), 1, C) if l.recurrent else None
+            w_e.append((wf, wr))
         lp = (LayerPtrs * N_LAYERS)()
         for i, l in enumerate(layers):
-            lp[i].w_ff = l.ff.weight.data_ptr()
-            lp[i].w_rec = l.rec.weight.data_ptr() if l.recurrent else None
-            lp[i].lam = lam[i].data_ptr()
-            lp[i].theta = theta[i].data_ptr()
+            lp[i].w_ff = w_e[i][0].data_ptr()
+            lp[i].w_rec = w_e[i][1].data_ptr() if l.recurrent else None
+            lp[i].lam = lam_e[i].data_ptr()
+            lp[i].theta = theta_e[i].data_ptr()
         arena = runner.lm_arena(desc, need_bwd, dev)
         flow = torch.empty((T, B, 2, H, W), dtype=torch.float32, device=dev)
-        states = net._states
+        states = runner.lm_states_in(net._states, Cr, C)
         sp, keep = _state_ptrs(states)
         pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
-        _lib.check(L.snnflow_window_forward(ctypes.byref(desc), lp, pw.data_ptr(), None if pb is None else pb.data_ptr(),
+        pw_e = _pad_dim(pw.detach(), 1, C)
+        _lib.check(L.snnflow_window_forward(ctypes.byref(desc), lp, pw_e.data_ptr(), None if pb is None else pb.data_ptr(),
                                             cnt.data_ptr(), sp, arena.data_ptr(), flow.data_ptr(), int(need_bwd),
                                             _lib.stream()), "snnflow_window_forward")
         runner._lm_calls = getattr(runner, "_lm_calls", 0) + 1
@@ -215,9 +245,12 @@ class _LayerMajorWindowFn(torch.autograd.Function):
         offs = (ctypes.c_size_t * N_LAYERS)()
         _lib.check(L.snnflow_window_state_offsets(ctypes.byref(desc), int(need_bwd), offs), "snnflow_window_state_offsets")
         nbytes = 2 * B * C * H * W * 4
-        runner.new_states = [arena[offs[i]:offs[i] + nbytes].view(torch.float32).view(2, B, C, H, W) for i in range(N_LAYERS)]
+        full = [arena[offs[i]:offs[i] + nbytes].view(torch.float32).view(2, B, C, H, W) for i in range(N_LAYERS)]
+        runner._lm_full_states = full
+        runner.new_states = full if C == Cr else [f[:, :, :Cr] for f in full]   # the network's channels of the padded state
         if need_bwd:
             ctx.runner, ctx.desc, ctx.lam, ctx.theta = runner, desc, lam, theta
+            ctx.lam_e, ctx.theta_e, ctx.w_e, ctx.pw_e, ctx.Cr = lam_e, theta_e, w_e, pw_e, Cr
             ctx.arena, ctx.flow, ctx.states_in = arena, flow, list(states)
         return flow
 
@@ -228,30 +261,36 @@ class _LayerMajorWindowFn(torch.autograd.Function):
         layers, net = runner.layers, runner.net
         dev = g_flow.device
         g_flow = g_flow.float().contiguous()
-        dlam = torch.zeros_like(lam)
-        dtheta = torch.zeros_like(theta)
+        Cr, C = ctx.Cr, desc.C
+        lam_e, theta_e, w_e, pw_e = ctx.lam_e, ctx.theta_e, ctx.w_e, ctx.pw_e
+        dlam = torch.zeros_like(lam_e)
+        dtheta = torch.zeros_like(theta_e)
         dws = []
         lp = (LayerPtrs * N_LAYERS)()
         for i, l in enumerate(layers):
-            dwf = torch.zeros_like(l.ff.weight)
-            dwr = torch.zeros_like(l.rec.weight) if l.recurrent else None
+            dwf = torch.zeros_like(w_e[i][0])
+            dwr = torch.zeros_like(w_e[i][1]) if l.recurrent else None
             dws.append((dwf, dwr))
-            lp[i].w_ff = l.ff.weight.data_ptr()
-            lp[i].w_rec = l.rec.weight.data_ptr() if l.recurrent else None
-            lp[i].lam = lam[i].data_ptr()
-            lp[i].theta = theta[i].data_ptr()
+            lp[i].w_ff = w_e[i][0].data_ptr()
+            lp[i].w_rec = w_e[i][1].data_ptr() if l.recurrent else None
+            lp[i].lam = lam_e[i].data_ptr()
+            lp[i].theta = theta_e[i].data_ptr()
             lp[i].dw_ff = dwf.data_ptr()
             lp[i].dw_rec = None if dwr is None else dwr.data_ptr()
             lp[i].dlam = dlam[i].data_ptr()
             lp[i].dtheta = dtheta[i].data_ptr()
         pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
-        d_pw = torch.zeros_like(pw)
+        d_pw = torch.zeros_like(pw_e)
         d_pb = torch.zeros(2, dtype=torch.float32, device=dev)
         ws = runner.lm_workspace(desc, dev)
         sp, keep = _state_ptrs(ctx.states_in)
-        _lib.check(L.snnflow_window_backward(ctypes.byref(desc), lp, pw.data_ptr(), sp, ctx.arena.data_ptr(),
+        _lib.check(L.snnflow_window_backward(ctypes.byref(desc), lp, pw_e.data_ptr(), sp, ctx.arena.data_ptr(),
                                              ctx.flow.data_ptr(), g_flow.data_ptr(), d_pw.data_ptr(), d_pb.data_ptr(),
                                              ws.data_ptr(), ws.numel(), _lib.stream()), "snnflow_window_backward")
+        if C != Cr:   # drop the padded neurons (their gradients are exactly zero)
+            dlam, dtheta, d_pw = dlam[:, :Cr], dtheta[:, :Cr], d_pw[:, :Cr].contiguous()
+            dws = [(f[:Cr, :(l.ff.weight.shape[1])].contiguous(), None if r is None else r[:Cr, :Cr].contiguous())
+                   for (f, r), l in zip(dws, layers)]
         d_leak = dlam * lam * (1.0 - lam)                                           # sigmoid'
         thr = torch.stack([l.thresh.detach().reshape(-1) for l in layers])
         d_thresh = dtheta * (thr >= 0.01).float()                                   # clamp_min'
@@ -301,10 +340,28 @@ class WindowRunner:
             self._ws = torch.empty(n, dtype=torch.uint8, device=dev)
         return self._ws
 
+    def lm_states_in(self, states, Cr, C):
+        """The network's states [2,B,Cr,H,W] as the engine's (zero-padded) [2,B,C,H,W] tensors.  States this runner
+        handed out last window are channel slices of padded state blocks in the arena: those are passed back as they are."""
+        if C == Cr:
+            return states
+        full = getattr(self, "_lm_full_states", None)
+        out = []
+        for i, st in enumerate(states):
+            if st is None or st.shape[2] == C:
+                out.append(st)
+                continue
+            f = full[i] if full is not None else None
+            if f is not None and st.data_ptr() == f.data_ptr() and st.shape[2] == Cr and st.stride() == f[:, :, :Cr].stride():
+                out.append(f)
+            else:
+                out.append(_pad_dim(st.detach(), 2, C))
+        return out
+
     def layer_major_ok(self, cnt_window, backward):
         L = _lib.lib()
         _bind(L)
-        desc = _make_desc(self, cnt_window)
+        desc = _make_desc(self, cnt_window, _lm_channels(self.layers[0].hidden_size))
         return bool(L.snnflow_window_supported(ctypes.byref(desc), int(backward)))
 
     def lm_arena(self, desc, save, dev):

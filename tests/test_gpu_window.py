@@ -51,6 +51,9 @@ CASES = [
     ("LIFFireFlowNet", 32, 6, 256, {}),
     ("LIFFireNet", 32, 10, 40, dict(hard_reset=False, activation="superspike")),
     ("LIFFireNet", 16, 9, 33, dict(activation="trianglespike")),
+    # narrower than the engine's smallest width (the shipped configs use C = 8): zero-padded to 16 by the host layer
+    ("LIFFireNet", 8, 12, 40, {}),
+    ("LIFFireFlowNet", 8, 10, 128, dict(hard_reset=False)),
 ]
 
 
@@ -254,3 +257,24 @@ def test_fused_window_loss_matches_per_bin_loss(mask_output, zero_flow):
     close = (ga - gb).abs() <= 1e-4 * ga.abs() + 1e-5 * scale
     assert float(close.float().mean()) >= 0.995, float(close.float().mean())   # see test_gpu_network.py on conditioning
     assert float((ga - gb).norm()) <= 3e-3 * float(ga.norm()) + 1e-7
+
+
+def test_padded_width_states_feed_per_bin_forward():
+    """C = 8 runs zero-padded on the layer-major engine; the states it hands back are channel slices of the padded blocks
+    and must be usable by the per-bin modules (and by the next window) like any other state."""
+    net = make_net("LIFFireNet", 8)
+    g = torch.Generator().manual_seed(11)
+    cnt = torch.poisson(torch.full((6, 2, 2, 12, 40), 0.25), generator=g).cuda()
+    with torch.no_grad():
+        net.reset_states()
+        ref = torch.stack([net(None, cnt[t])["flow"][0] for t in range(6)])
+        s_ref = [s.clone() for s in net._states]
+        net.reset_states()
+        runner_of(net, "layer_major")
+        a = net.forward_window(cnt[:2])
+        assert net._states[0].shape == (2, 2, 8, 12, 40)
+        b = torch.stack([net(None, cnt[t])["flow"][0] for t in range(2, 4)])     # per-bin calls on the sliced states
+        c = net.forward_window(cnt[4:])                                          # and back (re-padded copies)
+    assert torch.equal(ref, torch.cat([a, b, c]))
+    for x, y in zip(s_ref, net._states):
+        assert torch.equal(x, y)
