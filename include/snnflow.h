@@ -223,6 +223,40 @@ int snnflow_encode_voxel(const float* xs, const float* ys, const float* ts, cons
                          snnflow_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Loader window formatter: one raw window of events per batch slot -> the tensors of one batch
+ * item, the event branch of H5Loader.__getitem__ without the HDF5 file handling.  Replaces, per call:
+ *   BaseDataLoader.event_formatting   dataloader/base.py:71-99    (fp32 cast, p*2-1, min-max normalised timestamps)
+ *   BaseDataLoader.augment_events     dataloader/base.py:101-126  (flips[b] = {horizontal, vertical, polarity})
+ *   create_{cnt,mask,voxel,list}_encoding, create_polarity_mask   dataloader/base.py:160-235
+ *   create_hot_mask / get_hot_event_mask   dataloader/base.py:237-256, dataloader/encodings.py:88-103
+ *   hot-pixel application, avg_pool2d down-sampling, event-list rescaling + clamp   dataloader/h5.py:323-331,375-410
+ *   custom_collate                    dataloader/base.py:261-278  (lists come out as [B,N,4] / [B,N,2])
+ * Inputs (device): xs, ys, ps [B,N] fp32 - sensor coordinates and RAW polarity in {0,1}; ts [B,N] fp32, or fp64 with
+ * ts_is_f64 = 1 (t0 [B] fp64, may be NULL, is subtracted in fp64 before the fp32 cast like h5.py:129); flips [B,3]
+ * int32 or NULL.  hot_events [B,H,W] fp32 / hot_idx [B] int32: the filter's running state (read and updated), required
+ * when hot_enabled.  Outputs: event_cnt [B,2,h,w], event_voxel [B,num_bins,h,w], event_mask [B,1,h,w] with
+ * h = H / pool_h, w = W / pool_w; event_list [B,N,4] = (ts, y, x, p); event_pol [B,N,2].  pool_h = pool_w = 1: no
+ * down-sampling; otherwise the list coordinates are scaled by target/H, target/W and clamped to [0, target-1].
+ * Counts, masks and lists are bit-identical to the reference; the voxel grid is accumulated in 64-bit fixed point.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B;            /* batch slots                                   */
+  int32_t H, W;         /* encoding (sensor) resolution                  */
+  int64_t N;            /* events per slot                               */
+  int32_t num_bins;     /* voxel-grid bins                               */
+  int32_t round_ts;     /* round_encoding (encodings.py:58-59)           */
+  int32_t pool_h, pool_w;       /* original // target (h5.py:381-382)    */
+  int32_t target_h, target_w;   /* loader.resolution (list rescaling)    */
+  int32_t hot_enabled, hot_max_px, hot_min_obvs;
+  float hot_max_rate;
+} snnflow_loader_desc;
+size_t snnflow_format_window_workspace_bytes(const snnflow_loader_desc* d);
+int snnflow_format_window(const snnflow_loader_desc* d, const float* xs, const float* ys, const void* ts, int ts_is_f64,
+                          const double* t0, const float* ps, const int32_t* flips, float* hot_events, int32_t* hot_idx,
+                          float* event_cnt, float* event_voxel, float* event_mask, float* event_list, float* event_pol,
+                          void* workspace, size_t workspace_bytes, snnflow_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Image of warped events (utils/iwe.py, loss/flow.py).
  * events [B,N,4] = (ts, y, x, p); flow [B,2,H,W] (channel 0 = x, 1 = y); ev_flow [B,N,2] = (fy, fx).
  *

@@ -221,13 +221,127 @@ def train_fixture(ref, name, *, kind, C, B, H, W, T, n, seed, mask_output=False)
     _save(name, kind=kind, dims=np.array([C, B, H, W, T, n]), mask_output=int(mask_output), **arrs)
 
 
+
+# ------------------------------------------------------------------------------------------------
+# loader fixtures: the reference's own H5Loader.__getitem__ driven through an in-memory stand-in for h5py
+# ------------------------------------------------------------------------------------------------
+class _FakeDataset:
+    """h5py.Dataset stand-in: slicing returns a COPY (the loader subtracts t0 in place, h5.py:129)."""
+
+    def __init__(self, arr, attrs=None):
+        self.arr, self.attrs, self.dtype = arr, attrs or {}, arr.dtype
+
+    def __getitem__(self, k):
+        return np.array(self.arr[k], copy=True)
+
+    def __len__(self):
+        return len(self.arr)
+
+
+class _FakeGroup:
+    def __init__(self, items):
+        self.items = items
+
+    def visititems(self, cb):
+        for k, v in self.items.items():
+            cb(k, v)
+
+    def __getitem__(self, k):
+        return self.items[k]
+
+
+class _FakeFile:
+    registry = {}
+
+    def __init__(self, path, mode="r"):
+        self.d = _FakeFile.registry[os.path.basename(path)]
+        self.attrs = self.d["attrs"]
+
+    def __getitem__(self, k):
+        return self.d[k]
+
+    def close(self):
+        pass
+
+
+def _raw_stream(n, H, W, g, hot_px=()):
+    """A raw sensor stream as stored in the HDF5 files: integer coords, seconds, polarity in {0,1}; a few pixels fire in
+    (almost) every window so the hot-pixel filter has something to remove."""
+    xs = torch.randint(0, W, (n,), generator=g).numpy().astype(np.int16)
+    ys = torch.randint(0, H, (n,), generator=g).numpy().astype(np.int16)
+    for j, (hy, hx) in enumerate(hot_px):
+        xs[j::37], ys[j::37] = hx, hy
+    ts = 10.0 + np.sort(torch.rand(n, generator=g).double().numpy()) * 0.5
+    ps = torch.randint(0, 2, (n,), generator=g).numpy().astype(np.int8)
+    return xs, ys, ts, ps
+
+
+def loader_fixture(ref, name, *, mode, B, H, W, n_win, n_items, num_bins, round_enc, seed, augment_prob=(0.5, 0.5, 0.5),
+                   hot=None, target=None):
+    import importlib
+    import tempfile
+    import types
+    h5 = importlib.import_module("dataloader.h5")
+    h5.h5py = types.SimpleNamespace(File=_FakeFile)
+    g = torch.Generator().manual_seed(seed)
+    tmp = tempfile.mkdtemp()
+    arrs = {}
+    _FakeFile.registry = {}
+    for b in range(B):
+        fn = f"seq{b}.h5"
+        open(os.path.join(tmp, fn), "w").close()
+        n_tot = n_win * (n_items + 2)
+        xs, ys, ts, ps = _raw_stream(n_tot, H, W, g, hot_px=[(1, 2), (H - 2, W - 3), (3, 3)] if hot else ())
+        d = {"events/xs": _FakeDataset(xs), "events/ys": _FakeDataset(ys), "events/ts": _FakeDataset(ts),
+             "events/ps": _FakeDataset(ps), "attrs": {"t0": 10.0, "duration": 0.5}}
+        if mode == "gtflow_dt1":
+            # ground-truth maps every n_win events: the loader windows the stream between their timestamps
+            maps = {}
+            for i in range(n_items + 2):
+                fm = torch.randn(2, H, W, generator=g).numpy().astype(np.float32)
+                maps[f"{i:06d}"] = _FakeDataset(fm, {"timestamp": float(ts[min(i * n_win, n_tot - 1)])})
+            d["flow_dt1"] = _FakeGroup(maps)
+            for k, v in maps.items():
+                d["flow_dt1/" + k] = v
+            d["flow_dt1"].items = maps
+        _FakeFile.registry[fn] = d
+        d["raw"] = (xs, ys, ts, ps)
+    cfg = {"data": {"mode": mode, "window": n_win if mode == "events" else 1, "path": tmp},
+           "loader": {"resolution": list(target or (H, W)), "std_resolution": [H, W], "batch_size": B,
+                      "augment": ["Horizontal", "Vertical", "Polarity"], "augment_prob": list(augment_prob)},
+           "hot_filter": dict(enabled=bool(hot), **(hot or dict(max_px=100, min_obvs=5, max_rate=0.8))),
+           "vis": {"bars": False}}
+    if mode == "events":
+        cfg["loader"]["resolution"] = [H, W]
+    np.random.seed(seed)
+    loader = h5.H5Loader(cfg, num_bins, round_encoding=round_enc)
+    for b in range(B):   # os.walk order decides which file feeds which batch slot (h5.py:59-69)
+        raw = _FakeFile.registry[os.path.basename(loader.files[b])]["raw"]
+        arrs.update({f"raw{b}.{k}": v for k, v in zip(("xs", "ys", "ts", "ps"), raw)})
+    arrs["flips"] = np.array([[loader.batch_augmentation[m][b] for m in ("Horizontal", "Vertical", "Polarity")]
+                              for b in range(B)], dtype=np.int32)
+    for it in range(n_items):
+        items = [loader[b] for b in range(B)]
+        batch = loader.custom_collate(items)
+        if mode != "events":
+            # the window the loader cut out of the stream (indices into the raw arrays), to replay it elsewhere
+            f_obj = loader.open_files[0]
+            i0 = loader.find_ts_index(f_obj, loader.open_files_flowmaps[0].ts[it])
+            i1 = loader.find_ts_index(f_obj, loader.open_files_flowmaps[0].ts[it + 1])
+            arrs[f"item{it}.range"] = np.array([i0, i1])
+        for k in ("event_cnt", "event_voxel", "event_mask", "event_list", "event_list_pol_mask"):
+            arrs[f"item{it}.{k}"] = _np(batch[k])
+    dims = dict(B=B, H=H, W=W, n_win=n_win, n_items=n_items, num_bins=num_bins, round_enc=int(round_enc))
+    _save(name, mode=mode, hot=np.array([hot["max_px"], hot["min_obvs"], hot["max_rate"]]) if hot else np.zeros(0),
+          target=np.array(target or (H, W)), **{k: np.array(v) for k, v in dims.items()}, **arrs)
+
 def main(only=None):
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     ref = ref_shim.load()
     if only:   # regenerate selected fixtures only (python oracle/make_golden.py --only name[,name])
         g = globals()
-        for fn in ("layer_fixture", "net_fixture", "encode_fixture", "iwe_fixture", "train_fixture"):
+        for fn in ("layer_fixture", "net_fixture", "encode_fixture", "iwe_fixture", "train_fixture", "loader_fixture"):
             orig = g[fn]
             g[fn] = (lambda o: (lambda r, name, **kw: o(r, name, **kw) if name in only else None))(orig)
     # --- single layers (fwd + bwd), bit-exact tier (dyadic weights, spike inputs) ---
@@ -267,6 +381,13 @@ def main(only=None):
     # C = 16 / 32: inside the envelope of the layer-major window engine (tensor-core head layer included)
     train_fixture(ref, "train_firenet_c16", kind="LIFFireNet", C=16, B=2, H=16, W=16, T=3, n=120, seed=52)
     train_fixture(ref, "train_fireflownet_c32", kind="LIFFireFlowNet", C=32, B=1, H=12, W=20, T=4, n=150, seed=53)
+    # --- loader: raw event windows -> batch tensors (the reference's H5Loader on an in-memory stream) ---
+    loader_fixture(ref, "loader_events_hot", mode="events", B=3, H=20, W=24, n_win=400, n_items=5, num_bins=5,
+                   round_enc=False, seed=60, hot=dict(max_px=2, min_obvs=2, max_rate=0.7))
+    loader_fixture(ref, "loader_events_round", mode="events", B=2, H=16, W=16, n_win=300, n_items=2, num_bins=2,
+                   round_enc=True, seed=61, augment_prob=(1.0, 0.0, 1.0))
+    loader_fixture(ref, "loader_gtflow_pool", mode="gtflow_dt1", B=1, H=32, W=48, n_win=500, n_items=3, num_bins=3,
+                   round_enc=False, seed=62, target=(16, 24), hot=dict(max_px=100, min_obvs=1, max_rate=0.9))
 
 
 if __name__ == "__main__":

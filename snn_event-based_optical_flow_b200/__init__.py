@@ -11,6 +11,7 @@ from .submodules import ConvLayer  # noqa: F401
 from .model import LIFFireNet, LIFFireFlowNet  # noqa: F401
 from . import encodings, iwe  # noqa: F401
 from .flow_loss import EventWarping  # noqa: F401
+from .loader import EventWindowFormatter  # noqa: F401
 
 __all__ = ["ConvLIF", "ConvLIFRecurrent", "ConvLayer", "LIFFireNet", "LIFFireFlowNet", "EventWarping",
-           "encodings", "iwe"]
+           "EventWindowFormatter", "encodings", "iwe"]

@@ -54,7 +54,8 @@ class SnnflowError(RuntimeError):
 _ENGINE_SYMBOLS = ["snnflow_net_acts_floats", "snnflow_net_bwd_workspace_bytes", "snnflow_net_forward",
                    "snnflow_net_backward", "snnflow_window_supported", "snnflow_window_arena_bytes",
                    "snnflow_window_workspace_bytes", "snnflow_window_state_offsets", "snnflow_window_inexact_count",
-                   "snnflow_window_forward", "snnflow_window_backward"]   # struct-taking entry points, bound in engine.py
+                   "snnflow_window_forward", "snnflow_window_backward",
+                   "snnflow_format_window_workspace_bytes", "snnflow_format_window"]   # struct-taking entry points, bound in engine.py / loader.py
 
 
 def exported_symbols():

@@ -185,3 +185,43 @@ def test_train_window(name):
     for k, p in params.items():
         if "grad." + k in g:
             np.testing.assert_allclose(p.grad.numpy(), g["grad." + k], rtol=1e-4, atol=1e-6, err_msg=k)
+
+
+# ------------------------------------------------------------------------------------------------
+# loader: raw event window -> batch tensors (fixtures written by the reference's own H5Loader.__getitem__)
+# ------------------------------------------------------------------------------------------------
+from oracle import loader as oload  # noqa: E402
+from snnflow_testutil import LOADER_FIXTURES, LOADER_KEYS, loader_windows  # noqa: E402
+
+
+@pytest.mark.parametrize("name", LOADER_FIXTURES)
+def test_loader_oracle_matches_reference(name):
+    g = load_golden(name)
+    B, H, W, nb = int(g["B"]), int(g["H"]), int(g["W"]), int(g["num_bins"])
+    target = tuple(int(v) for v in g["target"])
+    hot = None
+    if g["hot"].size:
+        hot = oload.HotFilter(B, (H, W), max_px=int(g["hot"][0]), min_obvs=int(g["hot"][1]), max_rate=float(g["hot"][2]))
+    removed = 0
+    for it, wins in enumerate(loader_windows(g)):
+        items = []
+        for b, (xs, ys, ts, ps) in enumerate(wins):
+            ts32 = (ts - 10.0).astype(np.float32)                     # get_events: ts -= t0, then astype(float32)
+            items.append(oload.format_item(T(xs.astype(np.float32)), T(ys.astype(np.float32)), T(ts32),
+                                           T(ps.astype(np.float32)), resolution=(H, W), num_bins=nb,
+                                           round_ts=bool(g["round_enc"]), flips=tuple(bool(v) for v in g["flips"][b]),
+                                           hot=hot, batch=b, target=target))
+        batch = oload.collate(items)
+        for k in LOADER_KEYS:
+            ref = g[f"item{it}.{k}"]
+            assert batch[k].shape == ref.shape, (k, batch[k].shape, ref.shape)
+            assert np.array_equal(batch[k].numpy(), ref), f"{name} item {it} {k}"      # same ATen ops: bit-exact
+        if hot is not None and target == (H, W):
+            for b, (xs, ys, ts, ps) in enumerate(wins):
+                seen = np.zeros((H, W), bool)
+                fx = (W - 1 - xs) if g["flips"][b][0] else xs
+                fy = (H - 1 - ys) if g["flips"][b][1] else ys
+                seen[fy, fx] = True
+                removed += int((seen & (g[f"item{it}.event_mask"][b, 0] == 0)).sum())
+    if name == "loader_events_hot":
+        assert removed > 0, "the hot-pixel filter never fired: the fixture would be vacuous"
