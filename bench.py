@@ -44,11 +44,20 @@ def parse():
     ap.add_argument("--res", type=int, default=128)
     ap.add_argument("--bins", type=int, default=10)
     ap.add_argument("--events", type=int, default=1000, help="events per sample per bin")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="fixed GLOBAL batch split over the ranks (BASELINE.json configs[3]: 256); strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N > 1: NCCL all-reduce between two graphs instead of the peer-memory kernel inside one graph")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
-    return ap.parse_args()
+    a = ap.parse_args()
+    a.scaling = "weak"
+    if a.global_batch:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if a.global_batch % world:
+            ap.error("--global-batch must be divisible by the number of ranks")
+        a.batch, a.scaling = a.global_batch // world, "strong"
+    return a
 
 
 def workload_config(a, n_gpus):
@@ -135,7 +144,7 @@ def run_reference(a):
     sample = f"{a.steps} full optimizer steps (batch {a.batch}, {a.bins} bins) of the same workload after {a.warmup} warm-up"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, 1),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -383,7 +392,7 @@ def run_ours(a):
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
@@ -463,9 +472,17 @@ def run_micro(snnflow, dev):
         ms = ev0.elapsed_time(ev1) / 5
         return {"ms": round(ms, 4), "Mev_s": round(N / ms / 1e3, 1), "GBps": round(nbytes / ms / 1e6, 1)}
 
+    # the whole event branch of the loader for the same 10 M events (one batch slot): normalise, flip, count / mask / voxel
+    # encodings, event list + polarity mask, hot-pixel filter (snnflow_format_window; 16 B in + 24 B out per event)
+    fmt = snnflow.EventWindowFormatter(
+        {"data": {"mode": "events"}, "loader": {"resolution": [H, W], "std_resolution": [H, W], "batch_size": 1,
+                                                "augment": ["Horizontal", "Vertical", "Polarity"], "augment_prob": [1.0, 1.0, 1.0]},
+         "hot_filter": {"enabled": True, "max_px": 100, "min_obvs": 5, "max_rate": 0.8}}, 5)
+    raw = [t.reshape(1, N) for t in (xs, ys, ts, (ps > 0).float())]
     with torch.no_grad():
         return {
             "events": N, "resolution": [H, W],
+            "format_window": timed(lambda: fmt.format_batch(*raw), 40.0 * N + 52.0 * H * W),
             "events_to_channels": timed(lambda: enc.events_to_channels(xs, ys, ps, (H, W)), 12.0 * N + 8.0 * H * W),
             "events_to_voxel_5": timed(lambda: enc.events_to_voxel(xs, ys, ts, ps, 5, (H, W)), 16.0 * N + 20.0 * H * W),
             "events_to_image_mask": timed(lambda: enc.events_to_image(xs, ys, ps.abs(), (H, W), accumulate=False), 12.0 * N + 4.0 * H * W),

@@ -278,3 +278,42 @@ def test_padded_width_states_feed_per_bin_forward():
     assert torch.equal(ref, torch.cat([a, b, c]))
     for x, y in zip(s_ref, net._states):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("kind,B,R,T", [("LIFFireNet", 8, 128, 10),        # BASELINE.json configs[1]: train shape
+                                        ("LIFFireFlowNet", 16, 256, 4)])   # configs[2]: eval shape (4 of its bins)
+def test_full_size_window_vs_cpu_oracle(kind, B, R, T):
+    """BASELINE.json's full sizes (C=32): every spike and membrane of all seven layers after T bins, and every flow map,
+    against the CPU oracle (2^-12-grid weights: bit-exact tier), plus two size-independent properties of the path:
+    splitting the window in two calls changes nothing, and a batch permutation permutes the outputs."""
+    from oracle import firenet as ofn
+    net = make_net(kind, 32)
+    params = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(21)
+    cnt = torch.poisson(torch.full((T, B, 2, R, R), 0.06), generator=g)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    states, flows = [None] * 7, []
+    with torch.no_grad():
+        for t in range(T):
+            f, states, _ = ofn.forward(params, cnt[t], states)
+            flows.append(f)
+        runner_of(net, "layer_major")
+        net.reset_states()
+        got = net.forward_window(cnt.cuda())
+        s_got = [s.clone() for s in net._states]
+    n_neur = 0
+    for i, (v, z) in enumerate(states):
+        assert torch.equal(s_got[i][1].cpu(), z), f"layer {i}: {int((s_got[i][1].cpu() != z).sum())} spikes differ"
+        # the GPU sigmoid of the leak may differ from the CPU's by 1 ulp (DESIGN.md section 2): membranes to 4e-6
+        assert float((s_got[i][0].cpu() - v).abs().max()) < 4e-6, f"layer {i}: membranes differ"
+        n_neur += z.numel()
+    assert float(states[-1][1].mean()) > 0.01, "silent network: vacuous"
+    assert float((got.cpu() - torch.stack(flows)).abs().max()) < 1e-5
+    with torch.no_grad():
+        net.reset_states()
+        half = torch.cat([net.forward_window(cnt[:T // 2].cuda()), net.forward_window(cnt[T // 2:].cuda())])
+        assert torch.equal(half, got)
+        perm = torch.randperm(B, generator=g)
+        net.reset_states()
+        got_p = net.forward_window(cnt[:, perm].contiguous().cuda())
+        assert torch.equal(got_p, got[:, perm.cuda()])
