@@ -76,7 +76,7 @@ def kernels(path, out):
 
 
 BENCH_NAME = [("wt_fwd_kernel<1", "win_fwd_seq"), ("wt_fwd_kernel<(bool)1", "win_fwd_seq"), ("wt_fwd_kernel<0", "win_fwd_rec"),
-              ("wt_fwd_kernel<(bool)0", "win_fwd_rec"), ("wt_dgrad", "win_dgrad"), ("wt_recbwd", "win_rec_bwd"),
+              ("wt_fwd_kernel<(bool)0", "win_fwd_rec"), ("wt_dgpw", "win_dgrad_pw"), ("wt_dgrad", "win_dgrad"), ("win_reduce", "win_reduce"), ("wt_recbwd", "win_rec_bwd"),
               ("wg_planes", "win_wgrad"), ("pw_seq", "win_pw_seq")]
 
 

@@ -102,6 +102,9 @@ def test_formatter_empty_window_and_errors():
         fmt.format_batch(torch.zeros(3, 4).cuda(), torch.zeros(3, 4).cuda(), torch.zeros(3, 4).cuda(), torch.zeros(3, 4).cuda())
     # a window whose timestamps are all equal normalises to zeros (base.py:97-98)
     one = torch.ones((2, 5), device="cuda")
+    for m in fmt.batch_augmentation:
+        fmt.batch_augmentation[m] = [False, False]
+    fmt._flips = None
     b2 = fmt.format_batch(one, one, one * 7.0, one)
     assert float(b2["event_list"][..., 0].abs().sum()) == 0.0
     assert float(b2["event_cnt"][:, 0, 1, 1].sum()) == 10.0
