@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N > 1: NCCL all-reduce between two graphs instead of the peer-memory kernel inside one graph")
+    ap.add_argument("--torch-adam", action="store_true", help="torch.nn.utils.clip_grad_norm_ + torch.optim.Adam instead of the fused update")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     a = ap.parse_args()
     a.scaling = "weak"
@@ -244,7 +245,10 @@ def run_ours(a):
                                   neuron_kwargs=dict(leak=(0.0, 1.0), thresh=(0.3, 0.1)))).to(dev)
     cfg = {"loader": {"resolution": [a.res, a.res]}, "loss": {"flow_regul_weight": 0.001}, "model": {"mask_output": False}}
     lossf = snnflow.EventWarping(cfg, dev)
-    opt = torch.optim.Adam(net.parameters(), lr=2e-4, capturable=not a.no_graph)
+    if a.torch_adam:
+        opt = torch.optim.Adam(net.parameters(), lr=2e-4, capturable=not a.no_graph)
+    else:   # clip_grad_norm_(1.0) + Adam as one C call over the flat parameter buffer (snnflow_clip_adam)
+        opt = snnflow.FusedClipAdam(net.parameters(), lr=2e-4, max_norm=1.0)
     tw = TrainWindow(net, lossf, opt, clip_grad=1.0, peer_allreduce=not a.nccl_allreduce)
 
     host_pool = [{k: v.pin_memory() for k, v in make_window(a, 1000 * rank + i).items()} for i in range(4)]
@@ -477,12 +481,36 @@ def run_micro(snnflow, dev):
     fmt = snnflow.EventWindowFormatter(
         {"data": {"mode": "events"}, "loader": {"resolution": [H, W], "std_resolution": [H, W], "batch_size": 1,
                                                 "augment": ["Horizontal", "Vertical", "Polarity"], "augment_prob": [1.0, 1.0, 1.0]},
+         # 10 M uniform events hit every pixel of a 256x256 sensor in every window, which would declare the whole
+         # sensor "hot": the filter is exercised at the training shape below instead
+         "hot_filter": {"enabled": False, "max_px": 100, "min_obvs": 5, "max_rate": 0.8}}, 5)
+    # ... and at the training shape (BASELINE configs[1]: batch 8 x 1000 events, 128x128), hot-pixel filter on
+    Bt, Nt, Rt = 8, 1000, 128
+    fmt_t = snnflow.EventWindowFormatter(
+        {"data": {"mode": "events"}, "loader": {"resolution": [Rt, Rt], "std_resolution": [Rt, Rt], "batch_size": Bt,
+                                                "augment": ["Horizontal", "Vertical", "Polarity"], "augment_prob": [0.5, 0.5, 0.5]},
          "hot_filter": {"enabled": True, "max_px": 100, "min_obvs": 5, "max_rate": 0.8}}, 5)
+    raw_t = [torch.randint(0, Rt, (Bt, Nt), generator=g).float().to(dev), torch.randint(0, Rt, (Bt, Nt), generator=g).float().to(dev),
+             torch.sort(torch.rand(Bt, Nt, generator=g), dim=1).values.to(dev), torch.randint(0, 2, (Bt, Nt), generator=g).float().to(dev)]
+
+    def timed_small(fn, n_ev):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(20):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / 20
+        return {"ms": round(ms, 4), "Mev_s": round(n_ev / ms / 1e3, 1), "batches_s": round(1e3 / ms, 1)}
+
     raw = [t.reshape(1, N) for t in (xs, ys, ts, (ps > 0).float())]
     with torch.no_grad():
         return {
             "events": N, "resolution": [H, W],
             "format_window": timed(lambda: fmt.format_batch(*raw), 40.0 * N + 52.0 * H * W),
+            "format_window_train_shape": timed_small(lambda: fmt_t.format_batch(*raw_t), Bt * Nt),
             "events_to_channels": timed(lambda: enc.events_to_channels(xs, ys, ps, (H, W)), 12.0 * N + 8.0 * H * W),
             "events_to_voxel_5": timed(lambda: enc.events_to_voxel(xs, ys, ts, ps, 5, (H, W)), 16.0 * N + 20.0 * H * W),
             "events_to_image_mask": timed(lambda: enc.events_to_image(xs, ys, ps.abs(), (H, W), accumulate=False), 12.0 * N + 4.0 * H * W),

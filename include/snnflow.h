@@ -306,6 +306,19 @@ int snnflow_window_loss(const float* flow, const float* events, const float* pol
                         float flow_scaling, float regul_weight, int loss_scaling, snnflow_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Optimizer update of the training step (train_flow.py:264-271): torch.nn.utils.clip_grad.clip_grad_norm_(parameters,
+ * max_norm) followed by torch.optim.Adam.step() (no amsgrad, no weight decay) over ONE flat fp32 parameter buffer, as
+ * two launches (fixed-order sum of squares; clip coefficient + Adam per slice) instead of ~20 small PyTorch kernels.
+ *   params, grads, exp_avg, exp_avg_sq : n floats each (grads is read only: the clipped gradient is not written back)
+ *   hyper    device array {lr, beta1, beta2, eps, max_norm}; max_norm <= 0 disables clipping
+ *   step     device int64, Adam's step counter: incremented by the call (so a CUDA-graph replay advances it)
+ *   partials snnflow_clip_adam_partials(n) floats of scratch;  grad_norm: device float or NULL, receives the total norm
+ * --------------------------------------------------------------------------------------------- */
+int snnflow_clip_adam_partials(int64_t n);
+int snnflow_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* hyper,
+                      int64_t* step, float* partials, float* grad_norm, snnflow_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange (the reference has no distributed code): SUM all-reduce
  * of a flat fp32 buffer across the ranks of one NVLink domain as ONE kernel per rank, replayable inside a CUDA graph.
  *   peer_bufs  device array of `world` pointers: every rank's symmetric buffer (n floats) mapped into this process

@@ -12,6 +12,7 @@ from .model import LIFFireNet, LIFFireFlowNet  # noqa: F401
 from . import encodings, iwe  # noqa: F401
 from .flow_loss import EventWarping  # noqa: F401
 from .loader import EventWindowFormatter  # noqa: F401
+from .optim import FusedClipAdam  # noqa: F401
 
 __all__ = ["ConvLIF", "ConvLIFRecurrent", "ConvLayer", "LIFFireNet", "LIFFireFlowNet", "EventWarping",
-           "EventWindowFormatter", "encodings", "iwe"]
+           "EventWindowFormatter", "FusedClipAdam", "encodings", "iwe"]

@@ -8,6 +8,7 @@ Saved activations live in a preallocated arena ([v | z | I] per layer and bin), 
 or cloned per layer-step, and gradients accumulate straight into per-parameter buffers.
 """
 import ctypes
+import math
 
 import torch
 
@@ -263,13 +264,26 @@ class _LayerMajorWindowFn(torch.autograd.Function):
         g_flow = g_flow.float().contiguous()
         Cr, C = ctx.Cr, desc.C
         lam_e, theta_e, w_e, pw_e = ctx.lam_e, ctx.theta_e, ctx.w_e, ctx.pw_e
-        dlam = torch.zeros_like(lam_e)
-        dtheta = torch.zeros_like(theta_e)
+        # every gradient of the window is a slice of ONE zero-filled buffer (one fill instead of one per tensor)
+        shapes = [lam_e.shape, theta_e.shape]
+        for i, l in enumerate(layers):
+            shapes.append(w_e[i][0].shape)
+            if l.recurrent:
+                shapes.append(w_e[i][1].shape)
+        shapes += [pw_e.shape, (2,)]
+        sizes = [(math.prod(sh) + 63) // 64 * 64 for sh in shapes]
+        gbuf = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        carved, o = [], 0
+        for sh, n in zip(shapes, sizes):
+            carved.append(gbuf[o:o + math.prod(sh)].view(sh))
+            o += n
+        carved = iter(carved)
+        dlam, dtheta = next(carved), next(carved)
         dws = []
         lp = (LayerPtrs * N_LAYERS)()
         for i, l in enumerate(layers):
-            dwf = torch.zeros_like(w_e[i][0])
-            dwr = torch.zeros_like(w_e[i][1]) if l.recurrent else None
+            dwf = next(carved)
+            dwr = next(carved) if l.recurrent else None
             dws.append((dwf, dwr))
             lp[i].w_ff = w_e[i][0].data_ptr()
             lp[i].w_rec = w_e[i][1].data_ptr() if l.recurrent else None
@@ -280,8 +294,7 @@ class _LayerMajorWindowFn(torch.autograd.Function):
             lp[i].dlam = dlam[i].data_ptr()
             lp[i].dtheta = dtheta[i].data_ptr()
         pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
-        d_pw = torch.zeros_like(pw_e)
-        d_pb = torch.zeros(2, dtype=torch.float32, device=dev)
+        d_pw, d_pb = next(carved), next(carved)
         ws = runner.lm_workspace(desc, dev)
         sp, keep = _state_ptrs(ctx.states_in)
         _lib.check(L.snnflow_window_backward(ctypes.byref(desc), lp, pw_e.data_ptr(), sp, ctx.arena.data_ptr(),

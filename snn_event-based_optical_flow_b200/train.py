@@ -102,6 +102,10 @@ class TrainWindow:
 
     def __init__(self, model, loss_fn, optimizer, clip_grad=1.0, group=None, peer_allreduce=False):
         self.model, self.loss_fn, self.opt, self.clip = model, loss_fn, optimizer, clip_grad
+        if getattr(optimizer, "fused_clip", False):
+            have = float(optimizer.hyper[4])
+            if (clip_grad or 0.0) != have:
+                raise ValueError(f"FusedClipAdam clips at max_norm={have}, TrainWindow was given clip_grad={clip_grad}")
         self.reducer = FlatGradAllReduce(model.parameters(), group)
         if peer_allreduce and PeerGradAllReduce.available():
             try:   # NVLink peer memory: the exchange becomes one kernel inside the step graph
@@ -130,9 +134,12 @@ class TrainWindow:
         return loss.detach()
 
     def _update(self):
-        if self.clip is not None:
-            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
-        self.opt.step()
+        if getattr(self.opt, "fused_clip", False):
+            self.opt.step()          # optim.FusedClipAdam: clipping and Adam in one C call (max_norm given to the optimizer)
+        else:
+            if self.clip is not None:
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
+            self.opt.step()
         self.opt.zero_grad(set_to_none=True)
         self.model.detach_states()
         self.loss_fn.reset()

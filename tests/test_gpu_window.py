@@ -304,8 +304,10 @@ def test_full_size_window_vs_cpu_oracle(kind, B, R, T):
     n_neur = 0
     for i, (v, z) in enumerate(states):
         assert torch.equal(s_got[i][1].cpu(), z), f"layer {i}: {int((s_got[i][1].cpu() != z).sum())} spikes differ"
-        # the GPU sigmoid of the leak may differ from the CPU's by 1 ulp: membranes to 4e-6
-        assert float((s_got[i][0].cpu() - v).abs().max()) < 4e-6, f"layer {i}: membranes differ"
+        # the GPU sigmoid of the leak may differ from the CPU's by 1 ulp, and the difference
+        # compounds over the T bins: membranes to 1e-6 * T relative to the largest membrane of the layer
+        tol = 1e-6 * T * max(1.0, float(v.abs().max()))
+        assert float((s_got[i][0].cpu() - v).abs().max()) < tol, f"layer {i}: membranes differ"
         n_neur += z.numel()
     assert float(states[-1][1].mean()) > 0.01, "silent network: vacuous"
     assert float((got.cpu() - torch.stack(flows)).abs().max()) < 1e-5
