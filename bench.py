@@ -490,8 +490,14 @@ def run_micro(snnflow, dev):
         {"data": {"mode": "events"}, "loader": {"resolution": [Rt, Rt], "std_resolution": [Rt, Rt], "batch_size": Bt,
                                                 "augment": ["Horizontal", "Vertical", "Polarity"], "augment_prob": [0.5, 0.5, 0.5]},
          "hot_filter": {"enabled": True, "max_px": 100, "min_obvs": 5, "max_rate": 0.8}}, 5)
-    raw_t = [torch.randint(0, Rt, (Bt, Nt), generator=g).float().to(dev), torch.randint(0, Rt, (Bt, Nt), generator=g).float().to(dev),
-             torch.sort(torch.rand(Bt, Nt, generator=g), dim=1).values.to(dev), torch.randint(0, 2, (Bt, Nt), generator=g).float().to(dev)]
+    def raw_window():
+        return [torch.randint(0, Rt, (Bt, Nt), generator=g).float().to(dev), torch.randint(0, Rt, (Bt, Nt), generator=g).float().to(dev),
+                torch.sort(torch.rand(Bt, Nt, generator=g), dim=1).values.to(dev), torch.randint(0, 2, (Bt, Nt), generator=g).float().to(dev)]
+    raw_pool, raw_i = [raw_window() for _ in range(16)], [0]   # different windows: a repeated window would make every hit pixel "hot"
+
+    def format_next():
+        raw_i[0] += 1
+        return fmt_t.format_batch(*raw_pool[raw_i[0] % len(raw_pool)])
 
     def timed_small(fn, n_ev):
         for _ in range(3):
@@ -510,7 +516,7 @@ def run_micro(snnflow, dev):
         return {
             "events": N, "resolution": [H, W],
             "format_window": timed(lambda: fmt.format_batch(*raw), 40.0 * N + 52.0 * H * W),
-            "format_window_train_shape": timed_small(lambda: fmt_t.format_batch(*raw_t), Bt * Nt),
+            "format_window_train_shape": timed_small(format_next, Bt * Nt),
             "events_to_channels": timed(lambda: enc.events_to_channels(xs, ys, ps, (H, W)), 12.0 * N + 8.0 * H * W),
             "events_to_voxel_5": timed(lambda: enc.events_to_voxel(xs, ys, ts, ps, 5, (H, W)), 16.0 * N + 20.0 * H * W),
             "events_to_image_mask": timed(lambda: enc.events_to_image(xs, ys, ps.abs(), (H, W), accumulate=False), 12.0 * N + 4.0 * H * W),

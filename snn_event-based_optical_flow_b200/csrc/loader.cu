@@ -136,16 +136,20 @@ __global__ void __launch_bounds__(LD_THREADS) ld_scatter_kernel(const LdScatterA
 }
 
 // create_hot_mask + get_hot_event_mask: one CTA per batch slot.  The reference removes, one argmax at a time, up to
-// max_px pixels whose event rate exceeds max_rate (ties: lowest flat index first).  When no more than max_px pixels
-// exceed the rate the order is irrelevant and all of them go in one pass; otherwise the literal argmax loop runs.
+// max_px pixels whose event rate exceeds max_rate (ties: lowest flat index first), i.e. the first max_px candidates in
+// the order (rate descending, index ascending).  hot_events holds integer hit counts and every pixel is divided by the
+// same hot_idx, so that order is (count descending, index ascending):
+//   * no more than max_px candidates: all of them go, in one pass;
+//   * otherwise a binary search over the integer count finds the cut c* (largest c with >= max_px candidates of count
+//     >= c); everything above c* goes, and of the candidates AT c* the lowest-index ones fill the remaining places
+//     (one ordered pass with a block-wide prefix count).  log2(hot_idx) + 2 passes instead of max_px argmax passes.
 __global__ void __launch_bounds__(HOT_THREADS) ld_hot_kernel(const float* __restrict__ cnt, float* __restrict__ hot_events,
                                                              int32_t* __restrict__ hot_idx, float* __restrict__ hotmask,
                                                              int HW, int max_px, int min_obvs, float max_rate) {
   const int b = blockIdx.x;
   cnt += (size_t)b * 2 * HW; hot_events += (size_t)b * HW; hotmask += (size_t)b * HW;
   __shared__ int s_cand;
-  __shared__ unsigned long long s_best[HOT_THREADS / 32];
-  __shared__ unsigned long long s_pick;
+  __shared__ int s_warp[HOT_THREADS / 32];
   const int idx = hot_idx[b] + 1;                                    // base.py:249
   const float fidx = (float)idx;
   if (threadIdx.x == 0) s_cand = 0;
@@ -161,37 +165,70 @@ __global__ void __launch_bounds__(HOT_THREADS) ld_hot_kernel(const float* __rest
   if (cand) atomicAdd(&s_cand, cand);
   __syncthreads();
   if (threadIdx.x == 0) hot_idx[b] = idx;
-  if (!(idx > min_obvs) || s_cand == 0 || max_px <= 0) return;       // encodings.py:94
-  if (s_cand <= max_px) {
+  const int n_cand = s_cand;
+  if (!(idx > min_obvs) || n_cand == 0 || max_px <= 0) return;       // encodings.py:94
+  if (n_cand <= max_px) {
     for (int i = threadIdx.x; i < HW; i += HOT_THREADS)
       if (__fdiv_rn(hot_events[i], fidx) > max_rate) hotmask[i] = 0.f;
     return;
   }
-  for (int it = 0; it < max_px; ++it) {                              // encodings.py:95-102
-    unsigned long long best = 0ull;                                  // (rate bits << 32) | ~index: max = highest rate, lowest index
+  // more candidates than places: find the cut.  Invariant: #(cand, count >= lo) >= max_px > #(cand, count >= hi + 1)
+  int lo = 0, hi = idx;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    const float fm = (float)mid;
+    int c = 0;
     for (int i = threadIdx.x; i < HW; i += HOT_THREADS) {
-      if (hotmask[i] == 0.f) continue;                               // event_rate[index] = 0 for removed pixels
-      const float r = __fdiv_rn(hot_events[i], fidx);
-      if (r > max_rate) {
-        const unsigned long long key = ((unsigned long long)__float_as_uint(r) << 32) | (unsigned)(~(unsigned)i);
-        best = key > best ? key : best;
-      }
+      const float he = hot_events[i];
+      c += (he >= fm && __fdiv_rn(he, fidx) > max_rate) ? 1 : 0;
     }
+    // per-thread counts -> block total (warp shuffle + shared), identical in every thread
+    c = (int)warp_sum((float)c);                                      // < 2^24: exact in fp32
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    int tot = 0;
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, s);
-      best = o > best ? o : best;
-    }
-    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    for (int w = 0; w < HOT_THREADS / 32; ++w) tot += s_warp[w];
+    if (tot >= max_px) lo = mid; else hi = mid - 1;
+  }
+  const float cut = (float)lo;
+  int above = 0;
+  for (int i = threadIdx.x; i < HW; i += HOT_THREADS) {
+    const float he = hot_events[i];
+    above += (he > cut && __fdiv_rn(he, fidx) > max_rate) ? 1 : 0;
+  }
+  above = (int)warp_sum((float)above);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = above;
+  __syncthreads();
+  int n_above = 0;
+#pragma unroll
+  for (int w = 0; w < HOT_THREADS / 32; ++w) n_above += s_warp[w];
+  const int places = max_px - n_above;                               // >= 1 by the invariant
+  // ordered pass: pixels in flat-index order, 1024 at a time; rank of a pixel among the candidates AT the cut
+  int running = 0;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < HW; base += HOT_THREADS) {
+    const int i = base + threadIdx.x;
+    float he = 0.f;
+    bool is_cand = false;
+    if (i < HW) { he = hot_events[i]; is_cand = __fdiv_rn(he, fidx) > max_rate; }
+    const bool at_cut = is_cand && he == cut, over = is_cand && he > cut;
+    const unsigned bal = __ballot_sync(0xffffffffu, at_cut);
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long m = 0ull;
-      for (int w = 0; w < HOT_THREADS / 32; ++w) m = s_best[w] > m ? s_best[w] : m;
-      s_pick = m;
-      if (m) hotmask[~(unsigned)(m & 0xffffffffull)] = 0.f;
-    }
+    if (lane == 0) s_warp[warp] = __popc(bal);
     __syncthreads();
-    if (s_pick == 0ull) break;
+    int before = running, total = 0;
+#pragma unroll
+    for (int w = 0; w < HOT_THREADS / 32; ++w) {
+      const int n = s_warp[w];
+      before += (w < (int)warp) ? n : 0;
+      total += n;
+    }
+    const int rank = before + __popc(bal & ((1u << lane) - 1u));
+    if (over || (at_cut && rank < places)) hotmask[i] = 0.f;
+    running += total;
   }
 }
 

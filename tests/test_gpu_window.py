@@ -288,6 +288,16 @@ def test_full_size_window_vs_cpu_oracle(kind, B, R, T):
     splitting the window in two calls changes nothing, and a batch permutation permutes the outputs."""
     from oracle import firenet as ofn
     net = make_net(kind, 32)
+    # lam = sigmoid(leak) is evaluated by torch on the parameter's device: where the CUDA and the CPU sigmoid disagree in
+    # the last bit, a neuron within 1e-7 of threshold may flip (and ~3e8 neuron-steps do contain such neurons), so those
+    # channels get leak = 0 (sigmoid = 0.5 exactly on both sides).  Then every membrane must match bit for bit.
+    with torch.no_grad():
+        kept = 0
+        for l in (net.head, net.G1, net.R1a, net.R1b, net.G2, net.R2a, net.R2b):
+            same = torch.sigmoid(l.leak).cpu() == torch.sigmoid(l.leak.cpu())
+            l.leak.mul_(same.to(l.leak.device).float())
+            kept += int(same.sum())
+        assert kept >= 7 * 32 * 0.7, "most channels should keep their random leak"
     params = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
     g = torch.Generator().manual_seed(21)
     cnt = torch.poisson(torch.full((T, B, 2, R, R), 0.06), generator=g)
@@ -304,13 +314,10 @@ def test_full_size_window_vs_cpu_oracle(kind, B, R, T):
     n_neur = 0
     for i, (v, z) in enumerate(states):
         assert torch.equal(s_got[i][1].cpu(), z), f"layer {i}: {int((s_got[i][1].cpu() != z).sum())} spikes differ"
-        # the GPU sigmoid of the leak may differ from the CPU's by 1 ulp, and the difference
-        # compounds over the T bins: membranes to 1e-6 * T relative to the largest membrane of the layer
-        tol = 1e-6 * T * max(1.0, float(v.abs().max()))
-        assert float((s_got[i][0].cpu() - v).abs().max()) < tol, f"layer {i}: membranes differ"
+        assert torch.equal(s_got[i][0].cpu(), v), f"layer {i}: membranes differ ({float((s_got[i][0].cpu() - v).abs().max())})"
         n_neur += z.numel()
     assert float(states[-1][1].mean()) > 0.01, "silent network: vacuous"
-    assert float((got.cpu() - torch.stack(flows)).abs().max()) < 1e-5
+    assert float((got.cpu() - torch.stack(flows)).abs().max()) < 2e-6      # tanh of the CUDA vs the CPU libm
     with torch.no_grad():
         net.reset_states()
         half = torch.cat([net.forward_window(cnt[:T // 2].cuda()), net.forward_window(cnt[T // 2:].cuda())])
