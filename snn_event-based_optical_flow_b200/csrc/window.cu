@@ -120,7 +120,7 @@ static bool win_supported(const snnflow_net_desc* d, bool backward = true) {
 }
 
 struct WinWorkspace {
-  size_t off_g[2], off_gp[2], gp_term_stride, off_gv, off_wpart[2], off_cpart, off_ppart, total;
+  size_t off_g[2], off_gp[2], gp_term_stride, off_gv, off_wpart[WIN_LAYERS][2], off_cpart[WIN_LAYERS], off_ppart, total;
   int wg_grid_max, rb_grid, dp_grid, pw_parts, pred_parts;
 };
 
@@ -140,15 +140,19 @@ static WinWorkspace win_workspace(const snnflow_net_desc* d, const WinLayout& L,
     const int g = wg_grid(T * B, d->H, d->W, C, L.Kin[l] / 8, L.rec[l] ? C / 8 : 0);
     if (g > W.wg_grid_max) W.wg_grid_max = g;
   }
-  W.off_wpart[0] = take((size_t)W.wg_grid_max * 9 * C * C * sizeof(float));
-  W.off_wpart[1] = take((size_t)W.wg_grid_max * 9 * C * C * sizeof(float));
+  // per-layer partial blocks: the reductions of all layers run as ONE launch at the end of the backward pass
+  for (int l = 0; l < WIN_LAYERS; ++l) {
+    const int g = wg_grid(T * B, d->H, d->W, C, L.Kin[l] / 8, L.rec[l] ? C / 8 : 0);
+    W.off_wpart[l][0] = take((size_t)g * 9 * L.Kin[l] * C * sizeof(float));
+    W.off_wpart[l][1] = L.rec[l] ? take((size_t)g * 9 * C * C * sizeof(float)) : W.off_wpart[l][0];
+  }
   W.rb_grid = P.R_rb ? wt_grid(B * (d->H / P.R_rb)) : 0;
   W.pw_parts = B * ceil_div(d->H * d->W, 256);
   W.dp_grid = wt_grid(B * (d->H / P.R_dp));
   size_t c1 = (size_t)2 * C * W.pw_parts;
   const size_t c2 = (size_t)T * W.rb_grid * 2 * C, c3 = (size_t)W.dp_grid * 2 * C;
   c1 = c1 > c2 ? c1 : c2;
-  W.off_cpart = take((c1 > c3 ? c1 : c3) * sizeof(float));
+  for (int l = 0; l < WIN_LAYERS; ++l) W.off_cpart[l] = take((c1 > c3 ? c1 : c3) * sizeof(float));
   W.pred_parts = pred_planes_parts(T * B, d->H, d->W);
   const int pp = W.pred_parts > W.pw_parts ? W.pred_parts : W.pw_parts;
   W.off_ppart = take((size_t)pp * (2 * C + 2) * sizeof(float));
@@ -329,8 +333,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
   float* gbuf = (float*)(Wk + WS.off_g[0]);   // spike gradient of a recurrent layer (from the layer above), c8
   unsigned char* gplanes[2] = {Wk + WS.off_gp[0], Wk + WS.off_gp[1]};   // g_I planes of layer l live in gplanes[l & 1]
   float* g_v = (float*)(Wk + WS.off_gv);
-  float* wpart[2] = {(float*)(Wk + WS.off_wpart[0]), (float*)(Wk + WS.off_wpart[1])};
-  float* cpart = (float*)(Wk + WS.off_cpart);
+  WinReduceArgs reduces[WIN_LAYERS];   // queued per layer, executed by one launch after the loop
   float* ppart = (float*)(Wk + WS.off_ppart);
   const int hard = (d->flags & SNNFLOW_HARD_RESET) ? 1 : 0;
   const int top = WIN_LAYERS - 1;
@@ -357,6 +360,8 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
     const float* vbase = (const float*)(A + L.off_v[l]);
     const float* par = (const float*)(A + L.off_par[l]);
     unsigned char* gp = gplanes[l & 1];
+    float* wpart[2] = {(float*)(Wk + WS.off_wpart[l][0]), (float*)(Wk + WS.off_wpart[l][1])};
+    float* cpart = (float*)(Wk + WS.off_cpart[l]);
     if (L.rec[l]) {
       WtArgs a{};
       // hi planes x (w_hi, w_lo), then lo planes x w_hi: two pipeline units per tile
@@ -424,8 +429,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
       r.n_wpart = wg_grid(T * B, H, W, C, L.Kin[l] / 8, L.rec[l] ? C / 8 : 0);
       r.cpart = cpart; r.n_cpart = n_cpart; r.cpart_layout = cpart_layout;
       r.dlam = P_.dlam; r.dtheta = P_.dtheta; r.C = C;
-      rc = launch_win_reduce(r, st);
-      if (rc) return rc;
+      reduces[l] = r;
     }
 
     // (3) data gradient through W_ff: the spike gradient of the layer below
@@ -447,7 +451,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
         a.v_t = (const float*)(A + L.off_v[l - 1]);
         a.v_init = v_init_b; a.z_init = v_init_b ? v_init_b + n : nullptr;
         a.gp_out = gplanes[(l - 1) & 1]; a.gp_img_stride = L.zp_img_stride; a.gp_term_stride = WS.gp_term_stride;
-        a.part = cpart;
+        a.part = (float*)(Wk + WS.off_cpart[l - 1]);
         rc = launch_wt_dgpw(a, st, 4.0 * T * px * (C + 3 * L.Kin[l]) /* g_I in ; v (x2), g_I out */, 18.0 * T * px * C * L.Kin[l]);
         if (rc) return rc;
         n_cpart = WS.dp_grid; cpart_layout = 1;
@@ -460,5 +464,5 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
       }
     }
   }
-  return SNNFLOW_OK;
+  return launch_win_reduce(reduces, WIN_LAYERS, st);
 }

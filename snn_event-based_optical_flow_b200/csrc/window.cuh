@@ -157,7 +157,7 @@ struct WinReduceArgs {
   float *dlam, *dtheta;    // (+=)
   int C;
 };
-int launch_win_reduce(const WinReduceArgs& a, cudaStream_t st);
+int launch_win_reduce(const WinReduceArgs* layers, int n_layers, cudaStream_t st);   // all layers in one launch
 int launch_pred_reduce_planes(const float* part, float* dw, float* db, int C, int n_part, cudaStream_t st);
 int launch_pred_reduce_rows(const float* part, float* dw, float* db, int C, int n_part, cudaStream_t st);
 

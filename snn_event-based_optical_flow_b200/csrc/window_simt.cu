@@ -464,9 +464,17 @@ int launch_pred_reduce_planes(const float* part, float* dw, float* db, int C, in
 // ---- reductions of the per-CTA partials (fixed order: run-to-run deterministic) --------------------------
 //   blockIdx.y 0/1: dW_ff / dW_rec[co][ci][tap] += sum_p part[p][tap][ci][co]
 //   blockIdx.y 2  : dlam / dtheta[c] += sum_j cpart
-__global__ void __launch_bounds__(256) win_reduce_kernel(const WinReduceArgs a) {
+//   blockIdx.z    : layer - the reductions of all layers of a window are ONE launch at the end of the backward pass
+//                   (every layer keeps its own partial blocks in the workspace): 7 x 12 us of launch latency -> one
+constexpr int WIN_REDUCE_MAX_LAYERS = 8;
+struct WinReduceBatch {
+  WinReduceArgs layer[WIN_REDUCE_MAX_LAYERS];
+};
+
+__global__ void __launch_bounds__(256) win_reduce_kernel(const __grid_constant__ WinReduceBatch batch) {
   pdl_launch_dependents();
   pdl_wait();
+  const WinReduceArgs& a = batch.layer[blockIdx.z];
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, stripe = threadIdx.x >> 5;
   const int job = blockIdx.y;
@@ -514,12 +522,25 @@ __global__ void __launch_bounds__(256) win_reduce_kernel(const WinReduceArgs a) 
   }
 }
 
-int launch_win_reduce(const WinReduceArgs& a, cudaStream_t st) {
-  const int cmax = a.cin_real[0] > a.cin_real[1] ? a.cin_real[0] : a.cin_real[1];
-  int gx = ceil_div(a.C * cmax * 9, 32);
+int launch_win_reduce(const WinReduceArgs* layers, int n_layers, cudaStream_t st) {
+  if (n_layers < 1 || n_layers > WIN_REDUCE_MAX_LAYERS) {
+    set_error("launch_win_reduce: %d layers", n_layers);
+    return SNNFLOW_EINVAL;
+  }
+  WinReduceBatch batch{};
+  int gx = 1;
+  double bytes = 0.0;
+  for (int l = 0; l < n_layers; ++l) {
+    const WinReduceArgs& a = layers[l];
+    batch.layer[l] = a;
+    const int cmax = a.cin_real[0] > a.cin_real[1] ? a.cin_real[0] : a.cin_real[1];
+    const int g = ceil_div(a.C * cmax * 9, 32);
+    if (g > gx) gx = g;
+    bytes += 4.0 * a.n_wpart * 9.0 * a.C * (a.cin_alloc[0] + (a.wdst[1] ? a.cin_alloc[1] : 0)) + 8.0 * a.C * a.n_cpart;
+  }
   if (gx > 4 * sm_count()) gx = 4 * sm_count();
-  prof_begin("win_reduce", st, 4.0 * a.n_wpart * 9.0 * a.C * (a.cin_alloc[0] + (a.wdst[1] ? a.cin_alloc[1] : 0)) + 8.0 * a.C * a.n_cpart);
-  launch_pdl(win_reduce_kernel, dim3(gx, 3), dim3(256), 0, st, a);
+  prof_begin("win_reduce", st, bytes);
+  launch_pdl(win_reduce_kernel, dim3(gx, 3, n_layers), dim3(256), 0, st, batch);
   return check_launch("win_reduce_kernel");
 }
 
