@@ -312,11 +312,13 @@ int snnflow_window_loss(const float* flow, const float* events, const float* pol
  *   params, grads, exp_avg, exp_avg_sq : n floats each (grads is read only: the clipped gradient is not written back)
  *   hyper    device array {lr, beta1, beta2, eps, max_norm}; max_norm <= 0 disables clipping
  *   step     device int64, Adam's step counter: incremented by the call (so a CUDA-graph replay advances it)
+ *   state    4 device doubles owned by the optimizer {beta1^t, beta2^t, lr/(1-beta1^t), 1/sqrt(1-beta2^t)}: the powers
+ *            are running products, (re)initialised by the call whenever step == 0
  *   partials snnflow_clip_adam_partials(n) floats of scratch;  grad_norm: device float or NULL, receives the total norm
  * --------------------------------------------------------------------------------------------- */
 int snnflow_clip_adam_partials(int64_t n);
 int snnflow_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* hyper,
-                      int64_t* step, float* partials, float* grad_norm, snnflow_stream_t stream);
+                      int64_t* step, double* state, float* partials, float* grad_norm, snnflow_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange (the reference has no distributed code): SUM all-reduce

@@ -37,7 +37,7 @@ _PROTOS = {
     "snnflow_iwe_splat_fwd": (c_int, [P] * 5 + [c_int, c_int64, c_int, c_int, c_float, c_float, c_int, c_int, c_float,
                                                 c_int, P]),
     "snnflow_clip_adam_partials": (c_int, [c_int64]),
-    "snnflow_clip_adam": (c_int, [P] * 4 + [c_int64] + [P] * 5),
+    "snnflow_clip_adam": (c_int, [P] * 4 + [c_int64] + [P] * 6),
     "snnflow_dp_allreduce_ctas": (c_int, []),
     "snnflow_dp_allreduce_sum": (c_int, [P, P, P, P, c_int, c_int, c_size_t, P]),
     "snnflow_window_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int64, c_int, c_int]),

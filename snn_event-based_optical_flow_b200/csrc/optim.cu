@@ -29,9 +29,21 @@ __device__ __forceinline__ float opt_block_sum(float v, float* red) {
   return t;   // valid in thread 0
 }
 
+// state (device, 4 doubles): {beta1^t, beta2^t, lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)}.  The powers are running
+// products (one double multiply per step instead of a double-precision pow(), which costs ~20 us on this part's FP64
+// rate); block 0 of the first launch advances them while the other blocks already sum their slices.
 __global__ void __launch_bounds__(OPT_THREADS) opt_sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partials,
-                                                                long long* __restrict__ step) {
+                                                                long long* __restrict__ step, const float* __restrict__ hyper,
+                                                                double* __restrict__ state) {
   __shared__ float red[OPT_THREADS / 32];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long t = *step;
+    const double p1 = (t == 0 ? 1.0 : state[0]) * (double)hyper[1], p2 = (t == 0 ? 1.0 : state[1]) * (double)hyper[2];
+    state[0] = p1; state[1] = p2;
+    state[2] = (double)hyper[0] / (1.0 - p1);
+    state[3] = 1.0 / sqrt(1.0 - p2);
+    *step = t + 1;   // Adam's step counter lives on the device (graph replays advance it)
+  }
   const int64_t base = (int64_t)blockIdx.x * OPT_PER_BLOCK;
   float s = 0.f;
 #pragma unroll 4
@@ -40,38 +52,31 @@ __global__ void __launch_bounds__(OPT_THREADS) opt_sumsq_kernel(const float* __r
     if (k < n) { const float x = g[k]; s = fmaf(x, x, s); }
   }
   const float t = opt_block_sum(s, red);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x] = t;
-    if (blockIdx.x == 0) *step += 1;   // Adam's step counter lives on the device (graph replays advance it)
-  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = t;
 }
 
 __global__ void __launch_bounds__(OPT_THREADS) opt_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                                     float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                                                    const float* __restrict__ hyper, const long long* __restrict__ step,
+                                                                    const float* __restrict__ hyper, const double* __restrict__ state,
                                                                     const float* __restrict__ partials, int n_part,
                                                                     float* __restrict__ norm_out) {
-  __shared__ float s_coef, s_step_size, s_inv_bc2_sqrt;
+  __shared__ float s_coef;
   if (threadIdx.x < 32) {
     // fixed-order reduction of the block partials: lane-strided sums, then a butterfly - the same in every block
     float t = 0.f;
     for (int i = threadIdx.x; i < n_part; i += 32) t += partials[i];
     t = warp_sum(t);
     if (threadIdx.x == 0) {
-      const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], max_norm = hyper[4];
+      const float max_norm = hyper[4];
       const float total = sqrtf(t);
       float coef = 1.f;
       if (max_norm > 0.f) coef = fminf(max_norm / (total + 1e-6f), 1.0f);      // clip_grad.py: clamp(max=1.0)
-      const double ts = (double)*step;
-      const double bc1 = 1.0 - pow((double)b1, ts), bc2 = 1.0 - pow((double)b2, ts);
       s_coef = coef;
-      s_step_size = (float)((double)lr / bc1);
-      s_inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
       if (blockIdx.x == 0 && norm_out) *norm_out = total;
     }
   }
   __syncthreads();
-  const float coef = s_coef, step_size = s_step_size, inv_bc2_sqrt = s_inv_bc2_sqrt;
+  const float coef = s_coef, step_size = (float)state[2], inv_bc2_sqrt = (float)state[3];
   const float b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
   const int64_t base = (int64_t)blockIdx.x * OPT_PER_BLOCK;
 #pragma unroll 4
@@ -92,17 +97,17 @@ using namespace snnflow;
 extern "C" int snnflow_clip_adam_partials(int64_t n) { return n <= 0 ? 0 : (int)ceil_div64(n, OPT_PER_BLOCK); }
 
 extern "C" int snnflow_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                                 const float* hyper, int64_t* step, float* partials, float* grad_norm,
+                                 const float* hyper, int64_t* step, double* state, float* partials, float* grad_norm,
                                  snnflow_stream_t stream) {
-  SNNFLOW_REQUIRE(params && grads && exp_avg && exp_avg_sq && hyper && step && partials && n > 0, "bad arguments");
+  SNNFLOW_REQUIRE(params && grads && exp_avg && exp_avg_sq && hyper && step && state && partials && n > 0, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const int n_part = snnflow_clip_adam_partials(n);
   prof_begin("opt_sumsq", st, 4.0 * n);
-  opt_sumsq_kernel<<<n_part, OPT_THREADS, 0, st>>>(grads, n, partials, reinterpret_cast<long long*>(step));
+  opt_sumsq_kernel<<<n_part, OPT_THREADS, 0, st>>>(grads, n, partials, reinterpret_cast<long long*>(step), hyper, state);
   int rc = check_launch("opt_sumsq_kernel");
   if (rc) return rc;
   prof_begin("opt_clip_adam", st, 28.0 * n);
-  opt_clip_adam_kernel<<<n_part, OPT_THREADS, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, hyper, reinterpret_cast<const long long*>(step), partials, n_part,
+  opt_clip_adam_kernel<<<n_part, OPT_THREADS, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, hyper, state, partials, n_part,
                                                      grad_norm);
   return check_launch("opt_clip_adam_kernel");
 }

@@ -40,6 +40,7 @@ class FusedClipAdam:
                 self.grad_views.append(self.grad[o:o + p.numel()].view_as(p))
         self.hyper = torch.tensor([lr, betas[0], betas[1], eps, max_norm if max_norm else 0.0], dtype=torch.float32, device=dev)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.bias_state = torch.zeros(4, dtype=torch.float64, device=dev)   # beta^t running products, step size (kernel-owned)
         self.partials = torch.zeros(_lib.lib().snnflow_clip_adam_partials(n), dtype=torch.float32, device=dev)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)   # total norm of the last step (before clipping)
         self.param_groups = [{"params": self.params, "lr": lr, "betas": betas, "eps": eps}]
@@ -61,7 +62,8 @@ class FusedClipAdam:
         L = _lib
         L.check(L.lib().snnflow_clip_adam(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
                                           self.exp_avg_sq.data_ptr(), self.n, self.hyper.data_ptr(),
-                                          self.step_count.data_ptr(), self.partials.data_ptr(), self.grad_norm.data_ptr(),
+                                          self.step_count.data_ptr(), self.bias_state.data_ptr(), self.partials.data_ptr(),
+                                          self.grad_norm.data_ptr(),
                                           L.stream()), "snnflow_clip_adam")
         # the kernel wrote the parameters behind autograd's back: bump their version counters so that anything keyed on
         # them (the cells' packed-weight cache, spiking_submodules.py) sees the update
@@ -76,8 +78,8 @@ class FusedClipAdam:
 
     def state_dict(self):
         return {"step": self.step_count.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
-                "hyper": self.hyper.clone()}
+                "hyper": self.hyper.clone(), "bias_state": self.bias_state.clone()}
 
     def load_state_dict(self, sd):
         self.step_count.copy_(sd["step"]); self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        self.hyper.copy_(sd["hyper"])
+        self.hyper.copy_(sd["hyper"]); self.bias_state.copy_(sd["bias_state"])
