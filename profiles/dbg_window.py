@@ -1,8 +1,8 @@
-"""Debug helper (not a test): python tests/_dbg_window.py <stage> ; stages: eval | fwd | bwd [kind C H W]"""
+"""Debug helper (not a test): python profiles/dbg_window.py <stage> ; stages: eval | fwd | bwd [kind C H W]"""
 import os, sys
 os.environ.setdefault("CUDA_LAUNCH_BLOCKING", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import torch
 from test_gpu_window import make_net, runner_of
 
