@@ -14,7 +14,8 @@
 namespace snnflow {
 
 constexpr int OPT_THREADS = 256;
-constexpr int OPT_PER_BLOCK = 4096;   // elements per block (16 per thread)
+constexpr int OPT_PER_BLOCK = 1024;   // elements per block (4 per thread, all loads of a thread in flight together)
+constexpr int OPT_PER_THREAD = OPT_PER_BLOCK / OPT_THREADS;
 
 __device__ __forceinline__ float opt_block_sum(float v, float* red) {
   v = warp_sum(v);
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(OPT_THREADS) opt_sumsq_kernel(const float* __r
   }
   const int64_t base = (int64_t)blockIdx.x * OPT_PER_BLOCK;
   float s = 0.f;
-#pragma unroll 4
+#pragma unroll
   for (int i = threadIdx.x; i < OPT_PER_BLOCK; i += OPT_THREADS) {
     const int64_t k = base + i;
     if (k < n) { const float x = g[k]; s = fmaf(x, x, s); }
@@ -61,6 +62,15 @@ __global__ void __launch_bounds__(OPT_THREADS) opt_clip_adam_kernel(float* __res
                                                                     const float* __restrict__ partials, int n_part,
                                                                     float* __restrict__ norm_out) {
   __shared__ float s_coef;
+  // this thread's slice first: the loads are in flight while warp 0 derives the clip coefficient
+  const int64_t base = (int64_t)blockIdx.x * OPT_PER_BLOCK + threadIdx.x;
+  float gk[OPT_PER_THREAD], mk[OPT_PER_THREAD], vk[OPT_PER_THREAD], pk[OPT_PER_THREAD];
+#pragma unroll
+  for (int i = 0; i < OPT_PER_THREAD; ++i) {
+    const int64_t k = base + (int64_t)i * OPT_THREADS;
+    const bool ok = k < n;
+    gk[i] = ok ? g[k] : 0.f; mk[i] = ok ? m[k] : 0.f; vk[i] = ok ? v[k] : 0.f; pk[i] = ok ? p[k] : 0.f;
+  }
   if (threadIdx.x < 32) {
     // fixed-order reduction of the block partials: lane-strided sums, then a butterfly - the same in every block
     float t = 0.f;
@@ -78,16 +88,15 @@ __global__ void __launch_bounds__(OPT_THREADS) opt_clip_adam_kernel(float* __res
   __syncthreads();
   const float coef = s_coef, step_size = (float)state[2], inv_bc2_sqrt = (float)state[3];
   const float b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
-  const int64_t base = (int64_t)blockIdx.x * OPT_PER_BLOCK;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < OPT_PER_BLOCK; i += OPT_THREADS) {
-    const int64_t k = base + i;
+#pragma unroll
+  for (int i = 0; i < OPT_PER_THREAD; ++i) {
+    const int64_t k = base + (int64_t)i * OPT_THREADS;
     if (k >= n) break;
-    const float gk = g[k] * coef;
-    const float mk = fmaf(1.0f - b1, gk - m[k], m[k]);
-    const float vk = fmaf(1.0f - b2, gk * gk, v[k] * b2);
-    m[k] = mk; v[k] = vk;
-    p[k] = p[k] - step_size * (mk / (sqrtf(vk) * inv_bc2_sqrt + eps));
+    const float gc = gk[i] * coef;
+    const float mn = fmaf(1.0f - b1, gc - mk[i], mk[i]);
+    const float vn = fmaf(1.0f - b2, gc * gc, vk[i] * b2);
+    m[k] = mn; v[k] = vn;
+    p[k] = pk[i] - step_size * (mn / (sqrtf(vn) * inv_bc2_sqrt + eps));
   }
 }
 
