@@ -392,10 +392,13 @@ def run_ours(a):
     if not a.no_eval:
         eval_info = run_eval(a, snnflow, dev, world, barrier)
 
-    micro = None
+    micro, narrow = None, None
     if rank == 0 and not a.no_eval:
         phase("microbench")
         micro = run_micro(snnflow, dev)
+        if world == 1 and a.channels != 8:
+            phase("C=8 training step")
+            narrow = run_train_narrow(a, snnflow, TrainWindow, dev)
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
@@ -415,11 +418,40 @@ def run_ours(a):
                     "runs": [round(v, 1) for v in e2e_runs], "stat": "median of 3 timed K-step regions"},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "eval": eval_info,
-            "encode_iwe_microbench": micro,
+            "encode_iwe_microbench": micro, "train_c8": narrow,
             "loss": last_loss,
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_train_narrow(a, snnflow, TrainWindow, dev, channels=8):
+    """The same training step with the width the reference's shipped config uses (base_num_channels: 8,
+    configs/train_SNN.yml:19): runs zero-padded to 16 channels on the window engine.  Device-resident inputs, one graph."""
+    import copy
+    import torch
+    b = copy.copy(a)
+    b.channels = channels
+    torch.manual_seed(0)
+    net = snnflow.LIFFireNet(dict(num_bins=2, encoding="cnt", base_num_channels=channels, kernel_size=3,
+                                  neuron_kwargs=dict(leak=(0.0, 1.0), thresh=(0.3, 0.1)))).to(dev)
+    cfg = {"loader": {"resolution": [a.res, a.res]}, "loss": {"flow_regul_weight": 0.001}, "model": {"mask_output": False}}
+    tw = TrainWindow(net, snnflow.EventWarping(cfg, dev), snnflow.FusedClipAdam(net.parameters(), lr=2e-4, max_norm=1.0),
+                     clip_grad=1.0)
+    pool = [{k: v.to(dev) for k, v in make_window(b, 500 + i).items()} for i in range(4)]
+    launches = tw.capture(pool[0])
+    for i in range(3):
+        tw.step_graphed(pool[i % 4])
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(a.steps):
+        tw.step_graphed(pool[i % 4])
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / a.steps
+    return {"metric": f"LIFFireNet C={channels} train samples/s @{a.res}x{a.res}, batch {a.batch}", "value": a.batch / (ms / 1e3),
+            "unit": "samples/s", "ms_per_step": ms, "gpu_launches_per_step": int(launches)}
 
 
 def run_eval(a, snnflow, dev, world, barrier):
