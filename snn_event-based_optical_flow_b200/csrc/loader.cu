@@ -58,9 +58,19 @@ __global__ void __launch_bounds__(LD_THREADS) ld_minmax_kernel(const void* __res
   const double t0b = t0 ? t0[b] : 0.0;
   unsigned lo = 0xffffffffu, hi = 0u;
   const int64_t stride = (int64_t)gridDim.x * LD_THREADS;
-  for (int64_t k = (int64_t)blockIdx.x * LD_THREADS + threadIdx.x; k < N; k += stride) {
-    const unsigned o = f2ord(load_ts<TS64>(ts, (int64_t)b * N + k, t0b));
-    lo = min(lo, o); hi = max(hi, o);
+  // four independent loads per thread and trip: the reduction is latency bound otherwise (ncu: 1.6 TB/s with one)
+  for (int64_t k0 = (int64_t)blockIdx.x * LD_THREADS + threadIdx.x; k0 < N; k0 += 4 * stride) {
+    float t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t k = k0 + j * stride;
+      t[j] = load_ts<TS64>(ts, (int64_t)b * N + (k < N ? k : k0), t0b);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned o = f2ord(t[j]);
+      lo = min(lo, o); hi = max(hi, o);
+    }
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
@@ -155,12 +165,25 @@ __global__ void __launch_bounds__(HOT_THREADS) ld_hot_kernel(const float* __rest
   if (threadIdx.x == 0) s_cand = 0;
   __syncthreads();
   int cand = 0;
-  for (int i = threadIdx.x; i < HW; i += HOT_THREADS) {
-    const float s = __fadd_rn(cnt[i], cnt[HW + i]);                  // torch.sum(event_cnt, dim=0)   :246
-    const float he = __fadd_rn(hot_events[i], s > 0.f ? 1.f : s);    // hot_update[hot_update > 0] = 1 :247-248
-    hot_events[i] = he;
-    hotmask[i] = 1.f;
-    cand += (__fdiv_rn(he, fidx) > max_rate) ? 1 : 0;                // event_rate = hot_events / hot_idx :250
+  // eight pixels per thread and trip with all their loads in flight (one CTA per slot: latency bound otherwise)
+  for (int i0 = threadIdx.x; i0 < HW; i0 += 8 * HOT_THREADS) {
+    float c0[8], c1[8], h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + j * HOT_THREADS;
+      const bool ok = i < HW;
+      c0[j] = ok ? cnt[i] : 0.f; c1[j] = ok ? cnt[HW + i] : 0.f; h[j] = ok ? hot_events[i] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + j * HOT_THREADS;
+      if (i >= HW) break;
+      const float s = __fadd_rn(c0[j], c1[j]);                         // torch.sum(event_cnt, dim=0)   :246
+      const float he = __fadd_rn(h[j], s > 0.f ? 1.f : s);             // hot_update[hot_update > 0] = 1 :247-248
+      hot_events[i] = he;
+      hotmask[i] = 1.f;
+      cand += (__fdiv_rn(he, fidx) > max_rate) ? 1 : 0;                // event_rate = hot_events / hot_idx :250
+    }
   }
   if (cand) atomicAdd(&s_cand, cand);
   __syncthreads();
