@@ -55,6 +55,7 @@ class EventWindowFormatter:
         if self.device.type != "cuda":
             raise _lib.SnnflowError("EventWindowFormatter runs on a CUDA device only (no CPU fallback)")
         self.seq_num = 0
+        self._hot_reset = set()
         # base.py:24-27: events are encoded at loader.resolution in "events" mode, at std_resolution otherwise ...
         if config["data"]["mode"] == "events":
             self.resolution = list(config["loader"]["resolution"])
@@ -82,16 +83,26 @@ class EventWindowFormatter:
         # base.py:40-45: hot-pixel filter state
         hf = config["hot_filter"]
         self.hot_enabled = bool(hf["enabled"])
-        self.hot_idx = torch.zeros(B, dtype=torch.int32, device=self.device)
-        self.hot_events = torch.zeros((B, H, W), dtype=torch.float32, device=self.device) if self.hot_enabled else None
+        self.hot_idx = self.hot_events = None      # device state, allocated by the first format_batch()
         self._ws = None
+
+    def _hot_state(self):
+        if self.hot_idx is None:
+            B, (H, W) = self.batch_size, self.resolution
+            self.hot_idx = torch.zeros(B, dtype=torch.int32, device=self.device)
+            self.hot_events = torch.zeros((B, H, W), dtype=torch.float32, device=self.device) if self.hot_enabled else None
+            self._hot_reset.clear()
+        for b in sorted(self._hot_reset):
+            self.hot_idx[b] = 0
+            if self.hot_events is not None:
+                self.hot_events[b].zero_()
+        self._hot_reset.clear()
 
     # ---- sequence bookkeeping (base.py:53-69) ----
     def reset_sequence(self, batch):
         self.seq_num += 1
         if self.hot_enabled:
-            self.hot_idx[batch] = 0
-            self.hot_events[batch].zero_()
+            self._hot_reset.add(batch)             # applied on the device before the next window is formatted
         for i, m in enumerate(self.config["loader"]["augment"]):
             self.batch_augmentation[m][batch] = bool(np.random.random() < self.config["loader"]["augment_prob"][i])
         self._flips = None
@@ -132,6 +143,7 @@ class EventWindowFormatter:
             if not ts64:
                 raise ValueError("t0 is subtracted in float64: pass float64 timestamps with it")
             t0 = torch.as_tensor(t0, dtype=torch.float64, device=dev).reshape(B).contiguous()
+        self._hot_state()
         d = self._desc(N)
         H, W = self.resolution
         h, w = H // self.pool[0], W // self.pool[1]

@@ -124,3 +124,47 @@ def test_network_seam_and_state_dict(kind):
     from snnflow_b200 import _lib
     with pytest.raises(_lib.SnnflowError):
         seam(None, torch.zeros(1, 2, 8, 8))
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="needs the reference checkout")
+def test_window_formatter_host_state_matches_reference_loader():
+    """EventWindowFormatter draws its per-slot augmentation flags from np.random in the reference's order
+    (dataloader/base.py:29-38 at construction, :64-69 on reset_sequence): with the same seed the same slots flip.
+    Host logic only - nothing is computed here (the object allocates device memory on its first format_batch)."""
+    import importlib
+    import numpy as np
+    import snnflow_b200 as snnflow
+    ref_shim.install()
+    base = importlib.import_module("dataloader.base")
+
+    class RefLoader(base.BaseDataLoader):        # the abstract methods are not needed for the bookkeeping
+        def __getitem__(self, index):
+            raise NotImplementedError
+
+        def get_events(self, history):
+            raise NotImplementedError
+
+    cfg = {"data": {"mode": "gtflow_dt1"}, "loader": {"resolution": [128, 128], "std_resolution": [256, 256],
+                                                      "batch_size": 5, "augment": ["Horizontal", "Vertical", "Polarity"],
+                                                      "augment_prob": [0.5, 0.3, 0.7]},
+           "hot_filter": {"enabled": True, "max_px": 100, "min_obvs": 5, "max_rate": 0.8}}
+    np.random.seed(123)
+    ref = RefLoader(cfg, 5)
+    for b in (3, 0, 3):
+        ref.reset_sequence(b)
+    np.random.seed(123)
+    ours = snnflow.EventWindowFormatter(cfg, 5)
+    for b in (3, 0, 3):
+        ours.reset_sequence(b)
+    assert ours.batch_augmentation == ref.batch_augmentation
+    assert ours.seq_num == ref.seq_num == 3
+    assert list(ours.resolution) == list(ref.resolution) == [256, 256] and ours.pool == (2, 2)
+    with pytest.raises(ValueError):
+        snnflow.EventWindowFormatter(dict(cfg, loader=dict(cfg["loader"], resolution=[300, 128])), 5).pool
+    with pytest.raises(_lib_mod().SnnflowError):
+        snnflow.EventWindowFormatter(cfg, 5, device="cpu")
+
+
+def _lib_mod():
+    from snnflow_b200 import _lib
+    return _lib
