@@ -3,6 +3,8 @@
 
 #include "window.cuh"
 
+#include <stdlib.h>
+
 namespace snnflow {
 
 __device__ unsigned int g_win_inexact = 0;   // window inputs that one bf16 term does not represent exactly
@@ -274,6 +276,146 @@ __global__ void __launch_bounds__(256, 2) pw_seq_kernel(const PwSeqArgs a) {
   }
 }
 
+// The top-layer (flow head fused) kernel as launched by default (SNNFLOW_PW2=0 selects pw_seq_kernel<.., TOP> instead):
+// ncu shows pw_seq_kernel<.., TOP> long-scoreboard bound at 128 registers per thread with one 32-byte membrane load in
+// flight per thread (2.8 TB/s, 143 us); this variant measured 132 us on B200 with identical test results.  Here the per-channel constants (lam, 1-lam, theta,
+// 1/(1-lam), head weights) live in shared memory instead of 48 registers, which pays for a one-bin-deeper prefetch: while
+// bin t is processed, the membranes of bin t-2 and the flow / flow-gradient values of bin t-1 are already in flight.
+// Same arithmetic, same order of operations as pw_seq_kernel.
+template <int SG, bool HARD>
+__global__ void __launch_bounds__(256, 2) pw_seq_top2_kernel(const PwSeqArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float4 s_par[8];
+  __shared__ float s_w[2][8];
+  const int HW = a.H * a.W, Wp = a.W + 2;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  if (threadIdx.x < 8) {
+    s_par[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(a.par) + chunk * 8 + threadIdx.x);
+    s_w[0][threadIdx.x] = __ldg(a.pred_w + chunk * 8 + threadIdx.x);
+    s_w[1][threadIdx.x] = __ldg(a.pred_w + a.C + chunk * 8 + threadIdx.x);
+  }
+  __syncthreads();
+  const bool ok = p < HW;
+  const int y = ok ? p / a.W : 0, x = ok ? p - y * a.W : 0;
+  const size_t plane_bytes = (size_t)(a.H + 2) * Wp * 16;
+  const int nch = a.C >> 3;
+  const size_t img_stride = (size_t)nch * HW * 8, px_off = ((size_t)chunk * HW + (ok ? p : 0)) * 8;
+  float carry[8], s_lam[8], s_th[8], dw0[8], dw1[8], db0 = 0.f, db1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) carry[c] = s_lam[c] = s_th[c] = dw0[c] = dw1[c] = 0.f;
+  float va[8], vb[8], vc[8], fa[4], fb[4];   // v[t], v[t-1], v[t-2] ; (f0, f1, g0, g1) of bins t, t-1
+#pragma unroll
+  for (int c = 0; c < 8; ++c) va[c] = vb[c] = vc[c] = 0.f;
+  fa[0] = fa[1] = fa[2] = fa[3] = fb[0] = fb[1] = fb[2] = fb[3] = 0.f;
+  auto load_v = [&](int t, float (&dst)[8]) {   // t = -1: the window's initial membrane (NCHW tensor of the caller, or zero)
+    if (t >= 0) {
+      ld8_c8(a.v + (size_t)(t * a.B + b) * img_stride + px_off, dst);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dst[c] = a.v_init ? __ldg(a.v_init + ((size_t)b * a.C + chunk * 8 + c) * HW + p) : 0.f;
+    }
+  };
+  auto load_f = [&](int t, float (&dst)[4]) {
+    const size_t fo = (size_t)(t * a.B + b) * 2 * HW + p;
+    dst[0] = __ldg(a.flow + fo); dst[1] = __ldg(a.flow + fo + HW);
+    dst[2] = __ldg(a.g_flow + fo); dst[3] = __ldg(a.g_flow + fo + HW);
+  };
+  if (ok) {
+    load_v(a.T - 1, va);
+    load_v(a.T - 2, vb);
+    load_f(a.T - 1, fa);
+  }
+  for (int t = a.T - 1; t >= 0; --t) {
+    const size_t img = (size_t)(t * a.B + b);
+    if (ok) {
+      if (t >= 1) {          // prefetch for the next trip
+        load_v(t - 2, vc);
+        load_f(t - 1, fb);
+      }
+      float z0[8];
+      if (t == 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) z0[c] = a.z_init ? __ldg(a.z_init + ((size_t)b * a.C + chunk * 8 + c) * HW + p) : 0.f;
+      }
+      const float g0 = fa[2] * (1.0f - fa[0] * fa[0]), g1 = fa[3] * (1.0f - fa[1] * fa[1]);
+      db0 += g0; db1 += g1;
+      uint32_t hi[4], lo[4];
+      float gI[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 pr = s_par[c];   // (lam, 1 - lam, theta, 1 / (1 - lam))
+        const float go = g0 * s_w[0][c] + g1 * s_w[1][c];
+        const float z = (__fsub_rn(va[c], pr.z) > 0.f) ? 1.f : 0.f;   // this bin's spikes: the head's input
+        dw0[c] = fmaf(g0, z, dw0[c]);
+        dw1[c] = fmaf(g1, z, dw1[c]);
+        const float z_in = t > 0 ? ((__fsub_rn(vb[c], pr.z) > 0.f) ? 1.f : 0.f) : z0[c];
+        const float gs = go * surrogate_fast<SG>(va[c] - pr.z, a.width);
+        const float gv = carry[c] + gs;
+        gI[c] = gv * pr.y;
+        if (HARD) {
+          const float omz = 1.0f - z_in;
+          carry[c] = gv * pr.x * omz;
+          s_lam[c] += gv * (vb[c] * omz - va[c]);
+          s_th[c] -= gs;
+        } else {
+          carry[c] = gv * pr.x;
+          s_lam[c] += gv * (vb[c] - va[c] - z_in * pr.z);
+          s_th[c] -= gs + gv * z_in;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) split_bf16_pair(gI[2 * c], gI[2 * c + 1], hi[c], lo[c]);
+      unsigned char* gp = a.gp + img * a.gp_img_stride + (size_t)chunk * plane_bytes + ((size_t)(y + 1) * Wp + x + 1) * 16;
+      *reinterpret_cast<uint4*>(gp) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(gp + a.gp_term_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { va[c] = vb[c]; vb[c] = vc[c]; }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) fa[c] = fb[c];
+    }
+  }
+  // fixed-order block reductions, exactly as in pw_seq_kernel
+  __shared__ float red[8][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float l = warp_sum(ok ? s_lam[c] * s_par[c].w : 0.f), t = warp_sum(ok ? s_th[c] : 0.f);
+    if (lane == 0) { red[warp][c] = l; red[warp][8 + c] = t; }
+  }
+  __syncthreads();
+  const int j = b * gridDim.x + blockIdx.x;
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    const int which = threadIdx.x >> 3, c = threadIdx.x & 7;
+    a.part[((size_t)which * a.C + chunk * 8 + c) * a.n_part + j] = t;
+  }
+  __syncthreads();
+  __shared__ float pred[8][18];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float l = warp_sum(ok ? dw0[c] : 0.f), t = warp_sum(ok ? dw1[c] : 0.f);
+    if (lane == 0) { pred[warp][c] = l; pred[warp][8 + c] = t; }
+  }
+  const float e0 = warp_sum(ok ? db0 : 0.f), e1 = warp_sum(ok ? db1 : 0.f);
+  if (lane == 0) { pred[warp][16] = e0; pred[warp][17] = e1; }
+  __syncthreads();
+  if (threadIdx.x < 18) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += pred[w][threadIdx.x];
+    if (threadIdx.x < 16) {
+      const int which = threadIdx.x >> 3, c = threadIdx.x & 7;
+      a.pred_part[((size_t)which * a.C + chunk * 8 + c) * a.n_part + j] = t;
+    } else if (chunk == 0) {   // every chunk sees the same g_pre: count the bias gradient once
+      a.pred_part[((size_t)2 * a.C + (threadIdx.x - 16)) * a.n_part + j] = t;
+    }
+  }
+}
+
 int launch_pw_seq(const PwSeqArgs& a, cudaStream_t st) {
   const int gx = ceil_div(a.H * a.W, 256);
   if (a.n_part != a.B * gx) {
@@ -283,9 +425,11 @@ int launch_pw_seq(const PwSeqArgs& a, cudaStream_t st) {
   prof_begin("win_pw_seq", st, (double)a.T * a.B * a.C * a.H * a.W * 12.0);   // v, g_out in ; g_I out
   const dim3 grid(gx, a.C / 8, a.B);
   const bool top = a.g_out == nullptr;
+  static const int staged_v2 = [] { const char* v = getenv("SNNFLOW_PW2"); return (v && *v) ? atoi(v) : 1; }();
 #define PW_CASE(SGV, HARDV) \
   if (a.surrogate == SGV && (a.hard_reset != 0) == HARDV) { \
-    if (top) launch_pdl(pw_seq_kernel<SGV, HARDV, true>, grid, dim3(256), 0, st, a); \
+    if (top && staged_v2) launch_pdl(pw_seq_top2_kernel<SGV, HARDV>, grid, dim3(256), 0, st, a); \
+    else if (top) launch_pdl(pw_seq_kernel<SGV, HARDV, true>, grid, dim3(256), 0, st, a); \
     else launch_pdl(pw_seq_kernel<SGV, HARDV, false>, grid, dim3(256), 0, st, a); \
   }
   PW_CASE(0, true) PW_CASE(0, false) PW_CASE(1, true) PW_CASE(1, false) PW_CASE(2, true) PW_CASE(2, false)
