@@ -225,3 +225,58 @@ def test_loader_oracle_matches_reference(name):
                 removed += int((seen & (g[f"item{it}.event_mask"][b, 0] == 0)).sum())
     if name == "loader_events_hot":
         assert removed > 0, "the hot-pixel filter never fired: the fixture would be vacuous"
+
+
+def _hot_mask_by_cut(hot_events, idx, max_px, min_obvs, max_rate):
+    """The selection rule the CUDA kernel implements (csrc/loader.cu, ld_hot_kernel), restated in numpy: candidates are
+    pixels with hot_events / idx > max_rate; if there are more than max_px of them, a cut c* on the integer hit count is
+    found (largest c with >= max_px candidates of count >= c), everything above the cut goes and the remaining places are
+    filled with the lowest flat indices AT the cut."""
+    he = hot_events.reshape(-1)
+    mask = np.ones(he.shape, dtype=np.float32)
+    if not idx > min_obvs or max_px <= 0:
+        return mask.reshape(hot_events.shape)
+    cand = (he / np.float32(idx)).astype(np.float32) > np.float32(max_rate)
+    if cand.sum() <= max_px:
+        mask[cand] = 0
+        return mask.reshape(hot_events.shape)
+    lo, hi = 0, idx
+    while lo < hi:
+        mid = (lo + hi + 1) >> 1
+        if (cand & (he >= mid)).sum() >= max_px:
+            lo = mid
+        else:
+            hi = mid - 1
+    above = cand & (he > lo)
+    at = np.flatnonzero(cand & (he == lo))
+    mask[above] = 0
+    mask[at[:max_px - int(above.sum())]] = 0
+    return mask.reshape(hot_events.shape)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_hot_pixel_cut_rule_equals_the_reference_argmax_loop(seed):
+    """get_hot_event_mask (dataloader/encodings.py:88-103) removes one argmax at a time; the kernel uses a cut on the hit
+    count instead.  Both must pick the same pixels, ties included (many equal rates, more candidates than max_px)."""
+    rng = np.random.default_rng(seed)
+    H, W = int(rng.integers(3, 12)), int(rng.integers(3, 12))
+    idx = int(rng.integers(1, 40))
+    he = rng.integers(0, idx + 1, size=(H, W)).astype(np.float32)          # integer hit counts <= idx
+    if seed % 3 == 0:
+        he[rng.random((H, W)) < 0.5] = idx                                   # heavy ties at rate 1.0
+    max_px = int(rng.integers(1, 8))
+    min_obvs = int(rng.integers(0, 6))
+    max_rate = float(rng.choice([0.3, 0.5, 0.8, 0.95]))
+    want = oload.hot_event_mask(T(he) / idx, idx, max_px=max_px, min_obvs=min_obvs, max_rate=max_rate).numpy()
+    got = _hot_mask_by_cut(he, idx, max_px, min_obvs, max_rate)
+    assert np.array_equal(got, want), (H, W, idx, max_px, min_obvs, max_rate)
+    if ref_shim_available():
+        from oracle import ref_shim
+        ref = ref_shim.load().encodings.get_hot_event_mask(T(he) / idx, idx, max_px=max_px, min_obvs=min_obvs,
+                                                           max_rate=max_rate).numpy()
+        assert np.array_equal(want, ref)
+
+
+def ref_shim_available():
+    from oracle import ref_shim
+    return ref_shim.reference_available()
