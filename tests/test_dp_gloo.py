@@ -47,7 +47,7 @@ def _worker(rank, world, port, ret):
 
 def test_flat_sum_allreduce_matches_global_batch():
     port = _free_port()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()     # no fork() of this multi-threaded process
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     model = _make_model()
