@@ -280,3 +280,23 @@ def test_hot_pixel_cut_rule_equals_the_reference_argmax_loop(seed):
 def ref_shim_available():
     from oracle import ref_shim
     return ref_shim.reference_available()
+
+
+@pytest.mark.parametrize("name", LOADER_FIXTURES)
+def test_loader_numpy_restatement_matches_reference(name):
+    """A second, numpy-only restatement of the exact loader outputs (counts, mask, event list, polarity mask) against the
+    same reference-written fixtures - independent of oracle/loader.py and of torch's scatter / pooling ops."""
+    from oracle.loader_np import format_item_np
+    g = load_golden(name)
+    B, H, W = int(g["B"]), int(g["H"]), int(g["W"])
+    target = tuple(int(v) for v in g["target"])
+    hot_cfg = dict(max_px=int(g["hot"][0]), min_obvs=int(g["hot"][1]), max_rate=float(g["hot"][2])) if g["hot"].size else None
+    state = [dict(events=np.zeros((H, W), np.float32), idx=0) for _ in range(B)]
+    for it, wins in enumerate(loader_windows(g)):
+        for b, (xs, ys, ts, ps) in enumerate(wins):
+            out = format_item_np(xs, ys, (ts - 10.0).astype(np.float32), ps, resolution=(H, W),
+                                 flips=tuple(bool(v) for v in g["flips"][b]), hot_state=state[b], hot_cfg=hot_cfg, target=target)
+            assert np.array_equal(out["event_cnt"], g[f"item{it}.event_cnt"][b]), (name, it, b, "cnt")
+            assert np.array_equal(out["event_mask"], g[f"item{it}.event_mask"][b]), (name, it, b, "mask")
+            assert np.array_equal(out["event_list"].T, g[f"item{it}.event_list"][b]), (name, it, b, "list")
+            assert np.array_equal(out["event_list_pol_mask"].T, g[f"item{it}.event_list_pol_mask"][b]), (name, it, b, "pol")
