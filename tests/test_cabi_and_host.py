@@ -168,3 +168,31 @@ def test_window_formatter_host_state_matches_reference_loader():
 def _lib_mod():
     from snnflow_b200 import _lib
     return _lib
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/snnflow.h is a C header (no C++, no torch types): a C99 translation unit that includes it compiles with
+    -pedantic, links against libsnnflow.so and can call the entry points that need no GPU."""
+    import shutil
+    import subprocess
+    import __graft_entry__ as ge
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    ge.build()
+    from snnflow_b200 import _lib
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "snnflow.h"\n'
+                   "int main(void) {\n"
+                   "  snnflow_loader_desc d = {0};\n"
+                   "  d.B = 2; d.H = 16; d.W = 16; d.N = 100; d.num_bins = 5; d.pool_h = d.pool_w = 1;\n"
+                   "  size_t ws = snnflow_format_window_workspace_bytes(&d);\n"
+                   '  printf("%d %d %zu %d\\n", snnflow_abi_version(), SNNFLOW_ABI_VERSION, ws, snnflow_clip_adam_partials(5000));\n'
+                   "  return 0;\n}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{os.path.join(ROOT, 'include')}", str(src), "-o", str(exe),
+                    f"-L{libdir}", "-lsnnflow", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[0] == out[1] == "1"
+    assert int(out[2]) > 2 * 16 * 16 * (2 * 4 + 4 + 5 * 8)          # counts + last index + fixed-point voxels, per slot
+    assert int(out[3]) == 5                                          # ceil(5000 / 1024) partial sums
