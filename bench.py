@@ -139,6 +139,11 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm is entitled to every host core this process may use
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        torch.set_num_threads(os.cpu_count() or 1)
     sec = cpu_train_steps(a, a.steps, a.warmup)
     val = a.batch / sec
     cores = torch.get_num_threads()
