@@ -100,9 +100,38 @@ def make_window(a, seed):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference (torch-CPU fp32, all host threads)
+# CPU arm: the UNMODIFIED reference (oracle/ref_runner.py: its LIFFireNet with the ConvLIF / ConvLIFRecurrent cells of
+# models/spiking_submodules.py installed through the class attributes, its EventWarping, the loop body of
+# train_flow.py:232-279) on the host cores; the reference is read from /root/reference or from the copy staged under
+# the git-ignored baseline/_ref (oracle/stage_reference.py).  Falls back to the oracle port only when neither exists.
 # ------------------------------------------------------------------------------------------------
+def cpu_arm_kind():
+    from oracle import ref_runner
+    return "reference" if ref_runner.available() else "port"
+
+
 def cpu_train_steps(a, n_steps, n_warm):
+    import torch
+    if cpu_arm_kind() == "reference":
+        from oracle import ref_runner
+        cpu = torch.device("cpu")
+        net = ref_runner.build_net("LIFFireNet", a.channels, None, leak=(0.0, 1.0), thresh=(0.3, 0.1), seed=0)
+        opt = torch.optim.Adam(net.parameters(), lr=2e-4)
+        lossf = ref_runner.make_loss((a.res, a.res), cpu)
+        pool = [make_window(a, 100 + i) for i in range(2)]
+        times = []
+        for it in range(n_warm + n_steps):
+            w = pool[it % len(pool)]
+            t0 = time.perf_counter()
+            loss, _, _ = ref_runner.train_step(net, lossf, opt, w, cpu, clip_grad=1.0)
+            float(loss)
+            if it >= n_warm:
+                times.append(time.perf_counter() - t0)
+        return sum(times) / len(times)
+    return cpu_train_steps_port(a, n_steps, n_warm)
+
+
+def cpu_train_steps_port(a, n_steps, n_warm):
     import torch
     from oracle import firenet as ofn
     from oracle.loss import EventWarpingOracle
@@ -144,6 +173,7 @@ def run_reference(a):
         torch.set_num_threads(len(os.sched_getaffinity(0)))
     except (AttributeError, OSError):
         torch.set_num_threads(os.cpu_count() or 1)
+    kind = cpu_arm_kind()
     sec = cpu_train_steps(a, a.steps, a.warmup)
     val = a.batch / sec
     cores = torch.get_num_threads()
@@ -152,11 +182,13 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, 1),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "CPU oracle port (torch-CPU fp32 restatement of the reference, oracle/firenet.py + oracle/loss.py); "
-                "the Python reference itself cannot travel to the GPU box",
+        "note": ("the unmodified reference (its LIFFireNet class with the ConvLIF / ConvLIFRecurrent cells of "
+                 "models/spiking_submodules.py, EventWarping, clip_grad_norm_, Adam; train_flow.py:232-279), torch CPU fp32"
+                 if kind == "reference" else
+                 "CPU oracle port (oracle/firenet.py + oracle/loss.py): no reference checkout or staged copy found"),
     }))
 
 
@@ -409,7 +441,7 @@ def run_ours(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         sec = cpu_train_steps(a, 2, 1)
-        cpu = {"value": a.batch / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        cpu = {"value": a.batch / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": cpu_arm_kind(),
                "sample": f"2 full optimizer steps (batch {a.batch}, {a.bins} bins, C={a.channels}) after 1 warm-up, "
                          f"{sec:.2f} s/step"}
 

@@ -3,19 +3,38 @@
 The reference imports snntorch / brevitas / matplotlib / h5py / hdf5plugin / progress
 at module top but only uses them on branches outside the hot path (quantised layers,
 snn.Leaky cells, plotting, HDF5 IO).  None of them is installed here, so they are
-replaced by empty stub modules.  Used only by ``oracle/make_golden.py`` and by the
-CPU tests that compare the oracle with the live reference; never on the GPU box
-(``/root/reference`` does not exist there).
+replaced by empty stub modules.  Used by ``oracle/make_golden.py``, by the tests that compare the
+oracle / the CUDA cells with the live reference, and by the reference arm of ``bench.py``.  On the GPU
+box ``/root/reference`` does not exist: there the shim resolves to the unmodified copy of the hot-path
+files that ``oracle/stage_reference.py`` stages under the git-ignored ``baseline/_ref/``.
 """
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SNNFLOW_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED_ROOT = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")   # written by oracle/stage_reference.py
+
+
+def _pick_root():
+    """The reference checkout: $SNNFLOW_REFERENCE_ROOT, /root/reference (build container), or the unmodified copy of the
+    hot-path files staged under the git-ignored baseline/_ref (the only one that exists on the GPU box)."""
+    for cand in (os.environ.get("SNNFLOW_REFERENCE_ROOT"), "/root/reference", STAGED_ROOT):
+        if cand and os.path.isfile(os.path.join(cand, "models", "spiking_submodules.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "spiking_submodules.py"))
+
+
+def full_checkout() -> bool:
+    """True for a complete checkout (configs, train/eval scripts), False for the staged hot-path subset."""
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "train_flow.py"))
 
 
 class _Raising:

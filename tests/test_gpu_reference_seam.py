@@ -1,0 +1,103 @@
+"""GPU: the reference's OWN network classes running on the CUDA cells through the class-attribute seam
+(models/model.py:37-39: ``head_neuron / ff_neuron / rec_neuron``), executed forward + backward on the B200 and compared
+with the same classes on the reference's own cells on the CPU.
+
+The reference is imported UNMODIFIED through oracle/ref_shim.py: from /root/reference in the build container, from the
+copy staged by oracle/stage_reference.py under the git-ignored baseline/_ref on the GPU box.  Everything the reference
+does around the cells runs as the reference wrote it - ``LIFFireNet.forward`` state plumbing, ``ConvLayer`` flow head,
+``EventWarping`` (its own torch ops, on the GPU), ``clip_grad_norm_`` and ``torch.optim.Adam`` in the order of
+train_flow.py:232-279."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_runner, ref_shim
+from snnflow_testutil import grad_report, synth_window
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not ref_shim.reference_available(), reason="reference not staged (oracle/stage_reference.py)")]
+
+
+def _cuda_cells():
+    import snnflow_b200 as snnflow
+    return snnflow.ConvLIF, snnflow.ConvLIFRecurrent
+
+
+def _pair(kind, C, seed, pred_gain=20.0):
+    """(reference net on its own cells, CPU ; the same class on the CUDA cells, GPU) with identical parameters."""
+    ref_net = ref_runner.build_net(kind, C, None, seed=seed, dyadic=True, pred_gain=pred_gain)
+    seam = ref_runner.build_net(kind, C, _cuda_cells(), seed=seed, dyadic=True, pred_gain=pred_gain)
+    sa, sb = ref_net.state_dict(), seam.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    return ref_net, seam.cuda()
+
+
+@pytest.mark.parametrize("kind,C,B,H,W,T", [("LIFFireNet", 32, 2, 24, 40, 4), ("LIFFireFlowNet", 32, 2, 16, 128, 3),
+                                            ("LIFFireNet", 8, 3, 20, 36, 4)])
+def test_reference_network_on_cuda_cells_forward_backward(kind, C, B, H, W, T):
+    ref_net, seam = _pair(kind, C, seed=5)
+    g = torch.Generator().manual_seed(9)
+    cnt = torch.poisson(torch.full((T, B, 2, H, W), 0.25), generator=g)
+    gout = torch.randn(T, B, 2, H, W, generator=g)
+    loss_r, loss_s = 0, 0
+    for t in range(T):
+        fr = ref_net(None, cnt[t])["flow"][0]
+        fs = seam(None, cnt[t].cuda())["flow"][0]
+        np.testing.assert_allclose(fs.detach().cpu().numpy(), fr.detach().numpy(), rtol=1e-5, atol=2e-6)
+        loss_r = loss_r + (fr * gout[t]).sum()
+        loss_s = loss_s + (fs * gout[t].cuda()).sum()
+    # the reference's state layout: 7 tensors [2,B,C,H,W] = stack([v, z]) (spiking_submodules.py:151,300)
+    active = 0.0
+    for i, (a, b) in enumerate(zip(ref_net._states, seam._states)):
+        assert tuple(b.shape) == (2, B, C, H, W)
+        assert torch.equal(b[1].cpu(), a[1]), f"layer {i}: {int((b[1].cpu() != a[1]).sum())} spikes differ"
+        # lam = sigmoid(leak) is evaluated on the parameter's device (1 ulp apart): membranes to 2e-6
+        np.testing.assert_allclose(b[0].detach().cpu().numpy(), a[0].detach().numpy(), rtol=1e-5, atol=4e-6)
+        active = max(active, float(a[1].mean()))
+    assert active > 0.01, "silent network: the comparison would be vacuous"
+    loss_r.backward()
+    loss_s.backward()
+    ga = dict(ref_net.named_parameters())
+    for n, p in seam.named_parameters():
+        frac, rel = grad_report(p.grad.cpu().numpy(), ga[n].grad.numpy(), rtol=1e-4, atol_rel=1e-5)
+        assert frac >= 0.999 and rel <= 1e-4, (n, frac, rel)
+    # states() deep-clones, detach_states() keeps values (models/model.py:109-127)
+    st = seam.states
+    seam.detach_states()
+    for a, b in zip(st, seam._states):
+        assert torch.equal(a, b) and not b.requires_grad
+
+
+def test_reference_training_loop_on_cuda_cells():
+    """train_flow.py:232-279 verbatim - the reference's network class, flow head, EventWarping, clip_grad_norm_ and
+    torch.optim.Adam - with only the three class attributes pointing at the CUDA cells: loss, gradients and the updated
+    parameters of two consecutive optimizer steps against the all-reference CPU run."""
+    C, B, H, W, T, N = 16, 2, 32, 32, 4, 300
+    ref_net, seam = _pair("LIFFireNet", C, seed=3)
+    dev = torch.device("cuda")
+    lr = 1e-3
+    opt_r = torch.optim.Adam(ref_net.parameters(), lr=lr)
+    opt_s = torch.optim.Adam(seam.parameters(), lr=lr)
+    loss_r, loss_s = ref_runner.make_loss((H, W), torch.device("cpu")), ref_runner.make_loss((H, W), dev)
+    for step in range(2):
+        w = synth_window(T, B, N, H, W, seed=40 + step)
+        lr_, gr, _ = ref_runner.train_step(ref_net, loss_r, opt_r, copy.deepcopy(w), torch.device("cpu"))
+        ls_, gs, _ = ref_runner.train_step(seam, loss_s, opt_s, copy.deepcopy(w), dev)
+        if step == 0:   # identical (dyadic) parameters: spikes are identical, everything else is fp32 round-off
+            np.testing.assert_allclose(float(ls_), float(lr_), rtol=1e-5)
+            for n in gr:
+                frac, rel = grad_report(gs[n].cpu().numpy(), gr[n].numpy(), rtol=1e-4, atol_rel=1e-5)
+                assert frac >= 0.99 and rel <= 3e-3, (n, frac, rel)   # d loss/d flow conditioning: DESIGN.md section 2
+            pr = dict(ref_net.named_parameters())
+            for n, p in seam.named_parameters():
+                # Adam's first step moves every element by ~lr * sign(g): compare the step actually taken
+                # (elements whose gradient is ~0 may take a different step: at most 2 lr apart, and rare)
+                d = (p.detach().cpu() - pr[n].detach()).abs()
+                assert float(d.max()) <= 2.05 * lr and float((d <= 0.02 * lr + 1e-7).float().mean()) >= 0.99, (n, float(d.max()))
+        else:           # after an update the weights are off the dyadic grid: near-threshold spikes may flip
+            np.testing.assert_allclose(float(ls_), float(lr_), rtol=2e-2)
+    assert all(not s.requires_grad for s in seam._states)
