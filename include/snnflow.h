@@ -188,13 +188,16 @@ int snnflow_net_backward(const snnflow_net_desc* d, const snnflow_layer_ptrs* la
  * workspace (backward): snnflow_window_workspace_bytes() bytes, 256-byte aligned, zero-filled once as well.
  * state_in, layers, pred_*, input, flow, g_flow and the gradient accumulation semantics are those of
  * snnflow_net_forward / snnflow_net_backward (layers[l].packed is ignored: the engine packs per window).
- * snnflow_window_inexact_count: number of input values seen so far that were not bf16-exact (synchronises).
+ * snnflow_window_flags_offset: byte offset inside the arena of four uint32 status words owned by the engine;
+ *   word 0 = number of input values seen so far (by windows run in THIS arena) that were not bf16-exact - sticky until
+ *   the caller clears it.  The caller reads it (a device-to-host copy at a moment of its choosing) and may hand its
+ *   address to snnflow_clip_adam as the update gate.
  * --------------------------------------------------------------------------------------------- */
 int snnflow_window_supported(const snnflow_net_desc* d, int backward /* 0: forward (save == 0) only */);
 size_t snnflow_window_arena_bytes(const snnflow_net_desc* d, int save);
 size_t snnflow_window_workspace_bytes(const snnflow_net_desc* d);
 int snnflow_window_state_offsets(const snnflow_net_desc* d, int save, size_t* offsets_bytes /* [7] */);
-unsigned int snnflow_window_inexact_count(int reset);
+size_t snnflow_window_flags_offset(const snnflow_net_desc* d, int save);
 int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_layer_ptrs* layers, const float* pred_w,
                            const float* pred_b, const float* input, const float* const* state_in, void* arena,
                            float* flow, int save, snnflow_stream_t stream);
@@ -315,10 +318,16 @@ int snnflow_window_loss(const float* flow, const float* events, const float* pol
  *   state    4 device doubles owned by the optimizer {beta1^t, beta2^t, lr/(1-beta1^t), 1/sqrt(1-beta2^t)}: the powers
  *            are running products, (re)initialised by the call whenever step == 0
  *   partials snnflow_clip_adam_partials(n) floats of scratch;  grad_norm: device float or NULL, receives the total norm
+ *   gate     device uint32 or NULL: when *gate != 0 at execution time the whole update is skipped (parameters, moments
+ *            and the step counter stay as they are).  The training window passes the window engine's sticky
+ *            "input was not bf16-exact" flag (snnflow_window_flags_offset), so that a CUDA-graph replay can never
+ *            apply an update computed from rounded inputs; the host polls the flag and raises.
+ * A NaN gradient norm propagates into the parameters, as clip_grad_norm_ does.
  * --------------------------------------------------------------------------------------------- */
 int snnflow_clip_adam_partials(int64_t n);
 int snnflow_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* hyper,
-                      int64_t* step, double* state, float* partials, float* grad_norm, snnflow_stream_t stream);
+                      int64_t* step, double* state, float* partials, float* grad_norm, const unsigned int* gate,
+                      snnflow_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange (the reference has no distributed code): SUM all-reduce

@@ -222,6 +222,55 @@ def train_fixture(ref, name, *, kind, C, B, H, W, T, n, seed, mask_output=False)
 
 
 
+def train_step_fixture(ref, name, *, C, B, H, W, T, n, seed, default_params=False, lr=2e-4, clip=1.0):
+    """One FULL optimizer step at a benchmark shape (train_flow.py:232-279: T bins, EventWarping, backward,
+    clip_grad_norm_, Adam): loss, every parameter gradient (before clipping), the total gradient norm and the updated
+    parameters.  The window is regenerated from its seed by tests/snnflow_testutil.synth_window (a checksum guards the
+    generator); `default_params`: the cells' own init statistics and raw fp32 weights (a silent last layer: flow == 0,
+    every event on the integer-tie path of utils/iwe.py:57-59), else the active dyadic network of make_net."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT)))
+    from snnflow_testutil import synth_window
+    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
+    if default_params:
+        net = make_net(ref, "LIFFireNet", C, seed, dyadic_w=False, leak=(-4.0, 0.1), thresh=(0.8, 0.0))
+        with torch.no_grad():
+            net.pred.conv2d.weight.mul_(1.0 / 20)   # back to ~w_scale_pred (model.py:43)
+    else:
+        net = make_net(ref, "LIFFireNet", C, seed)
+    w = synth_window(T, B, n, H, W, seed + 1)
+    arrs = {"param." + k: _np(v) for k, v in net.state_dict().items()}
+    arrs["lam"] = _np(torch.stack([torch.sigmoid(getattr(net, l).leak).reshape(-1) for l in
+                                   ("head", "G1", "R1a", "R1b", "G2", "R2a", "R2b")]))
+    arrs["theta"] = _np(torch.stack([getattr(net, l).thresh.clamp_min(0.01).reshape(-1) for l in
+                                     ("head", "G1", "R1a", "R1b", "G2", "R2a", "R2b")]))
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": 0.001}, "model": {"mask_output": False}}
+    lossf = ref.flow.EventWarping(cfg, torch.device("cpu"))
+    opt = torch.optim.Adam(net.parameters(), lr=lr)
+    flows = []
+    for t in range(T):
+        out = net(None, w["event_cnt"][t])
+        out["flow"][0].retain_grad()
+        flows.append(out["flow"][0])
+        lossf.event_flow_association(out["flow"], w["event_list"][t].clone(), w["event_list_pol_mask"][t], w["event_mask"][t])
+    loss = lossf()
+    loss.backward()
+    for k, p in net.named_parameters():
+        arrs["grad." + k] = _np(p.grad)
+    total = torch.nn.utils.clip_grad.clip_grad_norm_(net.parameters(), clip)
+    opt.step()
+    for k, p in net.named_parameters():
+        arrs["new." + k] = _np(p)
+    gflow = torch.stack([f.grad for f in flows])
+    arrs.update(loss=_np(loss), grad_norm=_np(total), flow_last=_np(flows[-1]), gflow_last=_np(gflow[-1]),
+                flow_absmax=np.array([float(f.abs().max()) for f in flows]),
+                gflow_norm=np.array([float(g.norm()) for g in gflow]),
+                spike_rate=np.array([float(st[1].mean()) for st in net._states]),
+                window_checksum=np.array([float(w["event_cnt"].double().sum()), float(w["event_list"].double().sum()),
+                                          float((w["event_list"][..., 0].double() * w["event_list"][..., 2].double()).sum())]))
+    _save(name, dims=np.array([C, B, H, W, T, n]), seed=seed, lr=lr, clip=clip, default_params=int(default_params), **arrs)
+
+
 # ------------------------------------------------------------------------------------------------
 # loader fixtures: the reference's own H5Loader.__getitem__ driven through an in-memory stand-in for h5py
 # ------------------------------------------------------------------------------------------------
@@ -341,7 +390,8 @@ def main(only=None):
     ref = ref_shim.load()
     if only:   # regenerate selected fixtures only (python oracle/make_golden.py --only name[,name])
         g = globals()
-        for fn in ("layer_fixture", "net_fixture", "encode_fixture", "iwe_fixture", "train_fixture", "loader_fixture"):
+        for fn in ("layer_fixture", "net_fixture", "encode_fixture", "iwe_fixture", "train_fixture", "train_step_fixture",
+                   "loader_fixture"):
             orig = g[fn]
             g[fn] = (lambda o: (lambda r, name, **kw: o(r, name, **kw) if name in only else None))(orig)
     # --- single layers (fwd + bwd), bit-exact tier (dyadic weights, spike inputs) ---
@@ -381,6 +431,9 @@ def main(only=None):
     # C = 16 / 32: inside the envelope of the layer-major window engine (tensor-core head layer included)
     train_fixture(ref, "train_firenet_c16", kind="LIFFireNet", C=16, B=2, H=16, W=16, T=3, n=120, seed=52)
     train_fixture(ref, "train_fireflownet_c32", kind="LIFFireFlowNet", C=32, B=1, H=12, W=20, T=4, n=150, seed=53)
+    # --- one full optimizer step at BASELINE.json configs[1] (C=32, batch 8, 128x128, 10 bins x 1000 events) ---
+    train_step_fixture(ref, "step_cfg1_active", C=32, B=8, H=128, W=128, T=10, n=1000, seed=70)
+    train_step_fixture(ref, "step_cfg1_default", C=32, B=8, H=128, W=128, T=10, n=1000, seed=71, default_params=True)
     # --- loader: raw event windows -> batch tensors (the reference's H5Loader on an in-memory stream) ---
     loader_fixture(ref, "loader_events_hot", mode="events", B=3, H=20, W=24, n_win=400, n_items=5, num_bins=5,
                    round_enc=False, seed=60, hot=dict(max_px=2, min_obvs=2, max_rate=0.7))

@@ -37,7 +37,7 @@ _PROTOS = {
     "snnflow_iwe_splat_fwd": (c_int, [P] * 5 + [c_int, c_int64, c_int, c_int, c_float, c_float, c_int, c_int, c_float,
                                                 c_int, P]),
     "snnflow_clip_adam_partials": (c_int, [c_int64]),
-    "snnflow_clip_adam": (c_int, [P] * 4 + [c_int64] + [P] * 6),
+    "snnflow_clip_adam": (c_int, [P] * 4 + [c_int64] + [P] * 7),
     "snnflow_dp_allreduce_ctas": (c_int, []),
     "snnflow_dp_allreduce_sum": (c_int, [P, P, P, P, c_int, c_int, c_size_t, P]),
     "snnflow_window_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int64, c_int, c_int]),
@@ -55,7 +55,7 @@ class SnnflowError(RuntimeError):
 
 _ENGINE_SYMBOLS = ["snnflow_net_acts_floats", "snnflow_net_bwd_workspace_bytes", "snnflow_net_forward",
                    "snnflow_net_backward", "snnflow_window_supported", "snnflow_window_arena_bytes",
-                   "snnflow_window_workspace_bytes", "snnflow_window_state_offsets", "snnflow_window_inexact_count",
+                   "snnflow_window_workspace_bytes", "snnflow_window_state_offsets", "snnflow_window_flags_offset",
                    "snnflow_window_forward", "snnflow_window_backward",
                    "snnflow_format_window_workspace_bytes", "snnflow_format_window"]   # struct-taking entry points, bound in engine.py / loader.py
 

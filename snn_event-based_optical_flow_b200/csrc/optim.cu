@@ -35,8 +35,9 @@ __device__ __forceinline__ float opt_block_sum(float v, float* red) {
 // rate); block 0 of the first launch advances them while the other blocks already sum their slices.
 __global__ void __launch_bounds__(OPT_THREADS) opt_sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partials,
                                                                 long long* __restrict__ step, const float* __restrict__ hyper,
-                                                                double* __restrict__ state) {
+                                                                double* __restrict__ state, const unsigned int* __restrict__ gate) {
   __shared__ float red[OPT_THREADS / 32];
+  if (gate != nullptr && *gate != 0u) return;   // the step is vetoed (see snnflow_clip_adam): nothing advances
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const long long t = *step;
     const double p1 = (t == 0 ? 1.0 : state[0]) * (double)hyper[1], p2 = (t == 0 ? 1.0 : state[1]) * (double)hyper[2];
@@ -60,8 +61,9 @@ __global__ void __launch_bounds__(OPT_THREADS) opt_clip_adam_kernel(float* __res
                                                                     float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                                     const float* __restrict__ hyper, const double* __restrict__ state,
                                                                     const float* __restrict__ partials, int n_part,
-                                                                    float* __restrict__ norm_out) {
+                                                                    float* __restrict__ norm_out, const unsigned int* __restrict__ gate) {
   __shared__ float s_coef;
+  if (gate != nullptr && *gate != 0u) return;
   // this thread's slice first: the loads are in flight while warp 0 derives the clip coefficient
   const int64_t base = (int64_t)blockIdx.x * OPT_PER_BLOCK + threadIdx.x;
   float gk[OPT_PER_THREAD], mk[OPT_PER_THREAD], vk[OPT_PER_THREAD], pk[OPT_PER_THREAD];
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(OPT_THREADS) opt_clip_adam_kernel(float* __res
       const float total = sqrtf(t);
       float coef = 1.f;
       if (max_norm > 0.f) coef = fminf(max_norm / (total + 1e-6f), 1.0f);      // clip_grad.py: clamp(max=1.0)
+      if (max_norm > 0.f && total != total) coef = total;                      // ... which propagates a NaN norm (fminf would not)
       s_coef = coef;
       if (blockIdx.x == 0 && norm_out) *norm_out = total;
     }
@@ -107,16 +110,16 @@ extern "C" int snnflow_clip_adam_partials(int64_t n) { return n <= 0 ? 0 : (int)
 
 extern "C" int snnflow_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                                  const float* hyper, int64_t* step, double* state, float* partials, float* grad_norm,
-                                 snnflow_stream_t stream) {
+                                 const unsigned int* gate, snnflow_stream_t stream) {
   SNNFLOW_REQUIRE(params && grads && exp_avg && exp_avg_sq && hyper && step && state && partials && n > 0, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const int n_part = snnflow_clip_adam_partials(n);
   prof_begin("opt_sumsq", st, 4.0 * n);
-  opt_sumsq_kernel<<<n_part, OPT_THREADS, 0, st>>>(grads, n, partials, reinterpret_cast<long long*>(step), hyper, state);
+  opt_sumsq_kernel<<<n_part, OPT_THREADS, 0, st>>>(grads, n, partials, reinterpret_cast<long long*>(step), hyper, state, gate);
   int rc = check_launch("opt_sumsq_kernel");
   if (rc) return rc;
   prof_begin("opt_clip_adam", st, 28.0 * n);
   opt_clip_adam_kernel<<<n_part, OPT_THREADS, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, hyper, state, partials, n_part,
-                                                     grad_norm);
+                                                     grad_norm, gate);
   return check_launch("opt_clip_adam_kernel");
 }

@@ -16,7 +16,7 @@ struct WinLayout {
   int Kin[WIN_LAYERS];            // allocated input channels (multiple of 16)
   int Cin[WIN_LAYERS];            // real input channels
   bool rec[WIN_LAYERS];
-  size_t off_inplanes;
+  size_t off_inplanes, off_flags;
   size_t off_zp[WIN_LAYERS], zp_img_stride;   // bf16 planes; recurrent layers have B leading images (initial spikes)
   size_t off_v[WIN_LAYERS], off_cur[WIN_LAYERS], off_state[WIN_LAYERS], off_init[WIN_LAYERS];
   size_t off_fwd_blob[WIN_LAYERS], off_dg_blob[WIN_LAYERS], off_rb_blob[WIN_LAYERS], off_par[WIN_LAYERS], off_gridbar[WIN_LAYERS];
@@ -32,6 +32,7 @@ static WinLayout win_layout(const snnflow_net_desc* d, int save) {
   L.zp_img_stride = (size_t)(C / 8) * L.g.plane_bytes;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
+  L.off_flags = take(256);   // status words of the engine (word 0: sticky count of inputs that were not bf16-exact)
   L.off_inplanes = take((size_t)T * B * 2 * L.g.plane_bytes);
   for (int l = 0; l < WIN_LAYERS; ++l) {
     L.rec[l] = (d->recurrent_mask >> l) & 1u;
@@ -176,7 +177,10 @@ extern "C" size_t snnflow_window_workspace_bytes(const snnflow_net_desc* d) {
   return win_workspace(d, L, win_plan(d, L)).total;
 }
 
-extern "C" unsigned int snnflow_window_inexact_count(int reset) { return win_inexact_count(reset); }
+extern "C" size_t snnflow_window_flags_offset(const snnflow_net_desc* d, int save) {
+  if (!win_supported(d, save != 0)) return 0;
+  return win_layout(d, save).off_flags;
+}
 
 extern "C" int snnflow_window_state_offsets(const snnflow_net_desc* d, int save, size_t* offsets_bytes) {
   SNNFLOW_REQUIRE(win_supported(d, save != 0) && offsets_bytes, "unsupported shape or null pointer");
@@ -213,7 +217,7 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
   }
   int rc = launch_pack_weights(pk, st);
   if (rc) return rc;
-  rc = launch_pack_input(input, A + L.off_inplanes, T * B, d->num_bins, 2, H, W, st);
+  rc = launch_pack_input(input, A + L.off_inplanes, T * B, d->num_bins, 2, H, W, (unsigned int*)(A + L.off_flags), st);
   if (rc) return rc;
 
   if (save && state_in) {

@@ -114,8 +114,7 @@ int launch_wgrad_planes(WgArgs a, cudaStream_t st, double bytes, double flops);
 
 // ---- CUDA-core helpers (window_simt.cu) ---------------------------------------------------------------
 int launch_pack_input(const float* in, unsigned char* planes, int n_img, int nb, int n_chunks, int H, int W,
-                      cudaStream_t st);
-unsigned int win_inexact_count(int reset);
+                      unsigned int* inexact, cudaStream_t st);
 int launch_pack_spikes(const float* z, unsigned char* planes, int n_img, int C, int H, int W, cudaStream_t st);
 struct PackLayer {
   const float *w_ff, *w_rec;

@@ -7,12 +7,11 @@
 
 namespace snnflow {
 
-__device__ unsigned int g_win_inexact = 0;   // window inputs that one bf16 term does not represent exactly
-
 // ---- fp32 NCHW -> bf16 planes ------------------------------------------------------------------------
 // thread = one pixel of one (image, chunk): reads up to 8 channel planes (coalesced along x), writes one 16-B slot
 __global__ void __launch_bounds__(256) pack_planes_kernel(const float* __restrict__ in, unsigned char* __restrict__ planes,
-                                                          int n_ch, int n_chunks, int H, int W, int count_inexact) {
+                                                          int n_ch, int n_chunks, int H, int W,
+                                                          unsigned int* __restrict__ inexact) {
   const int HW = H * W, Wp = W + 2;
   const int p = blockIdx.x * 256 + threadIdx.x;
   const int chunk = blockIdx.y, img = blockIdx.z;
@@ -32,29 +31,20 @@ __global__ void __launch_bounds__(256) pack_planes_kernel(const float* __restric
   const size_t plane_bytes = (size_t)(H + 2) * Wp * 16;
   unsigned char* dst = planes + ((size_t)img * n_chunks + chunk) * plane_bytes + ((size_t)(y + 1) * Wp + x + 1) * 16;
   *reinterpret_cast<uint4*>(dst) = make_uint4(u[0], u[1], u[2], u[3]);
-  if (count_inexact && bad) atomicAdd(&g_win_inexact, bad);
-}
-
-unsigned int win_inexact_count(int reset) {
-  unsigned int v = 0;
-  cudaMemcpyFromSymbol(&v, g_win_inexact, sizeof(v));
-  if (reset) {
-    unsigned int z = 0;
-    cudaMemcpyToSymbol(g_win_inexact, &z, sizeof(z));
-  }
-  return v;
+  // values that one bf16 term does not represent exactly: counted into the arena's sticky status word
+  if (inexact != nullptr && bad) atomicAdd(inexact, bad);
 }
 
 int launch_pack_input(const float* in, unsigned char* planes, int n_img, int nb, int n_chunks, int H, int W,
-                      cudaStream_t st) {
+                      unsigned int* inexact, cudaStream_t st) {
   prof_begin("win_pack_input", st, (double)n_img * H * W * (4.0 * nb + 16.0 * n_chunks));
-  pack_planes_kernel<<<dim3(ceil_div(H * W, 256), n_chunks, n_img), 256, 0, st>>>(in, planes, nb, n_chunks, H, W, 1);
+  pack_planes_kernel<<<dim3(ceil_div(H * W, 256), n_chunks, n_img), 256, 0, st>>>(in, planes, nb, n_chunks, H, W, inexact);
   return check_launch("pack_planes_kernel");
 }
 
 int launch_pack_spikes(const float* z, unsigned char* planes, int n_img, int C, int H, int W, cudaStream_t st) {
   prof_begin("win_pack_state", st, (double)n_img * H * W * (4.0 * C + 2.0 * C));
-  pack_planes_kernel<<<dim3(ceil_div(H * W, 256), C / 8, n_img), 256, 0, st>>>(z, planes, C, C / 8, H, W, 0);
+  pack_planes_kernel<<<dim3(ceil_div(H * W, 256), C / 8, n_img), 256, 0, st>>>(z, planes, C, C / 8, H, W, nullptr);
   return check_launch("pack_planes_kernel");
 }
 

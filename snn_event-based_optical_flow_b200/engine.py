@@ -50,8 +50,8 @@ def _bind(L):
     L.snnflow_window_workspace_bytes.argtypes = [P]
     L.snnflow_window_state_offsets.restype = ctypes.c_int
     L.snnflow_window_state_offsets.argtypes = [P, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
-    L.snnflow_window_inexact_count.restype = ctypes.c_uint
-    L.snnflow_window_inexact_count.argtypes = [ctypes.c_int]
+    L.snnflow_window_flags_offset.restype = ctypes.c_size_t
+    L.snnflow_window_flags_offset.argtypes = [P, ctypes.c_int]
     L.snnflow_window_forward.restype = ctypes.c_int
     L.snnflow_window_forward.argtypes = [P, P, P, P, P, ctypes.POINTER(P), P, P,
                                          ctypes.c_int, P]
@@ -61,13 +61,40 @@ def _bind(L):
     L._net_bound = True
 
 
-def _state_ptrs(states):
+def _state_ptrs(states, shape=None, contiguous=True):
+    """The states as an array of raw pointers.  `shape` = (B, C, H, W) of the window: every state must be a contiguous
+    fp32 CUDA tensor [2,B,C,H,W] - the kernels read B*C*H*W floats per half through the raw pointer, so a state left
+    over from another batch size / resolution (no reset_states() in between) is an error here, as it is a shape error
+    in the reference (spiking_submodules.py:144: v * leak * (1 - z) + (1 - leak) * ff)."""
     arr = (ctypes.c_void_p * N_LAYERS)()
     if states is None or all(s is None for s in states):
         return None, arr
     for i, s in enumerate(states):
-        arr[i] = None if s is None else s.data_ptr()
+        if s is None:
+            arr[i] = None
+            continue
+        if shape is not None:
+            want = (2,) + tuple(shape)
+            if tuple(s.shape) != want or s.dtype != torch.float32 or not s.is_cuda or (contiguous and not s.is_contiguous()):
+                raise _lib.SnnflowError(
+                    f"layer {i}: state is {tuple(s.shape)} {s.dtype} on {s.device}"
+                    f"{'' if s.is_contiguous() else ' (non-contiguous)'}, the window needs a contiguous float32 CUDA "
+                    f"tensor {want}: call reset_states() when the batch size or the resolution changes")
+        arr[i] = s.data_ptr()
     return arr, arr
+
+
+def _effective_params(runner, layers):
+    """lam = sigmoid(leak) (spiking_submodules.py:136) and theta = clamp_min(thresh, 0.01) (:133) of all layers, [7,C]
+    each.  `runner.param_override = (lam, theta)` injects values evaluated elsewhere (the parity tests pass the
+    reference's CPU values: torch's CUDA and CPU sigmoid differ in the last bit)."""
+    ov = getattr(runner, "param_override", None)
+    if ov is not None:
+        dev = layers[0].leak.device
+        return ov[0].to(dev, torch.float32).contiguous(), ov[1].to(dev, torch.float32).contiguous()
+    lam = torch.sigmoid(torch.stack([l.leak.detach().reshape(-1) for l in layers]))
+    theta = torch.stack([l.thresh.detach().reshape(-1) for l in layers]).clamp_min(0.01)
+    return lam, theta
 
 
 class _WindowFn(torch.autograd.Function):
@@ -83,8 +110,7 @@ class _WindowFn(torch.autograd.Function):
         cnt = cnt.float().contiguous()
         need_bwd = any(ctx.needs_input_grad)   # (grad mode is off inside Function.forward)
         # effective leak / threshold of all layers in two launches (spiking_submodules.py:133,136)
-        lam = torch.sigmoid(torch.stack([l.leak.detach().reshape(-1) for l in layers]))
-        theta = torch.stack([l.thresh.detach().reshape(-1) for l in layers]).clamp_min(0.01)
+        lam, theta = _effective_params(runner, layers)
         first = layers[0]
         flags = (_lib.HARD_RESET if first.hard_reset else 0) | (_lib.DETACH_RESET if first.detach else 0)
         if not first.use_tensor_cores:
@@ -102,7 +128,7 @@ class _WindowFn(torch.autograd.Function):
         acts = runner.arena(desc, need_bwd, dev)
         flow = torch.empty((T, B, 2, H, W), dtype=torch.float32, device=dev)
         states = net._states
-        sp, keep = _state_ptrs(states)
+        sp, keep = _state_ptrs(states, (B, C, H, W))
         pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
         _lib.check(L.snnflow_net_forward(ctypes.byref(desc), lp, pw.data_ptr(), None if pb is None else pb.data_ptr(),
                                          cnt.data_ptr(), sp, acts.data_ptr(), flow.data_ptr(), int(need_bwd),
@@ -211,8 +237,7 @@ class _LayerMajorWindowFn(torch.autograd.Function):
         Cr = layers[0].hidden_size                 # the network's width ...
         C = _lm_channels(Cr)                       # ... and the (zero-padded) width the engine runs it at
         desc = _make_desc(runner, cnt, C)
-        lam = torch.sigmoid(torch.stack([l.leak.detach().reshape(-1) for l in layers]))      # spiking_submodules.py:136
-        theta = torch.stack([l.thresh.detach().reshape(-1) for l in layers]).clamp_min(0.01)  # :133
+        lam, theta = _effective_params(runner, layers)
         lam_e, theta_e = _pad_dim(lam, 1, C, 0.5), _pad_dim(theta, 1, C, 1.0)
         w_e = []
         for i, l in enumerate(layers):
@@ -229,20 +254,23 @@ class _LayerMajorWindowFn(torch.autograd.Function):
             lp[i].theta = theta_e[i].data_ptr()
         arena = runner.lm_arena(desc, need_bwd, dev)
         flow = torch.empty((T, B, 2, H, W), dtype=torch.float32, device=dev)
+        _state_ptrs(net._states, (B, Cr, H, W), contiguous=C == Cr)   # shape check on the network's own states
         states = runner.lm_states_in(net._states, Cr, C)
-        sp, keep = _state_ptrs(states)
+        sp, keep = _state_ptrs(states, (B, C, H, W))
         pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
         pw_e = _pad_dim(pw.detach(), 1, C)
         _lib.check(L.snnflow_window_forward(ctypes.byref(desc), lp, pw_e.data_ptr(), None if pb is None else pb.data_ptr(),
                                             cnt.data_ptr(), sp, arena.data_ptr(), flow.data_ptr(), int(need_bwd),
                                             _lib.stream()), "snnflow_window_forward")
+        # the arena's sticky "input was not bf16-exact" word (per arena, i.e. per runner and shape): polled here, and
+        # handed to the fused optimizer as its update gate (train.TrainWindow) so that graph replays cannot apply an
+        # update computed from rounded inputs before the host has looked
+        foff = L.snnflow_window_flags_offset(ctypes.byref(desc), int(need_bwd))
+        runner.input_flag = arena[foff:foff + 4].view(torch.int32)
         runner._lm_calls = getattr(runner, "_lm_calls", 0) + 1
         capturing = torch.cuda.is_current_stream_capturing()
         if not capturing and (runner.validate_input or runner._lm_calls == 1 or runner._lm_calls % runner.validate_every == 0):
-            bad = int(L.snnflow_window_inexact_count(1))
-            if bad:
-                raise _lib.SnnflowError(f"window engine: {bad} input values are not exactly representable in bfloat16 "
-                                        "(event counts above 256 or fractional values): use the per-step engine")
+            runner.check_input_flag()
         offs = (ctypes.c_size_t * N_LAYERS)()
         _lib.check(L.snnflow_window_state_offsets(ctypes.byref(desc), int(need_bwd), offs), "snnflow_window_state_offsets")
         nbytes = 2 * B * C * H * W * 4
@@ -318,8 +346,12 @@ class WindowRunner:
     """Runs windows of T bins through a snnflow LIFFireNet / LIFFireFlowNet with one C call per direction."""
 
     engine = "auto"          # "auto": layer-major engine when it covers the shape, else per-step; "per_step"; "layer_major"
-    validate_input = False   # True: check after EVERY window (host sync) that all input values were bf16-exact
-    validate_every = 64      # otherwise the check runs on the first window and then every `validate_every`-th one
+    validate_input = True    # check after EVERY eagerly launched window (one host sync) that all inputs were bf16-exact;
+    validate_every = 64      # False: only on the first window and then every `validate_every`-th one.  CUDA-graph
+                             # replays cannot sync: there the arena's sticky flag gates the fused optimizer update and
+                             # train.TrainWindow polls it (check_input_flag) every `validate_every` replays
+    param_override = None    # (lam [7,C], theta [7,C]) evaluated by the caller instead of sigmoid / clamp_min on the device
+    input_flag = None        # int32 view of the arena's status word of the last layer-major window
 
     def __init__(self, net):
         self.net = net
@@ -329,6 +361,17 @@ class WindowRunner:
         self._flip = 0
         self._ws = None
         self.new_states = None
+
+    def check_input_flag(self):
+        """Raise if any window run in this runner's arena saw input values that one bf16 term cannot represent (host sync)."""
+        if self.input_flag is None:
+            return
+        bad = int(self.input_flag.item())
+        if bad:
+            self.input_flag.zero_()
+            raise _lib.SnnflowError(f"window engine: {bad} input values were not exactly representable in bfloat16 (event "
+                                    "counts above 256 or fractional values, e.g. a voxel encoding): the results of this window "
+                                    "are rounded and any gated optimizer update was skipped - use engine='per_step'")
 
     def supported(self):
         l0 = self.layers[0]
@@ -410,9 +453,17 @@ class WindowRunner:
             params += [l.ff.weight, l.rec.weight if l.recurrent else None, l.leak, l.thresh]
         params += [self.net.pred.conv2d.weight, self.net.pred.conv2d.bias]
         need_bwd = torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in params)
-        use_lm = self.engine != "per_step" and self.layer_major_ok(cnt_window, need_bwd)
+        # the layer-major engine carries inputs as ONE bf16 term: event counts are exact, a voxel grid (fractional
+        # weights, encodings.py:48-67) is not - such networks run on the per-step engine (exact fp32 head layer)
+        exact_input = getattr(self.net, "encoding", "cnt") == "cnt"
+        use_lm = self.engine != "per_step" and (exact_input or self.engine == "layer_major") and self.layer_major_ok(cnt_window, need_bwd)
         if self.engine == "layer_major" and not use_lm:
             raise _lib.SnnflowError("the layer-major window engine does not cover this shape / these options")
+        if not use_lm and self.engine == "auto" and not getattr(self, "_warned_fallback", False):
+            import warnings
+            self._warned_fallback = True
+            warnings.warn("snnflow: this window runs on the per-step engine (shape / options / input encoding outside the "
+                          "layer-major engine's envelope: C in {16, 32}, W <= 256, detached reset, count encoding)")
         fn = _LayerMajorWindowFn if use_lm else _WindowFn
         flow = fn.apply(self, cnt_window, *params)
         self.net._states = self.new_states

@@ -4,11 +4,18 @@ On the GPU box the reference tree does not exist, so the benchmark and the GPU p
 the network container itself; this mirror keeps the reference's constructor (a ``unet_kwargs`` dict),
 the class-attribute seam ``head_neuron / ff_neuron / rec_neuron`` (models/model.py:37-39), the
 ``states`` / ``detach_states`` / ``reset_states`` plumbing (:109-130), the layer order and the
-``{"flow": [flow], "activity": ...}`` return, and the reference's state_dict keys.  In a checkout that
-has the reference, the same cells drop into the reference's own classes:
+``{"flow": [flow], "activity": ...}`` return, and the state_dict keys the reference's networks have WHEN THEY ARE
+BUILT ON THE ``ConvLIF`` / ``ConvLIFRecurrent`` CELLS of models/spiking_submodules.py (``head.ff.weight``,
+``G1.rec.weight``, ``R1a.leak``, ``R1a.thresh`` ...).  In a checkout that has the reference, the same cells drop into
+the reference's own classes (tests/test_gpu_reference_seam.py runs exactly this on the GPU):
 
     class Net(models.model.LIFFireNet):
         head_neuron = ff_neuron = snnflow.ConvLIF; rec_neuron = snnflow.ConvLIFRecurrent
+
+LIMITATION: the reference's ``LIFFireNet`` as shipped wires the ``SNNtorch_ConvLIF`` /
+``SNNtorch_ConvLIFRecurrent`` cells (models/model.py:37-39: snntorch ``Leaky`` + ``BatchNorm2d``, keys ``lif.beta``,
+``lif.threshold``, ``bn.*``), a different neuron equation.  Checkpoints of that default model do not load into this
+mirror: ``load_state_dict`` refuses them with an explicit error instead of reporting a wall of missing keys.
 """
 import torch
 import torch.nn as nn
@@ -66,6 +73,16 @@ class LIFFireNet(nn.Module):
 
     def init_cropping(self, width, height):
         pass
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        foreign = [k for k in state_dict if ".lif." in k or ".bn." in k or ".tebn." in k or ".mpbn." in k]
+        if foreign:
+            raise RuntimeError(
+                "snnflow LIFFireNet: this state_dict comes from the reference's SNNtorch_ConvLIF cells (keys such as "
+                f"{foreign[0]!r}: snntorch Leaky + BatchNorm2d, models/SNNtorch_spiking_submodules.py).  This network "
+                "implements the ConvLIF / ConvLIFRecurrent cells of models/spiking_submodules.py (keys ff.weight, "
+                "rec.weight, leak, thresh); the two neuron models are not weight-compatible.")
+        return super().load_state_dict(state_dict, *args, **kwargs)
 
     def forward_window(self, event_cnt_window):
         """T bins at once: [T,B,num_bins,H,W] -> flow [T,B,2,H,W], equivalent to T calls of forward() (same states,

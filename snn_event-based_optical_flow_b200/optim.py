@@ -50,9 +50,10 @@ class FusedClipAdam:
         self.param_groups[0]["lr"] = lr
 
     @torch.no_grad()
-    def step(self, grads=None):
+    def step(self, grads=None, gate=None):
         """Clip (if ``max_norm``) and update.  ``grads``: tensors to use instead of ``p.grad`` (missing gradients count
-        as zeros, like parameters torch's Adam skips while their moments are still zero)."""
+        as zeros, like parameters torch's Adam skips while their moments are still zero).  ``gate``: optional int32
+        device tensor; when it is non-zero at execution time the kernels skip the whole update (see snnflow.h)."""
         if grads is None:
             grads = [p.grad for p in self.params]
         have = [(v, g) for v, g in zip(self.grad_views, grads) if g is not None]
@@ -63,7 +64,7 @@ class FusedClipAdam:
         L.check(L.lib().snnflow_clip_adam(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
                                           self.exp_avg_sq.data_ptr(), self.n, self.hyper.data_ptr(),
                                           self.step_count.data_ptr(), self.bias_state.data_ptr(), self.partials.data_ptr(),
-                                          self.grad_norm.data_ptr(),
+                                          self.grad_norm.data_ptr(), None if gate is None else gate.data_ptr(),
                                           L.stream()), "snnflow_clip_adam")
         # the kernel wrote the parameters behind autograd's back: bump their version counters so that anything keyed on
         # them (the cells' packed-weight cache, spiking_submodules.py) sees the update
@@ -77,9 +78,51 @@ class FusedClipAdam:
                 p.grad.zero_()
 
     def state_dict(self):
-        return {"step": self.step_count.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
-                "hyper": self.hyper.clone(), "bias_state": self.bias_state.clone()}
+        """The layout of ``torch.optim.Adam.state_dict()`` - what the reference's checkpoints store as
+        ``optimizer_state_dict`` (train_flow.py save_data) - sliced out of the flat moment buffers, so a run can be resumed
+        from / handed back to the reference's optimizer."""
+        t = self.step_count.to(torch.float32).reshape(()).cpu()
+        state = {}
+        if int(t) > 0:
+            for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+                n = p.numel()
+                state[i] = {"step": t.clone(), "exp_avg": self.exp_avg[o:o + n].view_as(p).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p).clone()}
+        lr, b1, b2, eps, max_norm = [float(v) for v in self.hyper.tolist()]
+        group = {"lr": lr, "betas": (b1, b2), "eps": eps, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "params": list(range(len(self.params))), "max_norm": max_norm}
+        return {"state": state, "param_groups": [group]}
 
+    @torch.no_grad()
     def load_state_dict(self, sd):
-        self.step_count.copy_(sd["step"]); self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        self.hyper.copy_(sd["hyper"]); self.bias_state.copy_(sd["bias_state"])
+        """Accepts ``torch.optim.Adam.state_dict()`` (and this class's own output)."""
+        group = sd["param_groups"][0]
+        if group.get("amsgrad") or group.get("weight_decay"):
+            raise ValueError("FusedClipAdam implements Adam without amsgrad / weight decay")
+        if len(group["params"]) != len(self.params):
+            raise ValueError(f"optimizer state has {len(group['params'])} parameters, this optimizer {len(self.params)}")
+        b1, b2 = group["betas"]
+        self.hyper[:4] = torch.tensor([group["lr"], b1, b2, group["eps"]], dtype=torch.float32)
+        if "max_norm" in group:
+            self.hyper[4] = float(group["max_norm"])
+        self.param_groups[0].update(lr=group["lr"], betas=(b1, b2), eps=group["eps"])
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            if st is None:
+                continue
+            n = p.numel()
+            self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(st["step"]))
+        if len(steps) > 1:
+            raise ValueError(f"FusedClipAdam keeps ONE step counter; the state holds {sorted(steps)}")
+        t = steps.pop() if steps else 0
+        self.step_count.fill_(t)
+        # the kernel carries beta^t as running products in double precision (re-initialised by itself at step 0)
+        p1, p2 = float(b1) ** t, float(b2) ** t
+        self.bias_state.copy_(torch.tensor([p1, p2, group["lr"] / (1.0 - p1) if t else 0.0,
+                                            1.0 / (1.0 - p2) ** 0.5 if t else 0.0], dtype=torch.float64))

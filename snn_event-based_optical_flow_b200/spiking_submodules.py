@@ -48,6 +48,11 @@ class _ConvLIFStep(torch.autograd.Function):
         if w_rec is not None:
             w_rec = _f32c(w_rec)
         if prev_state is not None:
+            # the kernels read B*C*H*W floats per half through the raw pointer: a state left over from another batch
+            # size / resolution is a shape error here as it is in the reference (spiking_submodules.py:144)
+            if tuple(prev_state.shape) != (2, B, C, H, W):
+                raise _lib.SnnflowError(f"snnflow ConvLIF: prev_state is {tuple(prev_state.shape)}, this input needs "
+                                        f"{(2, B, C, H, W)} (reset the states when batch size or resolution change)")
             prev_state = _f32c(prev_state)
         if residual is not None:
             residual = _f32c(residual)

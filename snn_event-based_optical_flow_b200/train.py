@@ -114,6 +114,7 @@ class TrainWindow:
                 import warnings
                 warnings.warn(f"peer-memory all-reduce unavailable ({e}); using the NCCL all-reduce")
         self._graph = None
+        self._params = [p for p in model.parameters()]
         self.fused_loss = True   # False: per-bin event_flow_association + EventWarping.forward (the reference's call pattern)
 
     # ---- the step in two halves (train_flow.py:232-262 and :265-279) -------------------------------------
@@ -133,9 +134,15 @@ class TrainWindow:
         loss.backward()
         return loss.detach()
 
+    def _runner(self):
+        return getattr(self.model, "_window_runner", None)
+
     def _update(self):
         if getattr(self.opt, "fused_clip", False):
-            self.opt.step()          # optim.FusedClipAdam: clipping and Adam in one C call (max_norm given to the optimizer)
+            # optim.FusedClipAdam: clipping and Adam in one C call (max_norm given to the optimizer), gated by the window
+            # engine's sticky "input was not bf16-exact" flag: an update computed from rounded inputs is never applied
+            r = self._runner()
+            self.opt.step(gate=None if r is None else r.input_flag)
         else:
             if self.clip is not None:
                 torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
@@ -217,17 +224,17 @@ class TrainWindow:
         else:
             self._load(batch)
         self._graph.replay()
-        self._replays = getattr(self, "_replays", 0) + 1
-        if self._replays % 64 == 0:   # graph replays bypass the engine's Python-side input check: poll the device counter
-            from . import _lib
-            from . import engine
-            L = _lib.lib()
-            engine._bind(L)
-            bad = int(L.snnflow_window_inexact_count(1))
-            if bad:
-                raise _lib.SnnflowError(f"window engine: {bad} input values were not exactly representable in bfloat16 "
-                                        "(event counts above 256 or fractional values): use the per-step engine")
         if self._graph2 is not None:
             self.reducer(self._grads)
             self._graph2.replay()
+        # The replay rewrote the parameters in place without passing through autograd: bump their version counters so
+        # that everything keyed on them - the cells' packed tensor-core weights (spiking_submodules._packed_weights) -
+        # is rebuilt by the next eager forward() instead of running the weights of an earlier step.
+        torch.autograd.graph.increment_version(self._params)
+        self._replays = getattr(self, "_replays", 0) + 1
+        r = self._runner()
+        if r is not None and self._replays % r.validate_every == 0:
+            # graph replays bypass the engine's per-window input check: poll this runner's sticky flag (the fused
+            # optimizer skipped every update since the flag was raised)
+            r.check_input_flag()
         return self._static_loss

@@ -288,16 +288,13 @@ def test_full_size_window_vs_cpu_oracle(kind, B, R, T):
     splitting the window in two calls changes nothing, and a batch permutation permutes the outputs."""
     from oracle import firenet as ofn
     net = make_net(kind, 32)
-    # lam = sigmoid(leak) is evaluated by torch on the parameter's device: where the CUDA and the CPU sigmoid disagree in
-    # the last bit, a neuron within 1e-7 of threshold may flip (and ~3e8 neuron-steps do contain such neurons), so those
-    # channels get leak = 0 (sigmoid = 0.5 exactly on both sides).  Then every membrane must match bit for bit.
-    with torch.no_grad():
-        kept = 0
-        for l in (net.head, net.G1, net.R1a, net.R1b, net.G2, net.R2a, net.R2b):
-            same = torch.sigmoid(l.leak).cpu() == torch.sigmoid(l.leak.cpu())
-            l.leak.mul_(same.to(l.leak.device).float())
-            kept += int(same.sum())
-        assert kept >= 7 * 32 * 0.7, "most channels should keep their random leak"
+    # lam = sigmoid(leak) is evaluated by torch on the parameter's device, and the CUDA and the CPU sigmoid disagree in the
+    # last bit for ~30 % of the channels (a neuron within 1e-7 of threshold may then flip, and ~3e8 neuron-steps do contain
+    # such neurons): the runner is handed the values the CPU evaluated - what the C-ABI tests do - and every parameter
+    # keeps its random value.  Then every membrane must match bit for bit.
+    cells = (net.head, net.G1, net.R1a, net.R1b, net.G2, net.R2a, net.R2b)
+    lam_cpu = torch.stack([torch.sigmoid(l.leak.detach().cpu()).reshape(-1) for l in cells])
+    theta_cpu = torch.stack([l.thresh.detach().cpu().clamp_min(0.01).reshape(-1) for l in cells])
     params = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
     g = torch.Generator().manual_seed(21)
     cnt = torch.poisson(torch.full((T, B, 2, R, R), 0.06), generator=g)
@@ -307,7 +304,7 @@ def test_full_size_window_vs_cpu_oracle(kind, B, R, T):
         for t in range(T):
             f, states, _ = ofn.forward(params, cnt[t], states)
             flows.append(f)
-        runner_of(net, "layer_major")
+        runner_of(net, "layer_major").param_override = (lam_cpu, theta_cpu)
         net.reset_states()
         got = net.forward_window(cnt.cuda())
         s_got = [s.clone() for s in net._states]
