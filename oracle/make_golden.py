@@ -254,16 +254,41 @@ def train_step_fixture(ref, name, *, C, B, H, W, T, n, seed, default_params=Fals
         flows.append(out["flow"][0])
         lossf.event_flow_association(out["flow"], w["event_list"][t].clone(), w["event_list_pol_mask"][t], w["event_mask"][t])
     loss = lossf()
-    loss.backward()
+    loss.backward(retain_graph=True)
     for k, p in net.named_parameters():
         arrs["grad." + k] = _np(p.grad)
+    gflow = torch.stack([f.grad for f in flows])
+    names = [k for k, _ in net.named_parameters()]
+    plist = [p for _, p in net.named_parameters()]
+    # (a) BPTT alone, on a well-conditioned loss: sum(flow * G), G ~ N(0, 1) regenerated from the seed by the test
+    G = torch.randn(T, B, 2, H, W, generator=torch.Generator().manual_seed(seed + 2))
+    lin = torch.autograd.grad([f for f in flows], plist, grad_outputs=[G[t] for t in range(T)], retain_graph=True)
+    for k, gk in zip(names, lin):
+        arrs["gradlin." + k] = _np(gk)
+    # (b) how well is d loss / d flow defined in fp32?  The same loss arithmetic in float64 (oracle/loss.py restates
+    # loss/flow.py and reproduces it bit for bit in fp32) on the SAME fp32 flow maps gives the exact gradient; pixels
+    # holding ~1e-6 of bilinear weight divide by (count + 1e-9) (loss/flow.py:214-217) and lose every digit in fp32.
+    from .loss import EventWarpingOracle
+    f64 = torch.stack([f.detach() for f in flows]).double().requires_grad_(True)
+    l64 = EventWarpingOracle((H, W), 0.001)
+    for t in range(T):
+        l64.associate(f64[t], w["event_list"][t].clone().double(), w["event_list_pol_mask"][t].double(), w["event_mask"][t].double())
+    loss64 = l64()
+    loss64.backward()
+    g64 = f64.grad
+    arrs["gflow_relerr_fp32"] = np.array([float((gflow[t].double() - g64[t]).norm() / g64[t].norm()) for t in range(T)])
+    # ... and the reference's own (fp32) BPTT applied to that exact loss gradient: the parameter gradients an exact loss
+    # backward would have produced
+    ex = torch.autograd.grad([f for f in flows], plist, grad_outputs=[g64[t].float() for t in range(T)])
+    for k, gk in zip(names, ex):
+        arrs["grad64." + k] = _np(gk)
+    arrs["loss64"] = np.array(float(loss64))
     total = torch.nn.utils.clip_grad.clip_grad_norm_(net.parameters(), clip)
     opt.step()
     for k, p in net.named_parameters():
         arrs["new." + k] = _np(p)
-    gflow = torch.stack([f.grad for f in flows])
     arrs.update(loss=_np(loss), grad_norm=_np(total), flow_last=_np(flows[-1]), gflow_last=_np(gflow[-1]),
-                flow_absmax=np.array([float(f.abs().max()) for f in flows]),
+                flow_absmax=np.array([float(f.detach().abs().max()) for f in flows]),
                 gflow_norm=np.array([float(g.norm()) for g in gflow]),
                 spike_rate=np.array([float(st[1].mean()) for st in net._states]),
                 window_checksum=np.array([float(w["event_cnt"].double().sum()), float(w["event_list"].double().sum()),
