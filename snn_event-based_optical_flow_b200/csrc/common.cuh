@@ -125,6 +125,24 @@ __device__ __forceinline__ void grid_bar_wait(const unsigned int* bar, unsigned 
   }
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// ---- per-tile progress flags of the time-fused recurrent kernels -------------------------------------------------------
+// flag[tile] = number of time bins this launch has finished for the tile (monotonic; zeroed by the launcher).  The
+// epilogue that completes (tile, bin) publishes bin + 1 with release semantics after its plane writes; the TMA producer
+// of a CTA that needs halo rows of that tile for the next bin acquires it.  Point-to-point, so a CTA only ever waits for
+// the tiles it reads - a wavefront through (tile, bin) space with no grid-wide barrier.
+__device__ __forceinline__ void tile_flag_set(unsigned int* flag, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tile_flag_wait(const unsigned int* flag, unsigned int target) {
+  const long long t0 = clock64();
+  while (true) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= target) break;
+    __nanosleep(32);
+    if (clock64() - t0 > 4000000000LL) __trap();   // a protocol bug must not hang the device
+  }
+}
 // coherent 256-bit load (data written earlier by this same launch)
 __device__ __forceinline__ void ldg256_coherent(const float* p, float (&v)[8]) {
   asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

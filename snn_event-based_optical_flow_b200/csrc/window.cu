@@ -59,7 +59,7 @@ static WinLayout win_layout(const snnflow_net_desc* d, int save) {
     L.rb_blob_bytes[l] = L.rec[l] ? (uint32_t)((size_t)9 * 2 * C * C * 2) : 0;
     L.off_rb_blob[l] = take(L.rb_blob_bytes[l]);
     L.off_par[l] = take((size_t)C * 4 * sizeof(float));
-    L.off_gridbar[l] = take(256);   // grid barrier counter of the layer's persistent multi-bin launches
+    L.off_gridbar[l] = take((size_t)B * d->H * sizeof(unsigned int));   // per-tile progress flags of the layer's time-fused launches
   }
   L.total = o;
   return L;
@@ -264,13 +264,12 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
       a.n_src = 2;
       a.src[1] = a.src[0];
       a.src[1].img_stride = L.zp_img_stride; a.src[1].n_chunks = (uint32_t)(C / 8); a.src[1].w_off = L.rec_w_off[l];
-      static const int persistent = wt_env_int("SNNFLOW_FWD_PERSIST", 0);
+      static const int persistent = wt_env_int("SNNFLOW_FWD_PERSIST", 1);
       if (persistent && T > 1) {
-        // ONE cooperative launch walks the T bins: weights, barriers and TMEM stay set up, and a grid barrier between
-        // bins replaces T - 1 launch boundaries (the spike planes of bin t are the recurrent operand of bin t + 1).
-        // Opt-in (SNNFLOW_FWD_PERSIST=1): timed alone a bin costs 17.4 us instead of 22 us, but inside the captured
-        // step the per-bin launches already overlap their set-up with the previous bin's tail (programmatic dependent
-        // launch), and the cooperative launch gives that up: 3.34 ms/step against 3.30 ms/step with per-bin launches.
+        // ONE cooperative launch walks the T bins (time-fused ConvLIFRecurrent): weights, barriers and TMEM stay set up and
+        // the pipeline never drains; the spike planes of bin t are the recurrent operand of bin t + 1, and a tile only
+        // waits for the per-tile progress flags of itself and its two row neighbours (WtArgs.tile_flags).
+        // SNNFLOW_FWD_PERSIST=0 restores one launch per bin.
         a.src[0].planes = xin;
         a.src[1].planes = A + L.off_zp[l];
         a.zin_planes = a.src[1].planes; a.zin_img_stride = L.zp_img_stride;
@@ -283,7 +282,7 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
         a.bin_src_stride[1] = (long long)B * (long long)L.zp_img_stride;
         a.bin_zp_stride = (long long)B * (long long)L.zp_img_stride;
         a.bin_v_stride = (long long)n; a.bin_v_mask = save ? -1 : 1;
-        a.grid_bar = (unsigned int*)(A + L.off_gridbar[l]);
+        a.tile_flags = (unsigned int*)(A + L.off_gridbar[l]);
         rc = launch_wt_fwd(a, false, st, "win_fwd_rec", 4.0 * T * px * (L.Cin[l] + 4 * C),   /* x, v, z in ; v, z out */
                            18.0 * T * px * C * (L.Cin[l] + C));
         if (rc) return rc;

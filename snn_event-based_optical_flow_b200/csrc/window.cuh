@@ -71,16 +71,20 @@ struct WtArgs {
   float* part;                    // [grid][2][N] partial sums of dlam, dtheta
   int t_reverse;                  // sequence mode: walk the bins backwards (t = T-1 .. 0)
   uint32_t acc_lg;                // log2 of the accumulator ring length, 1 or 2 (set by the launcher)
-  // Persistent multi-bin mode of the per-bin (recurrent) kernels: one cooperative launch walks n_bins dependent bins;
-  // the operand planes of bin j are written by the epilogues of bin j-1 (of every CTA: halo rows), so the producers
-  // wait on a grid barrier between bins.  Pointers above describe bin 0; the strides below step them per bin.
+  // Time-fused mode of the per-bin (recurrent) kernels: ONE cooperative launch walks n_bins dependent bins.  The operand
+  // planes of (tile, bin j) are written by the epilogues of bin j-1 of the tile and of its two row neighbours (halo rows),
+  // possibly in other CTAs: the producer acquires their per-tile progress flags (common.cuh: tile_flag_*) before the bulk
+  // copy - a point-to-point wavefront, no grid barrier, and the pipeline never drains between bins.  Pointers above
+  // describe bin 0; the strides below step them per bin.
   int n_bins;                     // <= 1: single bin (plain launch)
   int bin_dep_mask;               // bit i: src[i] of bin j > 0 is produced by bin j-1 of this launch
   long long bin_src_stride[2];    // bytes per bin for src[i].planes
   long long bin_zp_stride;        // bytes per bin for zin_planes / zp_out
   long long bin_v_stride;         // floats per bin for the membrane arena (v_out; v_prev of bin j is v_out of bin j-1)
   int bin_v_mask;                 // membrane slot of bin j = j & bin_v_mask (eval keeps two slots, training all bins)
-  unsigned int* grid_bar;         // zeroed by the launcher
+  unsigned int* tile_flags;       // [n_outer * H / R] progress flags, zeroed by the launcher
+  int exp;                        // experiment switches (SNNFLOW_EXP), 0 in production
+  int l2_prefetch;                // epilogues issue prefetch.global.L2 for the next item's streamed inputs (set by the launcher)
   int has_gz, first_step, z_from_v;   // first_step: g_v starts at zero ; z_from_v: z_in = spike(v_in) else from z_init
   long long* dbg;                 // optional [grid][8] cycle counters (SNNFLOW_WT_TIMING=1): where each role waits
 };

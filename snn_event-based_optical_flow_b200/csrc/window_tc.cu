@@ -28,7 +28,9 @@
 namespace snnflow {
 
 constexpr int WT_EPI_WARPS = 16;   // 4 TMEM lane quarters x 4 eight-channel chunks
-constexpr int WT_THREADS = (WT_EPI_WARPS + 2) * 32;
+constexpr int WT_THREADS = (WT_EPI_WARPS + 3) * 32;   // + TMA producer, MMA issuer, tile-flag publisher (19 warps: still 5 per
+                                                      // scheduler at most, so the register cap per thread is unchanged)
+constexpr int WT_PUB_RING = 8;
 constexpr int WT_MAX_STAGES = 4;
 constexpr int WT_HDR = 4096;   // barriers, TMEM slot, per-channel parameters, reduction scratch
 constexpr int WT_TAIL = 2304;  // the last 128-pixel segment of a row may address up to 128 + 2 slots past its tile: keep
@@ -37,6 +39,8 @@ constexpr int WT_TAIL = 2304;  // the last 128-pixel segment of a row may addres
 struct WtSmem {
   uint64_t *full, *empty, *acc_full, *acc_empty, *wbar;
   uint32_t* tmem_slot;
+  uint64_t* pub_bar;        // [WT_PUB_RING] "every epilogue thread has issued the stores of item g" (time-fused mode)
+  volatile unsigned int* pub_count;   // items whose tile flag the publisher warp has raised
   float4* par;
   float* red;
   unsigned char *w, *stages;
@@ -50,6 +54,8 @@ __device__ __forceinline__ WtSmem wt_smem(unsigned char* smem, uint32_t wblob_by
   s.acc_empty = s.acc_full + 4;
   s.wbar = s.acc_empty + 4;
   s.tmem_slot = reinterpret_cast<uint32_t*>(smem + 192);
+  s.pub_count = reinterpret_cast<volatile unsigned int*>(smem + 208);
+  s.pub_bar = reinterpret_cast<uint64_t*>(smem + 3072);   // behind the reduction scratch (1280 .. 2304)
   s.par = reinterpret_cast<float4*>(smem + 256);
   s.red = reinterpret_cast<float*>(smem + 1280);
   s.w = smem + WT_HDR;
@@ -141,6 +147,8 @@ __device__ __forceinline__ uint32_t wt_prologue(const WtArgs& a, const WtSmem& s
       mbar_init(&s.acc_empty[i], WT_EPI_WARPS * 32);
     }
     mbar_init(s.wbar, 1);
+    for (int i = 0; i < WT_PUB_RING; ++i) mbar_init(&s.pub_bar[i], WT_EPI_WARPS * 32);
+    *s.pub_count = 0u;
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(s.tmem_slot, wt_tmem_cols(a));
@@ -179,21 +187,27 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
   }
   ItemIter<SEQ> it;
   uint32_t st = 0, use = 0;
-  long long t_wait = 0;
+  long long t_wait = 0, t_flag = 0;
   const long long t_begin = clock64();
   const int n_bins = (!SEQ && a.n_bins > 1) ? a.n_bins : 1, dep_mask = a.bin_dep_mask;
   for (int bin = 0; bin < n_bins; ++bin) {
     it.init(a);
-    bool synced = bin == 0;
     for (int k = 0; k < n_items; ++k) {
 #pragma unroll
       for (int si = 0; si < 2; ++si) {
         if (si >= n_src) break;
-        if (!synced && ((dep_mask >> si) & 1)) {   // planes written by every CTA's epilogue of the previous bin
-          if (lane == 0) grid_bar_wait(a.grid_bar, (unsigned int)bin * gridDim.x);
+        if (bin > 0 && ((dep_mask >> si) & 1) && !(a.exp & 2)) {
+          // rows y0-1 .. y0+R of this source were written by the epilogues of bin - 1 of this tile and of its two row
+          // neighbours in the image (other CTAs): lanes 0..2 acquire one progress flag each
+          const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+          const long long t0 = clock64();
+          if (lane < 3) {
+            const bool need = lane == 1 || (lane == 0 && it.y0 > 0) || (lane == 2 && it.y0 + it.R < it.H);
+            if (need) tile_flag_wait(a.tile_flags + tile + lane - 1, (unsigned int)bin);
+          }
           __syncwarp();
           fence_proxy_async_global();
-          synced = true;
+          t_flag += clock64() - t0;
         }
         if (lane == 0) {
           if (use > 0) {
@@ -217,7 +231,7 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
   }
   if (a.dbg && lane == 0) {
     a.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;   // producer: total
-    a.dbg[blockIdx.x * 8 + 1] = t_wait;                 // producer: waiting for a free stage
+    a.dbg[blockIdx.x * 8 + 1] = t_wait + (t_flag << 32);   // producer: waiting for a free stage | for neighbour tiles (high word)
   }
 }
 
@@ -298,6 +312,26 @@ __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
   }
 }
 
+// ---- tile-flag publisher (time-fused recurrent kernels): one thread ----------------------------------------------
+// For every item g of this CTA, in processing order: wait until all epilogue threads have issued the item's stores
+// (pub_bar, release.cta / acquire.cta), make them visible device-wide to the generic AND the async proxy (the readers are
+// other CTAs' bulk copies), raise the tile's progress flag.  Cumulativity of the release carries the epilogue threads'
+// stores; the only memory operations this thread ever has in flight are its own flag stores, so its fences are cheap.
+__device__ void wt_publisher(const WtArgs& a, const WtSmem& s) {
+  const int n_bins = a.n_bins > 1 ? a.n_bins : 1;
+  if (n_bins <= 1 || (a.exp & 2)) return;
+  const int n_items = wt_n_items<false>(a);
+  int g = 0;
+  for (int bin = 0; bin < n_bins; ++bin)
+    for (int k = 0; k < n_items; ++k, ++g) {
+      mbar_wait(&s.pub_bar[g & (WT_PUB_RING - 1)], (uint32_t)(g / WT_PUB_RING) & 1u);
+      fence_proxy_async_global();
+      __threadfence();
+      tile_flag_set(a.tile_flags + ((int)blockIdx.x + k * (int)gridDim.x), (unsigned int)(bin + 1));
+      *s.pub_count = (unsigned int)(g + 1);
+    }
+}
+
 __device__ __forceinline__ uint32_t bf16_pair(uint32_t mask, int i) {
   return (((mask >> (2 * i)) & 1u) ? 0x3F80u : 0u) | (((mask >> (2 * i + 1)) & 1u) ? 0x3F800000u : 0u);
 }
@@ -338,6 +372,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
     __syncwarp();
   } else if (warp == WT_EPI_WARPS + 1) {
     if (elect_one()) wt_mma<SEQ>(a, s, tmem_base);
+    __syncwarp();
+  } else if (warp == WT_EPI_WARPS + 2) {
+    if (!SEQ && lane == 0) wt_publisher(a, s);
     __syncwarp();
   } else {
     pdl_wait();
@@ -453,132 +490,159 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
         }
       }
     } else {
-    float vst[NSEG][8], zst[NSEG][8];   // membrane and spikes entering the bin
-    ItemIter<SEQ> it;
-    const int n_bins = (!SEQ && a.n_bins > 1) ? a.n_bins : 1;
-    const bool multi = n_bins > 1;
-    for (int bin = 0; bin < n_bins; ++bin) {
-    // per-bin views of the planes / membrane arena (bin 0 = the launch arguments)
-    float* const v_out = a.v_out ? a.v_out + (size_t)(bin & a.bin_v_mask) * a.bin_v_stride : nullptr;
-    const float* const v_prev = bin == 0 ? a.v_prev : a.v_out + (size_t)((bin - 1) & a.bin_v_mask) * a.bin_v_stride;
-    const bool v_prev_nchw = bin == 0 && a.v_prev_nchw;
-    unsigned char* const zp_out = a.zp_out + (long long)bin * a.bin_zp_stride + (size_t)ch * plane_bytes;
-    const unsigned char* const zin_planes = a.zin_planes ? a.zin_planes + (long long)bin * a.bin_zp_stride : nullptr;
-    const bool want_last = bin == n_bins - 1 && (a.v_last != nullptr || a.z_last != nullptr);
-    it.init(a);
-    for (int k = 0; k < n_items; ++k) {
-      const int kg = bin * n_items + k;
-      const uint32_t ab = (uint32_t)kg & acc_mask;
-      const bool load_state = SEQ ? (it.t == 0) : true;
-      if (load_state && act) {
+      // Step mode (ConvLIFRecurrent): one item per tile and bin.  The membrane and the spikes entering the bin come from
+      // memory (written by this very thread one bin earlier, or by the previous launch); they are requested ONE ITEM AHEAD,
+      // before the wait for the current accumulator, so their latency hides behind the current item's arithmetic.
+      // Time-fused launches (n_bins > 1) walk all bins of the window and publish a per-tile progress flag after every item.
+      const int n_bins = a.n_bins > 1 ? a.n_bins : 1;
+      const bool multi = n_bins > 1;
+      const int total = n_bins * n_items;
+      const bool ahead_ok = (!multi || n_items >= 2) && !(a.exp & 1);   // else the next item's inputs are this item's outputs
+      const float4* const par = s.par + (act ? ch * 8 : 0);
+      const long long bin_v_stride = a.bin_v_stride, bin_zp_stride = a.bin_zp_stride;
+      const int bin_v_mask = a.bin_v_mask;
+      const size_t zin_img_stride = a.zin_img_stride;
+
+      float vst[NSEG][8], vnx[NSEG][8];
+      uint4 zq[NSEG], znx[NSEG];
+      // inputs of item (b, y0) of bin `bin` -> v, z  (zeros where there is no state)
+      auto request = [&](int b, int y0, int bin, float (&v)[NSEG][8], uint4 (&z)[NSEG]) {
+        const float* v_prev = bin == 0 ? a.v_prev : a.v_out + (size_t)((bin - 1) & bin_v_mask) * bin_v_stride;
+        const bool nchw = bin == 0 && a.v_prev_nchw;
+        const unsigned char* zin = a.zin_planes ? a.zin_planes + (long long)bin * bin_zp_stride : nullptr;
 #pragma unroll
         for (int m = 0; m < NSEG; ++m) {
-          const int y = it.y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
-          const bool ok = x < W;
+          const int y = y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
+          const bool ok = act && x < W;
           const size_t pix = (size_t)y * W + x;
-          const size_t o = ((size_t)(it.b * N + ch * 8)) * HW + pix;   // NCHW (state tensors of the caller)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) vst[m][c] = zst[m][c] = 0.f;
-          if (SEQ) {
-            if (ok && a.v_init) {
+          for (int c = 0; c < 8; ++c) v[m][c] = 0.f;
+          z[m] = make_uint4(0u, 0u, 0u, 0u);
+          if (ok && v_prev) {
+            if (nchw) {
+              const size_t o = ((size_t)(b * N + ch * 8)) * HW + pix;   // the caller's NCHW state tensor
 #pragma unroll
-              for (int c = 0; c < 8; ++c) vst[m][c] = __ldg(a.v_init + o + (size_t)c * HW);
+              for (int c = 0; c < 8; ++c) v[m][c] = __ldg(v_prev + o + (size_t)c * HW);
+            } else if (multi) {
+              ldg256_coherent(v_prev + c8_off(b, nch, ch, HW, pix), v[m]);   // written by this thread one bin ago
+            } else {
+              ld8_c8(v_prev + c8_off(b, nch, ch, HW, pix), v[m]);
             }
-            if (ok && a.z_init) {
+          }
+          if (ok && zin) {
+            const uint4* zsrc = reinterpret_cast<const uint4*>(zin + (size_t)b * zin_img_stride + (size_t)ch * plane_bytes +
+                                                               ((size_t)(y + 1) * Wp + x + 1) * 16);
+            z[m] = multi ? ldg128_coherent(zsrc) : __ldg(zsrc);
+          }
+        }
+      };
+
+      // Time-fused launches: after the stores of an item every epilogue thread arrives on pub_bar[g % 8]; the publisher warp
+      // (wt_publisher) raises the tile's progress flag from there.  The epilogue threads themselves never execute a fence:
+      // a membar / proxy fence waits for the thread's outstanding loads and stores, i.e. for the inputs requested one item
+      // ahead (measured: +1300 cycles per item with the fences here).
+      const bool no_flags = (a.exp & 2) != 0;   // timing experiments only: results are wrong
+      ItemIter<false> it, nx;
+      it.init(a);
+      nx.init(a);
+      int bin = 0, k = 0, nbin = 0, nk = 0;
+      if (total > 0) request(it.b, it.y0, 0, vst, zq);
+      for (int g = 0; g < total; ++g) {
+        // position of the next item, and its inputs on their way
+        const bool have_next = g + 1 < total;
+        if (have_next) {
+          if (++nk == n_items) { nk = 0; ++nbin; nx.init(a); } else nx.next();
+          if (ahead_ok) request(nx.b, nx.y0, nbin, vnx, znx);
+        }
+        const uint32_t ab = (uint32_t)g & acc_mask;
+        const bool last = bin == n_bins - 1 && (a.v_last != nullptr || a.z_last != nullptr);
+        float* const v_out = a.v_out ? a.v_out + (size_t)(bin & bin_v_mask) * bin_v_stride : nullptr;
+        unsigned char* const zp_out = a.zp_out + (long long)bin * bin_zp_stride + (size_t)ch * plane_bytes;
+        {
+          const long long t0 = a.dbg ? clock64() : 0;
+          mbar_wait(&s.acc_full[ab], (uint32_t)(g >> acc_lg) & 1u);
+          if (a.dbg) t_wait += clock64() - t0;
+        }
+        tc_fence_after();
+        uint4 zz[NSEG];   // the new spikes as packed bf16 ({0, 1} are exact: one packed convert per channel pair)
+        if (act) {
+          uint32_t u0[NSEG][8], u1[NSEG][8], u2[NSEG][8];
 #pragma unroll
-              for (int c = 0; c < 8; ++c) zst[m][c] = __ldg(a.z_init + o + (size_t)c * HW);   // {0, 1}: no dependent op before the wait
+          for (int m = 0; m < NSEG; ++m) {
+            const uint32_t tcol = tmem_base + t_lane + ab * acc_cols + (uint32_t)m * ncat + (uint32_t)(ch * 8);
+            tmem_ld8_async(tcol, u0[m]);
+            tmem_ld8_async(tcol + (uint32_t)N, u1[m]);
+            tmem_ld8_async(tcol + 2u * (uint32_t)N, u2[m]);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int m = 0; m < NSEG; ++m) {
+            const uint32_t zw[4] = {zq[m].x, zq[m].y, zq[m].z, zq[m].w};
+            float zn[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 pr = par[c];   // (lam, 1 - lam, theta, .): broadcast read, keeps 24 registers free
+              const float zin_c = ((zw[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu) ? 1.f : 0.f;
+              const float cur = (__uint_as_float(u0[m][c]) + __uint_as_float(u1[m][c])) + __uint_as_float(u2[m][c]);   // hi + mid + lo terms
+              const float t1 = __fmul_rn(vst[m][c], pr.x), t3 = __fmul_rn(pr.y, cur);
+              float vn;
+              if (HARD) vn = __fadd_rn(__fmul_rn(t1, __fsub_rn(1.0f, zin_c)), t3);    // spiking_submodules.py:144
+              else vn = __fsub_rn(__fadd_rn(t1, t3), __fmul_rn(zin_c, pr.z));         // spiking_submodules.py:146
+              vst[m][c] = vn;
+              zn[c] = __fsub_rn(vn, pr.z) > 0.f ? 1.f : 0.f;                          // spiking_util.py:21
+            }
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz[m].x) : "f"(zn[1]), "f"(zn[0]));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz[m].y) : "f"(zn[3]), "f"(zn[2]));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz[m].z) : "f"(zn[5]), "f"(zn[4]));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz[m].w) : "f"(zn[7]), "f"(zn[6]));
+          }
+        }
+        if (act) {
+#pragma unroll
+          for (int m = 0; m < NSEG; ++m) {
+            const int y = it.y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
+            if (x < W) {
+              const size_t pix = (size_t)y * W + x;
+              *reinterpret_cast<uint4*>(zp_out + (size_t)it.img * zp_img_stride + ((size_t)(y + 1) * Wp + x + 1) * 16) = zz[m];
+              if (v_out) st8_c8(v_out + c8_off(it.img, nch, ch, HW, pix), vst[m]);
+              if (last) {   // the caller-visible state [2,B,C,H,W] after the window
+                const size_t o = ((size_t)(it.b * N + ch * 8)) * HW + pix;
+                if (a.v_last) {
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) a.v_last[o + (size_t)c * HW] = vst[m][c];
+                }
+                if (a.z_last) {
+                  const uint32_t zw[4] = {zz[m].x, zz[m].y, zz[m].z, zz[m].w};
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) a.z_last[o + (size_t)c * HW] = ((zw[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu) ? 1.f : 0.f;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&s.acc_empty[ab]);
+        if (multi && !no_flags) {
+          // back-pressure: the ring slot of item g was last used by item g - 8, which the publisher must have consumed
+          if (tid == 0 && g >= WT_PUB_RING) {
+            while (*s.pub_count < (unsigned int)(g - WT_PUB_RING + 1)) __nanosleep(20);
+          }
+          mbar_arrive(&s.pub_bar[g & (WT_PUB_RING - 1)]);   // release.cta: orders this thread's plane / membrane stores
+        }
+        if (have_next) {
+          if (ahead_ok) {
+#pragma unroll
+            for (int m = 0; m < NSEG; ++m) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) vst[m][c] = vnx[m][c];
+              zq[m] = znx[m];
             }
           } else {
-            if (ok && v_prev) {
-              if (v_prev_nchw) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) vst[m][c] = __ldg(v_prev + o + (size_t)c * HW);
-              } else if (multi) {
-                ldg256_coherent(v_prev + c8_off(it.b, nch, ch, HW, pix), vst[m]);   // written by this thread one bin ago
-              } else {
-                ld8_c8(v_prev + c8_off(it.b, nch, ch, HW, pix), vst[m]);
-              }
-            }
-            if (ok && zin_planes) {
-              const uint4* zsrc = reinterpret_cast<const uint4*>(zin_planes + (size_t)it.b * a.zin_img_stride + (size_t)ch * plane_bytes +
-                                                                 ((size_t)(y + 1) * Wp + x + 1) * 16);
-              const uint4 zz = multi ? ldg128_coherent(zsrc) : __ldg(zsrc);
-              const uint32_t w4[4] = {zz.x, zz.y, zz.z, zz.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                zst[m][2 * i] = (w4[i] & 0xFFFFu) ? 1.f : 0.f;
-                zst[m][2 * i + 1] = (w4[i] >> 16) ? 1.f : 0.f;
-              }
-            }
+            request(nx.b, nx.y0, nbin, vst, zq);
           }
         }
+        it = nx; bin = nbin; k = nk;
       }
-      const bool last = (SEQ ? (it.t == T - 1) : true) && want_last;
-      {
-        const long long t0 = clock64();
-        mbar_wait(&s.acc_full[ab], (uint32_t)(kg >> acc_lg) & 1u);
-        t_wait += clock64() - t0;
-      }
-      tc_fence_after();
-      if (act) {
-        uint32_t u0[NSEG][8], u1[NSEG][8], u2[NSEG][8];
-#pragma unroll
-        for (int m = 0; m < NSEG; ++m) {
-          const uint32_t tcol = tmem_base + t_lane + ab * acc_cols + (uint32_t)m * ncat + (uint32_t)(ch * 8);
-          tmem_ld8_async(tcol, u0[m]);
-          tmem_ld8_async(tcol + (uint32_t)N, u1[m]);
-          tmem_ld8_async(tcol + 2u * (uint32_t)N, u2[m]);
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int m = 0; m < NSEG; ++m) {
-          const int y = it.y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
-          const bool ok = x < W;
-          const size_t pix = (size_t)y * W + x;
-          float cur[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            cur[c] = (__uint_as_float(u0[m][c]) + __uint_as_float(u1[m][c])) + __uint_as_float(u2[m][c]);   // hi + mid + lo terms
-            const float t1 = __fmul_rn(vst[m][c], lam[c]), t3 = __fmul_rn(oml[c], cur[c]);
-            float vn;
-            if (HARD) vn = __fadd_rn(__fmul_rn(t1, __fsub_rn(1.0f, zst[m][c])), t3);    // spiking_submodules.py:144
-            else vn = __fsub_rn(__fadd_rn(t1, t3), __fmul_rn(zst[m][c], th[c]));         // spiking_submodules.py:146
-            vst[m][c] = vn;
-            zst[m][c] = __fsub_rn(vn, th[c]) > 0.f ? 1.f : 0.f;                          // spiking_util.py:21
-          }
-          if (ok) {
-            uint4 zz;   // {0, 1} are exact in bf16: one packed convert per channel pair
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz.x) : "f"(zst[m][1]), "f"(zst[m][0]));
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz.y) : "f"(zst[m][3]), "f"(zst[m][2]));
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz.z) : "f"(zst[m][5]), "f"(zst[m][4]));
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz.w) : "f"(zst[m][7]), "f"(zst[m][6]));
-            *reinterpret_cast<uint4*>(zp_out + (size_t)it.img * zp_img_stride + ((size_t)(y + 1) * Wp + x + 1) * 16) = zz;
-            if (v_out) st8_c8(v_out + c8_off(it.img, nch, ch, HW, pix), vst[m]);
-            if (cur_out) st8_c8(cur_out + c8_off(it.img, nch, ch, HW, pix), cur);
-            if (last) {   // the caller-visible state [2,B,C,H,W] after the window
-              const size_t o = ((size_t)(it.b * N + ch * 8)) * HW + pix;
-              if (a.v_last) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) a.v_last[o + (size_t)c * HW] = vst[m][c];
-              }
-              if (a.z_last) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) a.z_last[o + (size_t)c * HW] = zst[m][c];
-              }
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&s.acc_empty[ab]);
-      it.next();
-    }
-    if (bin + 1 < n_bins) {   // publish this CTA's spike planes of the bin to the other CTAs' producers
-      fence_proxy_async_global();
-      asm volatile("bar.sync 1, %0;" ::"n"(WT_EPI_WARPS * 32) : "memory");
-      if (tid == 0) grid_bar_arrive(a.grid_bar);
-    }
-    }
     }
     if (a.dbg && tid == 0) {
       a.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin;   // epilogue warp 0: total
@@ -604,6 +668,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgrad_kernel(const __grid_co
   } else if (warp == WT_EPI_WARPS + 1) {
     if (elect_one()) wt_mma<false>(a, s, tmem_base);
     __syncwarp();
+  } else if (warp >= WT_EPI_WARPS + 2) {
+    // (the publisher warp has no work in this kernel)
   } else {
     pdl_wait();
     const int q = warp & 3, ch = warp >> 2;
@@ -698,6 +764,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
   } else if (warp == WT_EPI_WARPS + 1) {
     if (a.has_gz && elect_one()) wt_mma<false>(a, s, tmem_base);
     __syncwarp();
+  } else if (warp >= WT_EPI_WARPS + 2) {
+    // (the publisher warp has no work in this kernel)
   } else {
     pdl_wait();
     const int q = warp & 3, ch = warp >> 2;
@@ -712,6 +780,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
     const int n_sub = wt_n_items<false>(a) * n_mt;   // 128-pixel segments this CTA processes, in order
     const float width = a.width;
     const float *g_out = a.g_out, *v_t = a.v_t, *v_in = a.v_in;
+    const bool l2_pf = a.l2_prefetch != 0;
     float* g_v = a.g_v;
     unsigned char* gp_out = a.gp_out;
     const size_t gp_img_stride = a.gp_img_stride, gp_term_stride = a.gp_term_stride;
@@ -735,6 +804,17 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
       float go[8], vt[8], vin[8], gv[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) go[c] = vt[c] = vin[c] = gv[c] = 0.f;
+      if (l2_pf && act && j + 1 < n_sub) {   // the next segment's streams (DRAM -> L2) while this one is processed
+        SegIter nxs = cur;
+        nxs.next();
+        const int xn = nxs.seg * 128 + q * 32 + lane;
+        if (xn < W) {
+          const size_t con = c8_off(nxs.b, nch, ch, HW, (size_t)(nxs.y0 + nxs.r) * W + xn);
+          prefetch_l2(g_out + con);
+          prefetch_l2(v_t + con);
+          if (!BIN0) prefetch_l2(v_in + con);
+        }
+      }
       if (act && ok) {
         ld8_c8(g_out + co, go);
         ld8_c8(v_t + co, vt);
@@ -843,9 +923,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
 //              carry = gv * lam * (1 - z_in)  (hard reset) / gv * lam  (soft)  stays in registers across the bins,
 //              d lam / d theta partial sums as in pw_seq_kernel.
 // The spike gradient g_out of layer l ([T*B,C,H,W] fp32) is never written to or read from memory.
-// Measured (B200, C=32, 128x128, B=8, T=10): this plain epilogue (v[t-1] loaded at the top of the item, one division-free
-// iterator) runs in 141 us; a variant with running pointers and a register prefetch of v[t-2] executed 26 % fewer
-// instructions but spilled 180 B per thread and took 161 us - the epilogue is latency bound, not issue bound.
+// Measured (B200, C=32, 128x128, B=8, T=10): this plain epilogue (v[t-1] requested at the top of the item that consumes it)
+// runs in 143 us.  Requesting the membranes one item ahead - a rolling window v[t], v[t-1], v[t-2] in registers with running
+// pointers - was tried twice (round 1: 161 us, 180 B of spills; round 2: 178 us, 48 B of spills): slower both times, so the
+// exposed load is not what bounds this epilogue (profiles/r2_dgpw_source.md has the per-instruction stall picture).
 // =================================================================================================
 template <int SG, bool HARD, int NSEG>
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_constant__ WtArgs a) {
@@ -859,6 +940,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
   } else if (warp == WT_EPI_WARPS + 1) {
     if (elect_one()) wt_mma<true>(a, s, tmem_base);
     __syncwarp();
+  } else if (warp >= WT_EPI_WARPS + 2) {
+    // (the publisher warp has no work in this kernel)
   } else {
     pdl_wait();
 
@@ -872,6 +955,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
     const int n_items = wt_n_items<true>(a);
     const float width = a.width;
     const float* const v = a.v_t;          // membranes of layer l, all bins (c8)
+    const bool l2_pf = a.l2_prefetch != 0;
     unsigned char* const gp_out = a.gp_out + (size_t)ch * plane_bytes;
     const size_t gp_img_stride = a.gp_img_stride, gp_term_stride = a.gp_term_stride;
     const float4* par = s.par + (act ? ch * 8 : 0);
@@ -900,6 +984,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
           if (ok) ld8_c8(v + c8_off(img, nch, ch, HW, pix), v_cur[m]);
         }
         if (ok) {
+          // the membrane the NEXT item will ask for (v[t-2]) starts its way from DRAM to L2 now
+          if (l2_pf && t > 1) prefetch_l2(v + c8_off(img - 2 * B, nch, ch, HW, pix));
           if (t > 0) {
             ld8_c8(v + c8_off(img - B, nch, ch, HW, pix), vin[m]);
           } else {
@@ -1054,6 +1140,10 @@ static int wt_launch(K kernel, const void* key, const WtArgs& a_in, cudaStream_t
     have = smem;
   }
   WtArgs a = a_in;
+  static const int l2_pf = env_int("SNNFLOW_L2_PREFETCH", 1);
+  a.l2_prefetch = l2_pf;
+  static const int exp_bits = env_int("SNNFLOW_EXP", 0);   // experiment switches (see wt_fwd_kernel); 0 in production
+  a.exp = exp_bits;
   const int n_tiles = a.n_outer * (a.H / a.R);
   {   // accumulator ring: as many buffers (2 or 4) as the 512 TMEM columns hold
     const uint32_t acc_cols = (uint32_t)(a.R * a.n_seg * a.N) * a.src[0].w_terms;
@@ -1067,7 +1157,7 @@ static int wt_launch(K kernel, const void* key, const WtArgs& a_in, cudaStream_t
     cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * grid, st);
     WtArgs b = a;
     b.dbg = dbg;
-    if (b.n_bins > 1) cudaMemsetAsync(b.grid_bar, 0, sizeof(unsigned int), st);
+    if (b.n_bins > 1) cudaMemsetAsync(b.tile_flags, 0, sizeof(unsigned int) * (size_t)n_tiles, st);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -1088,9 +1178,9 @@ static int wt_launch(K kernel, const void* key, const WtArgs& a_in, cudaStream_t
             what, a.R, a.S, a.n_src, a.N, (double)n_tiles * (a.T > 1 ? a.T : 1) / grid, avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7], ev_ms * 1e3);
     return check_launch(what);
   }
-  if (a.n_bins > 1) {   // persistent over the bins: every CTA must be resident (grid barrier between bins)
-    SNNFLOW_REQUIRE(a.grid_bar != nullptr, "multi-bin launch without a grid barrier counter");
-    SNNFLOW_CUDA(cudaMemsetAsync(a.grid_bar, 0, sizeof(unsigned int), st));
+  if (a.n_bins > 1) {   // time-fused over the bins: CTAs wait for each other's tiles, so every CTA must be resident
+    SNNFLOW_REQUIRE(a.tile_flags != nullptr, "multi-bin launch without tile progress flags");
+    SNNFLOW_CUDA(cudaMemsetAsync(a.tile_flags, 0, sizeof(unsigned int) * (size_t)n_tiles, st));
     static const int coop = env_int("SNNFLOW_COOP", 1);
     if (coop) SNNFLOW_CUDA(launch_coop(kernel, dim3(wt_grid(n_tiles)), dim3(WT_THREADS), smem, st, a));
     else SNNFLOW_CUDA(launch_pdl(kernel, dim3(wt_grid(n_tiles)), dim3(WT_THREADS), smem, st, a));

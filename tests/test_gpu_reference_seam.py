@@ -20,6 +20,17 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not ref_shim.reference_available(), reason="reference not staged (oracle/stage_reference.py)")]
 
 
+@pytest.fixture(autouse=True)
+def _fp32_reference_ops():
+    """The reference's own torch ops on the GPU (its ConvLayer flow head runs through cuDNN) default to TF32, which is not
+    the fp32 arithmetic the CPU gold runs (gold device = CPU fp32, or CUDA with TF32 off)."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def _cuda_cells():
     import snnflow_b200 as snnflow
     return snnflow.ConvLIF, snnflow.ConvLIFRecurrent
