@@ -71,6 +71,12 @@ struct WinPlan {   // tile plans of the tensor-core kernels for this shape
   bool ok;
 };
 
+// SNNFLOW_RB_FUSE=0: the data gradient through W_ff of the layer above a recurrent layer runs as its own launch again
+static bool win_fuse_dgrad() {
+  static const int v = wt_env_int("SNNFLOW_RB_FUSE", 1);
+  return v != 0;
+}
+
 static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool backward = true) {
   WinPlan P{};
   const int C = d->C;
@@ -88,7 +94,8 @@ static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool back
   if (any_rec) {
     // two-row tiles when they fit (measured faster than one-row tiles at 128x128); SNNFLOW_RB_R overrides
     const int rb_R = wt_env_int("SNNFLOW_RB_R", 0);
-    const uint32_t rb_blob = (uint32_t)((size_t)9 * 2 * C * C * 2);
+    // (the fused kernel also stages the data-gradient weights of the layer above: two blobs of this size)
+    const uint32_t rb_blob = (uint32_t)((size_t)9 * 2 * C * C * 2) * (win_fuse_dgrad() ? 2u : 1u);
     bool have = false;
     if (rb_R == 0 || rb_R == 2)
       have = wt_plan(d->H, d->W, C / 8, C, rb_blob, false, 2, false, &P.R_rb, &P.S_rb, &P.sub_rb, &P.cs_rb, &P.st_rb, 2);
@@ -367,31 +374,80 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
     float* cpart = (float*)(Wk + WS.off_cpart[l]);
     if (L.rec[l]) {
       WtArgs a{};
-      // hi planes x (w_hi, w_lo), then lo planes x w_hi: two pipeline units per tile
-      a.src[0].img_stride = L.zp_img_stride; a.src[0].n_chunks = (uint32_t)(C / 8);
-      a.src[0].w_off = 0; a.src[0].w_terms = 2; a.src[0].w_used = 2;
-      a.src[1] = a.src[0]; a.src[1].w_used = 1;
-      a.n_src = 2;
-      a.wblob = A + L.off_rb_blob[l]; a.wblob_bytes = L.rb_blob_bytes[l];
+      // Recurrent BPTT step t, one launch per bin.  Tensor cores: g_z = conv^T(g_I[t+1], W_rec) (hi planes x (w_hi, w_lo),
+      // then lo planes x w_hi: two pipeline units per tile) and - fused, when there is a layer above - the spike gradient
+      // coming down through that layer's W_ff, g_out[t] = conv^T(g_I^{l+1}[t], W_ff^{l+1}) (two more units into the SAME
+      // accumulator), so that g_out [T*B,C,H,W] is never written or read and the separate data-gradient launch is gone.
+      const bool fuse = win_fuse_dgrad() && l < top;
+      WtSrc rec_hi{}, rec_lo{};
+      rec_hi.img_stride = L.zp_img_stride; rec_hi.n_chunks = (uint32_t)(C / 8);
+      rec_hi.w_off = fuse ? L.dg_blob_bytes[l + 1] : 0; rec_hi.w_terms = 2; rec_hi.w_used = 2;
+      rec_lo = rec_hi; rec_lo.w_used = 1;
+      if (fuse) {
+        a.src[0] = rec_hi; a.src[0].w_off = 0;            // g_I planes of layer l + 1 (hi ; lo), weights: its data-gradient blob
+        a.src[1] = rec_lo; a.src[1].w_off = 0;
+        a.wblob = A + L.off_dg_blob[l + 1]; a.wblob_bytes = L.dg_blob_bytes[l + 1];
+        a.wblob2 = A + L.off_rb_blob[l]; a.wblob2_bytes = L.rb_blob_bytes[l];
+      } else {
+        a.wblob = A + L.off_rb_blob[l]; a.wblob_bytes = L.rb_blob_bytes[l];
+      }
       a.n_outer = B; a.T = 1; a.B = B; a.H = H; a.W = W; a.Wp = W + 2; a.n_seg = ceil_div(W, 128); a.N = C;
       a.R = P.R_rb; a.S = P.S_rb; a.sub_bytes = P.sub_rb; a.chunk_stride = P.cs_rb; a.stage_bytes = P.st_rb;
       a.hard_reset = hard; a.surrogate = d->surrogate; a.width = d->act_width;
       a.par = par;
       a.g_v = g_v; a.gp_img_stride = L.zp_img_stride; a.gp_term_stride = WS.gp_term_stride;
-      for (int t = T - 1; t >= 0; --t) {
-        a.has_gz = t < T - 1; a.first_step = t == T - 1;
-        a.src[0].planes = gp + (size_t)(t + 1) * B * L.zp_img_stride;
+      const unsigned char* gp_above = gplanes[(l + 1) & 1];
+      static const int rb_persist = wt_env_int("SNNFLOW_RB_PERSIST", 1);
+      const bool fused_time = fuse && rb_persist && T > 1;
+      if (fused_time) {
+        // ONE cooperative launch walks the window backwards (bin j of the launch = time bin T-1-j): weights, barriers and
+        // TMEM stay set up, d lam / d theta partial sums stay in registers over all bins, and the g_I planes a tile needs
+        // for its next bin are awaited through per-tile progress flags (WtArgs.tile_flags) instead of a launch boundary.
+        const long long bin_planes = (long long)B * (long long)L.zp_img_stride;
+        a.src[0].planes = gp_above + (size_t)(T - 1) * B * L.zp_img_stride;
         a.src[1].planes = a.src[0].planes + WS.gp_term_stride;
-        a.g_out = gbuf + (size_t)t * n; a.v_t = vbase + (size_t)t * n;
+        a.src[2] = rec_hi; a.src[3] = rec_lo;
+        a.src[2].planes = gp + (size_t)T * B * L.zp_img_stride;   // bin j reads the planes of t + 1 = T - j (bin 0: unused)
+        a.src[3].planes = a.src[2].planes + WS.gp_term_stride;
+        a.n_src = 4; a.n_src_bin0 = 2; a.has_gz = 1;
+        a.n_bins = T; a.bin_dep_mask = 0xC;
+        for (int i = 0; i < 4; ++i) a.bin_src_stride[i] = -bin_planes;
+        a.gp_out = gp + (size_t)(T - 1) * B * L.zp_img_stride; a.bin_zp_stride = -bin_planes;
+        a.g_out = nullptr;
+        a.v_t = vbase + (size_t)(T - 1) * n; a.v_in = vbase + (size_t)(T - 2) * n; a.bin_v_stride = -(long long)n;
+        a.v_init = v_init; a.z_init = z_init; a.z_from_v = 1;
+        a.part = cpart;
+        a.tile_flags = (unsigned int*)(const_cast<unsigned char*>(A) + L.off_gridbar[l]);   // scratch shared with the forward launch
+        rc = launch_wt_recbwd(a, st, 4.0 * T * px * C * 6, 18.0 * px * C * C * (2 * T - 1));
+        if (rc) return rc;
+      } else
+      for (int t = T - 1; t >= 0; --t) {
+        const bool have_rec = t < T - 1;
+        a.first_step = t == T - 1;
+        int ns = 0;
+        if (fuse) {
+          a.src[0].planes = gp_above + (size_t)t * B * L.zp_img_stride;
+          a.src[1].planes = a.src[0].planes + WS.gp_term_stride;
+          ns = 2;
+        }
+        if (have_rec) {
+          a.src[ns] = rec_hi; a.src[ns + 1] = rec_lo;
+          a.src[ns].planes = gp + (size_t)(t + 1) * B * L.zp_img_stride;
+          a.src[ns + 1].planes = a.src[ns].planes + WS.gp_term_stride;
+          ns += 2;
+        }
+        a.n_src = ns; a.has_gz = ns > 0;
+        a.g_out = fuse ? nullptr : gbuf + (size_t)t * n; a.v_t = vbase + (size_t)t * n;
         a.v_in = t > 0 ? vbase + (size_t)(t - 1) * n : v_init;
         a.v_in_nchw = t == 0;
         a.z_from_v = t > 0; a.z_init = z_init;
         a.gp_out = gp + (size_t)t * B * L.zp_img_stride;
         a.part = cpart + (size_t)t * WS.rb_grid * 2 * C;
-        rc = launch_wt_recbwd(a, st, 4.0 * px * C * (a.has_gz ? 7 : 6), a.has_gz ? 18.0 * px * C * C : 0.0);
+        rc = launch_wt_recbwd(a, st, 4.0 * px * C * (fuse ? 5 : (have_rec ? 7 : 6)) + (fuse ? 4.0 * px * C : 0.0),
+                              18.0 * px * C * C * (ns / 2));
         if (rc) return rc;
       }
-      n_cpart = T * WS.rb_grid; cpart_layout = 1;
+      n_cpart = (fused_time ? 1 : T) * WS.rb_grid; cpart_layout = 1;
     } else if (l == top) {
       PwSeqArgs a{};
       a.v = vbase; a.g_out = fuse_head ? nullptr : gbuf; a.v_init = v_init; a.z_init = z_init; a.par = par;
@@ -458,7 +514,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
         rc = launch_wt_dgpw(a, st, 4.0 * T * px * (C + 3 * L.Kin[l]) /* g_I in ; v (x2), g_I out */, 18.0 * T * px * C * L.Kin[l]);
         if (rc) return rc;
         n_cpart = WS.dp_grid; cpart_layout = 1;
-      } else {
+      } else if (!win_fuse_dgrad()) {   // (fused into the recurrent layer's own BPTT launches otherwise, see above)
         a.n_outer = T * B; a.T = 1;
         a.R = P.R_dg; a.S = P.S_dg; a.sub_bytes = P.sub_dg; a.chunk_stride = P.cs_dg; a.stage_bytes = P.st_dg;
         a.g_x = gbuf;

@@ -38,11 +38,16 @@ struct WtSrc {
                                      // {hi, lo}, lo planes x {hi})
 };
 
+constexpr int WT_MAX_SRC = 4;
+
 struct WtArgs {
-  WtSrc src[2];
+  WtSrc src[WT_MAX_SRC];
   int n_src;
-  const unsigned char* wblob;
-  uint32_t wblob_bytes;
+  int n_src_bin0;                 // time-fused launches: sources of the first bin (0: n_src); later bins use all n_src
+  const unsigned char* wblob;     // weight images, staged once per CTA; a second blob (wblob2) is placed right behind the
+  uint32_t wblob_bytes;           // first in shared memory (WtSrc.w_off of its sources counts from the start of the first)
+  const unsigned char* wblob2;
+  uint32_t wblob2_bytes;
   int n_outer;   // sequence mode: B sequences (image = t*B + b) ; otherwise the number of images
   int T, B;
   int H, W, Wp, R, S, n_seg, N;   // R rows per tile, S pipeline stages, n_seg 128-pixel segments per row, N = MMA N
@@ -78,7 +83,7 @@ struct WtArgs {
   // describe bin 0; the strides below step them per bin.
   int n_bins;                     // <= 1: single bin (plain launch)
   int bin_dep_mask;               // bit i: src[i] of bin j > 0 is produced by bin j-1 of this launch
-  long long bin_src_stride[2];    // bytes per bin for src[i].planes
+  long long bin_src_stride[WT_MAX_SRC];   // bytes per bin for src[i].planes
   long long bin_zp_stride;        // bytes per bin for zin_planes / zp_out
   long long bin_v_stride;         // floats per bin for the membrane arena (v_out; v_prev of bin j is v_out of bin j-1)
   int bin_v_mask;                 // membrane slot of bin j = j & bin_v_mask (eval keeps two slots, training all bins)

@@ -46,7 +46,7 @@ struct WtSmem {
   unsigned char *w, *stages;
 };
 
-__device__ __forceinline__ WtSmem wt_smem(unsigned char* smem, uint32_t wblob_bytes) {
+__device__ __forceinline__ WtSmem wt_smem(unsigned char* smem, uint32_t wblob_bytes /* both blobs */) {
   WtSmem s;
   s.full = reinterpret_cast<uint64_t*>(smem);
   s.empty = s.full + WT_MAX_STAGES;
@@ -166,8 +166,9 @@ template <bool SEQ>
 __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
   const int lane = threadIdx.x & 31;
   if (lane == 0 && a.wblob_bytes) {
-    mbar_expect_tx(s.wbar, a.wblob_bytes);
+    mbar_expect_tx(s.wbar, a.wblob_bytes + a.wblob2_bytes);
     tma_bulk_g2s(s.w, a.wblob, a.wblob_bytes, s.wbar);
+    if (a.wblob2_bytes) tma_bulk_g2s(s.w + a.wblob_bytes, a.wblob2, a.wblob2_bytes, s.wbar);
   }
   pdl_wait();   // the planes are written by the preceding launches (the weights were packed at the start of the pass)
   const int n_items = wt_n_items<SEQ>(a), n_src = a.n_src, S = a.S;
@@ -175,11 +176,11 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
   const uint32_t sub_bytes = a.sub_bytes, chunk_stride = a.chunk_stride, stage_bytes = a.stage_bytes;
   const bool t_rev = a.t_reverse != 0;
   // this lane's chunk of either source
-  const unsigned char* base[2];
-  size_t img_stride[2];
-  uint32_t n_chunks[2];
+  const unsigned char* base[WT_MAX_SRC];
+  size_t img_stride[WT_MAX_SRC];
+  uint32_t n_chunks[WT_MAX_SRC];
 #pragma unroll
-  for (int si = 0; si < 2; ++si) {
+  for (int si = 0; si < WT_MAX_SRC; ++si) {
     const WtSrc& Sr = a.src[si < n_src ? si : 0];
     base[si] = Sr.planes + (size_t)lane * plane_bytes;
     img_stride[si] = Sr.img_stride;
@@ -192,10 +193,11 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
   const int n_bins = (!SEQ && a.n_bins > 1) ? a.n_bins : 1, dep_mask = a.bin_dep_mask;
   for (int bin = 0; bin < n_bins; ++bin) {
     it.init(a);
+    const int n_src_b = (bin == 0 && a.n_src_bin0 > 0) ? a.n_src_bin0 : n_src;
     for (int k = 0; k < n_items; ++k) {
 #pragma unroll
-      for (int si = 0; si < 2; ++si) {
-        if (si >= n_src) break;
+      for (int si = 0; si < WT_MAX_SRC; ++si) {
+        if (si >= n_src_b) break;
         if (bin > 0 && ((dep_mask >> si) & 1) && !(a.exp & 2)) {
           // rows y0-1 .. y0+R of this source were written by the epilogues of bin - 1 of this tile and of its two row
           // neighbours in the image (other CTAs): lanes 0..2 acquire one progress flag each
@@ -236,7 +238,7 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
 }
 
 // ---- MMA issuer: one thread ----------------------------------------------------------------------------------
-template <bool SEQ>
+template <bool SEQ, int NS = 2>
 __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
   const int n_items = wt_n_items<SEQ>(a) * ((!SEQ && a.n_bins > 1) ? a.n_bins : 1);
   if (n_items == 0) return;
@@ -250,28 +252,35 @@ __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
   // The issuing thread shares its scheduler with four epilogue warps, so the per-MMA instruction count matters more
   // than anything else here: every descriptor low word is precomputed (18 = 9 taps x 2 k-steps per source), and one
   // integer add per MMA rebases the A descriptor onto the current stage / segment.
-  uint32_t aoff[9][2], bdesc[2][9][2], idesc[2], n_kk[2];
+  // Kernels with up to two sources keep all 36 B descriptor words in registers; the four-source kernel (fused recurrent
+  // backward) rebuilds them with one multiply-add per tap (a 72-word table would spill in this thread).
+  uint32_t aoff[9][2], bdesc[NS <= 2 ? 2 : 1][9][2], idesc[NS], n_kk[NS], bbase[NS], tile16[NS];
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) aoff[tap][kk] = a_lo_c | ((uint32_t)((tap / 3) * a.Wp + tap % 3) + 2u * kk * cs16);
 #pragma unroll
-  for (int si = 0; si < 2; ++si) {
+  for (int si = 0; si < NS; ++si) {
     const WtSrc& S = a.src[si < a.n_src ? si : 0];
-    const uint32_t tile16 = (S.n_chunks * 8u * ncat * 2u) >> 4;   // one tap of this source's weights
+    tile16[si] = (S.n_chunks * 8u * ncat * 2u) >> 4;   // one tap of this source's weights
     idesc[si] = make_idesc(128, (int)(S.w_used * (uint32_t)a.N), /*bf16*/ 1, 0, 0);
     n_kk[si] = S.n_chunks >> 1;
+    bbase[si] = b_lo_c | (w16 + (S.w_off >> 4));
+    if (NS <= 2) {
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap)
+      for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) bdesc[si][tap][kk] = b_lo_c | (w16 + (S.w_off >> 4) + (uint32_t)tap * tile16 + 2u * kk * blbo16);
+        for (int kk = 0; kk < 2; ++kk) bdesc[si][tap][kk] = bbase[si] + (uint32_t)tap * tile16[si] + 2u * kk * blbo16;
+    }
   }
   uint32_t st = 0, use = 0;
   const uint32_t n_stages = (uint32_t)a.S, acc_lg = a.acc_lg, acc_mask = (1u << acc_lg) - 1u;
   long long t_full = 0, t_acc = 0;
   const long long t_begin = clock64();
+  const int items_bin0 = a.n_src_bin0 > 0 ? wt_n_items<SEQ>(a) : 0;   // items whose source list is the first bin's
   for (int k = 0; k < n_items; ++k) {
     const uint32_t ab = (uint32_t)k & acc_mask;
+    const int n_src_k = k < items_bin0 ? a.n_src_bin0 : a.n_src;
     if (k > (int)acc_mask) {
       const long long t0 = clock64();
       mbar_wait(&s.acc_empty[ab], (uint32_t)((k >> acc_lg) - 1) & 1u);
@@ -279,8 +288,8 @@ __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
     }
     tc_fence_after();
 #pragma unroll
-    for (int si = 0; si < 2; ++si) {
-      if (si >= a.n_src) break;
+    for (int si = 0; si < NS; ++si) {
+      if (si >= n_src_k) break;
       {
         const long long t0 = clock64();
         mbar_wait(&s.full[st], use & 1);
@@ -293,8 +302,10 @@ __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
       for (int m = 0; m < n_mt; ++m) {
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          umma_f16_split(d, aoff[tap][0] + a_base, d_hi, bdesc[si][tap][0], d_hi, idesc[si], (si > 0 || tap > 0) ? 1u : 0u);
-          if (n_kk[si] > 1) umma_f16_split(d, aoff[tap][1] + a_base, d_hi, bdesc[si][tap][1], d_hi, idesc[si], 1u);
+          const uint32_t b0 = NS <= 2 ? bdesc[NS <= 2 ? si : 0][tap][0] : bbase[si] + (uint32_t)tap * tile16[si];
+          umma_f16_split(d, aoff[tap][0] + a_base, d_hi, b0, d_hi, idesc[si], (si > 0 || tap > 0) ? 1u : 0u);
+          const uint32_t b1 = NS <= 2 ? bdesc[NS <= 2 ? si : 0][tap][1] : b0 + 2u * blbo16;
+          if (n_kk[si] > 1) umma_f16_split(d, aoff[tap][1] + a_base, d_hi, b1, d_hi, idesc[si], 1u);
         }
         d += ncat;
         if (++seg == a.n_seg) { seg = 0; a_base += (uint32_t)(a.Wp - (a.n_seg - 1) * 128); }
@@ -363,7 +374,7 @@ __device__ __forceinline__ uint32_t nz8_mask(const uint4& a) {   // bit c set wh
 template <bool SEQ, int NSEG, bool HARD>
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const WtSmem s = wt_smem(smem, a.wblob_bytes);
+  const WtSmem s = wt_smem(smem, a.wblob_bytes + a.wblob2_bytes);
   const uint32_t tmem_base = wt_prologue(a, s);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -659,7 +670,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
 // =================================================================================================
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgrad_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const WtSmem s = wt_smem(smem, a.wblob_bytes);
+  const WtSmem s = wt_smem(smem, a.wblob_bytes + a.wblob2_bytes);
   const uint32_t tmem_base = wt_prologue(a, s);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == WT_EPI_WARPS) {
@@ -751,27 +762,31 @@ struct SegIter {
   }
 };
 
-// BIN0: the first bin of the window - v_in / z_in come from the caller's NCHW state tensors (or are zero)
-template <int SG, bool HARD, bool BIN0>
+// MODE 0: one bin per launch.  MODE 1: one bin per launch, the FIRST bin of the window (t = 0) - v_in / z_in come from the
+// caller's NCHW state tensors (or are zero).  MODE 2: time-fused - ONE cooperative launch walks the window backwards
+// (bin j of the launch is t = T-1-j; per-bin strides in WtArgs), the g_I planes of bin j being the recurrent operand of
+// bin j+1 under the per-tile progress flags (wt_publisher); d lam / d theta partial sums are carried over all bins.
+template <int SG, bool HARD, int MODE>
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const WtSmem s = wt_smem(smem, a.wblob_bytes);
+  const WtSmem s = wt_smem(smem, a.wblob_bytes + a.wblob2_bytes);
   const uint32_t tmem_base = wt_prologue(a, s);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == WT_EPI_WARPS) {
     if (a.has_gz) wt_producer<false>(a, s);
     __syncwarp();
   } else if (warp == WT_EPI_WARPS + 1) {
-    if (a.has_gz && elect_one()) wt_mma<false>(a, s, tmem_base);
+    if (a.has_gz && elect_one()) wt_mma<false, WT_MAX_SRC>(a, s, tmem_base);
     __syncwarp();
-  } else if (warp >= WT_EPI_WARPS + 2) {
-    // (the publisher warp has no work in this kernel)
+  } else if (warp == WT_EPI_WARPS + 2) {
+    if (MODE == 2 && lane == 0) wt_publisher(a, s);
+    __syncwarp();
   } else {
     pdl_wait();
     const int q = warp & 3, ch = warp >> 2;
     // kernel parameters used per segment live in registers (re-reading them from the constant bank stalls the epilogue)
     const int W = a.W, Wp = a.Wp, N = a.N, nch = N >> 3;
-    const bool act = ch * 8 < N, has_gz = a.has_gz != 0, first_step = a.first_step != 0;
+    const bool act = ch * 8 < N, has_gz = a.has_gz != 0;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     const size_t HW = (size_t)a.H * W;
     const size_t plane_bytes = (size_t)(a.H + 2) * Wp * 16;
@@ -779,10 +794,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
     const uint32_t ncat = 2u * (uint32_t)N, acc_cols = (uint32_t)n_mt * ncat;
     const int n_sub = wt_n_items<false>(a) * n_mt;   // 128-pixel segments this CTA processes, in order
     const float width = a.width;
-    const float *g_out = a.g_out, *v_t = a.v_t, *v_in = a.v_in;
+    const float* const g_out = a.g_out;
     const bool l2_pf = a.l2_prefetch != 0;
     float* g_v = a.g_v;
-    unsigned char* gp_out = a.gp_out;
     const size_t gp_img_stride = a.gp_img_stride, gp_term_stride = a.gp_term_stride;
     const float4* par = s.par + (act ? ch * 8 : 0);   // (lam, 1 - lam, theta, 1 / (1 - lam)) per channel, read where used
     float s_lam[8], s_th[8];
@@ -793,10 +807,20 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
     const uint32_t acc_lg = a.acc_lg, acc_mask = (1u << acc_lg) - 1u;
     // Inputs of a segment (g_out, v_t, v_in, g_v: 128 B per thread) are plain 256-bit loads at the top of the segment; a
     // cp.async prefetch through thread-private shared-memory slots was measured slower (38 vs 35 us per bin) and is gone.
+    const int n_bins = (MODE == 2 && a.n_bins > 1) ? a.n_bins : 1;
+    const int items_per_bin = wt_n_items<false>(a);
+    for (int bin = 0; bin < n_bins; ++bin) {
+    // this bin's views (bin 0 = the launch arguments; the strides are negative: the window is walked backwards)
+    const float* const v_t = a.v_t + (long long)bin * a.bin_v_stride;
+    const bool t0 = MODE == 1 || (MODE == 2 && bin == n_bins - 1);   // bin t = 0: state entering the window is the caller's
+    const float* const v_in = (MODE == 2) ? (t0 ? a.v_init : a.v_in + (long long)bin * a.bin_v_stride) : a.v_in;
+    const bool first_step = MODE == 2 ? bin == 0 : a.first_step != 0;
+    unsigned char* const gp_out = a.gp_out + (long long)bin * a.bin_zp_stride;
     SegIter cur;
     cur.init(a);
     for (int j = 0; j < n_sub; ++j) {
-      const int b = cur.b, y = cur.y0 + cur.r, x = cur.seg * 128 + q * 32 + lane, m = cur.r * cur.n_seg + cur.seg, k = cur.k;
+      const int b = cur.b, y = cur.y0 + cur.r, x = cur.seg * 128 + q * 32 + lane, m = cur.r * cur.n_seg + cur.seg;
+      const int k = bin * items_per_bin + cur.k;   // running item number of this CTA (accumulator ring, publisher ring)
       const uint32_t ab = (uint32_t)k & acc_mask;
       const bool ok = x < W;
       const size_t pix = (size_t)y * W + x;
@@ -810,20 +834,23 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
         const int xn = nxs.seg * 128 + q * 32 + lane;
         if (xn < W) {
           const size_t con = c8_off(nxs.b, nch, ch, HW, (size_t)(nxs.y0 + nxs.r) * W + xn);
-          prefetch_l2(g_out + con);
+          if (g_out) prefetch_l2(g_out + con);
           prefetch_l2(v_t + con);
-          if (!BIN0) prefetch_l2(v_in + con);
+          if (!t0) prefetch_l2(v_in + con);
         }
       }
       if (act && ok) {
-        ld8_c8(g_out + co, go);
+        if (g_out) ld8_c8(g_out + co, go);   // NULL: the spike gradient from the layer above arrives in the accumulator
         ld8_c8(v_t + co, vt);
-        if (!BIN0) ld8_c8(v_in + co, vin);
-        if (!first_step) ld8_c8(g_v + co, gv);   // written by the previous launch, rewritten below by this thread only
+        if (!t0) ld8_c8(v_in + co, vin);
+        if (!first_step) {   // written by the previous launch / bin, rewritten below by this thread only
+          if (MODE == 2) ldg256_coherent(g_v + co, gv);
+          else ld8_c8(g_v + co, gv);
+        }
       }
       if (act) {
         float zin[8];
-        if (BIN0) {   // window-initial state of the caller (NCHW) or zeros
+        if (t0) {   // window-initial state of the caller (NCHW) or zeros
           const size_t o = ((size_t)(b * N + ch * 8)) * HW + pix;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -834,9 +861,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
         float acc[8];
         if (has_gz) {
           if (m == 0) {
-            const long long t0 = clock64();
+            const long long t0c = a.dbg ? clock64() : 0;
             mbar_wait(&s.acc_full[ab], (uint32_t)(k >> acc_lg) & 1u);
-            t_wait += clock64() - t0;
+            if (a.dbg) t_wait += clock64() - t0c;
             tc_fence_after();
           }
           uint32_t u0[8], u1[8];
@@ -856,7 +883,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 pr = par[c];
-          const float z_in = BIN0 ? zin[c] : ((__fsub_rn(vin[c], pr.z) > 0.f) ? 1.f : 0.f);
+          const float z_in = t0 ? zin[c] : ((__fsub_rn(vin[c], pr.z) > 0.f) ? 1.f : 0.f);
           const float gs = (go[c] + acc[c]) * surrogate_fast<SG>(vt[c] - pr.z, width);
           const float gvv = gv[c] + gs;
           gI[c] = gvv * pr.y;
@@ -885,8 +912,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
       if (has_gz && m == n_mt - 1) {
         tc_fence_before();
         mbar_arrive(&s.acc_empty[ab]);
+        if (MODE == 2 && n_bins > 1 && !(a.exp & 2)) {   // hand the finished item to the publisher warp (see wt_fwd_kernel)
+          if (tid == 0 && k >= WT_PUB_RING) {
+            while (*s.pub_count < (unsigned int)(k - WT_PUB_RING + 1)) __nanosleep(20);
+          }
+          mbar_arrive(&s.pub_bar[k & (WT_PUB_RING - 1)]);
+        }
       }
       cur.next();
+    }
     }
     if (a.dbg && tid == 0) {
       a.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin;
@@ -931,7 +965,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
 template <int SG, bool HARD, int NSEG>
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const WtSmem s = wt_smem(smem, a.wblob_bytes);
+  const WtSmem s = wt_smem(smem, a.wblob_bytes + a.wblob2_bytes);
   const uint32_t tmem_base = wt_prologue(a, s);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == WT_EPI_WARPS) {
@@ -1123,7 +1157,7 @@ bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes
 }
 
 static size_t wt_smem_bytes(const WtArgs& a, size_t extra = 0) {
-  return (size_t)WT_HDR + align_up(a.wblob_bytes, 128) + (size_t)a.S * a.stage_bytes + WT_TAIL + extra;
+  return (size_t)WT_HDR + align_up((size_t)a.wblob_bytes + a.wblob2_bytes, 128) + (size_t)a.S * a.stage_bytes + WT_TAIL + extra;
 }
 
 template <typename K>
@@ -1226,11 +1260,13 @@ int launch_wt_dgpw(const WtArgs& a, cudaStream_t st, double bytes, double flops)
 
 int launch_wt_recbwd(const WtArgs& a, cudaStream_t st, double bytes, double flops) {
   prof_begin("win_rec_bwd", st, bytes, flops);
-  const bool bin0 = !a.z_from_v;   // first bin of the window: v_in / z_in are the caller's NCHW state (or zero)
+  // first bin of the window (t = 0): v_in / z_in are the caller's NCHW state (or zero); n_bins > 1: time-fused launch
+  const int mode = a.n_bins > 1 ? 2 : (!a.z_from_v ? 1 : 0);
 #define WT_RB_CASE(SGV, HARDV) \
   if (a.surrogate == SGV && (a.hard_reset != 0) == HARDV) { \
-    if (bin0) return wt_launch(wt_recbwd_kernel<SGV, HARDV, true>, (const void*)wt_recbwd_kernel<SGV, HARDV, true>, a, st, "wt_recbwd_kernel"); \
-    return wt_launch(wt_recbwd_kernel<SGV, HARDV, false>, (const void*)wt_recbwd_kernel<SGV, HARDV, false>, a, st, "wt_recbwd_kernel"); \
+    if (mode == 2) return wt_launch(wt_recbwd_kernel<SGV, HARDV, 2>, (const void*)wt_recbwd_kernel<SGV, HARDV, 2>, a, st, "wt_recbwd_kernel"); \
+    if (mode == 1) return wt_launch(wt_recbwd_kernel<SGV, HARDV, 1>, (const void*)wt_recbwd_kernel<SGV, HARDV, 1>, a, st, "wt_recbwd_kernel"); \
+    return wt_launch(wt_recbwd_kernel<SGV, HARDV, 0>, (const void*)wt_recbwd_kernel<SGV, HARDV, 0>, a, st, "wt_recbwd_kernel"); \
   }
   WT_RB_CASE(0, true) WT_RB_CASE(0, false) WT_RB_CASE(1, true) WT_RB_CASE(1, false) WT_RB_CASE(2, true) WT_RB_CASE(2, false)
 #undef WT_RB_CASE
