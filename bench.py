@@ -245,8 +245,72 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+# roofline helpers
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    return hbm, ("measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)")
+
+
+def load_traffic(section):
+    """DRAM bytes per launch measured by ncu (profiles/make_traffic.py) for the kernels of one workload section."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(section, {})
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+NOT_DATA_KERNELS = ("dp_allreduce",)   # its launch time is the wait for the slowest rank, not data movement
+
+
+def kernel_table(prof):
+    tot = sum(p["ms"] for p in prof.values()) or 1.0
+    return {k: {"launches": p["launches"], "ms": round(p["ms"], 4), "share": round(p["ms"] / tot, 4),
+                "GBps": round(p["bytes"] / (p["ms"] * 1e6), 1) if p["ms"] else None,
+                "TFLOPs": round(p["flops"] / (p["ms"] * 1e9), 2) if p["ms"] else None}
+            for k, p in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+
+def roofline_of(prof, section):
+    """The dominant kernel of a live per-launch profile (CUDA events on the launching stream) against the HBM peak.
+    `achieved` / `frac` are on the DRAM bytes ncu measured for that kernel (`traffic`, profiles/traffic.json) when the
+    capture exists, i.e. bytes that really crossed the HBM interface; `achieved_algorithmic` / `frac_algorithmic` are on
+    the bytes the formulation has to move in its storage formats (bf16 planes, fp32 membranes)."""
+    hbm_peak, peak_src = load_peaks()
+    data = {k: p for k, p in prof.items() if k not in NOT_DATA_KERNELS and p["ms"] > 0}
+    if not data:
+        return None
+    tot = sum(p["ms"] for p in prof.values()) or 1.0
+    top = max(data, key=lambda k: data[k]["ms"])
+    p = data[top]
+    us = 1e3 * p["ms"] / p["launches"]
+    alg_bytes = p["bytes"] / p["launches"]
+    alg = alg_bytes / (us * 1e3)                      # GB/s
+    t = load_traffic(section).get(top)
+    traffic = t["dram_bytes_per_launch"] if t else None
+    dram = traffic / (us * 1e3) if traffic else None
+    achieved = dram if dram is not None else alg
+    return {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+            "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
+            "basis": "DRAM bytes per launch measured by ncu (profiles/traffic.json) / live CUDA-event launch time" if dram is not None
+                     else "algorithmic bytes (no ncu capture for this kernel)",
+            "achieved_dram": None if dram is None else round(dram, 1), "frac_dram": None if dram is None else round(dram / hbm_peak, 4),
+            "achieved_algorithmic": round(alg, 1), "frac_algorithmic": round(alg / hbm_peak, 4),
+            "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "avg_launch_us": round(us, 2),
+            "launches_per_profile": p["launches"], "share_of_kernel_time": round(p["ms"] / tot, 4)}
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+MIN_TIMED_SECONDS = 0.5   # the K-step timed region is repeated until this much device time has been measured
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -264,7 +328,6 @@ def run_ours(a):
             sys.stderr.write(f"[bench rank {rank}] {msg}\n")
             sys.stderr.flush()
 
-
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -277,17 +340,43 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    torch.manual_seed(0)   # identical replicas on every rank
-    net = snnflow.LIFFireNet(dict(num_bins=2, encoding="cnt", base_num_channels=a.channels, kernel_size=3,
-                                  neuron_kwargs=dict(leak=(0.0, 1.0), thresh=(0.3, 0.1)))).to(dev)
-    cfg = {"loader": {"resolution": [a.res, a.res]}, "loss": {"flow_regul_weight": 0.001}, "model": {"mask_output": False}}
-    lossf = snnflow.EventWarping(cfg, dev)
-    if a.torch_adam:
-        opt = torch.optim.Adam(net.parameters(), lr=2e-4, capturable=not a.no_graph)
-    else:   # clip_grad_norm_(1.0) + Adam as one C call over the flat parameter buffer (snnflow_clip_adam)
-        opt = snnflow.FusedClipAdam(net.parameters(), lr=2e-4, max_norm=1.0)
-    tw = TrainWindow(net, lossf, opt, clip_grad=1.0, peer_allreduce=not a.nccl_allreduce)
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed_regions(step_fn, k_steps, min_seconds=MIN_TIMED_SECONDS, max_regions=200):
+        """Time EXACTLY k_steps steps between barrier + synchronize on both sides (CUDA events, max over ranks), and
+        repeat that region until >= min_seconds of device time are measured.  Returns (total ms, regions, per-region ms)."""
+        per, it = [], 0
+        while True:
+            barrier()
+            ev0.record()
+            for _ in range(k_steps):
+                step_fn(it)
+                it += 1
+            ev1.record()
+            barrier()
+            per.append(max_over_ranks(ev0.elapsed_time(ev1)))
+            if sum(per) >= 1e3 * min_seconds or len(per) >= max_regions:
+                return sum(per), len(per), per
+
+    def build_trainer(batch):
+        torch.manual_seed(0)   # identical replicas on every rank
+        net = snnflow.LIFFireNet(dict(num_bins=2, encoding="cnt", base_num_channels=a.channels, kernel_size=3,
+                                      neuron_kwargs=dict(leak=(0.0, 1.0), thresh=(0.3, 0.1)))).to(dev)
+        cfg = {"loader": {"resolution": [a.res, a.res]}, "loss": {"flow_regul_weight": 0.001}, "model": {"mask_output": False}}
+        lossf = snnflow.EventWarping(cfg, dev)
+        if a.torch_adam:
+            opt = torch.optim.Adam(net.parameters(), lr=2e-4, capturable=not a.no_graph)
+        else:   # clip_grad_norm_(1.0) + Adam as one C call over the flat parameter buffer (snnflow_clip_adam)
+            opt = snnflow.FusedClipAdam(net.parameters(), lr=2e-4, max_norm=1.0)
+        return TrainWindow(net, lossf, opt, clip_grad=1.0, peer_allreduce=not a.nccl_allreduce)
+
+    tw = build_trainer(a.batch)
     host_pool = [{k: v.pin_memory() for k, v in make_window(a, 1000 * rank + i).items()} for i in range(4)]
     dev_pool = [{k: v.to(dev) for k, v in w.items()} for w in host_pool]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_pool[0].values())
@@ -306,13 +395,6 @@ def run_ours(a):
         w = dict(w, event_list=w["event_list"].clone())
         return tw.step(w)
 
-    def step_e2e(i):
-        hw = host_pool[i % len(host_pool)]
-        if not a.no_graph:
-            return float(tw.step_graphed(hw).item())     # H2D into the static inputs, replay, D2H of the loss
-        w = {k: v.to(dev, non_blocking=True) for k, v in hw.items()}
-        return float(tw.step(w).item())          # D2H of the loss, synchronises
-
     # ---- device-resident timing ----
     phase("warm-up")
     for i in range(a.warmup):
@@ -322,21 +404,13 @@ def run_ours(a):
     sampler = ClockSampler(local)
     sampler.start()
     l0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(a.steps):
-        loss = step_resident(i)
-    ev1.record()
-    barrier()
+    ms_total, regions, per_region = timed_regions(step_resident, a.steps)
     clocks = sampler.stop()
+    n_steps_timed = regions * a.steps
     launches = _lib.launch_count() - l0
     if launches_per_step is not None:
-        launches = launches_per_step * a.steps   # graph replays do not pass through the library's launch counter
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    value = a.batch * world * a.steps / (ms_total / 1e3)
+        launches = launches_per_step * n_steps_timed   # graph replays do not pass through the library's launch counter
+    value = a.batch * world * n_steps_timed / (ms_total / 1e3)
 
     phase("end-to-end")
     # ---- end-to-end timing from pinned host buffers ----
@@ -344,6 +418,7 @@ def run_ours(a):
     # i+1 is issued on a side stream before the loss of window i is read back, so it overlaps window i's compute
     loss_pin = torch.empty(2, dtype=torch.float32).pin_memory()
     loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
+    last_loss = [None]
 
     def e2e_pass(n_steps):
         """Every step: H2D of its window (pinned -> staging on a side stream, overlapping the previous step), graph replay,
@@ -365,24 +440,14 @@ def run_ours(a):
             last = float(loss_pin[(n_steps - 1) % 2])
         else:
             for i in range(n_steps):
-                last = step_e2e(i)
-        return last
+                w = {k: v.to(dev, non_blocking=True) for k, v in host_pool[i % len(host_pool)].items()}
+                last = float(tw.step(w).item())          # D2H of the loss, synchronises
+        last_loss[0] = last
 
     e2e_pass(3)   # warm the same path (side stream, pinned staging) outside the timed region
-    # The host drives every step here (copy, replay, read-back), so one descheduling of the Python thread shows up as
-    # a 2x outlier over K short steps: the K-step region is timed three times and the MEDIAN is reported (all three listed).
-    e2e_runs = []
-    for rep in range(3):
-        barrier()
-        ev0.record()
-        last_loss = e2e_pass(a.steps)
-        ev1.record()
-        barrier()
-        ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        e2e_runs.append(a.batch * world * a.steps / (float(ms2.item()) / 1e3))
-    e2e_value = sorted(e2e_runs)[1]
+    # one "step" of the region driver is a whole K-step pass here (the pass pipelines copies against compute internally)
+    ms2, regions2, per2 = timed_regions(lambda _i: e2e_pass(a.steps), 1)
+    e2e_value = a.batch * world * a.steps * regions2 / (ms2 / 1e3)
 
     # ---- per-kernel profile of two steps (live CUDA events on the launching stream) ----
     # every rank runs the two steps (they contain the gradient all-reduce); only rank 0 records and reports
@@ -395,39 +460,25 @@ def run_ours(a):
         tw.step(dict(w, event_list=w["event_list"].clone()))
     barrier()
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:  # noqa: BLE001
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         prof = _lib.profile_summary()
         _lib.profile(False)
-        tot = sum(p["ms"] for p in prof.values()) or 1.0
-        kernels = {k: {"launches": p["launches"], "ms": round(p["ms"], 4), "share": round(p["ms"] / tot, 4),
-                       "GBps": round(p["bytes"] / (p["ms"] * 1e6), 1) if p["ms"] else None,
-                       "TFLOPs": round(p["flops"] / (p["ms"] * 1e9), 2) if p["ms"] else None}
-                   for k, p in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
-        top = max(prof, key=lambda k: prof[k]["ms"])
-        p = prof[top]
-        achieved = p["bytes"] / (p["ms"] * 1e6)   # GB/s
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
-        except Exception:  # noqa: BLE001
-            pass
-        roofline = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
-                    "avg_launch_us": round(1e3 * p["ms"] / p["launches"], 2),
-                    "algorithmic_bytes_per_launch": p["bytes"] / p["launches"],
-                    "share_of_kernel_time": round(p["ms"] / tot, 4)}
+        kernels = kernel_table(prof)
+        roofline = roofline_of(prof, "train")
 
-    # ---- eval (LIFFireFlowNet, 256x256, batch 16: BASELINE.json configs[2]) on rank 0's GPU, every rank ----
+    # ---- BASELINE.json configs[3] at N > 1: the same step at a fixed GLOBAL batch of 256 ----
+    g256 = None
+    if world > 1 and not a.global_batch and not a.no_eval and 256 % world == 0:
+        phase("global batch 256")
+        g256 = run_global256(a, build_trainer, dev, world, rank, timed_regions)
+
+    # ---- eval (LIFFireFlowNet, 256x256, batch 16: BASELINE.json configs[2]), every rank on its own GPU ----
     phase("eval")
-    eval_info = None
+    eval_info = cfg0 = None
     if not a.no_eval:
-        eval_info = run_eval(a, snnflow, dev, world, barrier)
+        eval_info = run_eval(a, snnflow, _lib, dev, world, rank, timed_regions)
+        if rank == 0:
+            phase("configs[0]")
+            cfg0 = run_cfg0(a, snnflow, dev)
 
     micro, narrow = None, None
     if rank == 0 and not a.no_eval:
@@ -448,18 +499,41 @@ def run_ours(a):
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
+            "ms_per_step": ms_total / n_steps_timed, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
+            "timed": {"regions": regions, "steps_per_region": a.steps, "total_ms": round(ms_total, 3),
+                      "region_ms_min_max": [round(min(per_region), 3), round(max(per_region), 3)],
+                      "note": f"the K-step region (barrier + synchronize on both sides, CUDA events, max over ranks) is "
+                              f"repeated until >= {MIN_TIMED_SECONDS} s are measured; value = all samples / all region time"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "runs": [round(v, 1) for v in e2e_runs], "stat": "median of 3 timed K-step regions"},
-            "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "eval": eval_info,
-            "encode_iwe_microbench": micro, "train_c8": narrow,
-            "loss": last_loss,
+                    "regions": regions2, "region_ms_min_max": [round(min(per2), 3), round(max(per2), 3)]},
+            "gpu_launches": int(launches), "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "eval": eval_info, "eval_cfg0": cfg0,
+            "global_batch_256": g256, "encode_iwe_microbench": micro, "train_c8": narrow,
+            "loss": last_loss[0],
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_global256(a, build_trainer, dev, world, rank, timed_regions):
+    """BASELINE.json configs[3]: data-parallel training at a fixed global batch of 256 (256 / N samples per GPU)."""
+    import copy
+    import torch
+    b = copy.copy(a)
+    b.batch = 256 // world
+    tw = build_trainer(b.batch)
+    pool = [{k: v.to(dev) for k, v in make_window(b, 7000 + 10 * rank + i).items()} for i in range(2)]
+    tw.capture(pool[0])
+    for i in range(3):
+        tw.step_graphed(pool[i % 2])
+    ms, regions, per = timed_regions(lambda i: tw.step_graphed(pool[i % 2]), max(2, a.steps // 4))
+    n = regions * max(2, a.steps // 4)
+    del tw, pool
+    torch.cuda.empty_cache()
+    return {"metric": "LIFFireNet train samples/s @128x128, GLOBAL batch 256 (BASELINE.json configs[3])", "value": 256 * n / (ms / 1e3),
+            "unit": UNIT, "per_gpu_batch": b.batch, "ms_per_step": ms / n, "steps_timed": n, "scaling": "strong"}
 
 
 def run_train_narrow(a, snnflow, TrainWindow, dev, channels=8):
@@ -481,51 +555,149 @@ def run_train_narrow(a, snnflow, TrainWindow, dev, channels=8):
         tw.step_graphed(pool[i % 4])
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = max(a.steps, 50)
     ev0.record()
-    for i in range(a.steps):
+    for i in range(n):
         tw.step_graphed(pool[i % 4])
     ev1.record()
     torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / a.steps
+    ms = ev0.elapsed_time(ev1) / n
     return {"metric": f"LIFFireNet C={channels} train samples/s @{a.res}x{a.res}, batch {a.batch}", "value": a.batch / (ms / 1e3),
             "unit": "samples/s", "ms_per_step": ms, "gpu_launches_per_step": int(launches)}
 
 
-def run_eval(a, snnflow, dev, world, barrier):
-    """eval frames/s: LIFFireFlowNet (feed-forward ConvLIF), 256x256, batch 16, no_grad (BASELINE configs[2]).
-    Two ways to drive the same network: one forward() per time bin through the drop-in cells (the reference's eval
-    loop, eval_flow.py:220), and forward_window() over T bins at once (layer-major engine, membranes stay in
-    registers across the T bins of a feed-forward layer)."""
+def run_eval(a, snnflow, _lib, dev, world, rank, timed_regions):
+    """The eval half of BASELINE.json's metric - LIFFireFlowNet (feed-forward ConvLIF) eval frames/s at 256x256, batch 16
+    per GPU, no_grad (configs[2]) - with its own roofline, end-to-end and CPU-reference numbers.
+    Two ways to drive the same network: forward_window() over the T = 10 bins of a window at once (layer-major engine:
+    membranes stay in registers across the bins of a layer) is the headline `value`; one forward() per time bin through
+    the drop-in cells is the reference's streaming loop (eval_flow.py:220) and is reported as `per_bin_forward`."""
     import torch
-    import torch.distributed as dist
     B, R, T = 16, 256, 10
     torch.manual_seed(0)
     net = snnflow.LIFFireFlowNet(dict(num_bins=2, encoding="cnt", base_num_channels=a.channels, kernel_size=3,
                                       neuron_kwargs=dict(leak=(0.0, 1.0), thresh=(0.3, 0.1)))).to(dev)
-    g = torch.Generator().manual_seed(7)
-    cnt = torch.poisson(torch.full((T, B, 2, R, R), 0.06), generator=g).to(dev)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-    def timed(fn, reps):
-        fn()
-        barrier()
-        ev0.record()
-        for _ in range(reps):
-            fn()
-        ev1.record()
-        barrier()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / reps
+    g = torch.Generator().manual_seed(7 + rank)
+    host = [torch.poisson(torch.full((T, B, 2, R, R), 0.06), generator=g).pin_memory() for _ in range(2)]
+    pool = [h.to(dev) for h in host]
+    frames = B * T
 
     with torch.no_grad():
-        ms_bin = timed(lambda: [net(None, cnt[t]) for t in range(T)], 3)
+        for i in range(3):
+            net.forward_window(pool[i % 2])
+        ms_win, reg_w, _ = timed_regions(lambda i: net.forward_window(pool[i % 2]), 5)
+        n_win = reg_w * 5
+        # end to end: the window's counts come from pinned host memory (84 MB), the per-frame mean flow magnitude goes back
+        stage = [torch.empty_like(pool[0]) for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        out_pin = torch.empty(2, T, B, dtype=torch.float32).pin_memory()
+
+        def e2e_window(i):
+            cur = torch.cuda.current_stream()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_stream(cur)          # the buffer's previous consumer has been queued before this point
+                stage[i % 2].copy_(host[i % 2], non_blocking=True)
+            cur.wait_stream(copy_stream)
+            flow = net.forward_window(stage[i % 2])
+            out_pin[i % 2].copy_(flow.abs().mean(dim=(2, 3, 4)), non_blocking=True)
+        for i in range(2):
+            e2e_window(i)
+        ms_e2e, reg_e, _ = timed_regions(e2e_window, 5)
+        n_e2e = reg_e * 5
+        # per-bin forward() through the drop-in cells (states carried between calls by the network)
         net.reset_states()
-        ms_win = timed(lambda: net.forward_window(cnt), 5)
-    return {"metric": "LIFFireFlowNet eval frames/s @256x256, batch 16/GPU", "value": B * world * T / (ms_win / 1e3),
-            "unit": "frames/s", "api": "forward_window (T = 10 bins per call)", "ms_per_window": ms_win,
-            "per_bin_forward": {"value": B * world * T / (ms_bin / 1e3), "unit": "frames/s", "ms_per_forward": ms_bin / T}}
+        for t in range(T):
+            net(None, pool[0][t])
+        ms_bin, reg_b, _ = timed_regions(lambda i: [net(None, pool[i % 2][t]) for t in range(T)], 2)
+        n_bin = reg_b * 2
+        # live per-launch profile of two windows
+        roofline = kernels = None
+        if rank == 0:
+            net.reset_states()
+            _lib.profile(True)
+            for i in range(2):
+                net.forward_window(pool[i % 2])
+            torch.cuda.synchronize()
+            prof = _lib.profile_summary()
+            _lib.profile(False)
+            kernels = kernel_table(prof)
+            roofline = roofline_of(prof, "eval")
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_eval_frames(a, B, R)
+    h2d = host[0].numel() * 4
+    return {"metric": "LIFFireFlowNet eval frames/s @256x256, batch 16/GPU", "value": frames * world * n_win / (ms_win / 1e3),
+            "unit": "frames/s", "api": "forward_window (T = 10 bins per call)", "ms_per_window": ms_win / n_win, "windows_timed": n_win,
+            "e2e": {"value": frames * world * n_e2e / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": T * B * 4, "note": "per window: counts from pinned host memory (side-stream copy), "
+                    "per-frame mean |flow| read back"},
+            "per_bin_forward": {"value": frames * world * n_bin / (ms_bin / 1e3), "unit": "frames/s",
+                                "ms_per_forward": ms_bin / n_bin / T},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+
+
+def cpu_eval_frames(a, B, R, n_forwards=2):
+    """The reference's LIFFireFlowNet forward under no_grad on the host cores (bounded sample: a few forwards)."""
+    import torch
+    if cpu_arm_kind() != "reference":
+        return None
+    from oracle import ref_runner
+    net = ref_runner.build_net("LIFFireFlowNet", a.channels, None, leak=(0.0, 1.0), thresh=(0.3, 0.1), seed=0)
+    g = torch.Generator().manual_seed(7)
+    cnt = torch.poisson(torch.full((n_forwards + 1, B, 2, R, R), 0.06), generator=g)
+    with torch.no_grad():
+        net(None, cnt[0])
+        t0 = time.perf_counter()
+        for i in range(n_forwards):
+            net(None, cnt[1 + i])
+        sec = (time.perf_counter() - t0) / n_forwards
+    return {"value": B / sec, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": f"{n_forwards} forwards of batch {B} at {R}x{R} after 1 warm-up, {sec:.2f} s/forward"}
+
+
+def run_cfg0(a, snnflow, dev, n_frames=200):
+    """BASELINE.json configs[0], the reference's eval call pattern (eval_flow.py:220-237): batch 1, 128x128, one model()
+    call per frame followed by compute_pol_iwe(round_idx=True) on its flow; GPU through the drop-in per-bin API, CPU =
+    the reference itself on a bounded sample."""
+    import torch
+    R, N = 128, 1000
+    torch.manual_seed(0)
+    net = snnflow.LIFFireNet(dict(num_bins=2, encoding="cnt", base_num_channels=a.channels, kernel_size=3,
+                                  neuron_kwargs=dict(leak=(0.0, 1.0), thresh=(0.3, 0.1)))).to(dev)
+    b = argparse.Namespace(bins=10, batch=1, events=N, res=R)
+    w = {k: v.to(dev) for k, v in make_window(b, 42).items()}
+    res = (R, R)
+
+    def frame(t):
+        flow = net(None, w["event_cnt"][t])["flow"][-1]
+        pm = w["event_list_pol_mask"][t]
+        return snnflow.iwe.compute_pol_iwe(flow, w["event_list"][t], res, pm[:, :, 0:1], pm[:, :, 1:2], flow_scaling=R, round_idx=True)
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for t in range(10):
+            frame(t)
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(n_frames):
+            frame(i % 10)
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / n_frames
+    out = {"metric": "LIFFireNet eval frames/s @128x128, batch 1, model() + compute_pol_iwe per frame (BASELINE.json configs[0])",
+           "value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "frames_timed": n_frames}
+    if not a.no_cpu_baseline and cpu_arm_kind() == "reference":
+        from oracle import ref_runner
+        cpu = torch.device("cpu")
+        rnet = ref_runner.build_net("LIFFireNet", a.channels, None, leak=(0.0, 1.0), thresh=(0.3, 0.1), seed=0)
+        hw = {k: v.cpu() for k, v in w.items()}
+        ref_runner.eval_frames(rnet, hw["event_cnt"][:2], cpu, hw["event_list"][:2], hw["event_list_pol_mask"][:2], res, R)
+        t0 = time.perf_counter()
+        ref_runner.eval_frames(rnet, hw["event_cnt"], cpu, hw["event_list"], hw["event_list_pol_mask"], res, R)
+        sec = (time.perf_counter() - t0) / 10
+        out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "reference",
+                               "sample": f"10 frames after 2 warm-up, {1e3 * sec:.1f} ms/frame"}
+    return out
 
 
 def run_micro(snnflow, dev):

@@ -259,7 +259,7 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
       a.v_out = save ? vbase : nullptr; a.cur_out = nullptr;
       a.zp_out = A + L.off_zp[l];
       a.v_last = state; a.z_last = state + n;
-      rc = launch_wt_fwd(a, true, st, "win_fwd_seq", 4.0 * T * px * (L.Cin[l] + 2 * C),   /* x in ; v, z out */
+      rc = launch_wt_fwd(a, true, st, "win_fwd_seq", (double)T * px * (2.0 * L.Kin[l] + 2.0 * C + (save ? 4.0 * C : 0.0)),   /* x planes (bf16) in ; z planes (bf16) [, v c8 fp32] out */
                          18.0 * T * px * C * L.Cin[l]);
       if (rc) return rc;
     } else {
@@ -290,7 +290,7 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
         a.bin_zp_stride = (long long)B * (long long)L.zp_img_stride;
         a.bin_v_stride = (long long)n; a.bin_v_mask = save ? -1 : 1;
         a.tile_flags = (unsigned int*)(A + L.off_gridbar[l]);
-        rc = launch_wt_fwd(a, false, st, "win_fwd_rec", 4.0 * T * px * (L.Cin[l] + 4 * C),   /* x, v, z in ; v, z out */
+        rc = launch_wt_fwd(a, false, st, "win_fwd_rec", (double)T * px * (2.0 * L.Kin[l] + 14.0 * C),   /* x, z planes (bf16), v (fp32), z again in the epilogue in ; v, z out */
                            18.0 * T * px * C * (L.Cin[l] + C));
         if (rc) return rc;
       } else
@@ -309,7 +309,7 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
         }
         a.v_last = last ? state : nullptr; a.z_last = last ? state + n : nullptr;
         a.zp_out = A + L.off_zp[l] + (size_t)(t + 1) * B * L.zp_img_stride;
-        rc = launch_wt_fwd(a, false, st, "win_fwd_rec", 4.0 * px * (L.Cin[l] + 4 * C),   /* x, v, z in ; v, z out */
+        rc = launch_wt_fwd(a, false, st, "win_fwd_rec", (double)px * (2.0 * L.Kin[l] + 14.0 * C),   /* x, z planes (bf16), v (fp32), z again in the epilogue in ; v, z out */
                            18.0 * px * C * (L.Cin[l] + C));
         if (rc) return rc;
       }
@@ -418,7 +418,8 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
         a.v_init = v_init; a.z_init = z_init; a.z_from_v = 1;
         a.part = cpart;
         a.tile_flags = (unsigned int*)(const_cast<unsigned char*>(A) + L.off_gridbar[l]);   // scratch shared with the forward launch
-        rc = launch_wt_recbwd(a, st, 4.0 * T * px * C * 6, 18.0 * px * C * C * (2 * T - 1));
+        rc = launch_wt_recbwd(a, st, (double)T * px * C * 28.0 /* 2 x (hi + lo) planes in, v[t], v[t-1], g_v in/out, hi + lo planes out */,
+                              18.0 * px * C * C * (2 * T - 1));
         if (rc) return rc;
       } else
       for (int t = T - 1; t >= 0; --t) {
@@ -443,7 +444,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
         a.z_from_v = t > 0; a.z_init = z_init;
         a.gp_out = gp + (size_t)t * B * L.zp_img_stride;
         a.part = cpart + (size_t)t * WS.rb_grid * 2 * C;
-        rc = launch_wt_recbwd(a, st, 4.0 * px * C * (fuse ? 5 : (have_rec ? 7 : 6)) + (fuse ? 4.0 * px * C : 0.0),
+        rc = launch_wt_recbwd(a, st, (double)px * C * (20.0 + (fuse ? 4.0 : 4.0) + (have_rec ? 4.0 : 0.0)),   /* planes bf16, the rest fp32 */
                               18.0 * px * C * C * (ns / 2));
         if (rc) return rc;
       }
@@ -479,7 +480,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
       a.gp = gp; a.g_img_stride = L.zp_img_stride; a.g_term_stride = WS.gp_term_stride;
       a.part[0] = wpart[0]; a.part[1] = wpart[1];
       a.n_img = T * B; a.H = H; a.W = W; a.C = C;
-      rc = launch_wgrad_planes(a, st, 4.0 * T * px * (C + L.Cin[l] + (L.rec[l] ? C : 0)),
+      rc = launch_wgrad_planes(a, st, (double)T * px * (4.0 * C + 2.0 * L.Kin[l] + (L.rec[l] ? 2.0 * C : 0.0)),   /* g hi + lo, x [, z] planes (bf16) */
                                18.0 * T * px * C * (L.Cin[l] + (L.rec[l] ? C : 0)));
       if (rc) return rc;
       WinReduceArgs r{};
@@ -511,14 +512,14 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
         a.v_init = v_init_b; a.z_init = v_init_b ? v_init_b + n : nullptr;
         a.gp_out = gplanes[(l - 1) & 1]; a.gp_img_stride = L.zp_img_stride; a.gp_term_stride = WS.gp_term_stride;
         a.part = (float*)(Wk + WS.off_cpart[l - 1]);
-        rc = launch_wt_dgpw(a, st, 4.0 * T * px * (C + 3 * L.Kin[l]) /* g_I in ; v (x2), g_I out */, 18.0 * T * px * C * L.Kin[l]);
+        rc = launch_wt_dgpw(a, st, (double)T * px * (4.0 * C + 8.0 * L.Kin[l]) /* g_I hi + lo in ; v in, g_I hi + lo out */, 18.0 * T * px * C * L.Kin[l]);
         if (rc) return rc;
         n_cpart = WS.dp_grid; cpart_layout = 1;
       } else if (!win_fuse_dgrad()) {   // (fused into the recurrent layer's own BPTT launches otherwise, see above)
         a.n_outer = T * B; a.T = 1;
         a.R = P.R_dg; a.S = P.S_dg; a.sub_bytes = P.sub_dg; a.chunk_stride = P.cs_dg; a.stage_bytes = P.st_dg;
         a.g_x = gbuf;
-        rc = launch_wt_dgrad(a, st, 4.0 * T * px * (C + L.Kin[l]), 18.0 * T * px * C * L.Kin[l]);
+        rc = launch_wt_dgrad(a, st, (double)T * px * (4.0 * C + 4.0 * L.Kin[l]), 18.0 * T * px * C * L.Kin[l]);
         if (rc) return rc;
       }
     }

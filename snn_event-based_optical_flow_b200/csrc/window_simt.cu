@@ -412,7 +412,7 @@ int launch_pw_seq(const PwSeqArgs& a, cudaStream_t st) {
     set_error("launch_pw_seq: n_part mismatch");
     return SNNFLOW_EINVAL;
   }
-  prof_begin("win_pw_seq", st, (double)a.T * a.B * a.C * a.H * a.W * 12.0);   // v, g_out in ; g_I out
+  prof_begin("win_pw_seq", st, (double)a.T * a.B * a.H * a.W * (8.0 * a.C + (a.g_out ? 4.0 * a.C : 16.0)));   // v in, g_I hi + lo planes out ; g_out or flow + g_flow in
   const dim3 grid(gx, a.C / 8, a.B);
   const bool top = a.g_out == nullptr;
   static const int staged_v2 = [] { const char* v = getenv("SNNFLOW_PW2"); return (v && *v) ? atoi(v) : 1; }();
