@@ -309,6 +309,26 @@ int snnflow_window_loss(const float* flow, const float* events, const float* pol
                         float flow_scaling, float regul_weight, int loss_scaling, snnflow_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * snntorch-style Leaky neuron step: the LIF of SNNtorch_ConvLIF / SNNtorch_ConvLIFRecurrent
+ * (models/SNNtorch_spiking_submodules.py:124-322, :324-567 - what models/model.py:37-39 wires into LIFFireNet by default),
+ * i.e. snn.Leaky(beta, threshold, reset_mechanism, reset_delay=False) applied to the batch-normalised input current.
+ * PARITY UNPINNED: snntorch 0.9.4 is absent offline; the arithmetic restates its published Leaky.forward (csrc/leaky.cu
+ * header).  The convolution(s) run through snnflow_convlif_fwd / _bwd (lam = 0 turns the cell
+ * into a plain fused conv [+ recurrent conv]); BatchNorm2d stays with the caller.
+ *   cur [B,C,H,W] batch-normalised current; mem_in [B,C,H,W] or NULL (zeros); beta, theta [C] raw parameters (beta is
+ *   clamped to [0,1] inside, theta is already >= 0.01); subtract: 0 = reset to zero, 1 = reset by subtraction
+ *   mem_out, spk [B,C,H,W]; m_pre [B,C,H,W] or NULL: the membrane before the reset, saved for the backward
+ * backward (the cell detaches mem_out, so spk is the only differentiable output):
+ *   g_cur = g_spk / (1 + (pi (m_pre - theta))^2)  (ATan surrogate, alpha = 2);  d_beta, d_theta [C] are overwritten
+ * --------------------------------------------------------------------------------------------- */
+int snnflow_leaky_fwd(const float* cur, const float* mem_in, const float* beta, const float* theta, float* mem_out,
+                      float* spk, float* m_pre, int B, int C, int H, int W, int subtract, snnflow_stream_t stream);
+size_t snnflow_leaky_bwd_workspace_bytes(int B, int C, int H, int W);
+int snnflow_leaky_bwd(const float* g_spk, const float* m_pre, const float* mem_in, const float* beta, const float* theta,
+                      float* g_cur, float* d_beta, float* d_theta, void* workspace, size_t workspace_bytes, int B, int C,
+                      int H, int W, int subtract, snnflow_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Optimizer update of the training step (train_flow.py:264-271): torch.nn.utils.clip_grad.clip_grad_norm_(parameters,
  * max_norm) followed by torch.optim.Adam.step() (no amsgrad, no weight decay) over ONE flat fp32 parameter buffer, as
  * two launches (fixed-order sum of squares; clip coefficient + Adam per slice) instead of ~20 small PyTorch kernels.

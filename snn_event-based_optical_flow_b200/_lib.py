@@ -36,6 +36,9 @@ _PROTOS = {
     "snnflow_flow_gather_bwd": (c_int, [P] * 3 + [c_int, c_int64, c_int, c_int, P]),
     "snnflow_iwe_splat_fwd": (c_int, [P] * 5 + [c_int, c_int64, c_int, c_int, c_float, c_float, c_int, c_int, c_float,
                                                 c_int, P]),
+    "snnflow_leaky_fwd": (c_int, [P] * 7 + [c_int] * 5 + [P]),
+    "snnflow_leaky_bwd_workspace_bytes": (c_size_t, [c_int] * 4),
+    "snnflow_leaky_bwd": (c_int, [P] * 8 + [P, c_size_t] + [c_int] * 5 + [P]),
     "snnflow_clip_adam_partials": (c_int, [c_int64]),
     "snnflow_clip_adam": (c_int, [P] * 4 + [c_int64] + [P] * 7),
     "snnflow_dp_allreduce_ctas": (c_int, []),

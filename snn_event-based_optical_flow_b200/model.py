@@ -12,10 +12,11 @@ the reference's own classes (tests/test_gpu_reference_seam.py runs exactly this 
     class Net(models.model.LIFFireNet):
         head_neuron = ff_neuron = snnflow.ConvLIF; rec_neuron = snnflow.ConvLIFRecurrent
 
-LIMITATION: the reference's ``LIFFireNet`` as shipped wires the ``SNNtorch_ConvLIF`` /
-``SNNtorch_ConvLIFRecurrent`` cells (models/model.py:37-39: snntorch ``Leaky`` + ``BatchNorm2d``, keys ``lif.beta``,
-``lif.threshold``, ``bn.*``), a different neuron equation.  Checkpoints of that default model do not load into this
-mirror: ``load_state_dict`` refuses them with an explicit error instead of reporting a wall of missing keys.
+The reference's ``LIFFireNet`` as shipped wires the ``SNNtorch_ConvLIF`` / ``SNNtorch_ConvLIFRecurrent`` cells
+(models/model.py:37-39: snntorch ``Leaky`` + ``BatchNorm2d``, keys ``lif.beta``, ``lif.threshold``, ``bn.*``), a
+different neuron equation: that network is ``SNNtorchLIFFireNet`` below (cells in snntorch_submodules.py, parity unpinned
+because snntorch is absent offline).  A checkpoint of one kind does not load into the other: ``load_state_dict`` says so
+explicitly instead of reporting a wall of missing keys.
 """
 import torch
 import torch.nn as nn
@@ -76,12 +77,13 @@ class LIFFireNet(nn.Module):
 
     def load_state_dict(self, state_dict, *args, **kwargs):
         foreign = [k for k in state_dict if ".lif." in k or ".bn." in k or ".tebn." in k or ".mpbn." in k]
-        if foreign:
+        if foreign and not hasattr(self.head, "lif"):
             raise RuntimeError(
                 "snnflow LIFFireNet: this state_dict comes from the reference's SNNtorch_ConvLIF cells (keys such as "
                 f"{foreign[0]!r}: snntorch Leaky + BatchNorm2d, models/SNNtorch_spiking_submodules.py).  This network "
                 "implements the ConvLIF / ConvLIFRecurrent cells of models/spiking_submodules.py (keys ff.weight, "
-                "rec.weight, leak, thresh); the two neuron models are not weight-compatible.")
+                "rec.weight, leak, thresh); the two neuron models are not weight-compatible.  SNNtorchLIFFireNet is the "
+                "network built on the SNNtorch_* cells.")
         return super().load_state_dict(state_dict, *args, **kwargs)
 
     def forward_window(self, event_cnt_window):
@@ -125,6 +127,18 @@ class LIFFireNet(nn.Module):
             acts = torch.stack([t.detach().ne(0).float().mean() for t in (x, x1, x2, x3, x4, x5, x6, x7, flow)])
             activity = dict(zip(names, acts.tolist()))                    # one host sync instead of nine
         return {"flow": [flow], "activity": activity}
+
+
+class SNNtorchLIFFireNet(LIFFireNet):
+    """The reference's LIFFireNet AS SHIPPED (models/model.py:37-39): SNNtorch_ConvLIF / SNNtorch_ConvLIFRecurrent cells
+    (snntorch Leaky + BatchNorm2d).  Runs bin by bin through the cells (snntorch_submodules.py); the layer-major window engine
+    covers the ConvLIF cells only.  PARITY UNPINNED (snntorch is absent offline)."""
+
+    from .snntorch_submodules import SNNtorch_ConvLIF as head_neuron, SNNtorch_ConvLIF as ff_neuron, \
+        SNNtorch_ConvLIFRecurrent as rec_neuron
+
+    def forward_window(self, event_cnt_window):
+        return torch.stack([self.forward(None, event_cnt_window[t])["flow"][0] for t in range(event_cnt_window.shape[0])])
 
 
 class LIFFireFlowNet(LIFFireNet):

@@ -300,3 +300,24 @@ def test_loader_numpy_restatement_matches_reference(name):
             assert np.array_equal(out["event_mask"], g[f"item{it}.event_mask"][b]), (name, it, b, "mask")
             assert np.array_equal(out["event_list"].T, g[f"item{it}.event_list"][b]), (name, it, b, "list")
             assert np.array_equal(out["event_list_pol_mask"].T, g[f"item{it}.event_list_pol_mask"][b]), (name, it, b, "pol")
+
+
+def test_snntorch_leaky_restatement_basics():
+    """oracle/snntorch_lif.py (PARITY UNPINNED restatement of snntorch 0.9.4's Leaky.forward): the properties its
+    docstring promises - clamp of beta, immediate reset without double reset, ATan(alpha=2) surrogate."""
+    import math
+    import torch
+    from oracle import snntorch_lif as osl
+    beta, thr = torch.tensor([[[1.7]], [[0.5]]]), torch.tensor([[[1.0]], [[1.0]]])
+    cur = torch.tensor([[[[0.4, 1.5]], [[0.4, 1.5]]]], requires_grad=True)       # [1,2,1,2]
+    mem = torch.tensor([[[[0.8, 0.8]], [[0.8, 0.8]]]])
+    spk, out = osl.leaky_step(cur, mem, beta, thr, "zero")
+    assert spk.tolist() == [[[[1.0, 1.0]], [[0.0, 1.0]]]]                         # channel 0: beta clamped to 1 -> 1.2 > 1
+    assert out[0, 0].tolist() == [[0.0, 0.0]] and abs(float(out[0, 1, 0, 0]) - 0.8) < 1e-6 and float(out[0, 1, 0, 1]) == 0.0
+    spk.sum().backward()
+    m = 0.5 * 0.8 + 0.4
+    assert abs(float(cur.grad[0, 1, 0, 0]) - 1 / (1 + (math.pi * (m - 1.0)) ** 2)) < 1e-6
+    # membrane entering above threshold, no new spike: the state function subtracts theta (reset = 1) and the "no double
+    # reset" correction do_reset = spk - reset = -1 adds it back (the published code, literally)
+    spk2, out2 = osl.leaky_step(cur.detach(), torch.full_like(mem, 1.5), beta, thr, "subtract")
+    assert abs(float(out2[0, 1, 0, 0]) - (0.5 * 1.5 + 0.4)) < 1e-6 and float(spk2[0, 1, 0, 0]) == 0.0
