@@ -364,6 +364,36 @@ int snnflow_dp_allreduce_ctas(void);
 int snnflow_dp_allreduce_sum(const void* peer_bufs, const void* peer_pads, float* out, unsigned int* counter, int rank, int world,
                              size_t n, snnflow_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The whole parameter update of a (data-parallel) step as ONE kernel per rank: gradient SUM over the ranks through NVLink
+ * peer memory + clip_grad_norm_ + Adam (train_flow.py:262-271 behind the exchange of SURVEY.md section 8e).  The peers'
+ * gradients are read once, the reduced gradient never goes back to memory, and there is ONE cross-rank barrier per step:
+ * the symmetric buffers hold two slots that alternate with the launch parity (a device-side counter, so the launch replays
+ * from a CUDA graph), which makes the trailing "everybody has finished reading" barrier of snnflow_dp_allreduce_sum
+ * unnecessary.  world == 1: the single-GPU optimizer step in one launch (no symmetric memory needed).
+ *   grad_local  this rank's flat gradient, n floats (plain device memory; staged into the symmetric slot by the kernel)
+ *   peer_bufs   device array of `world` pointers to the ranks' symmetric buffers, 2 * slot_floats floats each,
+ *               slot_floats >= n + snnflow_dp_clip_adam_ctas();  peer_pads, counter: as for snnflow_dp_allreduce_sum, with
+ *               counter holding snnflow_dp_clip_adam_ctas() words (do not share pads / counters between the two kernels)
+ *   params, exp_avg, exp_avg_sq, hyper, step, state, grad_norm, gate: as for snnflow_clip_adam; a raised gate on ANY rank
+ *               vetoes the update on all ranks (replicas stay identical);  partials: snnflow_dp_clip_adam_ctas() floats
+ *   grid_counter one uint32, zeroed once (grid barrier of the kernel's CTAs; the launch is cooperative)
+ *   reduced     NULL, or n floats that receive the summed gradient (tests)
+ * n <= snnflow_dp_clip_adam_max_n() (131072; LIFFireNet C = 32 has 74 818 parameters).
+ * --------------------------------------------------------------------------------------------- */
+int snnflow_dp_clip_adam_ctas(void);
+int64_t snnflow_dp_clip_adam_max_n(void);
+int snnflow_dp_clip_adam(const float* grad_local, const void* peer_bufs, const void* peer_pads, unsigned int* counter, int rank,
+                         int world, int64_t n, int64_t slot_floats, float* params, float* exp_avg, float* exp_avg_sq,
+                         const float* hyper, int64_t* step, double* state, float* partials, unsigned int* grid_counter,
+                         float* grad_norm, const unsigned int* gate, float* reduced, snnflow_stream_t stream);
+/* Test hook: the same kernel body with all `world` ranks emulated on ONE GPU by one cooperative launch (a single-GPU box
+ * cannot run ranks that wait for each other as separate launches).  rank_ptrs: device array [world][13] of the per-rank
+ * pointers of snnflow_dp_clip_adam in argument order (grad_local, counter, params, exp_avg, exp_avg_sq, hyper, step, state,
+ * partials, grid_counter, grad_norm, gate, reduced); peer_bufs / peer_pads: ordinary device allocations. */
+int snnflow_dp_clip_adam_emulated(const void* rank_ptrs, const void* peer_bufs, const void* peer_pads, int world, int64_t n,
+                                  int64_t slot_floats, snnflow_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

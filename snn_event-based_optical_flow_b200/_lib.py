@@ -43,6 +43,10 @@ _PROTOS = {
     "snnflow_clip_adam": (c_int, [P] * 4 + [c_int64] + [P] * 7),
     "snnflow_dp_allreduce_ctas": (c_int, []),
     "snnflow_dp_allreduce_sum": (c_int, [P, P, P, P, c_int, c_int, c_size_t, P]),
+    "snnflow_dp_clip_adam_ctas": (c_int, []),
+    "snnflow_dp_clip_adam_max_n": (c_int64, []),
+    "snnflow_dp_clip_adam": (c_int, [P, P, P, P, c_int, c_int, c_int64, c_int64] + [P] * 11 + [P]),
+    "snnflow_dp_clip_adam_emulated": (c_int, [P, P, P, c_int, c_int64, c_int64, P]),
     "snnflow_window_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int64, c_int, c_int]),
     "snnflow_window_loss": (c_int, [P] * 7 + [c_size_t, c_int, c_int, c_int64, c_int, c_int, c_float, c_float, c_int, P]),
     "snnflow_iwe_splat_bwd": (c_int, [P] * 5 + [c_int, c_int64, c_int, c_int, c_float, c_float, c_int, c_int, c_float,

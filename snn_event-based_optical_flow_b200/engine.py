@@ -222,76 +222,75 @@ def _desc_key(d):
     return (d.B, d.C, d.H, d.W, d.T, d.num_bins, d.recurrent_mask, d.flags, d.surrogate, d.act_width)
 
 
-class _LayerMajorWindowFn(torch.autograd.Function):
-    """The window on the layer-major engine (snnflow_window_forward / snnflow_window_backward, include/snnflow.h)."""
+def _lm_forward(runner, cnt, need_bwd):
+    """One window through snnflow_window_forward.  Returns (flow, saved) where `saved` is what _lm_backward needs."""
+    L = _lib.lib()
+    _bind(L)
+    net, layers = runner.net, runner.layers
+    T, B, nb, H, W = cnt.shape
+    dev = cnt.device
+    cnt = cnt.float().contiguous()
+    Cr = layers[0].hidden_size                 # the network's width ...
+    C = _lm_channels(Cr)                       # ... and the (zero-padded) width the engine runs it at
+    desc = _make_desc(runner, cnt, C)
+    lam, theta = _effective_params(runner, layers)
+    lam_e, theta_e = _pad_dim(lam, 1, C, 0.5), _pad_dim(theta, 1, C, 1.0)
+    w_e = []
+    for i, l in enumerate(layers):
+        wf = _pad_dim(l.ff.weight.detach(), 0, C)
+        if i > 0:
+            wf = _pad_dim(wf, 1, C)
+        wr = _pad_dim(_pad_dim(l.rec.weight.detach(), 0, C), 1, C) if l.recurrent else None
+        w_e.append((wf, wr))
+    lp = (LayerPtrs * N_LAYERS)()
+    for i, l in enumerate(layers):
+        lp[i].w_ff = w_e[i][0].data_ptr()
+        lp[i].w_rec = w_e[i][1].data_ptr() if l.recurrent else None
+        lp[i].lam = lam_e[i].data_ptr()
+        lp[i].theta = theta_e[i].data_ptr()
+    arena = runner.lm_arena(desc, need_bwd, dev)
+    flow = torch.empty((T, B, 2, H, W), dtype=torch.float32, device=dev)
+    _state_ptrs(net._states, (B, Cr, H, W), contiguous=C == Cr)   # shape check on the network's own states
+    states = runner.lm_states_in(net._states, Cr, C)
+    sp, keep = _state_ptrs(states, (B, C, H, W))
+    pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
+    pw_e = _pad_dim(pw.detach(), 1, C)
+    _lib.check(L.snnflow_window_forward(ctypes.byref(desc), lp, pw_e.data_ptr(), None if pb is None else pb.data_ptr(),
+                                        cnt.data_ptr(), sp, arena.data_ptr(), flow.data_ptr(), int(need_bwd),
+                                        _lib.stream()), "snnflow_window_forward")
+    # the arena's sticky "input was not bf16-exact" word (per arena, i.e. per runner and shape): polled here, and
+    # handed to the fused optimizer as its update gate (train.TrainWindow) so that graph replays cannot apply an
+    # update computed from rounded inputs before the host has looked
+    foff = L.snnflow_window_flags_offset(ctypes.byref(desc), int(need_bwd))
+    runner.input_flag = arena[foff:foff + 4].view(torch.int32)
+    runner._lm_calls = getattr(runner, "_lm_calls", 0) + 1
+    capturing = torch.cuda.is_current_stream_capturing()
+    if not capturing and (runner.validate_input or runner._lm_calls == 1 or runner._lm_calls % runner.validate_every == 0):
+        runner.check_input_flag()
+    offs = (ctypes.c_size_t * N_LAYERS)()
+    _lib.check(L.snnflow_window_state_offsets(ctypes.byref(desc), int(need_bwd), offs), "snnflow_window_state_offsets")
+    nbytes = 2 * B * C * H * W * 4
+    full = [arena[offs[i]:offs[i] + nbytes].view(torch.float32).view(2, B, C, H, W) for i in range(N_LAYERS)]
+    runner._lm_full_states = full
+    runner.new_states = full if C == Cr else [f[:, :, :Cr] for f in full]   # the network's channels of the padded state
+    saved = None
+    if need_bwd:
+        saved = dict(desc=desc, lam=lam, theta=theta, lam_e=lam_e, theta_e=theta_e, w_e=w_e, pw_e=pw_e, Cr=Cr, arena=arena,
+                     flow=flow, states_in=list(states))
+    return flow, saved
 
-    @staticmethod
-    def forward(ctx, runner, cnt, *params):
-        L = _lib.lib()
-        _bind(L)
-        net, layers = runner.net, runner.layers
-        T, B, nb, H, W = cnt.shape
-        dev = cnt.device
-        cnt = cnt.float().contiguous()
-        need_bwd = any(ctx.needs_input_grad)
-        Cr = layers[0].hidden_size                 # the network's width ...
-        C = _lm_channels(Cr)                       # ... and the (zero-padded) width the engine runs it at
-        desc = _make_desc(runner, cnt, C)
-        lam, theta = _effective_params(runner, layers)
-        lam_e, theta_e = _pad_dim(lam, 1, C, 0.5), _pad_dim(theta, 1, C, 1.0)
-        w_e = []
-        for i, l in enumerate(layers):
-            wf = _pad_dim(l.ff.weight.detach(), 0, C)
-            if i > 0:
-                wf = _pad_dim(wf, 1, C)
-            wr = _pad_dim(_pad_dim(l.rec.weight.detach(), 0, C), 1, C) if l.recurrent else None
-            w_e.append((wf, wr))
-        lp = (LayerPtrs * N_LAYERS)()
-        for i, l in enumerate(layers):
-            lp[i].w_ff = w_e[i][0].data_ptr()
-            lp[i].w_rec = w_e[i][1].data_ptr() if l.recurrent else None
-            lp[i].lam = lam_e[i].data_ptr()
-            lp[i].theta = theta_e[i].data_ptr()
-        arena = runner.lm_arena(desc, need_bwd, dev)
-        flow = torch.empty((T, B, 2, H, W), dtype=torch.float32, device=dev)
-        _state_ptrs(net._states, (B, Cr, H, W), contiguous=C == Cr)   # shape check on the network's own states
-        states = runner.lm_states_in(net._states, Cr, C)
-        sp, keep = _state_ptrs(states, (B, C, H, W))
-        pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
-        pw_e = _pad_dim(pw.detach(), 1, C)
-        _lib.check(L.snnflow_window_forward(ctypes.byref(desc), lp, pw_e.data_ptr(), None if pb is None else pb.data_ptr(),
-                                            cnt.data_ptr(), sp, arena.data_ptr(), flow.data_ptr(), int(need_bwd),
-                                            _lib.stream()), "snnflow_window_forward")
-        # the arena's sticky "input was not bf16-exact" word (per arena, i.e. per runner and shape): polled here, and
-        # handed to the fused optimizer as its update gate (train.TrainWindow) so that graph replays cannot apply an
-        # update computed from rounded inputs before the host has looked
-        foff = L.snnflow_window_flags_offset(ctypes.byref(desc), int(need_bwd))
-        runner.input_flag = arena[foff:foff + 4].view(torch.int32)
-        runner._lm_calls = getattr(runner, "_lm_calls", 0) + 1
-        capturing = torch.cuda.is_current_stream_capturing()
-        if not capturing and (runner.validate_input or runner._lm_calls == 1 or runner._lm_calls % runner.validate_every == 0):
-            runner.check_input_flag()
-        offs = (ctypes.c_size_t * N_LAYERS)()
-        _lib.check(L.snnflow_window_state_offsets(ctypes.byref(desc), int(need_bwd), offs), "snnflow_window_state_offsets")
-        nbytes = 2 * B * C * H * W * 4
-        full = [arena[offs[i]:offs[i] + nbytes].view(torch.float32).view(2, B, C, H, W) for i in range(N_LAYERS)]
-        runner._lm_full_states = full
-        runner.new_states = full if C == Cr else [f[:, :, :Cr] for f in full]   # the network's channels of the padded state
-        if need_bwd:
-            ctx.runner, ctx.desc, ctx.lam, ctx.theta = runner, desc, lam, theta
-            ctx.lam_e, ctx.theta_e, ctx.w_e, ctx.pw_e, ctx.Cr = lam_e, theta_e, w_e, pw_e, Cr
-            ctx.arena, ctx.flow, ctx.states_in = arena, flow, list(states)
-        return flow
 
-    @staticmethod
-    def backward(ctx, g_flow):
-        L = _lib.lib()
-        runner, desc, lam, theta = ctx.runner, ctx.desc, ctx.lam, ctx.theta
-        layers, net = runner.layers, runner.net
-        dev = g_flow.device
-        g_flow = g_flow.float().contiguous()
-        Cr, C = ctx.Cr, desc.C
-        lam_e, theta_e, w_e, pw_e = ctx.lam_e, ctx.theta_e, ctx.w_e, ctx.pw_e
+def _lm_backward(runner, saved, g_flow, dst=None):
+    """snnflow_window_backward for a window run by _lm_forward(..., need_bwd=True).
+    dst None: returns [(dw_ff, dw_rec)] x 7, dlam [7,C], dtheta [7,C], d_pred_w, d_pred_b as slices of ONE fresh zero-filled
+    buffer.  dst = dict(dw=[(ff, rec)], dlam, dtheta, d_pw, d_pb) of caller-owned ZEROED tensors (un-padded width only):
+    the kernels accumulate straight into them (the direct training step: slices of the optimizer's flat gradient)."""
+    L = _lib.lib()
+    desc, layers, net = saved["desc"], runner.layers, runner.net
+    dev = g_flow.device
+    g_flow = g_flow.float().contiguous()
+    lam_e, theta_e, w_e, pw_e = saved["lam_e"], saved["theta_e"], saved["w_e"], saved["pw_e"]
+    if dst is None:
         # every gradient of the window is a slice of ONE zero-filled buffer (one fill instead of one per tensor)
         shapes = [lam_e.shape, theta_e.shape]
         for i, l in enumerate(layers):
@@ -308,26 +307,48 @@ class _LayerMajorWindowFn(torch.autograd.Function):
         carved = iter(carved)
         dlam, dtheta = next(carved), next(carved)
         dws = []
-        lp = (LayerPtrs * N_LAYERS)()
         for i, l in enumerate(layers):
             dwf = next(carved)
-            dwr = next(carved) if l.recurrent else None
-            dws.append((dwf, dwr))
-            lp[i].w_ff = w_e[i][0].data_ptr()
-            lp[i].w_rec = w_e[i][1].data_ptr() if l.recurrent else None
-            lp[i].lam = lam_e[i].data_ptr()
-            lp[i].theta = theta_e[i].data_ptr()
-            lp[i].dw_ff = dwf.data_ptr()
-            lp[i].dw_rec = None if dwr is None else dwr.data_ptr()
-            lp[i].dlam = dlam[i].data_ptr()
-            lp[i].dtheta = dtheta[i].data_ptr()
-        pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
+            dws.append((dwf, next(carved) if l.recurrent else None))
         d_pw, d_pb = next(carved), next(carved)
-        ws = runner.lm_workspace(desc, dev)
-        sp, keep = _state_ptrs(ctx.states_in)
-        _lib.check(L.snnflow_window_backward(ctypes.byref(desc), lp, pw_e.data_ptr(), sp, ctx.arena.data_ptr(),
-                                             ctx.flow.data_ptr(), g_flow.data_ptr(), d_pw.data_ptr(), d_pb.data_ptr(),
-                                             ws.data_ptr(), ws.numel(), _lib.stream()), "snnflow_window_backward")
+    else:
+        dws, dlam, dtheta, d_pw, d_pb = dst["dw"], dst["dlam"], dst["dtheta"], dst["d_pw"], dst["d_pb"]
+    lp = (LayerPtrs * N_LAYERS)()
+    for i, l in enumerate(layers):
+        lp[i].w_ff = w_e[i][0].data_ptr()
+        lp[i].w_rec = w_e[i][1].data_ptr() if l.recurrent else None
+        lp[i].lam = lam_e[i].data_ptr()
+        lp[i].theta = theta_e[i].data_ptr()
+        lp[i].dw_ff = dws[i][0].data_ptr()
+        lp[i].dw_rec = None if dws[i][1] is None else dws[i][1].data_ptr()
+        lp[i].dlam = dlam[i].data_ptr()
+        lp[i].dtheta = dtheta[i].data_ptr()
+    ws = runner.lm_workspace(desc, dev)
+    sp, keep = _state_ptrs(saved["states_in"])
+    _lib.check(L.snnflow_window_backward(ctypes.byref(desc), lp, pw_e.data_ptr(), sp, saved["arena"].data_ptr(),
+                                         saved["flow"].data_ptr(), g_flow.data_ptr(), d_pw.data_ptr(), d_pb.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), _lib.stream()), "snnflow_window_backward")
+    return dws, dlam, dtheta, d_pw, d_pb
+
+
+class _LayerMajorWindowFn(torch.autograd.Function):
+    """The window on the layer-major engine (snnflow_window_forward / snnflow_window_backward, include/snnflow.h)."""
+
+    @staticmethod
+    def forward(ctx, runner, cnt, *params):
+        need_bwd = any(ctx.needs_input_grad)
+        flow, saved = _lm_forward(runner, cnt, need_bwd)
+        if need_bwd:
+            ctx.runner, ctx.saved = runner, saved
+        return flow
+
+    @staticmethod
+    def backward(ctx, g_flow):
+        runner, saved = ctx.runner, ctx.saved
+        layers, net = runner.layers, runner.net
+        lam, theta, Cr, C = saved["lam"], saved["theta"], saved["Cr"], saved["desc"].C
+        dws, dlam, dtheta, d_pw, d_pb = _lm_backward(runner, saved, g_flow)
+        pb = net.pred.conv2d.bias
         if C != Cr:   # drop the padded neurons (their gradients are exactly zero)
             dlam, dtheta, d_pw = dlam[:, :Cr], dtheta[:, :Cr], d_pw[:, :Cr].contiguous()
             dws = [(f[:Cr, :(l.ff.weight.shape[1])].contiguous(), None if r is None else r[:Cr, :Cr].contiguous())
@@ -443,6 +464,46 @@ class WindowRunner:
             buf = torch.zeros(n, dtype=torch.uint8, device=dev)
             self._lm[key] = buf
         return buf
+
+    # ---- direct (autograd-free) training interface: train.TrainWindow.step_direct ------------------------------------
+    def direct_ok(self, cnt_window, optimizer):
+        """The direct training step covers: layer-major engine, un-padded width, every parameter trainable and managed by
+        a FusedClipAdam whose flat gradient buffer receives the kernels' output."""
+        layers = self.layers
+        if not (self.supported() and self.engine != "per_step" and getattr(self.net, "encoding", "cnt") == "cnt"):
+            return False
+        if _lm_channels(layers[0].hidden_size) != layers[0].hidden_size or not hasattr(optimizer, "grad_view"):
+            return False
+        ps = [p for l in layers for p in ((l.ff.weight, l.rec.weight, l.leak, l.thresh) if l.recurrent else (l.ff.weight, l.leak, l.thresh))]
+        ps += [self.net.pred.conv2d.weight, self.net.pred.conv2d.bias]
+        managed = {id(p) for p in optimizer.params}
+        if any(p is None or not isinstance(p, torch.nn.Parameter) or id(p) not in managed for p in ps) or len(managed) != len(ps):
+            return False
+        return self.layer_major_ok(cnt_window, True)
+
+    def direct_forward(self, cnt_window):
+        flow, self._direct_saved = _lm_forward(self, cnt_window, True)
+        self.net._states = self.new_states
+        return flow
+
+    def direct_backward(self, g_flow, optimizer):
+        """BPTT of the window run by direct_forward(): every parameter gradient is accumulated by the kernels straight into
+        its slice of ``optimizer.grad`` (zeroed here); d leak / d thresh go through the sigmoid / clamp_min chain rule."""
+        saved, layers, net = self._direct_saved, self.layers, self.net
+        self._direct_saved = None
+        lam, C = saved["lam"], saved["desc"].C
+        optimizer.grad.zero_()
+        tmp = torch.zeros((2, N_LAYERS, C), dtype=torch.float32, device=g_flow.device)
+        dst = dict(dw=[(optimizer.grad_view(l.ff.weight), optimizer.grad_view(l.rec.weight) if l.recurrent else None) for l in layers],
+                   dlam=tmp[0], dtheta=tmp[1], d_pw=optimizer.grad_view(net.pred.conv2d.weight),
+                   d_pb=optimizer.grad_view(net.pred.conv2d.bias))
+        _lm_backward(self, saved, g_flow, dst)
+        thr = torch.stack([l.thresh.detach().reshape(-1) for l in layers])
+        d_leak = tmp[0] * lam * (1.0 - lam)                                         # sigmoid'
+        d_thresh = tmp[1] * (thr >= 0.01).float()                                   # clamp_min'
+        torch._foreach_copy_([optimizer.grad_view(l.leak) for l in layers] + [optimizer.grad_view(l.thresh) for l in layers],
+                             [d_leak[i].view_as(l.leak) for i, l in enumerate(layers)] +
+                             [d_thresh[i].view_as(l.thresh) for i, l in enumerate(layers)])
 
     def __call__(self, cnt_window):
         """cnt_window [T,B,num_bins,H,W] -> flow [T,B,2,H,W]; updates net._states like T forward calls would."""

@@ -70,6 +70,24 @@ class EventWarping(torch.nn.Module):
             raise _lib.SnnflowError("snnflow EventWarping.window_loss runs on CUDA tensors only (no CPU fallback)")
         return _WindowLoss.apply(flows, event_list, pol_mask, event_mask, self)
 
+    def window_loss_and_grad(self, flows, event_list, pol_mask, event_mask=None):
+        """window_loss() without autograd: returns (loss [scalar tensor], d loss / d flows [T,B,2,H,W]) - one C call.
+        Used by the direct training step (train.TrainWindow.step_direct)."""
+        if not flows.is_cuda:
+            raise _lib.SnnflowError("snnflow EventWarping.window_loss runs on CUDA tensors only (no CPU fallback)")
+        L = _lib.lib()
+        flow, events, pol = _f32c(flows.detach()), _f32c(event_list), _f32c(pol_mask)
+        T, B, N = events.shape[0], events.shape[1], events.shape[2]
+        H, W = flow.shape[-2], flow.shape[-1]
+        mask = _f32c(event_mask) if (self.smoothing_mask and event_mask is not None) else None
+        ws = self._workspace(L.snnflow_window_loss_workspace_bytes(T, B, N, H, W), flow.device)
+        loss = torch.empty(1, dtype=torch.float32, device=flow.device)
+        g_flow = torch.empty_like(flow)
+        _lib.check(L.snnflow_window_loss(_lib.ptr(flow), _lib.ptr(events), _lib.ptr(pol), _lib.ptr(mask), _lib.ptr(loss),
+                                         _lib.ptr(g_flow), ws.data_ptr(), ws.numel(), T, B, N, H, W, float(self.flow_scaling),
+                                         float(self.weight), int(bool(self.loss_scaling)), _lib.stream()), "snnflow_window_loss")
+        return loss.reshape(()), g_flow
+
     def reset(self):
         self._passes = 0
         self._event_list = None

@@ -44,6 +44,14 @@ class FusedClipAdam:
         self.partials = torch.zeros(_lib.lib().snnflow_clip_adam_partials(n), dtype=torch.float32, device=dev)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)   # total norm of the last step (before clipping)
         self.param_groups = [{"params": self.params, "lr": lr, "betas": betas, "eps": eps}]
+        # one-launch update (snnflow_dp_clip_adam): per-CTA launch counters, norm partials, grid-barrier counter
+        L = _lib.lib()
+        self._one_launch_ok = n <= int(L.snnflow_dp_clip_adam_max_n())
+        ctas = int(L.snnflow_dp_clip_adam_ctas())
+        self._dp_counter = torch.zeros(ctas, dtype=torch.int32, device=dev)
+        self._dp_partials = torch.zeros(ctas, dtype=torch.float32, device=dev)
+        self._dp_gridcnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._peers = None
 
     def set_lr(self, lr):
         self.hyper[0] = lr
@@ -69,6 +77,49 @@ class FusedClipAdam:
         # the kernel wrote the parameters behind autograd's back: bump their version counters so that anything keyed on
         # them (the cells' packed-weight cache, spiking_submodules.py) sees the update
         torch.autograd.graph.increment_version(self.params)
+
+    # ---- the whole update as ONE launch, optionally with the data-parallel gradient SUM in front -----------------------
+    def attach_peers(self, group=None):
+        """Data parallel: allocate this rank's symmetric gradient buffer (two slots, torch symmetric memory over NVLink)
+        and exchange the peers' addresses.  Afterwards step_flat() sums the flat gradient over the ranks of `group` inside
+        the same launch that clips and applies Adam."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        ctas = int(_lib.lib().snnflow_dp_clip_adam_ctas())
+        slot = (self.n + ctas + 63) // 64 * 64
+        dev = self.flat.device
+        sym = symm_mem.empty(2 * slot, dtype=torch.float32, device=dev)
+        hdl = symm_mem.rendezvous(sym, group)
+        sym.zero_()
+        self._peers = {"sym": sym, "hdl": hdl, "slot": slot, "rank": dist.get_rank(group), "world": dist.get_world_size(group),
+                       "bufs": torch.tensor([int(x) for x in hdl.buffer_ptrs], dtype=torch.int64, device=dev),
+                       "pads": torch.tensor([int(x) for x in hdl.signal_pad_ptrs], dtype=torch.int64, device=dev)}
+        hdl.barrier()
+        return self
+
+    @torch.no_grad()
+    def step_flat(self, gate=None, reduced=None):
+        """Clip + Adam on the flat gradient buffer ``self.grad`` (filled directly by the caller, e.g. the window engine's
+        backward) in ONE kernel launch (snnflow_dp_clip_adam); with attach_peers() the gradient is first summed over the
+        ranks inside the same launch.  ``reduced``: optional flat tensor that receives the (summed) gradient."""
+        L = _lib
+        pr = self._peers
+        L.check(L.lib().snnflow_dp_clip_adam(
+            self.grad.data_ptr(), None if pr is None else pr["bufs"].data_ptr(), None if pr is None else pr["pads"].data_ptr(),
+            self._dp_counter.data_ptr(), 0 if pr is None else pr["rank"], 1 if pr is None else pr["world"], self.n,
+            0 if pr is None else pr["slot"], self.flat.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+            self.hyper.data_ptr(), self.step_count.data_ptr(), self.bias_state.data_ptr(), self._dp_partials.data_ptr(),
+            self._dp_gridcnt.data_ptr(), self.grad_norm.data_ptr(), None if gate is None else gate.data_ptr(),
+            None if reduced is None else reduced.data_ptr(), L.stream()), "snnflow_dp_clip_adam")
+        torch.autograd.graph.increment_version(self.params)
+
+    def grad_view(self, param):
+        """The slice of the flat gradient buffer that belongs to `param` (shaped like it)."""
+        for p, v in zip(self.params, self.grad_views):
+            if p is param:
+                return v
+        raise KeyError("parameter is not managed by this optimizer")
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:

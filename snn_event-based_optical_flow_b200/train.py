@@ -114,6 +114,15 @@ class TrainWindow:
                 import warnings
                 warnings.warn(f"peer-memory all-reduce unavailable ({e}); using the NCCL all-reduce")
         self._graph = None
+        self._direct_cache = {}
+        self._peer_direct = False
+        if peer_allreduce and isinstance(self.reducer, PeerGradAllReduce) and hasattr(optimizer, "attach_peers"):
+            try:   # the direct step sums the gradient inside the optimizer's own launch (optim.FusedClipAdam.step_flat)
+                optimizer.attach_peers(group)
+                self._peer_direct = True
+            except Exception as e:  # noqa: BLE001
+                import warnings
+                warnings.warn(f"one-launch data-parallel update unavailable ({e}); using the all-reduce kernel + fused Adam")
         self._params = [p for p in model.parameters()]
         self.fused_loss = True   # False: per-bin event_flow_association + EventWarping.forward (the reference's call pattern)
 
@@ -152,9 +161,47 @@ class TrainWindow:
         self.loss_fn.reset()
 
     def step(self, batch, use_window=True):
+        if use_window and self.direct_ok(batch):
+            return self.step_direct(batch)
         loss = self._forward_backward(batch, use_window)
         self.reducer()
         self._update()
+        return loss
+
+    # ---- the direct step: no autograd, no gradient copies, one launch for all-reduce + clip + Adam ---------------------
+    direct = True   # False: always go through torch.autograd (p.grad is populated, any optimizer works)
+
+    def direct_ok(self, batch):
+        """The direct step needs: the layer-major window engine at the network's own width, the fused window loss, a
+        FusedClipAdam over exactly the network's parameters and - data parallel - the peer-memory exchange."""
+        if not self.direct or not self.fused_loss or not getattr(self.opt, "fused_clip", False) or not getattr(self.opt, "_one_launch_ok", False):
+            return False
+        if not hasattr(self.model, "forward_window") or not hasattr(self.loss_fn, "window_loss_and_grad") or not torch.is_grad_enabled():
+            return False
+        if self.reducer.active() and not self._peer_direct:
+            return False
+        from .engine import WindowRunner
+        r = self._runner()
+        if r is None:
+            r = WindowRunner(self.model)
+            object.__setattr__(self.model, "_window_runner", r)
+        key = tuple(batch["event_cnt"].shape)
+        ok = self._direct_cache.get(key)
+        if ok is None:
+            ok = self._direct_cache[key] = bool(r.direct_ok(batch["event_cnt"], self.opt))
+        return ok
+
+    def step_direct(self, batch):
+        """train_flow.py:232-279 as a fixed sequence of C calls: window forward (T bins), fused contrast loss with its flow
+        gradient, window BPTT writing every parameter gradient into the optimizer's flat buffer, then ONE kernel that sums
+        the gradient over the ranks (peer memory), clips and applies Adam.  p.grad is not populated."""
+        r = self._runner()
+        flows = r.direct_forward(batch["event_cnt"])
+        loss, g_flow = self.loss_fn.window_loss_and_grad(flows, batch["event_list"], batch["event_list_pol_mask"], batch["event_mask"])
+        r.direct_backward(g_flow, self.opt)
+        self.opt.step_flat(gate=r.input_flag)
+        self.model.detach_states()
+        self.loss_fn.reset()
         return loss
 
     # ---- whole-step CUDA graph -----------------------------------------------------------------------------

@@ -89,6 +89,41 @@ for peer in (True, False):
         ok = False
         print(f"rank {rank} [{name}]: replicas diverged after one step")
     print(f"rank {rank}: {name}: sharded step == global-batch step: {'OK' if ok else 'FAILED'}")
+# the direct step: gradients straight into the flat buffer, SUM over the ranks + clip + Adam in ONE launch (two-slot
+# symmetric buffer, one flag barrier per step): three consecutive steps against the single-process global-batch run
+ref_net2 = make_net()
+ref2 = train.TrainWindow(ref_net2, snnflow.EventWarping(cfg, dev), snnflow.FusedClipAdam(ref_net2.parameters(), lr=1e-3, max_norm=1.0),
+                         clip_grad=1.0)
+ref2.reducer = type("NoReduce", (), {"__call__": lambda self, grads=None: None, "active": lambda self: False})()
+net2 = make_net()
+opt2 = snnflow.FusedClipAdam(net2.parameters(), lr=1e-3, max_norm=1.0)
+tw2 = train.TrainWindow(net2, snnflow.EventWarping(cfg, dev), opt2, clip_grad=1.0, peer_allreduce=True)
+direct_ok = True
+for step in range(3):
+    w = synth_window(T, B, N, H, W, seed=90 + step)
+    glob2 = {k: v.to(dev) for k, v in w.items()}
+    shard2 = {k: v[:, rank * Bl:(rank + 1) * Bl].contiguous().to(dev) for k, v in w.items()}
+    assert ref2.direct_ok(glob2) and tw2.direct_ok(shard2), "direct step not available"
+    ref2.step(glob2)
+    tw2.step(shard2)
+    if step == 0:
+        if abs(float(opt2.grad_norm) - float(ref2.opt.grad_norm)) > 1e-5 * float(ref2.opt.grad_norm):
+            direct_ok = False
+            print(f"rank {rank} [direct]: norm {float(opt2.grad_norm)} vs {float(ref2.opt.grad_norm)}")
+        for (n, p), q in zip(net2.named_parameters(), ref_net2.parameters()):
+            d = (p.detach() - q.detach()).abs()
+            if float(d.max()) > 2.05e-3 or float((d <= 2e-5).float().mean()) < 0.99:
+                direct_ok = False
+                print(f"rank {rank} [direct]: updated {n} differs: max {float(d.max()):.3e}")
+    flat = torch.cat([p.detach().reshape(-1) for p in net2.parameters()])
+    lo, hi = flat.clone(), flat.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if not torch.equal(lo, hi):
+        direct_ok = False
+        print(f"rank {rank} [direct]: replicas diverged after step {step}")
+print(f"rank {rank}: one-launch DP update: sharded step == global-batch step: {'OK' if direct_ok else 'FAILED'}")
+ok = ok and direct_ok
 torch.cuda.synchronize()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -51,3 +51,4 @@ def test_peer_allreduce_kernel_matches_nccl():
 def test_sharded_step_equals_global_batch_step():
     out = _torchrun("_dp_train_check.py", _world())
     assert "FAILED" not in out and out.count("PeerGradAllReduce: sharded step == global-batch step: OK") == _world()
+    assert out.count("one-launch DP update: sharded step == global-batch step: OK") == _world()

@@ -295,3 +295,114 @@ def test_fused_adam_state_dict_is_torch_adams():
     for pa, pb_, pc in zip(a.parameters(), b.parameters(), c.parameters()):
         torch.testing.assert_close(pc, pa, rtol=1e-4, atol=1e-5)   # lr = 1: the step itself is O(1)
         torch.testing.assert_close(pb_, pa, rtol=1e-4, atol=1e-5)
+
+
+def test_direct_step_equals_autograd_step():
+    """TrainWindow.step_direct (C calls in sequence, gradients written straight into the optimizer's flat buffer, clip +
+    Adam in one launch) against the same step through torch.autograd + the two-launch FusedClipAdam."""
+    import snnflow_b200 as snnflow
+    TrainWindow = importlib.import_module("snn_event-based_optical_flow_b200.train").TrainWindow
+    T, B, N, H, W = 4, 2, 400, 32, 64
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": 0.001}, "model": {"mask_output": False}}
+    nets, tws = [], []
+    for direct in (False, True):
+        net = _small_net(C=32, seed=3)
+        tw = TrainWindow(net, snnflow.EventWarping(cfg, torch.device("cuda")),
+                         snnflow.FusedClipAdam(net.parameters(), lr=1e-3, max_norm=1.0), clip_grad=1.0)
+        tw.direct = direct
+        nets.append(net)
+        tws.append(tw)
+    for step in range(3):
+        batch = {k: v.cuda() for k, v in synth_window(T, B, N, H, W, 60 + step).items()}
+        la = tws[0].step({k: v.clone() for k, v in batch.items()})
+        assert tws[1].direct_ok(batch)
+        lb = tws[1].step({k: v.clone() for k, v in batch.items()})
+        np.testing.assert_allclose(float(lb), float(la), rtol=1e-6 if step == 0 else 2e-2)
+        if step == 0:
+            np.testing.assert_allclose(float(tws[1].opt.grad_norm), float(tws[0].opt.grad_norm), rtol=1e-5)
+            for (n, p), q in zip(nets[0].named_parameters(), nets[1].parameters()):
+                d = (p.detach() - q.detach()).abs()   # same gradients up to the fp32 atomics of the loss scatter; Adam's first
+                # step is lr * g / (|g| + eps): an element whose gradient is ~eps in size may move differently
+                assert float(d.max()) <= 2.05e-3 and float((d <= 2e-6).float().mean()) >= 0.99, (n, float(d.max()))
+    assert all(p.grad is None for p in nets[1].parameters())
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_one_launch_dp_update_emulated_ranks(world):
+    """snnflow_dp_clip_adam - stage, ONE cross-rank flag barrier, rank-ordered SUM, clip, Adam in one kernel, two-slot
+    symmetric buffers - with all `world` ranks emulated on ONE GPU by a cooperative launch (the same kernel body;
+    snnflow_dp_clip_adam_emulated), four consecutive steps (both slots, flag epochs), against torch on the CPU: sum of the
+    ranks' gradients, clip_grad_norm_, Adam.  One rank raises its gate at step 2: every rank must skip that update."""
+    import ctypes
+    from snnflow_b200 import _lib
+    L = _lib.lib()
+    ctas = int(L.snnflow_dp_clip_adam_ctas())
+    if world * ctas > torch.cuda.get_device_properties(0).multi_processor_count:
+        pytest.skip("not enough SMs to emulate this many ranks")
+    n = 74818
+    slot = (n + ctas + 63) // 64 * 64
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(5)
+    p0 = torch.randn(n, generator=g)
+    hyper = torch.tensor([1e-2, 0.9, 0.999, 1e-8, 1.0])
+    ranks = []
+    for r in range(world):
+        ranks.append(dict(grad=torch.zeros(n, device=dev), counter=torch.zeros(ctas, dtype=torch.int32, device=dev),
+                          p=p0.clone().to(dev), m=torch.zeros(n, device=dev), v=torch.zeros(n, device=dev), hyper=hyper.to(dev),
+                          step=torch.zeros(1, dtype=torch.int64, device=dev), state=torch.zeros(4, dtype=torch.float64, device=dev),
+                          partials=torch.zeros(ctas, device=dev), gridcnt=torch.zeros(1, dtype=torch.int32, device=dev),
+                          norm=torch.zeros(1, device=dev), gate=torch.zeros(1, dtype=torch.int32, device=dev),
+                          reduced=torch.zeros(n, device=dev)))
+    order = ("grad", "counter", "p", "m", "v", "hyper", "step", "state", "partials", "gridcnt", "norm", "gate", "reduced")
+    ptrs = torch.tensor([[rk[k].data_ptr() for k in order] for rk in ranks], dtype=torch.int64, device=dev)
+    syms = [torch.zeros(2 * slot, device=dev) for _ in range(world)]
+    pads = [torch.zeros(1024, dtype=torch.int32, device=dev) for _ in range(world)]
+    bufs_t = torch.tensor([s.data_ptr() for s in syms], dtype=torch.int64, device=dev)
+    pads_t = torch.tensor([s.data_ptr() for s in pads], dtype=torch.int64, device=dev)
+    ref_p = p0.clone().requires_grad_(True)
+    ref_opt = torch.optim.Adam([ref_p], lr=1e-2)
+    for step in range(4):
+        grads = [torch.randn(n, generator=g) * (0.01 if step == 3 else 1.0) for _ in range(world)]
+        for rk, gr in zip(ranks, grads):
+            rk["grad"].copy_(gr)
+        veto = step == 2
+        ranks[world - 1]["gate"].fill_(1 if veto else 0)
+        _lib.check(L.snnflow_dp_clip_adam_emulated(ptrs.data_ptr(), bufs_t.data_ptr(), pads_t.data_ptr(), world, n, slot,
+                                                   _lib.stream()), "snnflow_dp_clip_adam_emulated")
+        torch.cuda.synchronize()
+        total = torch.zeros(n)
+        for gr in grads:           # rank order, fp32: the kernel's order
+            total = total + gr
+        for rk in ranks:
+            assert torch.equal(rk["reduced"].cpu(), total), "rank-ordered sum is not bit-identical"
+        if not veto:
+            ref_p.grad = total.clone()
+            norm = torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+            ref_opt.step()
+        for rk in ranks:
+            if not veto:
+                np.testing.assert_allclose(float(rk["norm"]), float(norm), rtol=1e-5)
+            np.testing.assert_allclose(rk["p"].cpu().numpy(), ref_p.detach().numpy(), rtol=0, atol=2e-6)
+            assert torch.equal(rk["p"], ranks[0]["p"]), "replicas diverged"
+        assert int(ranks[0]["step"]) == (step + 1 if step < 2 else step)
+
+
+def test_one_launch_update_single_gpu_matches_two_launch_update():
+    import snnflow_b200 as snnflow
+    torch.manual_seed(2)
+    a = torch.nn.Sequential(torch.nn.Conv2d(2, 8, 3), torch.nn.Conv2d(8, 2, 1)).cuda()
+    b = copy.deepcopy(a)
+    oa = snnflow.FusedClipAdam(a.parameters(), lr=3e-3, max_norm=0.5)
+    ob = snnflow.FusedClipAdam(b.parameters(), lr=3e-3, max_norm=0.5)
+    x = torch.randn(2, 2, 8, 8, device="cuda")
+    for _ in range(3):
+        oa.zero_grad()
+        a(x).square().sum().backward()
+        oa.step()
+        ob.zero_grad()
+        b(x).square().sum().backward()
+        torch._foreach_copy_(ob.grad_views, [p.grad for p in ob.params])
+        ob.step_flat()
+        np.testing.assert_allclose(float(ob.grad_norm), float(oa.grad_norm), rtol=1e-5)
+    for pa, pb_ in zip(a.parameters(), b.parameters()):
+        torch.testing.assert_close(pb_, pa, rtol=1e-5, atol=1e-7)
