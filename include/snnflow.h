@@ -42,6 +42,7 @@ extern "C" {
 #define SNNFLOW_SG_ARCTAN 0     /* 1/(1+w*u^2)      spiking_util.py:92 */
 #define SNNFLOW_SG_SUPERSPIKE 1 /* 1/(1+w*|u|)^2    spiking_util.py:42 */
 #define SNNFLOW_SG_TRIANGLE 2   /* relu(1-w*|u|)    spiking_util.py:78 */
+#define SNNFLOW_SG_MULTIGAUSS 3 /* 1.15 G(u;0,w) - 0.15 G(u;w,6w) - 0.15 G(u;-w,6w)   spiking_util.py:46-65 (per-step engine only) */
 
 typedef void* snnflow_stream_t; /* cudaStream_t */
 

@@ -17,17 +17,25 @@ section 8(a3) that the CUDA backward kernel implements.
 import torch
 import torch.nn.functional as F
 
-SURROGATES = ("arctanspike", "superspike", "trianglespike")
+SURROGATES = ("arctanspike", "superspike", "trianglespike", "mgspike")
+
+
+def _gaussian(x, mu, sigma):
+    """spiking_util.py:6-10."""
+    import math
+    return torch.exp(-((x - mu) * (x - mu)) / (2 * sigma * sigma)) / (sigma * math.sqrt(2 * math.pi))
 
 
 def surrogate_grad(u, width, kind):
-    """d spike / d u for u = v' - theta.  spiking_util.py:42 (superspike), :78 (triangle), :92 (arctan)."""
+    """d spike / d u for u = v' - theta.  spiking_util.py:42 (superspike), :60-64 (multi-Gauss), :78 (triangle), :92 (arctan)."""
     if kind == "arctanspike":
         return 1 / (1 + width * u * u)
     if kind == "superspike":
         return 1 / (1 + width * u.abs()) ** 2
     if kind == "trianglespike":
         return F.relu(1 - width * u.abs())
+    if kind == "mgspike":                                    # spiking_util.py:56-64 (MultiGaussSpike)
+        return 1.15 * _gaussian(u, 0.0, width) - 0.15 * _gaussian(u, width, 6 * width) - 0.15 * _gaussian(u, -width, 6 * width)
     raise ValueError(kind)
 
 

@@ -428,6 +428,8 @@ def main(only=None):
                   hard_reset=True, activation="arctanspike", seed=12)
     layer_fixture(ref, "layer_rec_soft_triangle", recurrent=True, Cin=5, C=8, B=1, H=8, W=8, T=4,
                   hard_reset=False, activation="trianglespike", seed=13)
+    layer_fixture(ref, "layer_rec_hard_mgspike", recurrent=True, Cin=6, C=8, B=2, H=10, W=12, T=4,
+                  hard_reset=True, activation="mgspike", seed=19)
     layer_fixture(ref, "layer_rec_nodetach", recurrent=True, Cin=4, C=4, B=1, H=8, W=9, T=3,
                   hard_reset=True, activation="arctanspike", seed=14, detach=False)
     layer_fixture(ref, "layer_head_counts", recurrent=False, Cin=2, C=32, B=2, H=16, W=20, T=3,

@@ -10,7 +10,7 @@ HARD_RESET = 1
 DETACH_RESET = 2
 NO_TENSOR_CORES = 4
 INPUT_EXACT16 = 8
-SURROGATE_ID = {"arctanspike": 0, "superspike": 1, "trianglespike": 2}
+SURROGATE_ID = {"arctanspike": 0, "superspike": 1, "trianglespike": 2, "mgspike": 3}
 
 P = c_void_p
 _PROTOS = {

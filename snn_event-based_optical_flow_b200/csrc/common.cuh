@@ -168,8 +168,15 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
-// surrogate gradient d spike / d u  (models/spiking_util.py:42,78,92)
+// Gaussian pdf (models/spiking_util.py:6-10)
+__device__ __forceinline__ float gauss_pdf(float x, float mu, float sigma) {
+  const float d = x - mu;
+  return expf(-(d * d) / (2.0f * sigma * sigma)) / (sigma * 2.50662827463100050242f);   // sigma * sqrt(2 pi)
+}
+// surrogate gradient d spike / d u  (models/spiking_util.py:42,60-64,78,92)
 __device__ __forceinline__ float surrogate(float u, float width, int kind) {
+  if (kind == SNNFLOW_SG_MULTIGAUSS)   // MultiGaussSpike, Yin et al. 2021 (:60-64)
+    return 1.15f * gauss_pdf(u, 0.f, width) - 0.15f * gauss_pdf(u, width, 6.0f * width) - 0.15f * gauss_pdf(u, -width, 6.0f * width);
   if (kind == SNNFLOW_SG_ARCTAN) return 1.0f / (1.0f + width * u * u);
   if (kind == SNNFLOW_SG_SUPERSPIKE) {
     float d = 1.0f + width * fabsf(u);

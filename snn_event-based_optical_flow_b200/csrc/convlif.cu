@@ -456,7 +456,7 @@ extern "C" int snnflow_convlif_bwd(const float* x, const float* w_ff, const floa
   SNNFLOW_REQUIRE(x && w_ff && v_out && cur && lam && theta && g_v_in && workspace, "null pointer");
   SNNFLOW_REQUIRE((v_in == nullptr) == (z_in == nullptr), "v_in and z_in must both be given or both be NULL");
   SNNFLOW_REQUIRE(B > 0 && Cin > 0 && C > 0 && H > 0 && W > 0, "bad dims");
-  SNNFLOW_REQUIRE(surrogate >= 0 && surrogate <= 2, "unknown surrogate");
+  SNNFLOW_REQUIRE(surrogate >= 0 && surrogate <= 3, "unknown surrogate");
   const int recurrent = w_rec != nullptr;
   const int detach = (flags & SNNFLOW_DETACH_RESET) ? 1 : 0;
   SNNFLOW_REQUIRE(g_z_in || (!recurrent && detach), "g_z_in required for recurrent cells / non-detached reset");

@@ -49,8 +49,6 @@ class EventWarping(torch.nn.Module):
         self.weight = config["loss"]["flow_regul_weight"]
         self.smoothing_mask = config["model"].get("mask_output", False)
         self.overwrite_intermediate = config["loss"].get("overwrite_intermediate", False)
-        if self.overwrite_intermediate:
-            raise NotImplementedError("snnflow EventWarping: overwrite_intermediate=True is not covered")
         self.device = device
         self.reset()
 
@@ -60,6 +58,11 @@ class EventWarping(torch.nn.Module):
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             self._ws = ws
         return ws
+
+    @property
+    def fused_window_loss_ok(self):
+        """The one-call window loss covers the training configuration of the reference (per-bin flow association)."""
+        return not self.overwrite_intermediate
 
     def window_loss(self, flows, event_list, pol_mask, event_mask=None):
         """The loss of one window from its T flow maps and event lists at once - what T calls of
@@ -103,7 +106,19 @@ class EventWarping(torch.nn.Module):
 
     @property
     def event_mask(self):
-        return self._event_mask[:, -1:, :, :]
+        if self.overwrite_intermediate:
+            return self._event_mask                 # mask of the training window (loss/flow.py:170-175)
+        return self._event_mask[:, -1:, :, :]       # mask of the last forward pass
+
+    def overwrite_intermediate_flow(self, flow_list):
+        """loss/flow.py:123-153: every event of the window is re-associated with the FINAL flow estimate (one flow map per
+        scale instead of one per bin), and the event mask becomes the union over the window."""
+        self._flow_list, self._flow_maps_x, self._flow_maps_y = [], [], []
+        for flow in flow_list:
+            self._flow_maps_x.append(flow[:, 0:1])
+            self._flow_maps_y.append(flow[:, 1:2])
+            self._flow_list.append(gather_event_flow(flow, self._event_list, self.res))
+        self._event_mask = torch.sum(self._event_mask, dim=1, keepdim=True).clamp_(max=1)
 
     def event_flow_association(self, flow_list, event_list, pol_mask, event_mask):
         """loss/flow.py:58-121."""
@@ -152,13 +167,17 @@ class EventWarping(torch.nn.Module):
             charb(fx[:, :, 1:, :-1] - fx[:, :, :-1, 1:], fy[:, :, 1:, :-1] - fy[:, :, :-1, 1:]),
             charb(fx[:, :-1] - fx[:, 1:], fy[:, :-1] - fy[:, 1:]),
         ]
+        if self.overwrite_intermediate:
+            terms = terms[:4]
         if self.smoothing_mask:
             m = self._event_mask
             masks = [m[:, :, :, :-1] * m[:, :, :, 1:], m[:, :, :-1, :] * m[:, :, 1:, :],
                      m[:, :, :-1, :-1] * m[:, :, 1:, 1:], m[:, :, 1:, :-1] * m[:, :, :-1, 1:], m[:, :-1] * m[:, 1:]]
             terms = [a * b for a, b in zip(masks, terms)]
-        total = terms[0].sum() + terms[1].sum() + terms[2].sum() + terms[3].sum() + terms[4].sum()
-        return total / 5 / fx.shape[1]
+        total = terms[0].sum() + terms[1].sum() + terms[2].sum() + terms[3].sum()
+        if self.overwrite_intermediate:                       # loss/flow.py:289-295: no temporal term, four components
+            return total / 4 / fx.shape[1]
+        return (total + terms[4].sum()) / 5 / fx.shape[1]
 
     def forward(self):
         max_ts = self._passes

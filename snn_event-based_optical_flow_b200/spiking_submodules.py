@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from . import _lib
 
-_SUPPORTED_ACTIVATIONS = ("arctanspike", "superspike", "trianglespike")
+_SUPPORTED_ACTIVATIONS = ("arctanspike", "superspike", "trianglespike", "mgspike")   # mgspike: per-step engine only
 _workspaces = {}
 
 

@@ -130,7 +130,7 @@ class TrainWindow:
     def _forward_backward(self, batch, use_window=True):
         T = batch["event_cnt"].shape[0]
         flows = self.model.forward_window(batch["event_cnt"]) if (use_window and hasattr(self.model, "forward_window")) else None
-        if flows is not None and self.fused_loss and hasattr(self.loss_fn, "window_loss"):
+        if flows is not None and self.fused_loss and hasattr(self.loss_fn, "window_loss") and getattr(self.loss_fn, "fused_window_loss_ok", True):
             # the whole window's association + contrast loss + its gradient as one fused call (flow_loss.window_loss)
             loss = self.loss_fn.window_loss(flows, batch["event_list"], batch["event_list_pol_mask"], batch["event_mask"])
             loss.backward()
@@ -139,6 +139,8 @@ class TrainWindow:
             flow = flows[t] if flows is not None else self.model(None, batch["event_cnt"][t])["flow"][0]
             self.loss_fn.event_flow_association([flow], batch["event_list"][t], batch["event_list_pol_mask"][t],
                                                 batch["event_mask"][t])
+        if getattr(self.loss_fn, "overwrite_intermediate", False):       # train_flow.py:244-246
+            self.loss_fn.overwrite_intermediate_flow([flow])
         loss = self.loss_fn()
         loss.backward()
         return loss.detach()
@@ -174,7 +176,7 @@ class TrainWindow:
     def direct_ok(self, batch):
         """The direct step needs: the layer-major window engine at the network's own width, the fused window loss, a
         FusedClipAdam over exactly the network's parameters and - data parallel - the peer-memory exchange."""
-        if not self.direct or not self.fused_loss or not getattr(self.opt, "fused_clip", False) or not getattr(self.opt, "_one_launch_ok", False):
+        if not self.direct or not self.fused_loss or not getattr(self.loss_fn, "fused_window_loss_ok", True) or not getattr(self.opt, "fused_clip", False) or not getattr(self.opt, "_one_launch_ok", False):
             return False
         if not hasattr(self.model, "forward_window") or not hasattr(self.loss_fn, "window_loss_and_grad") or not torch.is_grad_enabled():
             return False

@@ -53,12 +53,16 @@ def test_product_never_imports_oracle():
 
 def test_unsupported_options_raise():
     import snnflow_b200 as snnflow
-    for kw in (dict(stride=2), dict(norm="weight"), dict(norm="group"), dict(activation="mgspike"),
+    for kw in (dict(stride=2), dict(norm="weight"), dict(norm="group"), dict(activation="no_such_spike"),
                dict(quantization_config={"enabled": True})):
         with pytest.raises(NotImplementedError):
             snnflow.ConvLIF(4, 4, 3, **kw)
     with pytest.raises(NotImplementedError):
         snnflow.ConvLIFRecurrent(4, 4, 5)
+    snnflow.ConvLIF(4, 4, 3, activation="mgspike")   # all four surrogates of models/spiking_util.py:96-109
+    for kw in (dict(tebn=True), dict(mpbn=True), dict(detach=False), dict(norm="group")):
+        with pytest.raises(NotImplementedError):
+            snnflow.SNNtorch_ConvLIF(4, 4, 3, **kw)
     # LIFFireNet passes quantization_config={} and these extra kwargs (models/model.py:71,83)
     snnflow.ConvLIF(4, 4, 3, quantization_config={}, exporting=False, tebn=False, num_timesteps=4, mpbn=False)
 

@@ -10,7 +10,7 @@ from snnflow_testutil import load_golden, spike_mismatch_outside_band
 pytestmark = pytest.mark.gpu
 
 LAYER_FIXTURES = ["layer_ff_hard_arctan", "layer_ff_soft_super_res", "layer_rec_hard_arctan",
-                  "layer_rec_soft_triangle", "layer_rec_nodetach", "layer_head_counts", "layer_ff_c32",
+                  "layer_rec_soft_triangle", "layer_rec_hard_mgspike", "layer_rec_nodetach", "layer_head_counts", "layer_ff_c32",
                   "layer_rec_c32", "layer_rec_c32_rand"]
 
 
@@ -202,6 +202,6 @@ def test_error_paths():
     with pytest.raises(NotImplementedError):
         snnflow.ConvLIF(2, 8, 5)
     with pytest.raises(NotImplementedError):
-        snnflow.ConvLIF(2, 8, 3, activation="mgspike")
+        snnflow.ConvLIF(2, 8, 3, activation="no_such_spike")
     with pytest.raises(_lib.SnnflowError):
         snnflow.ConvLIF(2, 8, 3)(torch.zeros(1, 2, 8, 8), None)

@@ -121,3 +121,33 @@ def test_reference_training_loop_on_cuda_cells():
         else:           # after an update the weights are off the dyadic grid: near-threshold spikes may flip
             np.testing.assert_allclose(float(ls_), float(lr_), rtol=2e-2)
     assert all(not s.requires_grad for s in seam._states)
+
+
+@pytest.mark.parametrize("mask_output", [False, True])
+def test_overwrite_intermediate_loss_matches_reference_class(mask_output):
+    """config loss.overwrite_intermediate (loss/flow.py:45-46,123-153,289-295; train_flow.py:244-246): the mirror's
+    EventWarping against the reference's own class run on the GPU, on the same flow maps - loss and d loss / d flow."""
+    import snnflow_b200 as snnflow
+    ref = ref_shim.load()
+    T, B, N, H, W = 3, 2, 300, 24, 32
+    w = synth_window(T, B, N, H, W, seed=13)
+    g = torch.Generator().manual_seed(14)
+    flows = (0.05 * torch.tanh(torch.randn(T, B, 2, H, W, generator=g))).cuda()
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": 0.01, "overwrite_intermediate": True},
+           "model": {"mask_output": mask_output}}
+    out = []
+    for cls in (ref.flow.EventWarping, snnflow.EventWarping):
+        f = flows.clone().requires_grad_(True)
+        lossf = cls(cfg, torch.device("cuda"))
+        for t in range(T):
+            lossf.event_flow_association([f[t]], w["event_list"][t].clone().cuda(), w["event_list_pol_mask"][t].cuda(),
+                                         w["event_mask"][t].cuda())
+        lossf.overwrite_intermediate_flow([f[T - 1]])
+        assert tuple(lossf.event_mask.shape) == (B, 1, H, W)
+        loss = lossf()
+        loss.backward()
+        out.append((float(loss), f.grad.clone()))
+    np.testing.assert_allclose(out[1][0], out[0][0], rtol=2e-5)
+    frac, rel = grad_report(out[1][1].cpu().numpy(), out[0][1].cpu().numpy(), rtol=1e-4, atol_rel=1e-5)
+    assert frac >= 0.99 and rel <= 3e-3, (frac, rel)
+    assert float(out[0][1][:T - 1].abs().max()) == 0.0 and float(out[1][1][:T - 1].abs().max()) == 0.0   # only the final flow matters

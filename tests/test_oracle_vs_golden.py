@@ -17,7 +17,7 @@ from snnflow_testutil import load_golden
 T = torch.from_numpy
 
 LAYER_FIXTURES = ["layer_ff_hard_arctan", "layer_ff_soft_super_res", "layer_rec_hard_arctan",
-                  "layer_rec_soft_triangle", "layer_rec_nodetach", "layer_head_counts", "layer_ff_c32",
+                  "layer_rec_soft_triangle", "layer_rec_hard_mgspike", "layer_rec_nodetach", "layer_head_counts", "layer_ff_c32",
                   "layer_rec_c32", "layer_rec_c32_rand"]
 
 
