@@ -67,6 +67,7 @@ static WinLayout win_layout(const snnflow_net_desc* d, int save) {
 
 struct WinPlan {   // tile plans of the tensor-core kernels for this shape
   int R_ff, S_ff, R_head, S_head, R_rec, S_rec, R_dg, S_dg, R_rb, S_rb, R_dp, S_dp;
+  uint32_t dp_aux_bytes;   // shared memory set aside for the staged epilogue inputs of the fused dgrad + pointwise kernel
   uint32_t sub_ff, cs_ff, st_ff, sub_head, cs_head, st_head, sub_rec, cs_rec, st_rec, sub_dg, cs_dg, st_dg, sub_rb, cs_rb, st_rb, sub_dp, cs_dp, st_dp;
   bool ok;
 };
@@ -105,8 +106,20 @@ static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool back
   P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), false, 2, true, &P.R_dg, &P.S_dg, &P.sub_dg,
                          &P.cs_dg, &P.st_dg);
   // data gradient fused with the time-fused pointwise chain of the layer below (state in registers: short tiles)
-  P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), true, 2, false, &P.R_dp, &P.S_dp, &P.sub_dp,
-                         &P.cs_dp, &P.st_dp, wt_env_int("SNNFLOW_DP_R", 0));
+  // ... whose epilogue input v[t-1] can be staged by the producer into a ring of three shared-memory buffers (one-row
+  // tiles only; SNNFLOW_DP_AUX=1).  Off by default: measured equal (3.012 vs 3.018 ms per step) - the producer's bulk copies
+  // are throttled by the memory system either way (66 KB per item and SM; 3x halo re-reads of one-row tiles from L2), so
+  // the epilogue's own global load was not the limiter (profiles/r2_experiments.md).
+  static const int dp_aux = wt_env_int("SNNFLOW_DP_AUX", 0);
+  P.dp_aux_bytes = dp_aux ? 3u * (uint32_t)align_up((size_t)(C / 8) * d->W * 32, 128) : 0u;
+  bool dp_ok = P.dp_aux_bytes && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2) + P.dp_aux_bytes, true, 2, false,
+                                         &P.R_dp, &P.S_dp, &P.sub_dp, &P.cs_dp, &P.st_dp, 1);
+  if (!dp_ok || P.S_dp < 3) {
+    P.dp_aux_bytes = 0;
+    dp_ok = wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2), true, 2, false, &P.R_dp, &P.S_dp, &P.sub_dp,
+                    &P.cs_dp, &P.st_dp, wt_env_int("SNNFLOW_DP_R", 0));
+  }
+  P.ok = P.ok && dp_ok;
   if (P.ok && P.R_dp * ceil_div(d->W, 128) > 2) P.ok = false;   // the fused kernel is instantiated for 1 or 2 segments per item
   return P;
 }
@@ -512,6 +525,10 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
         a.v_init = v_init_b; a.z_init = v_init_b ? v_init_b + n : nullptr;
         a.gp_out = gplanes[(l - 1) & 1]; a.gp_img_stride = L.zp_img_stride; a.gp_term_stride = WS.gp_term_stride;
         a.part = (float*)(Wk + WS.off_cpart[l - 1]);
+        if (P.dp_aux_bytes && P.R_dp == 1) {
+          a.aux = a.v_t; a.aux_chunk_bytes = (uint32_t)W * 32u;
+          a.aux_stage_bytes = P.dp_aux_bytes / 3u; a.aux_slots = 3;
+        }
         rc = launch_wt_dgpw(a, st, (double)T * px * (4.0 * C + 8.0 * L.Kin[l]) /* g_I hi + lo in ; v in, g_I hi + lo out */, 18.0 * T * px * C * L.Kin[l]);
         if (rc) return rc;
         n_cpart = WS.dp_grid; cpart_layout = 1;

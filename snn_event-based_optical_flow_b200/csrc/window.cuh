@@ -88,6 +88,13 @@ struct WtArgs {
   long long bin_v_stride;         // floats per bin for the membrane arena (v_out; v_prev of bin j is v_out of bin j-1)
   int bin_v_mask;                 // membrane slot of bin j = j & bin_v_mask (eval keeps two slots, training all bins)
   unsigned int* tile_flags;       // [n_outer * H / R] progress flags, zeroed by the launcher
+  // Epilogue inputs staged by the producer ("aux ring", sequence mode of wt_dgpw_kernel): the c8 row(s) of `aux` the epilogue
+  // of an item needs - v[t-1] of the tile - arrive by bulk copy in a ring of aux_slots buffers behind the operand stages, so
+  // the epilogue reads them from shared memory instead of waiting for a global load at the top of every item.
+  const float* aux;               // c8 tensor [T*B][N/8][H*W][8] or NULL (epilogue loads from global memory itself)
+  uint32_t aux_chunk_bytes;       // R * W * 32: one 8-channel chunk of a tile's rows
+  uint32_t aux_stage_bytes;       // (N/8) chunks, 128-byte aligned
+  int aux_slots;
   int exp;                        // experiment switches (SNNFLOW_EXP), 0 in production
   int l2_prefetch;                // epilogues issue prefetch.global.L2 for the next item's streamed inputs (set by the launcher)
   int has_gz, first_step, z_from_v;   // first_step: g_v starts at zero ; z_from_v: z_in = spike(v_in) else from z_init

@@ -41,12 +41,14 @@ struct WtSmem {
   uint32_t* tmem_slot;
   uint64_t* pub_bar;        // [WT_PUB_RING] "every epilogue thread has issued the stores of item g" (time-fused mode)
   volatile unsigned int* pub_count;   // items whose tile flag the publisher warp has raised
+  uint64_t *aux_full, *aux_empty;     // [4] ring of staged epilogue inputs (WtArgs.aux)
+  unsigned char* aux;
   float4* par;
   float* red;
   unsigned char *w, *stages;
 };
 
-__device__ __forceinline__ WtSmem wt_smem(unsigned char* smem, uint32_t wblob_bytes /* both blobs */) {
+__device__ __forceinline__ WtSmem wt_smem(unsigned char* smem, uint32_t wblob_bytes /* both blobs */, uint32_t stages_bytes = 0) {
   WtSmem s;
   s.full = reinterpret_cast<uint64_t*>(smem);
   s.empty = s.full + WT_MAX_STAGES;
@@ -60,6 +62,9 @@ __device__ __forceinline__ WtSmem wt_smem(unsigned char* smem, uint32_t wblob_by
   s.red = reinterpret_cast<float*>(smem + 1280);
   s.w = smem + WT_HDR;
   s.stages = s.w + ((wblob_bytes + 127u) & ~127u);
+  s.aux_full = reinterpret_cast<uint64_t*>(smem + 3200);
+  s.aux_empty = s.aux_full + 4;
+  s.aux = s.stages + stages_bytes + WT_TAIL;   // behind the operand stages and their read-past tail
   return s;
 }
 
@@ -148,6 +153,10 @@ __device__ __forceinline__ uint32_t wt_prologue(const WtArgs& a, const WtSmem& s
     }
     mbar_init(s.wbar, 1);
     for (int i = 0; i < WT_PUB_RING; ++i) mbar_init(&s.pub_bar[i], WT_EPI_WARPS * 32);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s.aux_full[i], 1);
+      mbar_init(&s.aux_empty[i], WT_EPI_WARPS * 32);
+    }
     *s.pub_count = 0u;
     fence_barrier_init();
   }
@@ -187,7 +196,7 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
     n_chunks[si] = Sr.n_chunks;
   }
   ItemIter<SEQ> it;
-  uint32_t st = 0, use = 0;
+  uint32_t st = 0, use = 0, as = 0, aux_use = 0;
   long long t_wait = 0, t_flag = 0;
   const long long t_begin = clock64();
   const int n_bins = (!SEQ && a.n_bins > 1) ? a.n_bins : 1, dep_mask = a.bin_dep_mask;
@@ -227,6 +236,23 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
                        sub_bytes, &s.full[st]);
         }
         if (++st == (uint32_t)S) { st = 0; ++use; }
+      }
+      if (SEQ && a.aux != nullptr) {
+        // the epilogue input of this item: v of the bin BEFORE the one being processed (bins walk backwards), tile rows
+        const int t = t_rev ? it.T - 1 - it.t : it.t;
+        if (t > 0) {
+          if (lane == 0) {
+            if (aux_use > 0) mbar_wait(&s.aux_empty[as], (aux_use - 1) & 1);
+            mbar_expect_tx(&s.aux_full[as], (uint32_t)(a.N >> 3) * a.aux_chunk_bytes);
+          }
+          __syncwarp();
+          if (lane < (a.N >> 3)) {
+            const size_t HWp = (size_t)a.H * a.W;
+            const float* src = a.aux + ((((size_t)((t - 1) * it.B + it.b) * (a.N >> 3) + lane) * HWp + (size_t)it.y0 * a.W) << 3);
+            tma_bulk_g2s(s.aux + (size_t)as * a.aux_stage_bytes + (size_t)lane * a.aux_chunk_bytes, src, a.aux_chunk_bytes, &s.aux_full[as]);
+          }
+          if (++as == (uint32_t)a.aux_slots) { as = 0; ++aux_use; }
+        }
       }
       it.next();
     }
@@ -374,7 +400,7 @@ __device__ __forceinline__ uint32_t nz8_mask(const uint4& a) {   // bit c set wh
 template <bool SEQ, int NSEG, bool HARD>
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const WtSmem s = wt_smem(smem, a.wblob_bytes + a.wblob2_bytes);
+  const WtSmem s = wt_smem(smem, a.wblob_bytes + a.wblob2_bytes, (uint32_t)a.S * a.stage_bytes);
   const uint32_t tmem_base = wt_prologue(a, s);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -670,7 +696,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
 // =================================================================================================
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgrad_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const WtSmem s = wt_smem(smem, a.wblob_bytes + a.wblob2_bytes);
+  const WtSmem s = wt_smem(smem, a.wblob_bytes + a.wblob2_bytes, (uint32_t)a.S * a.stage_bytes);
   const uint32_t tmem_base = wt_prologue(a, s);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == WT_EPI_WARPS) {
@@ -769,7 +795,7 @@ struct SegIter {
 template <int SG, bool HARD, int MODE>
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const WtSmem s = wt_smem(smem, a.wblob_bytes + a.wblob2_bytes);
+  const WtSmem s = wt_smem(smem, a.wblob_bytes + a.wblob2_bytes, (uint32_t)a.S * a.stage_bytes);
   const uint32_t tmem_base = wt_prologue(a, s);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == WT_EPI_WARPS) {
@@ -965,7 +991,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
 template <int SG, bool HARD, int NSEG>
 __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_constant__ WtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const WtSmem s = wt_smem(smem, a.wblob_bytes + a.wblob2_bytes);
+  const WtSmem s = wt_smem(smem, a.wblob_bytes + a.wblob2_bytes, (uint32_t)a.S * a.stage_bytes);
   const uint32_t tmem_base = wt_prologue(a, s);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == WT_EPI_WARPS) {
@@ -989,7 +1015,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
     const int n_items = wt_n_items<true>(a);
     const float width = a.width;
     const float* const v = a.v_t;          // membranes of layer l, all bins (c8)
-    const bool l2_pf = a.l2_prefetch != 0;
+    const bool use_aux = a.aux != nullptr;
+    const bool l2_pf = a.l2_prefetch != 0 && !use_aux;
+    uint32_t aux_slot = 0, aux_phase = 0;
     unsigned char* const gp_out = a.gp_out + (size_t)ch * plane_bytes;
     const size_t gp_img_stride = a.gp_img_stride, gp_term_stride = a.gp_term_stride;
     const float4* par = s.par + (act ? ch * 8 : 0);
@@ -1021,7 +1049,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
           // the membrane the NEXT item will ask for (v[t-2]) starts its way from DRAM to L2 now
           if (l2_pf && t > 1) prefetch_l2(v + c8_off(img - 2 * B, nch, ch, HW, pix));
           if (t > 0) {
-            ld8_c8(v + c8_off(img - B, nch, ch, HW, pix), vin[m]);
+            if (!use_aux) ld8_c8(v + c8_off(img - B, nch, ch, HW, pix), vin[m]);
           } else {
             const size_t o = ((size_t)(it.b * N + ch * 8)) * HW + pix;   // NCHW state tensors of the caller
 #pragma unroll
@@ -1034,6 +1062,24 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
       }
       mbar_wait(&s.acc_full[ab], (uint32_t)(k >> acc_lg) & 1u);
       tc_fence_after();
+      if (use_aux && t > 0) {   // v[t-1] of this tile was staged by the producer (all epilogue threads keep the ring in step)
+        mbar_wait(&s.aux_full[aux_slot], aux_phase);
+        if (act) {
+          const unsigned char* base = s.aux + (size_t)aux_slot * a.aux_stage_bytes + (size_t)ch * a.aux_chunk_bytes;
+#pragma unroll
+          for (int m = 0; m < NSEG; ++m) {
+            const int x = (m % n_seg) * 128 + q * 32 + lane;
+            if (x < W) {
+              const float4* p4 = reinterpret_cast<const float4*>(base + ((size_t)(m / n_seg) * W + x) * 32);
+              const float4 lo4 = p4[0], hi4 = p4[1];
+              vin[m][0] = lo4.x; vin[m][1] = lo4.y; vin[m][2] = lo4.z; vin[m][3] = lo4.w;
+              vin[m][4] = hi4.x; vin[m][5] = hi4.y; vin[m][6] = hi4.z; vin[m][7] = hi4.w;
+            }
+          }
+        }
+        mbar_arrive(&s.aux_empty[aux_slot]);
+        if (++aux_slot == (uint32_t)a.aux_slots) { aux_slot = 0; aux_phase ^= 1u; }
+      }
       if (act) {
         uint32_t u0[NSEG][8], u1[NSEG][8];
 #pragma unroll
@@ -1157,7 +1203,8 @@ bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes
 }
 
 static size_t wt_smem_bytes(const WtArgs& a, size_t extra = 0) {
-  return (size_t)WT_HDR + align_up((size_t)a.wblob_bytes + a.wblob2_bytes, 128) + (size_t)a.S * a.stage_bytes + WT_TAIL + extra;
+  return (size_t)WT_HDR + align_up((size_t)a.wblob_bytes + a.wblob2_bytes, 128) + (size_t)a.S * a.stage_bytes + WT_TAIL +
+         (a.aux ? (size_t)a.aux_slots * a.aux_stage_bytes : 0) + extra;
 }
 
 template <typename K>
