@@ -664,6 +664,7 @@ def run_cfg0(a, snnflow, dev, n_frames=200):
     torch.manual_seed(0)
     net = snnflow.LIFFireNet(dict(num_bins=2, encoding="cnt", base_num_channels=a.channels, kernel_size=3,
                                   neuron_kwargs=dict(leak=(0.0, 1.0), thresh=(0.3, 0.1)))).to(dev)
+    net.graph_forward()   # the per-bin forward() replayed as a CUDA graph (same call pattern; model.LIFFireNet.graph_forward)
     b = argparse.Namespace(bins=10, batch=1, events=N, res=R)
     w = {k: v.to(dev) for k, v in make_window(b, 42).items()}
     res = (R, R)
@@ -685,7 +686,20 @@ def run_cfg0(a, snnflow, dev, n_frames=200):
         torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / n_frames
     out = {"metric": "LIFFireNet eval frames/s @128x128, batch 1, model() + compute_pol_iwe per frame (BASELINE.json configs[0])",
-           "value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "frames_timed": n_frames}
+           "value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "frames_timed": n_frames,
+           "api": "per-bin forward() with model.graph_forward() (CUDA-graph replay of the 7 cells + flow head), eager compute_pol_iwe"}
+    net.graph_forward(False)
+    with torch.no_grad():
+        net.reset_states()
+        for t in range(10):
+            frame(t)
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(n_frames):
+            frame(i % 10)
+        ev1.record()
+        torch.cuda.synchronize()
+    out["eager_per_bin"] = {"value": 1e3 * n_frames / ev0.elapsed_time(ev1), "unit": "frames/s"}
     if not a.no_cpu_baseline and cpu_arm_kind() == "reference":
         from oracle import ref_runner
         cpu = torch.device("cpu")

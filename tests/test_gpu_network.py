@@ -94,3 +94,42 @@ def test_state_plumbing():
     assert not any(s.requires_grad for s in net._states)
     net.reset_states()
     assert net._states == [None] * 7
+
+
+def test_graphed_per_bin_forward_equals_eager():
+    """model.graph_forward(): the per-bin forward() replayed as a CUDA graph under no_grad - same flows, same states, state
+    plumbing (reset_states, externally assigned states, .states clones) intact."""
+    import snnflow_b200 as snnflow
+    torch.manual_seed(0)
+    net = snnflow.LIFFireNet(dict(num_bins=2, encoding="cnt", base_num_channels=32, kernel_size=3,
+                                  neuron_kwargs=dict(leak=(0.0, 1.0), thresh=(0.3, 0.1)))).cuda()
+    with torch.no_grad():
+        net.pred.conv2d.weight.mul_(20)
+    g = torch.Generator().manual_seed(3)
+    cnt = torch.poisson(torch.full((6, 1, 2, 32, 48), 0.3), generator=g).cuda()
+    with torch.no_grad():
+        ref = [net(None, cnt[t])["flow"][0].clone() for t in range(6)]
+        s_ref = net.states
+        net.reset_states()
+        net.graph_forward()
+        got = []
+        for t in range(3):
+            got.append(net(None, cnt[t])["flow"][0].clone())
+        kept = net.states                                  # deep clones survive the next replays
+        for t in range(3, 6):
+            got.append(net(None, cnt[t])["flow"][0].clone())
+        for a, b in zip(ref, got):
+            assert torch.equal(a, b)
+        for a, b in zip(s_ref, net._states):
+            assert torch.equal(a, b)
+        # rewind to the state after bin 2 (assigned from outside) and replay bins 3..5
+        net._states = kept
+        again = [net(None, cnt[t])["flow"][0].clone() for t in range(3, 6)]
+        for a, b in zip(ref[3:], again):
+            assert torch.equal(a, b)
+        net.reset_states()
+        assert torch.equal(net(None, cnt[0])["flow"][0], ref[0])
+    # with autograd on, the call goes through the eager cells
+    net.reset_states()
+    out = net(None, cnt[0])["flow"][0]
+    assert out.requires_grad
