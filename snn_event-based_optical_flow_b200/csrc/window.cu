@@ -73,10 +73,8 @@ struct WinPlan {   // tile plans of the tensor-core kernels for this shape
 };
 
 // SNNFLOW_RB_FUSE=0: the data gradient through W_ff of the layer above a recurrent layer runs as its own launch again
-static bool win_fuse_dgrad() {
-  static const int v = wt_env_int("SNNFLOW_RB_FUSE", 1);
-  return v != 0;
-}
+// (read per call, not cached: the tests flip these switches inside one process)
+static bool win_fuse_dgrad() { return wt_env_int("SNNFLOW_RB_FUSE", 1) != 0; }
 
 static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool backward = true) {
   WinPlan P{};
@@ -110,7 +108,7 @@ static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool back
   // tiles only; SNNFLOW_DP_AUX=1).  Off by default: measured equal (3.012 vs 3.018 ms per step) - the producer's bulk copies
   // are throttled by the memory system either way (66 KB per item and SM; 3x halo re-reads of one-row tiles from L2), so
   // the epilogue's own global load was not the limiter (profiles/r2_experiments.md).
-  static const int dp_aux = wt_env_int("SNNFLOW_DP_AUX", 0);
+  const int dp_aux = wt_env_int("SNNFLOW_DP_AUX", 0);
   P.dp_aux_bytes = dp_aux ? 3u * (uint32_t)align_up((size_t)(C / 8) * d->W * 32, 128) : 0u;
   bool dp_ok = P.dp_aux_bytes && wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 2 * C * C * 2) + P.dp_aux_bytes, true, 2, false,
                                          &P.R_dp, &P.S_dp, &P.sub_dp, &P.cs_dp, &P.st_dp, 1);
@@ -284,12 +282,16 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
       a.n_src = 2;
       a.src[1] = a.src[0];
       a.src[1].img_stride = L.zp_img_stride; a.src[1].n_chunks = (uint32_t)(C / 8); a.src[1].w_off = L.rec_w_off[l];
-      static const int persistent = wt_env_int("SNNFLOW_FWD_PERSIST", 1);
+      const int persistent = wt_env_int("SNNFLOW_FWD_PERSIST", 0);
       if (persistent && T > 1) {
-        // ONE cooperative launch walks the T bins (time-fused ConvLIFRecurrent): weights, barriers and TMEM stay set up and
-        // the pipeline never drains; the spike planes of bin t are the recurrent operand of bin t + 1, and a tile only
-        // waits for the per-tile progress flags of itself and its two row neighbours (WtArgs.tile_flags).
-        // SNNFLOW_FWD_PERSIST=0 restores one launch per bin.
+        // SNNFLOW_FWD_PERSIST=1: ONE cooperative launch walks the T bins (time-fused ConvLIFRecurrent forward): weights,
+        // barriers and TMEM stay set up and the pipeline never drains; the spike planes of bin t are the recurrent operand
+        // of bin t + 1, and a tile only waits for the per-tile progress flags of itself and its two row neighbours
+        // (WtArgs.tile_flags, raised by the publisher warp).  Timed alone the window of a layer costs 183 us against
+        // 10 x 24.6 us of per-bin launches; inside the captured training step, where consecutive per-bin launches overlap
+        // their set-up with the previous bin's tail (programmatic dependent launch), the two are equal within noise
+        // (3.005 vs 2.984 ms per step, profiles/r2_experiments.md), so one launch per bin stays the default here.  The
+        // recurrent BACKWARD uses the same machinery by default (it gains: 3.053 -> 3.005 ms).
         a.src[0].planes = xin;
         a.src[1].planes = A + L.off_zp[l];
         a.zin_planes = a.src[1].planes; a.zin_img_stride = L.zp_img_stride;
@@ -410,7 +412,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
       a.par = par;
       a.g_v = g_v; a.gp_img_stride = L.zp_img_stride; a.gp_term_stride = WS.gp_term_stride;
       const unsigned char* gp_above = gplanes[(l + 1) & 1];
-      static const int rb_persist = wt_env_int("SNNFLOW_RB_PERSIST", 1);
+      const int rb_persist = wt_env_int("SNNFLOW_RB_PERSIST", 1);
       const bool fused_time = fuse && rb_persist && T > 1;
       if (fused_time) {
         // ONE cooperative launch walks the window backwards (bin j of the launch = time bin T-1-j): weights, barriers and

@@ -93,6 +93,43 @@ def test_layer_major_equals_per_bin(kind, C, H, W, nk):
         assert torch.allclose(g_a[n], g_b[n], rtol=1e-4, atol=1e-5 * scale), (n, float((g_a[n] - g_b[n]).abs().max()), scale)
 
 
+@pytest.mark.parametrize("env", [dict(SNNFLOW_FWD_PERSIST="1"), dict(SNNFLOW_RB_PERSIST="0"),
+                                 dict(SNNFLOW_RB_FUSE="0"), dict(SNNFLOW_FWD_PERSIST="1", SNNFLOW_RB_PERSIST="0", SNNFLOW_RB_FUSE="0"),
+                                 dict(SNNFLOW_DP_AUX="1"), dict(SNNFLOW_RB_R="1")])
+@pytest.mark.parametrize("H,W,B", [(24, 136, 2), (130, 128, 3)])
+def test_execution_plan_switches_keep_results(env, H, W, B, monkeypatch):
+    """Every execution plan of the recurrent layers - time-fused forward (SNNFLOW_FWD_PERSIST=1), per-bin BPTT launches
+    (SNNFLOW_RB_PERSIST=0), unfused data gradient (SNNFLOW_RB_FUSE=0), one-row BPTT tiles, staged epilogue inputs - gives
+    the spikes / membranes / flows of the default plan bit for bit and the same gradients up to summation order.  (130 rows x
+    3 images: more tiles than SMs, several tiles per CTA and bin - the per-tile progress flags across CTAs.)"""
+    def run():
+        net = make_net("LIFFireNet", 32)
+        g = torch.Generator().manual_seed(15)
+        T = 4
+        cnt = torch.poisson(torch.full((2, T, B, 2, H, W), 0.25), generator=g).cuda()
+        gout = torch.randn(2, T, B, 2, H, W, generator=g).cuda()
+        flows = []
+        for k in range(2):
+            runner_of(net, "layer_major")
+            f = net.forward_window(cnt[k])
+            (f * gout[k]).sum().backward()
+            net.detach_states()
+            flows.append(f.detach().clone())
+        return flows, [s.clone() for s in net._states], {n: p.grad.clone() for n, p in net.named_parameters()}
+    f_a, s_a, g_a = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    f_b, s_b, g_b = run()
+    for a, b in zip(f_a, f_b):
+        assert torch.equal(a, b)
+    for i, (a, b) in enumerate(zip(s_a, s_b)):
+        assert torch.equal(a, b), f"layer {i}: states differ"
+    assert float(s_a[1][1].mean()) > 0.01
+    for n in g_a:
+        scale = float(g_a[n].abs().max()) + 1e-12
+        assert torch.allclose(g_a[n], g_b[n], rtol=1e-4, atol=1e-5 * scale), (n, float((g_a[n] - g_b[n]).abs().max()), scale)
+
+
 @pytest.mark.parametrize("kind,H,W", [("LIFFireFlowNet", 16, 130), ("LIFFireNet", 12, 64)])
 def test_layer_major_eval_mode(kind, H, W):
     net = make_net(kind, 32)
