@@ -7,13 +7,17 @@ Workload (BASELINE.json configs[1]): LIFFireNet (C=32) training step with the ev
 loss on synthetic UZH-FPV-shaped input: 128x128, batch 8 per GPU, 10 time bins x 1000 events per sample,
 clip 1.0, Adam.  One "step" = one optimizer step over one window (train_flow.py:232-279); "samples" are
 batch elements per window.  N > 1: data parallel, one process per GPU (torchrun), weak scaling (per-GPU
-batch fixed), SUM all-reduce of the flat gradient over NCCL.
+batch fixed), gradient SUM over the ranks through NVLink peer memory inside the update kernel.
 
-Prints ONE JSON line (rank 0).  `value` = device-resident inputs, CUDA-event timed, max over ranks;
-`e2e` = the same step driven from pinned HOST buffers (H2D of the window's tensors and D2H of the loss inside
-the timed region); `roofline` = the dominant kernel of the step, timed live with CUDA events on its stream
-by the library's per-launch profiler; `cpu_baseline` = the CPU oracle port of the reference timed on this
-box's host cores on a bounded sample.  `--impl reference` times only that CPU path (rank 0).
+Prints ONE JSON line (rank 0).  `value` = device-resident inputs, CUDA-event timed, max over ranks, the K-step
+region repeated until >= 0.5 s are measured; `e2e` = the same step driven from pinned HOST buffers (H2D of the
+window's tensors and D2H of the loss inside the timed region); `roofline` = the dominant kernel of the step,
+timed live with CUDA events on its stream by the library's per-launch profiler, on the DRAM bytes ncu measured
+for it (profiles/traffic.json) and on its algorithmic bytes; `cpu_baseline` = the unmodified reference (staged
+copy, oracle/stage_reference.py) timed on this box's host cores on a bounded sample.  The same line carries the
+eval half of the metric (`eval`: LIFFireFlowNet 256x256 batch 16, with its own roofline / e2e / cpu_baseline),
+`eval_cfg0` (configs[0]), `global_batch_256` (configs[3], N > 1) and `encode_iwe_microbench` (configs[4]).
+`--impl reference` times only the reference's CPU path (rank 0).
 """
 import argparse
 import importlib
@@ -46,6 +50,8 @@ def parse():
     ap.add_argument("--events", type=int, default=1000, help="events per sample per bin")
     ap.add_argument("--global-batch", type=int, default=0,
                     help="fixed GLOBAL batch split over the ranks (BASELINE.json configs[3]: 256); strong scaling")
+    ap.add_argument("--min-seconds", type=float, default=0.5,
+                    help="repeat the K-step timed region until this much device time is measured (0: one region; profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N > 1: NCCL all-reduce between two graphs instead of the peer-memory kernel inside one graph")
@@ -308,7 +314,7 @@ def roofline_of(prof, section):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-MIN_TIMED_SECONDS = 0.5   # the K-step timed region is repeated until this much device time has been measured
+MIN_TIMED_SECONDS = 0.5   # the K-step timed region is repeated until this much device time has been measured (--min-seconds)
 
 
 def run_ours(a):
@@ -348,9 +354,11 @@ def run_ours(a):
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def timed_regions(step_fn, k_steps, min_seconds=MIN_TIMED_SECONDS, max_regions=200):
+    def timed_regions(step_fn, k_steps, min_seconds=None, max_regions=200):
         """Time EXACTLY k_steps steps between barrier + synchronize on both sides (CUDA events, max over ranks), and
         repeat that region until >= min_seconds of device time are measured.  Returns (total ms, regions, per-region ms)."""
+        if min_seconds is None:
+            min_seconds = a.min_seconds
         per, it = [], 0
         while True:
             barrier()
@@ -504,7 +512,7 @@ def run_ours(a):
             "timed": {"regions": regions, "steps_per_region": a.steps, "total_ms": round(ms_total, 3),
                       "region_ms_min_max": [round(min(per_region), 3), round(max(per_region), 3)],
                       "note": f"the K-step region (barrier + synchronize on both sides, CUDA events, max over ranks) is "
-                              f"repeated until >= {MIN_TIMED_SECONDS} s are measured; value = all samples / all region time"},
+                              f"repeated until >= {a.min_seconds} s are measured; value = all samples / all region time"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "regions": regions2, "region_ms_min_max": [round(min(per2), 3), round(max(per2), 3)]},

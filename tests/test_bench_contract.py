@@ -1,5 +1,5 @@
 """CPU: the JSON contract of bench.py - the reference arm is run here on a tiny workload, and the committed line of the
-GPU arm (profiles/bench/r1_bench_1gpu.json, written by bench.py on a B200) is checked for the keys the driver reads."""
+GPU arm (profiles/bench/r2_bench_1gpu.json, written by bench.py on a B200) is checked for the keys the driver reads."""
 import json
 import os
 import subprocess
@@ -30,13 +30,18 @@ def test_reference_arm_prints_one_contract_line():
 
 
 def test_committed_gpu_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "bench", "r1_bench_1gpu.json")))
+    d = json.loads(open(os.path.join(ROOT, "profiles", "bench", "r2_bench_1gpu.json")).read().strip().splitlines()[-1])
     for k in COMMON + ["clocks", "roofline"]:
         assert k in d, k
     assert d["n_gpus"] == 1 and d["gpu_launches"] > 0 and d["data"] == "synthetic" and d["dtype"] == "f32"
     r = d["roofline"]
     assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s")
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3 and r["traffic"] is not None
+    assert r["frac"] == r["frac_dram"] and r["frac_algorithmic"] is not None and r["kernel"] != "dp_allreduce"
+    assert d["timed"]["total_ms"] >= 500 and d["gpu_launches_per_step"] > 0
+    ev = d["eval"]   # the eval half of the metric carries its own roofline / e2e / CPU reference
+    assert ev["roofline"]["frac"] > 0 and ev["e2e"]["h2d_bytes_per_step"] > 0 and ev["cpu_baseline"]["kind"] == "reference"
+    assert d["eval_cfg0"]["value"] > 0 and d["eval_cfg0"]["cpu_baseline"]["kind"] == "reference"
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= 1.05 * d["value"]
     c = d["cpu_baseline"]
