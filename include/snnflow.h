@@ -156,6 +156,12 @@ typedef struct {
   const float *w_ff, *w_rec, *lam, *theta; /* parameters (lam/theta already sigmoid'ed / clamped)        */
   const void* packed;                      /* snnflow_convlif_pack blob or NULL (CUDA-core forward)      */
   float *dw_ff, *dw_rec, *dlam, *dtheta;   /* gradient accumulators (backward only; may be NULL forward) */
+  /* snnflow_window_backward only, optional (NULL: off): the chain rule through lam = sigmoid(leak) and theta =
+   * clamp_min(thresh, 0.01) (spiking_submodules.py:133,136) applied inside the final reduction launch,
+   *   d_leak[c] += dlam_c * lam_c * (1 - lam_c),   d_thresh[c] += dtheta_c * (thresh_raw[c] >= 0.01),
+   * so that the caller's gradient buffers of the RAW parameters are written directly (dlam / dtheta may then be NULL). */
+  const float* thresh_raw;
+  float *d_leak, *d_thresh;
 } snnflow_layer_ptrs;
 
 size_t snnflow_net_acts_floats(const snnflow_net_desc* d, int save);

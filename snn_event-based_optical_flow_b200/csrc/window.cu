@@ -504,6 +504,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
       r.n_wpart = wg_grid(T * B, H, W, C, L.Kin[l] / 8, L.rec[l] ? C / 8 : 0);
       r.cpart = cpart; r.n_cpart = n_cpart; r.cpart_layout = cpart_layout;
       r.dlam = P_.dlam; r.dtheta = P_.dtheta; r.C = C;
+      r.lam = P_.lam; r.thresh_raw = P_.thresh_raw; r.d_leak = P_.d_leak; r.d_thresh = P_.thresh_raw ? P_.d_thresh : nullptr;
       reduces[l] = r;
     }
 

@@ -170,6 +170,9 @@ struct WinReduceArgs {
   const float* cpart;      // channel partials, rows of length n_cpart: row r < 2C
   int n_cpart, cpart_layout;   // layout 0: [2][C][n_cpart] ; 1: [n_cpart][2][C]
   float *dlam, *dtheta;    // (+=)
+  // optional chain rule to the raw parameters (snnflow_layer_ptrs): d_leak += dlam * lam (1 - lam), d_thresh += dtheta [thresh >= 0.01]
+  const float *lam, *thresh_raw;
+  float *d_leak, *d_thresh;
   int C;
 };
 int launch_win_reduce(const WinReduceArgs* layers, int n_layers, cudaStream_t st);   // all layers in one launch

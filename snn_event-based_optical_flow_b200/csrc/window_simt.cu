@@ -649,8 +649,17 @@ __global__ void __launch_bounds__(256) win_reduce_kernel(const __grid_constant__
       }
       s = warp_sum(s);
       if (lane == 0) {
+        const int c = r % a.C;
         float* dst = r < a.C ? a.dlam : a.dtheta;
-        if (dst) dst[r % a.C] += s;
+        if (dst) dst[c] += s;
+        if (r < a.C) {
+          if (a.d_leak) {                                                          // sigmoid'
+            const float lam = a.lam[c];
+            a.d_leak[c] += __fmul_rn(__fmul_rn(s, lam), __fsub_rn(1.0f, lam));
+          }
+        } else if (a.d_thresh) {                                                   // clamp_min'
+          a.d_thresh[c] += (a.thresh_raw[c] >= 0.01f) ? s : 0.f;
+        }
       }
     }
   }

@@ -25,7 +25,7 @@ class NetDesc(ctypes.Structure):
 
 class LayerPtrs(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("w_ff", "w_rec", "lam", "theta", "packed", "dw_ff", "dw_rec", "dlam",
-                                               "dtheta")]
+                                               "dtheta", "thresh_raw", "d_leak", "d_thresh")]
 
 
 def _bind(L):
@@ -321,8 +321,12 @@ def _lm_backward(runner, saved, g_flow, dst=None):
         lp[i].theta = theta_e[i].data_ptr()
         lp[i].dw_ff = dws[i][0].data_ptr()
         lp[i].dw_rec = None if dws[i][1] is None else dws[i][1].data_ptr()
-        lp[i].dlam = dlam[i].data_ptr()
-        lp[i].dtheta = dtheta[i].data_ptr()
+        lp[i].dlam = None if dlam is None else dlam[i].data_ptr()
+        lp[i].dtheta = None if dtheta is None else dtheta[i].data_ptr()
+        if dst is not None and dst.get("d_leak") is not None:   # chain rule to the raw parameters inside the reduction launch
+            lp[i].thresh_raw = l.thresh.data_ptr()
+            lp[i].d_leak = dst["d_leak"][i].data_ptr()
+            lp[i].d_thresh = dst["d_thresh"][i].data_ptr()
     ws = runner.lm_workspace(desc, dev)
     sp, keep = _state_ptrs(saved["states_in"])
     _lib.check(L.snnflow_window_backward(ctypes.byref(desc), lp, pw_e.data_ptr(), sp, saved["arena"].data_ptr(),
@@ -488,22 +492,16 @@ class WindowRunner:
 
     def direct_backward(self, g_flow, optimizer):
         """BPTT of the window run by direct_forward(): every parameter gradient is accumulated by the kernels straight into
-        its slice of ``optimizer.grad`` (zeroed here); d leak / d thresh go through the sigmoid / clamp_min chain rule."""
+        its slice of ``optimizer.grad`` (zeroed here); the sigmoid / clamp_min chain rule of d leak / d thresh is applied by
+        the final reduction launch (snnflow_layer_ptrs.d_leak / d_thresh)."""
         saved, layers, net = self._direct_saved, self.layers, self.net
         self._direct_saved = None
-        lam, C = saved["lam"], saved["desc"].C
         optimizer.grad.zero_()
-        tmp = torch.zeros((2, N_LAYERS, C), dtype=torch.float32, device=g_flow.device)
         dst = dict(dw=[(optimizer.grad_view(l.ff.weight), optimizer.grad_view(l.rec.weight) if l.recurrent else None) for l in layers],
-                   dlam=tmp[0], dtheta=tmp[1], d_pw=optimizer.grad_view(net.pred.conv2d.weight),
-                   d_pb=optimizer.grad_view(net.pred.conv2d.bias))
+                   dlam=None, dtheta=None, d_pw=optimizer.grad_view(net.pred.conv2d.weight),
+                   d_pb=optimizer.grad_view(net.pred.conv2d.bias),
+                   d_leak=[optimizer.grad_view(l.leak) for l in layers], d_thresh=[optimizer.grad_view(l.thresh) for l in layers])
         _lm_backward(self, saved, g_flow, dst)
-        thr = torch.stack([l.thresh.detach().reshape(-1) for l in layers])
-        d_leak = tmp[0] * lam * (1.0 - lam)                                         # sigmoid'
-        d_thresh = tmp[1] * (thr >= 0.01).float()                                   # clamp_min'
-        torch._foreach_copy_([optimizer.grad_view(l.leak) for l in layers] + [optimizer.grad_view(l.thresh) for l in layers],
-                             [d_leak[i].view_as(l.leak) for i, l in enumerate(layers)] +
-                             [d_thresh[i].view_as(l.thresh) for i, l in enumerate(layers)])
 
     def __call__(self, cnt_window):
         """cnt_window [T,B,num_bins,H,W] -> flow [T,B,2,H,W]; updates net._states like T forward calls would."""
