@@ -35,6 +35,12 @@ extern "C" {
 #define SNNFLOW_HARD_RESET 1u   /* v' = v*lam*(1-z) + (1-lam)*I ; else soft: v' = v*lam + (1-lam)*I - z*theta */
 #define SNNFLOW_DETACH_RESET 2u /* reset path does not carry gradient (spiking_submodules.py:139-140)      */
 #define SNNFLOW_NO_TENSOR_CORES 4u /* force the exact-fp32 CUDA-core convolution                           */
+#define SNNFLOW_STATE_INTERNAL 16u /* snnflow_window_forward (save = 0) streaming mode: the layer states stay inside the arena in
+                                     the engine's own layout between calls (see snnflow_window_export_state)             */
+#define SNNFLOW_STREAM_PHASE 32u   /* streaming mode: ping-pong phase of the recurrent layers' membrane slots (caller toggles
+                                     it by T & 1 after every call, starting from 0 after an import)                      */
+#define SNNFLOW_REUSE_PACKED 64u   /* snnflow_window_forward: the weights have not changed since the previous call on this
+                                     arena: skip the weight packing launch                                               */
 #define SNNFLOW_INPUT_EXACT16 8u /* caller guarantees x holds spikes / small integers (exact in fp16 AND bf16):
                                     lets the backward use the tensor-core weight-gradient kernel               */
 
@@ -208,6 +214,18 @@ size_t snnflow_window_flags_offset(const snnflow_net_desc* d, int save);
 int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_layer_ptrs* layers, const float* pred_w,
                            const float* pred_b, const float* input, const float* const* state_in, void* arena,
                            float* flow, int save, snnflow_stream_t stream);
+/* Streaming inference (flags & SNNFLOW_STATE_INTERNAL, save = 0): the reference's eval loop calls the network once per time
+ * bin (eval_flow.py:220) and hands the 7 states [2,B,C,H,W] back in each time (models/model.py:172-182) - 16 B per neuron
+ * and layer-step of fp32 NCHW traffic that the arithmetic does not need.  In this mode snnflow_window_forward ignores
+ * state_in and continues from the state the previous call left INSIDE the arena in the engine's layout (membranes c8,
+ * spikes = the layers' bf16 planes); the two calls below convert to / from the reference's layout only when somebody
+ * looks (the network's `states` getter) or assigns (reset_states, a caller-provided state).  All calls of a stream use the
+ * same descriptor (T included) and arena.
+ *   import: state_in[l] [2,B,C,H,W] or NULL (zeros) -> arena; the next forward call must pass phase 0
+ *   export: arena -> state_out[l] [2,B,C,H,W]; `phase` = the SNNFLOW_STREAM_PHASE bit the NEXT forward call would pass */
+int snnflow_window_import_state(const snnflow_net_desc* d, const float* const* state_in, void* arena, snnflow_stream_t stream);
+int snnflow_window_export_state(const snnflow_net_desc* d, const void* arena, int phase, float* const* state_out,
+                                snnflow_stream_t stream);
 int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_layer_ptrs* layers, const float* pred_w,
                             const float* const* state_in, const void* arena, const float* flow, const float* g_flow,
                             float* d_pred_w, float* d_pred_b, void* workspace, size_t workspace_bytes,

@@ -10,6 +10,9 @@ HARD_RESET = 1
 DETACH_RESET = 2
 NO_TENSOR_CORES = 4
 INPUT_EXACT16 = 8
+STATE_INTERNAL = 16
+STREAM_PHASE = 32
+REUSE_PACKED = 64
 SURROGATE_ID = {"arctanspike": 0, "superspike": 1, "trianglespike": 2, "mgspike": 3}
 
 P = c_void_p
@@ -63,7 +66,8 @@ class SnnflowError(RuntimeError):
 _ENGINE_SYMBOLS = ["snnflow_net_acts_floats", "snnflow_net_bwd_workspace_bytes", "snnflow_net_forward",
                    "snnflow_net_backward", "snnflow_window_supported", "snnflow_window_arena_bytes",
                    "snnflow_window_workspace_bytes", "snnflow_window_state_offsets", "snnflow_window_flags_offset",
-                   "snnflow_window_forward", "snnflow_window_backward",
+                   "snnflow_window_forward", "snnflow_window_backward", "snnflow_window_import_state",
+                   "snnflow_window_export_state",
                    "snnflow_format_window_workspace_bytes", "snnflow_format_window"]   # struct-taking entry points, bound in engine.py / loader.py
 
 

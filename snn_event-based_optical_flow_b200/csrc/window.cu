@@ -213,6 +213,11 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
   SNNFLOW_REQUIRE(win_supported(d, save != 0), "shape / options not covered by the window engine (use snnflow_net_forward)");
   SNNFLOW_REQUIRE(layers && pred_w && input && arena && flow, "null pointer");
   SNNFLOW_REQUIRE(((uintptr_t)arena & 255) == 0, "arena must be 256-byte aligned");
+  // streaming mode: the states stay inside the arena in the engine's layout between calls (snnflow.h)
+  const bool stream_mode = (d->flags & SNNFLOW_STATE_INTERNAL) != 0;
+  SNNFLOW_REQUIRE(!stream_mode || !save, "SNNFLOW_STATE_INTERNAL is an inference mode (save = 0)");
+  const int phase = (d->flags & SNNFLOW_STREAM_PHASE) ? 1 : 0;
+  if (stream_mode) state_in = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   const WinLayout L = win_layout(d, save);
   const WinPlan P = win_plan(d, L, save != 0);
@@ -233,8 +238,11 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
     pk.L[l].leak_lam = P_.lam; pk.L[l].theta = P_.theta;
     pk.L[l].par = (float*)(A + L.off_par[l]);
   }
-  int rc = launch_pack_weights(pk, st);
-  if (rc) return rc;
+  int rc = SNNFLOW_OK;
+  if (!(d->flags & SNNFLOW_REUSE_PACKED)) {
+    rc = launch_pack_weights(pk, st);
+    if (rc) return rc;
+  }
   rc = launch_pack_input(input, A + L.off_inplanes, T * B, d->num_bins, 2, H, W, (unsigned int*)(A + L.off_flags), st);
   if (rc) return rc;
 
@@ -262,8 +270,15 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
     a.hard_reset = (d->flags & SNNFLOW_HARD_RESET) ? 1 : 0;
     a.par = (const float*)(A + L.off_par[l]);
     a.zp_img_stride = L.zp_img_stride;
+    if (stream_mode) a.state_c8 = 1;
     if (!L.rec[l]) {
       a.n_outer = B; a.T = T;
+      if (stream_mode) {
+        // membrane: c8, in place in the layer's state block; spikes entering the window: the layer's own planes of the
+        // previous call's last bin (the slots this launch overwrites at ITS last bin - read first by the same thread)
+        v_init = state; z_init = nullptr;
+        a.zin_planes = A + L.off_zp[l] + (size_t)(T - 1) * B * L.zp_img_stride; a.zin_img_stride = L.zp_img_stride;
+      }
       if (l == 0) { a.R = P.R_head; a.S = P.S_head; a.sub_bytes = P.sub_head; a.chunk_stride = P.cs_head; a.stage_bytes = P.st_head; }
       else { a.R = P.R_ff; a.S = P.S_ff; a.sub_bytes = P.sub_ff; a.chunk_stride = P.cs_ff; a.stage_bytes = P.st_ff; }
       a.v_init = v_init; a.z_init = z_init;
@@ -275,15 +290,20 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
       if (rc) return rc;
     } else {
       // initial spikes of the window -> image block 0 of this layer's planes (zeros when there is no state)
-      rc = launch_pack_spikes(z_init, A + L.off_zp[l], B, C, H, W, st);
-      if (rc) return rc;
+      if (stream_mode) {   // ... which are the planes the previous call's last bin wrote (block T)
+        SNNFLOW_CUDA(cudaMemcpyAsync(A + L.off_zp[l], A + L.off_zp[l] + (size_t)T * B * L.zp_img_stride, (size_t)B * L.zp_img_stride,
+                                     cudaMemcpyDeviceToDevice, st));
+      } else {
+        rc = launch_pack_spikes(z_init, A + L.off_zp[l], B, C, H, W, st);
+        if (rc) return rc;
+      }
       a.n_outer = B; a.T = 1;
       a.R = P.R_rec; a.S = P.S_rec; a.sub_bytes = P.sub_rec; a.chunk_stride = P.cs_rec; a.stage_bytes = P.st_rec;
       a.n_src = 2;
       a.src[1] = a.src[0];
       a.src[1].img_stride = L.zp_img_stride; a.src[1].n_chunks = (uint32_t)(C / 8); a.src[1].w_off = L.rec_w_off[l];
       const int persistent = wt_env_int("SNNFLOW_FWD_PERSIST", 0);
-      if (persistent && T > 1) {
+      if (persistent && T > 1 && !stream_mode) {
         // SNNFLOW_FWD_PERSIST=1: ONE cooperative launch walks the T bins (time-fused ConvLIFRecurrent forward): weights,
         // barriers and TMEM stay set up and the pipeline never drains; the spike planes of bin t are the recurrent operand
         // of bin t + 1, and a tile only waits for the per-tile progress flags of itself and its two row neighbours
@@ -318,6 +338,12 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
         if (save) {
           a.v_prev = t > 0 ? vbase + (size_t)(t - 1) * n : v_init;
           a.v_out = vbase + (size_t)t * n; a.cur_out = nullptr;
+        } else if (stream_mode) {
+          // two membrane slots, ping-pong across bins AND calls: bin t of this call writes slot (t + phase) & 1 and reads the
+          // other one, which is where the previous call's last bin wrote (the caller toggles the phase by T & 1)
+          a.v_prev_nchw = 0;
+          a.v_prev = vbase + (size_t)((t + phase + 1) & 1) * n;
+          a.v_out = vbase + (size_t)((t + phase) & 1) * n; a.cur_out = nullptr;
         } else {
           a.v_prev = t > 0 ? vbase + (size_t)((t - 1) & 1) * n : v_init;
           a.v_out = vbase + (size_t)(t & 1) * n; a.cur_out = nullptr;
@@ -333,6 +359,50 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
   const int top = WIN_LAYERS - 1;
   return launch_pred_fwd_planes(A + L.off_zp[top] + (L.rec[top] ? (size_t)B * L.zp_img_stride : 0), L.zp_img_stride, pred_w,
                                 pred_b, flow, T * B, C, H, W, st);
+}
+
+// where the streaming state of layer l lives: membrane (c8) and the planes image block that holds the spikes
+static void win_stream_state(const WinLayout& L, const snnflow_net_desc* d, int l, int phase_next, unsigned char* A, float** v,
+                             unsigned char** z_planes) {
+  const int T = d->T, B = d->B;
+  if (!L.rec[l]) {
+    *v = (float*)(A + L.off_state[l]);
+    *z_planes = A + L.off_zp[l] + (size_t)(T - 1) * B * L.zp_img_stride;
+  } else {
+    // the next call reads slot (0 + phase_next + 1) & 1 and copies planes block T to block 0
+    *v = (float*)(A + L.off_v[l]) + (size_t)((phase_next + 1) & 1) * L.n;
+    *z_planes = A + L.off_zp[l] + (size_t)T * B * L.zp_img_stride;
+  }
+}
+
+extern "C" int snnflow_window_import_state(const snnflow_net_desc* d, const float* const* state_in, void* arena,
+                                           snnflow_stream_t stream) {
+  SNNFLOW_REQUIRE(win_supported(d, false) && arena, "unsupported shape or null arena");
+  const WinLayout L = win_layout(d, 0);
+  for (int l = 0; l < WIN_LAYERS; ++l) {
+    float* v;
+    unsigned char* zp;
+    win_stream_state(L, d, l, /*phase_next=*/0, (unsigned char*)arena, &v, &zp);
+    const float* s = state_in ? state_in[l] : nullptr;
+    int rc = launch_state_import(s, s ? s + L.n : nullptr, v, zp, L.zp_img_stride, d->B, d->C, d->H, d->W, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return SNNFLOW_OK;
+}
+
+extern "C" int snnflow_window_export_state(const snnflow_net_desc* d, const void* arena, int phase, float* const* state_out,
+                                           snnflow_stream_t stream) {
+  SNNFLOW_REQUIRE(win_supported(d, false) && arena && state_out, "unsupported shape or null pointer");
+  const WinLayout L = win_layout(d, 0);
+  for (int l = 0; l < WIN_LAYERS; ++l) {
+    if (!state_out[l]) continue;
+    float* v;
+    unsigned char* zp;
+    win_stream_state(L, d, l, phase & 1, const_cast<unsigned char*>((const unsigned char*)arena), &v, &zp);
+    int rc = launch_state_export(v, zp, L.zp_img_stride, state_out[l], state_out[l] + L.n, d->B, d->C, d->H, d->W, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return SNNFLOW_OK;
 }
 
 extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_layer_ptrs* layers, const float* pred_w,

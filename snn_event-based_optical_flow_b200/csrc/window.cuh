@@ -65,6 +65,8 @@ struct WtArgs {
   unsigned char* zp_out;          // spike planes written by this launch (image 0 = first image of the launch)
   unsigned long long zp_img_stride;
   float *v_last, *z_last;         // [B][N][H][W] or NULL: state after the last step
+  int state_c8;                   // streaming mode: v_init / v_last are c8 tensors, the spikes entering the window are read from
+                                  // zin_planes (sequence mode too), no NCHW state is written
   // data gradient
   float* g_x;                     // c8 layout [images][N/8][H*W][8]
   // recurrent backward step
@@ -132,6 +134,11 @@ int launch_wgrad_planes(WgArgs a, cudaStream_t st, double bytes, double flops);
 int launch_pack_input(const float* in, unsigned char* planes, int n_img, int nb, int n_chunks, int H, int W,
                       unsigned int* inexact, cudaStream_t st);
 int launch_pack_spikes(const float* z, unsigned char* planes, int n_img, int C, int H, int W, cudaStream_t st);
+// streaming state conversion: NCHW fp32 (v, z) <-> c8 membranes + bf16 spike planes, one layer
+int launch_state_import(const float* v_nchw, const float* z_nchw, float* v_c8, unsigned char* planes, unsigned long long img_stride,
+                        int B, int C, int H, int W, cudaStream_t st);
+int launch_state_export(const float* v_c8, const unsigned char* planes, unsigned long long img_stride, float* v_nchw, float* z_nchw,
+                        int B, int C, int H, int W, cudaStream_t st);
 struct PackLayer {
   const float *w_ff, *w_rec;
   unsigned char *fwd_blob, *dg_blob, *rb_blob;   // forward (ff [+ rec]) ; data gradient through W_ff ; through W_rec

@@ -48,6 +48,67 @@ int launch_pack_spikes(const float* z, unsigned char* planes, int n_img, int C, 
   return check_launch("pack_planes_kernel");
 }
 
+// ---- streaming state: NCHW fp32 (v, z) <-> c8 membranes + bf16 spike planes -----------------------------------------------
+// thread = one pixel of one (image, 8-channel chunk); NCHW side coalesced along x, engine side one 32-byte + one 16-byte vector
+__global__ void __launch_bounds__(256) state_import_kernel(const float* __restrict__ v_nchw, const float* __restrict__ z_nchw,
+                                                           float* __restrict__ v_c8, unsigned char* __restrict__ planes,
+                                                           unsigned long long img_stride, int C, int H, int W) {
+  const int HW = H * W, Wp = W + 2, nch = C >> 3;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  const int chunk = blockIdx.y, img = blockIdx.z;
+  if (p >= HW) return;
+  const int y = p / W, x = p - y * W;
+  float v[8];
+  uint32_t u[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const size_t o = ((size_t)img * C + chunk * 8 + c) * HW + p;
+    v[c] = v_nchw ? __ldg(v_nchw + o) : 0.f;
+    const float z = z_nchw ? __ldg(z_nchw + o) : 0.f;
+    u[c >> 1] |= (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(z)) << ((c & 1) * 16);
+  }
+  stg256(v_c8 + (((size_t)img * nch + chunk) * HW + p) * 8, v);
+  const size_t plane_bytes = (size_t)(H + 2) * Wp * 16;
+  *reinterpret_cast<uint4*>(planes + (size_t)img * img_stride + (size_t)chunk * plane_bytes + ((size_t)(y + 1) * Wp + x + 1) * 16) =
+      make_uint4(u[0], u[1], u[2], u[3]);
+}
+
+__global__ void __launch_bounds__(256) state_export_kernel(const float* __restrict__ v_c8, const unsigned char* __restrict__ planes,
+                                                           unsigned long long img_stride, float* __restrict__ v_nchw,
+                                                           float* __restrict__ z_nchw, int C, int H, int W) {
+  const int HW = H * W, Wp = W + 2, nch = C >> 3;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  const int chunk = blockIdx.y, img = blockIdx.z;
+  if (p >= HW) return;
+  const int y = p / W, x = p - y * W;
+  float v[8];
+  ldg256_coherent(v_c8 + (((size_t)img * nch + chunk) * HW + p) * 8, v);
+  const size_t plane_bytes = (size_t)(H + 2) * Wp * 16;
+  const uint4 zz = *reinterpret_cast<const uint4*>(planes + (size_t)img * img_stride + (size_t)chunk * plane_bytes +
+                                                   ((size_t)(y + 1) * Wp + x + 1) * 16);
+  const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const size_t o = ((size_t)img * C + chunk * 8 + c) * HW + p;
+    v_nchw[o] = v[c];
+    z_nchw[o] = __bfloat162float(__ushort_as_bfloat16((unsigned short)((zw[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu)));
+  }
+}
+
+int launch_state_import(const float* v_nchw, const float* z_nchw, float* v_c8, unsigned char* planes, unsigned long long img_stride,
+                        int B, int C, int H, int W, cudaStream_t st) {
+  prof_begin("win_state_import", st, (double)B * C * H * W * 14.0);
+  state_import_kernel<<<dim3(ceil_div(H * W, 256), C / 8, B), 256, 0, st>>>(v_nchw, z_nchw, v_c8, planes, img_stride, C, H, W);
+  return check_launch("state_import_kernel");
+}
+
+int launch_state_export(const float* v_c8, const unsigned char* planes, unsigned long long img_stride, float* v_nchw, float* z_nchw,
+                        int B, int C, int H, int W, cudaStream_t st) {
+  prof_begin("win_state_export", st, (double)B * C * H * W * 14.0);
+  state_export_kernel<<<dim3(ceil_div(H * W, 256), C / 8, B), 256, 0, st>>>(v_c8, planes, img_stride, v_nchw, z_nchw, C, H, W);
+  return check_launch("state_export_kernel");
+}
+
 // ---- weights -> UMMA shared-memory images, per-channel parameters ---------------------------------------
 // The bf16 terms of a weight sit side by side along the MMA N dimension (column n' = term * N + n), so one MMA per tap
 // and k-step produces all partial products and the epilogue adds the column groups.

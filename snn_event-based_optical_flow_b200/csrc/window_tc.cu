@@ -442,12 +442,13 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
       const long long v_bin = (long long)B * nch * (long long)HW * 8;          // floats between bins (c8 membranes)
       const long long zp_bin = (long long)B * (long long)zp_img_stride;        // bytes between bins (spike planes)
       const bool have_v = a.v_out != nullptr, want_last = a.v_last != nullptr || a.z_last != nullptr;
+      const bool state_c8 = a.state_c8 != 0;
       uint32_t k = 0;
       for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
         const int b = tile / tpi, y0 = (tile - b * tpi) * a.R;
         float* vp[NSEG];
         unsigned char* zp[NSEG];
-        size_t o_state[NSEG];
+        size_t o_state[NSEG], o_c8[NSEG];
         bool okm[NSEG];
         float vst[NSEG][8], zst[NSEG][8];
 #pragma unroll
@@ -458,15 +459,29 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
           vp[m] = have_v ? a.v_out + c8_off(b, nch, ch, HW, pix) : nullptr;
           zp[m] = a.zp_out + (size_t)ch * plane_bytes + (size_t)b * zp_img_stride + ((size_t)(y + 1) * Wp + x + 1) * 16;
           o_state[m] = ((size_t)(b * N + ch * 8)) * HW + pix;   // NCHW (state tensors of the caller)
+          o_c8[m] = c8_off(b, nch, ch, HW, pix);
 #pragma unroll
           for (int c = 0; c < 8; ++c) vst[m][c] = zst[m][c] = 0.f;
-          if (okm[m] && a.v_init) {
+          if (state_c8) {
+            // streaming mode: the state lives in the engine's own layout between calls - membrane c8 (one 32-byte vector),
+            // spikes = this layer's planes of the previous call (the slot this thread overwrites at the last bin)
+            if (okm[m] && a.v_init) ld8_c8(a.v_init + c8_off(b, nch, ch, HW, pix), vst[m]);
+            if (okm[m] && a.zin_planes) {
+              const uint4 zz = *reinterpret_cast<const uint4*>(a.zin_planes + (size_t)b * a.zin_img_stride + (size_t)ch * plane_bytes +
+                                                               ((size_t)(y + 1) * Wp + x + 1) * 16);
+              const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
 #pragma unroll
-            for (int c = 0; c < 8; ++c) vst[m][c] = __ldg(a.v_init + o_state[m] + (size_t)c * HW);
-          }
-          if (okm[m] && a.z_init) {
+              for (int c = 0; c < 8; ++c) zst[m][c] = ((zw[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu) ? 1.f : 0.f;
+            }
+          } else {
+            if (okm[m] && a.v_init) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) zst[m][c] = __ldg(a.z_init + o_state[m] + (size_t)c * HW);
+              for (int c = 0; c < 8; ++c) vst[m][c] = __ldg(a.v_init + o_state[m] + (size_t)c * HW);
+            }
+            if (okm[m] && a.z_init) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) zst[m][c] = __ldg(a.z_init + o_state[m] + (size_t)c * HW);
+            }
           }
         }
         for (int t = 0; t < T; ++t, ++k) {
@@ -508,11 +523,13 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
                 *reinterpret_cast<uint4*>(zp[m]) = zz;
                 if (have_v) st8_c8(vp[m], vst[m]);
                 if (t == T - 1 && want_last) {   // the caller-visible state [2,B,C,H,W] after the window
-                  if (a.v_last) {
+                  if (state_c8) {
+                    st8_c8(a.v_last + (o_c8[m]), vst[m]);   // (the spikes of the last bin are already in the planes)
+                  } else if (a.v_last) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) a.v_last[o_state[m] + (size_t)c * HW] = vst[m][c];
                   }
-                  if (a.z_last) {
+                  if (a.z_last && !state_c8) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) a.z_last[o_state[m] + (size_t)c * HW] = zst[m][c];
                   }
@@ -592,7 +609,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
           if (ahead_ok) request(nx.b, nx.y0, nbin, vnx, znx);
         }
         const uint32_t ab = (uint32_t)g & acc_mask;
-        const bool last = bin == n_bins - 1 && (a.v_last != nullptr || a.z_last != nullptr);
+        const bool last = bin == n_bins - 1 && (a.v_last != nullptr || a.z_last != nullptr) && !a.state_c8;
         float* const v_out = a.v_out ? a.v_out + (size_t)(bin & bin_v_mask) * bin_v_stride : nullptr;
         unsigned char* const zp_out = a.zp_out + (long long)bin * bin_zp_stride + (size_t)ch * plane_bytes;
         {

@@ -55,6 +55,10 @@ def _bind(L):
     L.snnflow_window_forward.restype = ctypes.c_int
     L.snnflow_window_forward.argtypes = [P, P, P, P, P, ctypes.POINTER(P), P, P,
                                          ctypes.c_int, P]
+    L.snnflow_window_import_state.restype = ctypes.c_int
+    L.snnflow_window_import_state.argtypes = [P, ctypes.POINTER(P), P, P]
+    L.snnflow_window_export_state.restype = ctypes.c_int
+    L.snnflow_window_export_state.argtypes = [P, P, ctypes.c_int, ctypes.POINTER(P), P]
     L.snnflow_window_backward.restype = ctypes.c_int
     L.snnflow_window_backward.argtypes = [P, P, P, ctypes.POINTER(P), P, P, P,
                                           P, P, P, ctypes.c_size_t, P]
@@ -454,6 +458,8 @@ class WindowRunner:
             n = _lib.lib().snnflow_window_arena_bytes(ctypes.byref(desc), int(save))
             for k in [k for k in self._lm if k[0] == "arena" and k[1] != key[1]]:
                 del self._lm[k]
+            self._stream = None          # a streamed state lived in one of the arenas just dropped: the NCHW list is the truth
+            self.stream_live = False
             buf = torch.zeros(n, dtype=torch.uint8, device=dev)
             self._lm[key] = buf
         return buf
@@ -468,6 +474,100 @@ class WindowRunner:
             buf = torch.zeros(n, dtype=torch.uint8, device=dev)
             self._lm[key] = buf
         return buf
+
+    # ---- streaming inference: one call per time bin, states kept in the engine's layout between calls --------------------
+    # (the reference's eval loop, eval_flow.py:220; models/model.py:172-182 hands 7 NCHW states back in per call)
+    stream_live = False     # the arena holds a state that is newer than the network's NCHW state list
+    _stream = None
+
+    def stream_ok(self, x):
+        """x [B,num_bins,H,W]: the layer-major engine covers this shape at the network's own width, under no_grad."""
+        if not x.is_cuda or x.dim() != 4 or self.engine == "per_step" or not self.supported():
+            return False
+        if getattr(self.net, "encoding", "cnt") != "cnt" or _lm_channels(self.layers[0].hidden_size) != self.layers[0].hidden_size:
+            return False
+        key = ("stream_ok", tuple(x.shape))
+        ok = self._lm.get(key)
+        if ok is None:
+            ok = self._lm[key] = self.layer_major_ok(x[None], False)
+        return ok
+
+    def _stream_desc(self, x, extra_flags=0):
+        desc = _make_desc(self, x[None])
+        desc.flags |= _lib.STATE_INTERNAL | extra_flags
+        return desc
+
+    def stream_forward(self, x, states):
+        """One time bin through snnflow_window_forward (T = 1, SNNFLOW_STATE_INTERNAL).  `states`: the network's NCHW state
+        list - imported into the arena only when it is newer than the arena's own state (first call, reset_states(), a
+        state assigned by the caller).  Returns flow [B,2,H,W]."""
+        L = _lib.lib()
+        _bind(L)
+        layers, net = self.layers, self.net
+        B, nb, H, W = x.shape
+        dev = x.device
+        x = x.float().contiguous()
+        desc0 = self._stream_desc(x)
+        arena = self.lm_arena(desc0, False, dev)      # (a NEW arena drops self._stream: the list is imported below)
+        st = self._stream
+        wkey = tuple((p.data_ptr(), p._version) for l in layers for p in ((l.ff.weight, l.rec.weight, l.leak, l.thresh) if l.recurrent
+                                                                        else (l.ff.weight, l.leak, l.thresh)))
+        if st is None or st["shape"] != tuple(x.shape) or st["dev"] != dev:
+            st = self._stream = dict(shape=tuple(x.shape), dev=dev, phase=0, wkey=None, lam=None, theta=None)
+            self.stream_live = False
+        if not self.stream_live:      # the NCHW list is the truth: bring it into the arena
+            C = layers[0].hidden_size
+            _state_ptrs(states, (B, C, H, W))
+            arr = (ctypes.c_void_p * N_LAYERS)()
+            keep = []
+            for i, s_ in enumerate(states):
+                if s_ is not None:
+                    s_ = s_.detach().float().contiguous()
+                    keep.append(s_)
+                    arr[i] = s_.data_ptr()
+            _lib.check(L.snnflow_window_import_state(ctypes.byref(desc0), arr, arena.data_ptr(), _lib.stream()),
+                       "snnflow_window_import_state")
+            st["phase"] = 0
+        reuse = st["wkey"] == wkey
+        if not reuse:
+            st["lam"], st["theta"] = _effective_params(self, layers)
+            st["wkey"] = wkey
+        lam, theta = st["lam"], st["theta"]
+        desc = self._stream_desc(x, (_lib.STREAM_PHASE if st["phase"] else 0) | (_lib.REUSE_PACKED if reuse else 0))
+        lp = (LayerPtrs * N_LAYERS)()
+        for i, l in enumerate(layers):
+            lp[i].w_ff = l.ff.weight.data_ptr()
+            lp[i].w_rec = l.rec.weight.data_ptr() if l.recurrent else None
+            lp[i].lam = lam[i].data_ptr()
+            lp[i].theta = theta[i].data_ptr()
+        flow = torch.empty((1, B, 2, H, W), dtype=torch.float32, device=dev)
+        pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
+        _lib.check(L.snnflow_window_forward(ctypes.byref(desc), lp, pw.data_ptr(), None if pb is None else pb.data_ptr(), x.data_ptr(),
+                                            None, arena.data_ptr(), flow.data_ptr(), 0, _lib.stream()), "snnflow_window_forward")
+        foff = L.snnflow_window_flags_offset(ctypes.byref(desc0), 0)
+        self.input_flag = arena[foff:foff + 4].view(torch.int32)
+        st["phase"] = (st["phase"] + 1) & 1       # T = 1
+        st["calls"] = st.get("calls", 0) + 1
+        if self.validate_input and not torch.cuda.is_current_stream_capturing() and (st["calls"] == 1 or st["calls"] % self.validate_every == 0):
+            self.check_input_flag()               # streaming: polled, not synchronised every frame
+        self.stream_live = True
+        return flow[0]
+
+    def stream_export(self):
+        """The arena's state as the reference's list of 7 tensors [2,B,C,H,W] = stack([v, z])."""
+        L = _lib.lib()
+        st = self._stream
+        B, nb, H, W = st["shape"]
+        C = self.layers[0].hidden_size
+        x_like = torch.empty((1,) + st["shape"], device="meta")
+        desc = _make_desc(self, x_like)
+        desc.flags |= _lib.STATE_INTERNAL
+        arena = self.lm_arena(desc, False, st["dev"])
+        out = [torch.empty((2, B, C, H, W), dtype=torch.float32, device=st["dev"]) for _ in range(N_LAYERS)]
+        arr = (ctypes.c_void_p * N_LAYERS)(*[o.data_ptr() for o in out])
+        _lib.check(L.snnflow_window_export_state(ctypes.byref(desc), arena.data_ptr(), st["phase"], arr, _lib.stream()),
+                   "snnflow_window_export_state")
+        return out
 
     # ---- direct (autograd-free) training interface: train.TrainWindow.step_direct ------------------------------------
     def direct_ok(self, cnt_window, optimizer):
@@ -507,6 +607,7 @@ class WindowRunner:
         """cnt_window [T,B,num_bins,H,W] -> flow [T,B,2,H,W]; updates net._states like T forward calls would."""
         if not cnt_window.is_cuda:
             raise _lib.SnnflowError("snnflow WindowRunner runs on CUDA tensors only (no CPU fallback)")
+        self.net._states                      # (getter: materialises a streamed state before the arenas change hands)
         params = []
         for l in self.layers:
             params += [l.ff.weight, l.rec.weight if l.recurrent else None, l.leak, l.thresh]

@@ -58,6 +58,28 @@ class LIFFireNet(nn.Module):
         self.reset_states()
 
     # --- state plumbing (models/model.py:109-130) ---
+    # `_states` is the reference's list of 7 tensors [2,B,C,H,W].  Under no_grad the per-bin forward() keeps the state inside
+    # the window engine's arena in its own layout (engine.WindowRunner.stream_forward) and this list is materialised only when
+    # somebody reads it; assigning it (reset_states, detach_states, a caller-provided state) makes the list the truth again.
+    stream_forward = True    # False: every per-bin forward() goes through the cells (fp32 NCHW state each call)
+
+    @property
+    def _states(self):
+        r = self.__dict__.get("_window_runner")
+        if r is not None and r.stream_live:
+            self.__dict__["_states_list"] = r.stream_export()
+            r.stream_live = False          # the list is current (the arena stays valid until the list is assigned again)
+            self.__dict__["_states_from_stream"] = True
+        return self.__dict__.get("_states_list")
+
+    @_states.setter
+    def _states(self, value):
+        self.__dict__["_states_list"] = value
+        self.__dict__["_states_from_stream"] = False
+        r = self.__dict__.get("_window_runner")
+        if r is not None:
+            r.stream_live = False
+
     @property
     def states(self):
         return [None if s is None else s.clone() for s in self._states]   # model_util.py:95-101
@@ -144,7 +166,30 @@ class LIFFireNet(nn.Module):
         self._states = list(g["states"])
         return g["flow"]
 
+    def _forward_streamed(self, x):
+        """Per-bin inference on the window engine with the state kept in the engine's layout between calls."""
+        from .engine import WindowRunner
+        r = self.__dict__.get("_window_runner")
+        if r is None:
+            r = WindowRunner(self)
+            object.__setattr__(self, "_window_runner", r)
+        if not r.stream_ok(x):
+            return None
+        if self.__dict__.get("_states_from_stream") and not r.stream_live and r._stream is not None and r._stream["shape"] == tuple(x.shape):
+            # the list was only READ since the last streamed call (states getter): the arena is still current
+            r.stream_live = True
+        states = self.__dict__.get("_states_list")
+        flow = r.stream_forward(x, states)
+        self.__dict__["_states_from_stream"] = False
+        return flow
+
     def forward(self, event_voxel=None, event_cnt=None, log=False, return_dict=True):
+        if (self.stream_forward and getattr(self, "_graphs", None) is None and not torch.is_grad_enabled()
+                and not (isinstance(log, bool) and log) and not self.norm_input and self.encoding == "cnt" and self.num_bins == 2
+                and event_cnt is not None and event_cnt.is_cuda and not self.residual):
+            flow = self._forward_streamed(event_cnt)
+            if flow is not None:
+                return {"flow": [flow], "activity": None} if return_dict else flow
         if getattr(self, "_graphs", None) is not None and not torch.is_grad_enabled() and not (isinstance(log, bool) and log):
             x = event_voxel if self.encoding == "voxel" else event_cnt
             if x is not None and x.is_cuda and not self.norm_input and (self.encoding == "voxel" or self.num_bins == 2):
@@ -176,6 +221,7 @@ class LIFFireNet(nn.Module):
         x6, s[5] = self.R2a(x5, s[5])
         x7, s[6] = self.R2b(x6, s[6], residual=x5 if self.residual else 0)
         flow = self.pred(x7)
+        self._states = s          # (through the setter: the list is the truth, a streamed state in the arena is stale)
         if not return_dict:
             return flow
         activity = None

@@ -107,6 +107,7 @@ def test_graphed_per_bin_forward_equals_eager():
         net.pred.conv2d.weight.mul_(20)
     g = torch.Generator().manual_seed(3)
     cnt = torch.poisson(torch.full((6, 1, 2, 32, 48), 0.3), generator=g).cuda()
+    net.stream_forward = False      # eager reference = the per-bin cells (what the graph captures)
     with torch.no_grad():
         ref = [net(None, cnt[t])["flow"][0].clone() for t in range(6)]
         s_ref = net.states
@@ -133,3 +134,61 @@ def test_graphed_per_bin_forward_equals_eager():
     net.reset_states()
     out = net(None, cnt[0])["flow"][0]
     assert out.requires_grad
+
+
+@pytest.mark.parametrize("kind,C,B,H,W", [("LIFFireNet", 32, 2, 24, 136), ("LIFFireFlowNet", 32, 3, 16, 128), ("LIFFireNet", 16, 1, 130, 64)])
+def test_streamed_per_bin_forward_equals_cells(kind, C, B, H, W):
+    """Under no_grad the per-bin forward() runs on the window engine with the state kept in the engine's layout between calls
+    (SNNFLOW_STATE_INTERNAL) and `_states` materialised lazily: flows, spikes and membranes must equal the per-bin cells bit for
+    bit (2^-12-grid weights), through reads of .states, reset_states(), externally assigned states, a forward_window() call in
+    between and a switch back to autograd mode."""
+    import snnflow_b200 as snnflow
+    from oracle.lif import dyadic as snap
+    torch.manual_seed(1)
+    net = getattr(snnflow, kind)(dict(num_bins=2, encoding="cnt", base_num_channels=C, kernel_size=3,
+                                      neuron_kwargs=dict(leak=(0.0, 1.0), thresh=(0.3, 0.1))))
+    with torch.no_grad():
+        net.pred.conv2d.weight.mul_(20)
+        for n, p in net.named_parameters():
+            if n.endswith("weight"):
+                p.copy_(snap(p))
+    net = net.cuda()
+    g = torch.Generator().manual_seed(8)
+    cnt = torch.poisson(torch.full((9, B, 2, H, W), 0.25), generator=g).cuda()
+    with torch.no_grad():
+        net.stream_forward = False
+        ref = [net(None, cnt[t])["flow"][0].clone() for t in range(9)]
+        s_ref_3 = None
+        net.reset_states()
+        for t in range(3):
+            net(None, cnt[t])
+        s_ref_3 = net.states
+        for t in range(3, 9):
+            net(None, cnt[t])
+        s_ref = net.states
+        # streamed
+        net.stream_forward = True
+        net.reset_states()
+        got = [net(None, cnt[t])["flow"][0].clone() for t in range(3)]
+        assert net._window_runner.stream_live, "the streamed path was not taken"
+        mid = net.states                                   # lazily materialised, deep-cloned
+        for a, b in zip(s_ref_3, mid):
+            assert torch.equal(a, b)
+        got += [net(None, cnt[t])["flow"][0].clone() for t in range(3, 5)]      # continues from the arena (list only read)
+        # a T = 2 window in between (other arena), then streaming again
+        got += list(net.forward_window(cnt[5:7]).clone())
+        got += [net(None, cnt[t])["flow"][0].clone() for t in range(7, 9)]
+        for t, (a, b) in enumerate(zip(ref, got)):
+            assert torch.equal(a, b), f"bin {t}: flows differ ({float((a - b).abs().max())})"
+        for i, (a, b) in enumerate(zip(s_ref, net.states)):
+            assert torch.equal(a[1], b[1]), f"layer {i}: spikes differ"
+            assert torch.equal(a[0], b[0]), f"layer {i}: membranes differ"
+        assert float(s_ref[-1][1].mean()) > 0.01
+        # externally assigned state: rewind to bin 3
+        net._states = [s.clone() for s in s_ref_3]
+        again = [net(None, cnt[t])["flow"][0].clone() for t in range(3, 6)]
+        for a, b in zip(ref[3:6], again):
+            assert torch.equal(a, b)
+    # autograd on: the cells, continuing from the streamed state
+    out = net(None, cnt[6])["flow"][0]
+    assert out.requires_grad and torch.equal(out.detach(), ref[6])

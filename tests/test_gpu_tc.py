@@ -135,6 +135,7 @@ def test_module_uses_tensor_cores_and_matches_simt():
                 p.copy_(dyadic(p))
     g = torch.Generator().manual_seed(3)
     cnt = torch.poisson(torch.full((4, 2, 2, 32, 160), 0.25), generator=g).cuda()
+    net.stream_forward = False      # this test is about the per-bin cells (the streamed path uses the window engine)
 
     def run(tc):
         snnflow.ConvLIF.use_tensor_cores = tc

@@ -192,6 +192,7 @@ def test_graph_replays_invalidate_packed_weight_cache():
                      snnflow.FusedClipAdam(net.parameters(), lr=1e-2, max_norm=1.0), clip_grad=1.0)
     batch = {k: v.cuda() for k, v in synth_window(T, B, N, H, W, 5).items()}
     cnt = batch["event_cnt"]
+    net.stream_forward = False      # the cells' packed-weight cache is what is under test (the streamed path: below)
 
     def eval_flow(tc):
         cells = [net.head, net.G1, net.R1a, net.R1b, net.G2, net.R2a, net.R2b]
@@ -216,6 +217,15 @@ def test_graph_replays_invalidate_packed_weight_cache():
     a, b = eval_flow(True), eval_flow(False)
     assert float((a - before).abs().max()) > 1e-4, "the updated weights changed nothing: vacuous"
     assert float((a - b).abs().max()) < 5e-3 * float(b.abs().max() + 1e-6), "tensor-core cells ran stale packed weights"
+    # the streamed per-bin path (window engine, weights repacked when their versions change) sees the update as well
+    net.stream_forward = True
+    saved = net._states
+    net.reset_states()
+    with torch.no_grad():
+        c = torch.stack([net(None, cnt[t])["flow"][0] for t in range(T)])
+    assert net._window_runner.stream_live
+    net._states = saved
+    assert float((c - b).abs().max()) < 5e-3 * float(b.abs().max() + 1e-6), "the streamed path ran stale packed weights"
 
 
 def test_state_shape_mismatch_raises():
