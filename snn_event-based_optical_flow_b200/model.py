@@ -178,6 +178,9 @@ class LIFFireNet(nn.Module):
         if self.__dict__.get("_states_from_stream") and not r.stream_live and r._stream is not None and r._stream["shape"] == tuple(x.shape):
             # the list was only READ since the last streamed call (states getter): the arena is still current
             r.stream_live = True
+        if r.stream_live and r._stream is not None and r._stream["shape"] != tuple(x.shape):
+            self._states      # another input shape: the streamed state becomes the list (and fails the shape check below, like
+                              # the reference does when batch size / resolution change without reset_states())
         states = self.__dict__.get("_states_list")
         flow = r.stream_forward(x, states)
         self.__dict__["_states_from_stream"] = False
