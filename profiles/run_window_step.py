@@ -19,6 +19,7 @@ ap.add_argument("--bins", type=int, default=10)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--kind", default="LIFFireNet")
 ap.add_argument("--eval", action="store_true", help="forward only, no_grad (eval path)")
+ap.add_argument("--time", type=int, default=0, help="also time this many further windows with CUDA events (not under ncu)")
 a = ap.parse_args()
 snnflow = importlib.import_module("snn_event-based_optical_flow_b200")
 torch.manual_seed(0)
@@ -39,4 +40,20 @@ for rep in range(a.reps):
     (flow * gout).sum().backward()
     net.detach_states()
 torch.cuda.synchronize()
+if a.time:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for rep in range(a.time):
+        if a.eval:
+            with torch.no_grad():
+                flow = net.forward_window(cnt)
+        else:
+            net.zero_grad(set_to_none=True)
+            flow = net.forward_window(cnt)
+            (flow * gout).sum().backward()
+            net.detach_states()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.time
+    print(f"{ms:.3f} ms per window, {a.bins * a.batch / ms * 1e3:.0f} frames/s")
 print("ok", float(flow.abs().mean()), [round(float(s[1].mean()), 4) for s in net._states])

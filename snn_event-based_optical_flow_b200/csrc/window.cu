@@ -68,6 +68,7 @@ static WinLayout win_layout(const snnflow_net_desc* d, int save) {
 struct WinPlan {   // tile plans of the tensor-core kernels for this shape
   int R_ff, S_ff, R_head, S_head, R_rec, S_rec, R_dg, S_dg, R_rb, S_rb, R_dp, S_dp;
   uint32_t dp_aux_bytes;   // shared memory set aside for the staged epilogue inputs of the fused dgrad + pointwise kernel
+  int n_col;               // forward kernels: 128-pixel column tiles per row (1: whole-row tiles)
   uint32_t sub_ff, cs_ff, st_ff, sub_head, cs_head, st_head, sub_rec, cs_rec, st_rec, sub_dg, cs_dg, st_dg, sub_rb, cs_rb, st_rb, sub_dp, cs_dp, st_dp;
   bool ok;
 };
@@ -84,11 +85,18 @@ static WinPlan win_plan(const snnflow_net_desc* d, const WinLayout& L, bool back
   uint32_t max_fwd_rec_blob = 0;
   for (int l = 0; l < WIN_LAYERS; ++l)
     if (L.rec[l] && L.fwd_blob_bytes[l] > max_fwd_rec_blob) max_fwd_rec_blob = L.fwd_blob_bytes[l];
-  P.ok = wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 3 * C * C * 2), true, 3, false, &P.R_ff, &P.S_ff, &P.sub_ff, &P.cs_ff, &P.st_ff);
+  // Rows wider than one 128-pixel MMA segment: the forward kernels walk 128-pixel COLUMN tiles (one accumulator segment
+  // per item, as at W = 128) instead of whole rows with two segments per item - the two-segment epilogues spill at the
+  // 96-register cap and measured 25-45 % slower per segment (profiles/r2_experiments.md).  Not for the time-fused forward
+  // (its progress flags are per row tile).  SNNFLOW_COL_TILES=0 restores whole-row tiles.
+  const bool col = d->W > 128 && d->W % 128 == 0 && wt_env_int("SNNFLOW_COL_TILES", 1) != 0 &&
+                   !(any_rec && wt_env_int("SNNFLOW_FWD_PERSIST", 0) != 0);
+  P.n_col = col ? d->W / 128 : 1;
+  P.ok = wt_plan(d->H, d->W, C / 8, C, (uint32_t)((size_t)9 * 3 * C * C * 2), true, 3, false, &P.R_ff, &P.S_ff, &P.sub_ff, &P.cs_ff, &P.st_ff, 0, col);
   P.ok = P.ok && wt_plan(d->H, d->W, 2, C, (uint32_t)((size_t)9 * 3 * 16 * C * 2), true, 3, false, &P.R_head, &P.S_head, &P.sub_head,
-                         &P.cs_head, &P.st_head);
+                         &P.cs_head, &P.st_head, 0, col);
   if (any_rec)
-    P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, max_fwd_rec_blob, true, 3, false, &P.R_rec, &P.S_rec, &P.sub_rec, &P.cs_rec, &P.st_rec);
+    P.ok = P.ok && wt_plan(d->H, d->W, C / 8, C, max_fwd_rec_blob, true, 3, false, &P.R_rec, &P.S_rec, &P.sub_rec, &P.cs_rec, &P.st_rec, 0, col);
   if (!backward) return P;
   if (any_rec) {
     // two-row tiles when they fit (measured faster than one-row tiles at 128x128); SNNFLOW_RB_R overrides
@@ -182,6 +190,10 @@ static WinWorkspace win_workspace(const snnflow_net_desc* d, const WinLayout& L,
 }  // namespace snnflow
 using namespace snnflow;
 
+// Planes of a recurrent layer: block 0 = the spikes entering the window, block 1 + t = the spikes of bin t.  Streaming
+// with T == 1 swaps the two blocks from call to call (no copy): the call with phase p reads block 1 - p and writes block p.
+static inline int win_rec_out_block(bool stream_mode, int T, int phase) { return (stream_mode && T == 1) ? phase : 1; }
+
 extern "C" int snnflow_window_supported(const snnflow_net_desc* d, int backward) { return win_supported(d, backward != 0) ? 1 : 0; }
 
 extern "C" size_t snnflow_window_arena_bytes(const snnflow_net_desc* d, int save) {
@@ -260,13 +272,13 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
     const unsigned char* xin;
     size_t x_img_stride;
     if (l == 0) { xin = A + L.off_inplanes; x_img_stride = 2 * L.g.plane_bytes; }
-    else { xin = A + L.off_zp[l - 1] + (L.rec[l - 1] ? (size_t)B * L.zp_img_stride : 0); x_img_stride = L.zp_img_stride; }
+    else { xin = A + L.off_zp[l - 1] + (L.rec[l - 1] ? (size_t)win_rec_out_block(stream_mode, T, phase) * B * L.zp_img_stride : 0); x_img_stride = L.zp_img_stride; }
     WtArgs a{};
     a.src[0].planes = xin; a.src[0].img_stride = x_img_stride;
     a.src[0].n_chunks = (uint32_t)(L.Kin[l] / 8); a.src[0].w_off = 0; a.src[0].w_terms = 3; a.src[0].w_used = 3;
     a.n_src = 1;
     a.wblob = A + L.off_fwd_blob[l]; a.wblob_bytes = L.fwd_blob_bytes[l];
-    a.B = B; a.H = H; a.W = W; a.Wp = W + 2; a.n_seg = ceil_div(W, 128); a.N = C;
+    a.B = B; a.H = H; a.W = W; a.Wp = W + 2; a.n_seg = P.n_col > 1 ? 1 : ceil_div(W, 128); a.n_col = P.n_col; a.N = C;
     a.hard_reset = (d->flags & SNNFLOW_HARD_RESET) ? 1 : 0;
     a.par = (const float*)(A + L.off_par[l]);
     a.zp_img_stride = L.zp_img_stride;
@@ -281,6 +293,18 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
       }
       if (l == 0) { a.R = P.R_head; a.S = P.S_head; a.sub_bytes = P.sub_head; a.chunk_stride = P.cs_head; a.stage_bytes = P.st_head; }
       else { a.R = P.R_ff; a.S = P.S_ff; a.sub_bytes = P.sub_ff; a.chunk_stride = P.cs_ff; a.stage_bytes = P.st_ff; }
+      if (stream_mode && T == 1 && wt_env_int("SNNFLOW_STREAM_STEP", 1)) {
+        // one bin per call: the step-mode epilogue requests the membrane and the spikes of the NEXT tile before it waits for
+        // the current accumulator (the sequence-mode epilogue loads them at the top of the tile and stalls on them: 59 % of
+        // its stall samples at T = 1; 121 vs 128 us per layer at 256x256 batch 16, profiles/r2_experiments.md); the state
+        // is read and written in place (a pixel is read by the thread that later writes it)
+        a.v_prev = state; a.v_prev_nchw = 0; a.v_out = state; a.cur_out = nullptr;
+        a.zp_out = A + L.off_zp[l];
+        a.v_last = nullptr; a.z_last = nullptr;
+        rc = launch_wt_fwd(a, false, st, "win_fwd_seq", px * (2.0 * L.Kin[l] + 12.0 * C), 18.0 * px * C * L.Cin[l]);
+        if (rc) return rc;
+        continue;
+      }
       a.v_init = v_init; a.z_init = z_init;
       a.v_out = save ? vbase : nullptr; a.cur_out = nullptr;
       a.zp_out = A + L.off_zp[l];
@@ -291,8 +315,11 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
     } else {
       // initial spikes of the window -> image block 0 of this layer's planes (zeros when there is no state)
       if (stream_mode) {   // ... which are the planes the previous call's last bin wrote (block T)
-        SNNFLOW_CUDA(cudaMemcpyAsync(A + L.off_zp[l], A + L.off_zp[l] + (size_t)T * B * L.zp_img_stride, (size_t)B * L.zp_img_stride,
-                                     cudaMemcpyDeviceToDevice, st));
+        if (T > 1)         // (T == 1: the two blocks swap roles from call to call instead, win_rec_out_block)
+          SNNFLOW_CUDA(cudaMemcpyAsync(A + L.off_zp[l], A + L.off_zp[l] + (size_t)T * B * L.zp_img_stride,
+                                       (size_t)B * L.zp_img_stride, cudaMemcpyDeviceToDevice, st));
+      } else if (z_init == nullptr) {
+        SNNFLOW_CUDA(cudaMemsetAsync(A + L.off_zp[l], 0, (size_t)B * L.zp_img_stride, st));
       } else {
         rc = launch_pack_spikes(z_init, A + L.off_zp[l], B, C, H, W, st);
         if (rc) return rc;
@@ -330,8 +357,9 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
         if (rc) return rc;
       } else
       for (int t = 0; t < T; ++t) {
+        const int blk_out = win_rec_out_block(stream_mode, T, phase) + t, blk_in = (stream_mode && T == 1) ? 1 - blk_out : t;
         a.src[0].planes = xin + (size_t)t * B * x_img_stride;
-        a.src[1].planes = A + L.off_zp[l] + (size_t)t * B * L.zp_img_stride;
+        a.src[1].planes = A + L.off_zp[l] + (size_t)blk_in * B * L.zp_img_stride;
         a.zin_planes = a.src[1].planes; a.zin_img_stride = L.zp_img_stride;
         const bool last = t == T - 1;
         a.v_prev_nchw = t == 0;   // the window's initial state is the caller's NCHW tensor
@@ -349,7 +377,7 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
           a.v_out = vbase + (size_t)(t & 1) * n; a.cur_out = nullptr;
         }
         a.v_last = last ? state : nullptr; a.z_last = last ? state + n : nullptr;
-        a.zp_out = A + L.off_zp[l] + (size_t)(t + 1) * B * L.zp_img_stride;
+        a.zp_out = A + L.off_zp[l] + (size_t)blk_out * B * L.zp_img_stride;
         rc = launch_wt_fwd(a, false, st, "win_fwd_rec", (double)px * (2.0 * L.Kin[l] + 14.0 * C),   /* x, z planes (bf16), v (fp32), z again in the epilogue in ; v, z out */
                            18.0 * px * C * (L.Cin[l] + C));
         if (rc) return rc;
@@ -357,7 +385,8 @@ extern "C" int snnflow_window_forward(const snnflow_net_desc* d, const snnflow_l
     }
   }
   const int top = WIN_LAYERS - 1;
-  return launch_pred_fwd_planes(A + L.off_zp[top] + (L.rec[top] ? (size_t)B * L.zp_img_stride : 0), L.zp_img_stride, pred_w,
+  return launch_pred_fwd_planes(A + L.off_zp[top] + (L.rec[top] ? (size_t)win_rec_out_block(stream_mode, T, phase) * B * L.zp_img_stride : 0),
+                                L.zp_img_stride, pred_w,
                                 pred_b, flow, T * B, C, H, W, st);
 }
 
@@ -369,9 +398,9 @@ static void win_stream_state(const WinLayout& L, const snnflow_net_desc* d, int 
     *v = (float*)(A + L.off_state[l]);
     *z_planes = A + L.off_zp[l] + (size_t)(T - 1) * B * L.zp_img_stride;
   } else {
-    // the next call reads slot (0 + phase_next + 1) & 1 and copies planes block T to block 0
+    // the next call reads slot (0 + phase_next + 1) & 1 and copies planes block T to block 0 (T == 1: reads block 1 - phase_next)
     *v = (float*)(A + L.off_v[l]) + (size_t)((phase_next + 1) & 1) * L.n;
-    *z_planes = A + L.off_zp[l] + (size_t)T * B * L.zp_img_stride;
+    *z_planes = A + L.off_zp[l] + (size_t)(T == 1 ? 1 - (phase_next & 1) : T) * B * L.zp_img_stride;
   }
 }
 

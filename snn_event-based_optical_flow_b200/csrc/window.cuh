@@ -51,6 +51,7 @@ struct WtArgs {
   int n_outer;   // sequence mode: B sequences (image = t*B + b) ; otherwise the number of images
   int T, B;
   int H, W, Wp, R, S, n_seg, N;   // R rows per tile, S pipeline stages, n_seg 128-pixel segments per row, N = MMA N
+  int n_col, Wsm;                 // forward kernels: 128-pixel column tiles per row (1 = whole rows); pitch of a tile row in shared memory
   uint32_t sub_bytes, chunk_stride, stage_bytes;
   int hard_reset, surrogate;
   float width;
@@ -110,7 +111,7 @@ int launch_wt_recbwd(const WtArgs& a, cudaStream_t st, double bytes, double flop
 int launch_wt_dgpw(const WtArgs& a, cudaStream_t st, double bytes, double flops);
 // picks rows-per-tile / stages for the given shapes; returns false when the shape does not fit
 bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int w_terms, bool tall, int* R, int* S,
-             uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes, int only_R = 0);
+             uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes, int only_R = 0, bool column_tiles = false);
 int wt_env_int(const char* name, int dflt);
 int wt_grid(int n_tiles);
 

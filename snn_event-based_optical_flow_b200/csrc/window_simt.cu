@@ -8,29 +8,44 @@
 namespace snnflow {
 
 // ---- fp32 NCHW -> bf16 planes ------------------------------------------------------------------------
-// thread = one pixel of one (image, chunk): reads up to 8 channel planes (coalesced along x), writes one 16-B slot
+// thread = four consecutive pixels of one (image, chunk): reads up to 8 channel planes (float4, coalesced along x), writes
+// four 16-B slots (64 contiguous bytes)
+// (PX = 1: any width / alignment)
+template <int PX>
 __global__ void __launch_bounds__(256) pack_planes_kernel(const float* __restrict__ in, unsigned char* __restrict__ planes,
                                                           int n_ch, int n_chunks, int H, int W,
                                                           unsigned int* __restrict__ inexact) {
   const int HW = H * W, Wp = W + 2;
-  const int p = blockIdx.x * 256 + threadIdx.x;
+  const int p = (blockIdx.x * 256 + threadIdx.x) * PX;
   const int chunk = blockIdx.y, img = blockIdx.z;
   if (p >= HW) return;
-  const int y = p / W, x = p - y * W;
-  uint32_t u[4] = {0, 0, 0, 0};
+  const int y = p / W, x = p - y * W;   // W is a multiple of 4: the four pixels share a row
+  uint32_t u[PX][4] = {};
   unsigned int bad = 0;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int ch = chunk * 8 + c;
-    float v = 0.f;
-    if (in != nullptr && ch < n_ch) v = __ldg(in + ((size_t)img * n_ch + ch) * HW + p);
-    const __nv_bfloat16 b = __float2bfloat16_rn(v);
-    bad += (__bfloat162float(b) != v);
-    u[c >> 1] |= (uint32_t)__bfloat16_as_ushort(b) << ((c & 1) * 16);
+    float v[PX] = {};
+    if (in != nullptr && ch < n_ch) {
+      const float* src = in + ((size_t)img * n_ch + ch) * HW + p;
+      if constexpr (PX == 4) {
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(src));
+        v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
+      } else {
+        v[0] = __ldg(src);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+      const __nv_bfloat16 b = __float2bfloat16_rn(v[k]);
+      bad += (__bfloat162float(b) != v[k]);
+      u[k][c >> 1] |= (uint32_t)__bfloat16_as_ushort(b) << ((c & 1) * 16);
+    }
   }
   const size_t plane_bytes = (size_t)(H + 2) * Wp * 16;
   unsigned char* dst = planes + ((size_t)img * n_chunks + chunk) * plane_bytes + ((size_t)(y + 1) * Wp + x + 1) * 16;
-  *reinterpret_cast<uint4*>(dst) = make_uint4(u[0], u[1], u[2], u[3]);
+#pragma unroll
+  for (int k = 0; k < PX; ++k) reinterpret_cast<uint4*>(dst)[k] = make_uint4(u[k][0], u[k][1], u[k][2], u[k][3]);
   // values that one bf16 term does not represent exactly: counted into the arena's sticky status word
   if (inexact != nullptr && bad) atomicAdd(inexact, bad);
 }
@@ -38,13 +53,19 @@ __global__ void __launch_bounds__(256) pack_planes_kernel(const float* __restric
 int launch_pack_input(const float* in, unsigned char* planes, int n_img, int nb, int n_chunks, int H, int W,
                       unsigned int* inexact, cudaStream_t st) {
   prof_begin("win_pack_input", st, (double)n_img * H * W * (4.0 * nb + 16.0 * n_chunks));
-  pack_planes_kernel<<<dim3(ceil_div(H * W, 256), n_chunks, n_img), 256, 0, st>>>(in, planes, nb, n_chunks, H, W, inexact);
+  if ((W & 3) == 0 && ((uintptr_t)in & 15) == 0)
+    pack_planes_kernel<4><<<dim3(ceil_div(H * W, 1024), n_chunks, n_img), 256, 0, st>>>(in, planes, nb, n_chunks, H, W, inexact);
+  else
+    pack_planes_kernel<1><<<dim3(ceil_div(H * W, 256), n_chunks, n_img), 256, 0, st>>>(in, planes, nb, n_chunks, H, W, inexact);
   return check_launch("pack_planes_kernel");
 }
 
 int launch_pack_spikes(const float* z, unsigned char* planes, int n_img, int C, int H, int W, cudaStream_t st) {
   prof_begin("win_pack_state", st, (double)n_img * H * W * (4.0 * C + 2.0 * C));
-  pack_planes_kernel<<<dim3(ceil_div(H * W, 256), C / 8, n_img), 256, 0, st>>>(z, planes, C, C / 8, H, W, nullptr);
+  if ((W & 3) == 0 && ((uintptr_t)z & 15) == 0)
+    pack_planes_kernel<4><<<dim3(ceil_div(H * W, 1024), C / 8, n_img), 256, 0, st>>>(z, planes, C, C / 8, H, W, nullptr);
+  else
+    pack_planes_kernel<1><<<dim3(ceil_div(H * W, 256), C / 8, n_img), 256, 0, st>>>(z, planes, C, C / 8, H, W, nullptr);
   return check_launch("pack_planes_kernel");
 }
 
@@ -684,9 +705,20 @@ __global__ void __launch_bounds__(256) win_reduce_kernel(const __grid_constant__
       const int co = i % C, rest = i / C, ci = rest % cr, tap = rest / cr;
       float s = 0.f;
       if (i < n) {
+        // all partials of a thread in flight at once (20 x 8 stripes covers one partial block per SM): the kernel is
+        // a handful of dependent DRAM round trips, not bandwidth (45 MB); the sum keeps its order
         const float* src = a.wpart[job] + ((size_t)tap * ca + ci) * C + co;
-#pragma unroll 4
-        for (int p = stripe; p < a.n_wpart; p += 8) s += src[(size_t)p * pstride];
+#pragma unroll 1
+        for (int p0 = stripe; p0 < a.n_wpart; p0 += 8 * 20) {
+          float v[20];
+#pragma unroll
+          for (int k = 0; k < 20; ++k) {
+            const int p = p0 + 8 * k;
+            v[k] = p < a.n_wpart ? __ldg(src + (size_t)p * pstride) : 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 20; ++k) s += v[k];
+        }
       }
       red[stripe][lane] = s;
       __syncthreads();
@@ -703,10 +735,18 @@ __global__ void __launch_bounds__(256) win_reduce_kernel(const __grid_constant__
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int r = warp_global; r < 2 * a.C; r += n_warps) {
       float s = 0.f;
-      if (a.cpart_layout == 0) {
-        for (int j = lane; j < a.n_cpart; j += 32) s += a.cpart[(size_t)r * a.n_cpart + j];
-      } else {
-        for (int j = lane; j < a.n_cpart; j += 32) s += a.cpart[(size_t)j * 2 * a.C + r];
+      const float* src = a.cpart_layout == 0 ? a.cpart + (size_t)r * a.n_cpart : a.cpart + r;
+      const size_t js = a.cpart_layout == 0 ? 1 : (size_t)2 * a.C;
+#pragma unroll 1
+      for (int j0 = lane; j0 < a.n_cpart; j0 += 32 * 16) {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int j = j0 + 32 * k;
+          v[k] = j < a.n_cpart ? __ldg(src + (size_t)j * js) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s += v[k];
       }
       s = warp_sum(s);
       if (lane == 0) {

@@ -68,35 +68,11 @@ __device__ __forceinline__ WtSmem wt_smem(unsigned char* smem, uint32_t wblob_by
   return s;
 }
 
-struct ItemPos {
-  int img, b, y0, t;
-};
-
 template <bool SEQ>
 __device__ __forceinline__ int wt_n_items(const WtArgs& a) {
-  const int n_tiles = a.n_outer * (a.H / a.R);
+  const int n_tiles = a.n_outer * (a.H / a.R) * a.n_col;
   const int mine = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   return SEQ ? mine * a.T : mine;
-}
-
-template <bool SEQ>
-__device__ __forceinline__ ItemPos wt_item(const WtArgs& a, int k) {
-  const int tpi = a.H / a.R;
-  ItemPos p;
-  if (SEQ) {
-    const int tile = blockIdx.x + (k / a.T) * gridDim.x;
-    p.t = k % a.T;
-    p.b = tile / tpi;
-    p.y0 = (tile - p.b * tpi) * a.R;
-    p.img = p.t * a.B + p.b;
-  } else {
-    const int tile = blockIdx.x + k * gridDim.x;
-    p.t = 0;
-    p.img = tile / tpi;
-    p.b = p.img;
-    p.y0 = (tile - p.img * tpi) * a.R;
-  }
-  return p;
 }
 
 // Walks this CTA's pipeline items in launch order without per-item divisions.
@@ -104,13 +80,27 @@ __device__ __forceinline__ ItemPos wt_item(const WtArgs& a, int k) {
 //   step mode    : one item per tile, images and row blocks advance by gridDim.x tiles.
 template <bool SEQ>
 struct ItemIter {
-  int img, b, y0, t;
-  int tile, tpi, T, B, R, H, grid, step_rows;
-  __device__ __forceinline__ void init(const WtArgs& a) {
-    tpi = a.H / a.R; T = a.T; B = a.B; R = a.R; H = a.H; grid = (int)gridDim.x; step_rows = grid * a.R;
-    tile = (int)blockIdx.x;
+  int img, b, y0, x0, t;
+  int tile, tpi, T, B, R, H, grid, step_rows, n_col;
+  // tile -> (b, y0, x0).  Column tiling (n_col > 1, forward kernels on rows wider than one 128-pixel segment): consecutive
+  // tiles are the column tiles of one row block, so neighbours in launch order share their halo rows in L2.
+  __device__ __forceinline__ void locate() {
     b = tile / tpi;
-    y0 = (tile - b * tpi) * R;
+    const int r = tile - b * tpi;
+    if (n_col > 1) {
+      const int yb = r / n_col;
+      x0 = (r - yb * n_col) * 128;
+      y0 = yb * R;
+    } else {
+      x0 = 0;
+      y0 = r * R;
+    }
+  }
+  __device__ __forceinline__ void init(const WtArgs& a) {
+    n_col = a.n_col;
+    tpi = (a.H / a.R) * n_col; T = a.T; B = a.B; R = a.R; H = a.H; grid = (int)gridDim.x; step_rows = grid * a.R;
+    tile = (int)blockIdx.x;
+    locate();
     t = 0;
     img = b;
   }
@@ -119,8 +109,11 @@ struct ItemIter {
       if (++t < T) { img += B; return; }
       t = 0;
       tile += grid;
-      b = tile / tpi;
-      y0 = (tile - b * tpi) * R;
+      locate();
+      img = b;
+    } else if (n_col > 1) {
+      tile += grid;
+      locate();
       img = b;
     } else {
       y0 += step_rows;
@@ -184,6 +177,8 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
   const size_t plane_bytes = (size_t)(a.H + 2) * a.Wp * 16, row_bytes = (size_t)a.Wp * 16;
   const uint32_t sub_bytes = a.sub_bytes, chunk_stride = a.chunk_stride, stage_bytes = a.stage_bytes;
   const bool t_rev = a.t_reverse != 0;
+  const int n_col = a.n_col;
+  const uint32_t col_row_bytes = (uint32_t)a.Wsm * 16u;
   // this lane's chunk of either source
   const unsigned char* base[WT_MAX_SRC];
   size_t img_stride[WT_MAX_SRC];
@@ -229,7 +224,17 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
           mbar_expect_tx(&s.full[st], n_chunks[si] * sub_bytes);
         }
         __syncwarp();
-        if ((uint32_t)lane < n_chunks[si]) {
+        if (n_col > 1) {
+          // column tile: (R + 2) rows of 128 + 2 pixels per chunk, one bulk copy per row and chunk (lane = chunk * rows + row)
+          const int rows = it.R + 2, chunk = lane / rows, row = lane - chunk * rows;
+          if ((uint32_t)chunk < n_chunks[si]) {
+            const int img = (SEQ && t_rev) ? (it.T - 1 - it.t) * it.B + it.b : it.img;
+            tma_bulk_g2s(s.stages + (size_t)st * stage_bytes + (size_t)chunk * chunk_stride + (size_t)row * col_row_bytes,
+                         a.src[si].planes + (size_t)chunk * plane_bytes + (long long)bin * a.bin_src_stride[si] +
+                             (size_t)img * img_stride[si] + (size_t)(it.y0 + row) * row_bytes + (size_t)it.x0 * 16,
+                         col_row_bytes, &s.full[st]);
+          }
+        } else if ((uint32_t)lane < n_chunks[si]) {
           const int img = (SEQ && t_rev) ? (it.T - 1 - it.t) * it.B + it.b : it.img;
           tma_bulk_g2s(s.stages + (size_t)st * stage_bytes + (size_t)lane * chunk_stride,
                        base[si] + (long long)bin * a.bin_src_stride[si] + (size_t)img * img_stride[si] + (size_t)it.y0 * row_bytes,
@@ -284,7 +289,7 @@ __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) aoff[tap][kk] = a_lo_c | ((uint32_t)((tap / 3) * a.Wp + tap % 3) + 2u * kk * cs16);
+    for (int kk = 0; kk < 2; ++kk) aoff[tap][kk] = a_lo_c | ((uint32_t)((tap / 3) * a.Wsm + tap % 3) + 2u * kk * cs16);
 #pragma unroll
   for (int si = 0; si < NS; ++si) {
     const WtSrc& S = a.src[si < a.n_src ? si : 0];
@@ -334,7 +339,7 @@ __device__ void wt_mma(const WtArgs& a, const WtSmem& s, uint32_t tmem_base) {
           if (n_kk[si] > 1) umma_f16_split(d, aoff[tap][1] + a_base, d_hi, b1, d_hi, idesc[si], 1u);
         }
         d += ncat;
-        if (++seg == a.n_seg) { seg = 0; a_base += (uint32_t)(a.Wp - (a.n_seg - 1) * 128); }
+        if (++seg == a.n_seg) { seg = 0; a_base += (uint32_t)(a.Wsm - (a.n_seg - 1) * 128); }
         else a_base += 128u;
       }
       umma_commit(&s.empty[st]);
@@ -438,14 +443,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
     if constexpr (SEQ) {
       // Time-fused feed-forward layer: a tile (b, y0) is walked through its T bins with the membrane and the previous
       // spikes in registers and RUNNING output pointers - one bin ahead is a constant step, nothing is re-derived per item.
-      const int tpi = a.H / a.R, n_tiles = a.n_outer * tpi, B = a.B;
+      const int n_col = a.n_col, tpi = (a.H / a.R) * n_col, n_tiles = a.n_outer * tpi, B = a.B;
       const long long v_bin = (long long)B * nch * (long long)HW * 8;          // floats between bins (c8 membranes)
       const long long zp_bin = (long long)B * (long long)zp_img_stride;        // bytes between bins (spike planes)
       const bool have_v = a.v_out != nullptr, want_last = a.v_last != nullptr || a.z_last != nullptr;
       const bool state_c8 = a.state_c8 != 0;
       uint32_t k = 0;
       for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
-        const int b = tile / tpi, y0 = (tile - b * tpi) * a.R;
+        const int b = tile / tpi, rt = tile - b * tpi;
+        const int y0 = (n_col > 1 ? rt / n_col : rt) * a.R, x0 = n_col > 1 ? (rt % n_col) * 128 : 0;
         float* vp[NSEG];
         unsigned char* zp[NSEG];
         size_t o_state[NSEG], o_c8[NSEG];
@@ -453,7 +459,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
         float vst[NSEG][8], zst[NSEG][8];
 #pragma unroll
         for (int m = 0; m < NSEG; ++m) {
-          const int y = y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
+          const int y = y0 + m / n_seg, x = x0 + (m % n_seg) * 128 + q * 32 + lane;
           const size_t pix = (size_t)y * W + x;
           okm[m] = act && x < W;
           vp[m] = have_v ? a.v_out + c8_off(b, nch, ch, HW, pix) : nullptr;
@@ -560,13 +566,13 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
       float vst[NSEG][8], vnx[NSEG][8];
       uint4 zq[NSEG], znx[NSEG];
       // inputs of item (b, y0) of bin `bin` -> v, z  (zeros where there is no state)
-      auto request = [&](int b, int y0, int bin, float (&v)[NSEG][8], uint4 (&z)[NSEG]) {
+      auto request = [&](int b, int y0, int x0, int bin, float (&v)[NSEG][8], uint4 (&z)[NSEG]) {
         const float* v_prev = bin == 0 ? a.v_prev : a.v_out + (size_t)((bin - 1) & bin_v_mask) * bin_v_stride;
         const bool nchw = bin == 0 && a.v_prev_nchw;
         const unsigned char* zin = a.zin_planes ? a.zin_planes + (long long)bin * bin_zp_stride : nullptr;
 #pragma unroll
         for (int m = 0; m < NSEG; ++m) {
-          const int y = y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
+          const int y = y0 + m / n_seg, x = x0 + (m % n_seg) * 128 + q * 32 + lane;
           const bool ok = act && x < W;
           const size_t pix = (size_t)y * W + x;
 #pragma unroll
@@ -599,15 +605,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
       ItemIter<false> it, nx;
       it.init(a);
       nx.init(a);
-      int bin = 0, k = 0, nbin = 0, nk = 0;
-      if (total > 0) request(it.b, it.y0, 0, vst, zq);
-      for (int g = 0; g < total; ++g) {
-        // position of the next item, and its inputs on their way
-        const bool have_next = g + 1 < total;
-        if (have_next) {
-          if (++nk == n_items) { nk = 0; ++nbin; nx.init(a); } else nx.next();
-          if (ahead_ok) request(nx.b, nx.y0, nbin, vnx, znx);
-        }
+      int bin = 0, nbin = 0, nk = 0;
+      // one item: accumulator + (v, z) of set `vs / zs` -> new membrane and spikes, stored; the accumulator is handed back
+      auto process = [&](int g, float (&vs)[NSEG][8], uint4 (&zs)[NSEG]) {
         const uint32_t ab = (uint32_t)g & acc_mask;
         const bool last = bin == n_bins - 1 && (a.v_last != nullptr || a.z_last != nullptr) && !a.state_c8;
         float* const v_out = a.v_out ? a.v_out + (size_t)(bin & bin_v_mask) * bin_v_stride : nullptr;
@@ -631,18 +631,18 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
           tmem_ld_wait();
 #pragma unroll
           for (int m = 0; m < NSEG; ++m) {
-            const uint32_t zw[4] = {zq[m].x, zq[m].y, zq[m].z, zq[m].w};
+            const uint32_t zw[4] = {zs[m].x, zs[m].y, zs[m].z, zs[m].w};
             float zn[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               const float4 pr = par[c];   // (lam, 1 - lam, theta, .): broadcast read, keeps 24 registers free
               const float zin_c = ((zw[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu) ? 1.f : 0.f;
               const float cur = (__uint_as_float(u0[m][c]) + __uint_as_float(u1[m][c])) + __uint_as_float(u2[m][c]);   // hi + mid + lo terms
-              const float t1 = __fmul_rn(vst[m][c], pr.x), t3 = __fmul_rn(pr.y, cur);
+              const float t1 = __fmul_rn(vs[m][c], pr.x), t3 = __fmul_rn(pr.y, cur);
               float vn;
               if (HARD) vn = __fadd_rn(__fmul_rn(t1, __fsub_rn(1.0f, zin_c)), t3);    // spiking_submodules.py:144
               else vn = __fsub_rn(__fadd_rn(t1, t3), __fmul_rn(zin_c, pr.z));         // spiking_submodules.py:146
-              vst[m][c] = vn;
+              vs[m][c] = vn;
               zn[c] = __fsub_rn(vn, pr.z) > 0.f ? 1.f : 0.f;                          // spiking_util.py:21
             }
             asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz[m].x) : "f"(zn[1]), "f"(zn[0]));
@@ -650,20 +650,18 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
             asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz[m].z) : "f"(zn[5]), "f"(zn[4]));
             asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(zz[m].w) : "f"(zn[7]), "f"(zn[6]));
           }
-        }
-        if (act) {
 #pragma unroll
           for (int m = 0; m < NSEG; ++m) {
-            const int y = it.y0 + m / n_seg, x = (m % n_seg) * 128 + q * 32 + lane;
+            const int y = it.y0 + m / n_seg, x = it.x0 + (m % n_seg) * 128 + q * 32 + lane;
             if (x < W) {
               const size_t pix = (size_t)y * W + x;
               *reinterpret_cast<uint4*>(zp_out + (size_t)it.img * zp_img_stride + ((size_t)(y + 1) * Wp + x + 1) * 16) = zz[m];
-              if (v_out) st8_c8(v_out + c8_off(it.img, nch, ch, HW, pix), vst[m]);
+              if (v_out) st8_c8(v_out + c8_off(it.img, nch, ch, HW, pix), vs[m]);
               if (last) {   // the caller-visible state [2,B,C,H,W] after the window
                 const size_t o = ((size_t)(it.b * N + ch * 8)) * HW + pix;
                 if (a.v_last) {
 #pragma unroll
-                  for (int c = 0; c < 8; ++c) a.v_last[o + (size_t)c * HW] = vst[m][c];
+                  for (int c = 0; c < 8; ++c) a.v_last[o + (size_t)c * HW] = vs[m][c];
                 }
                 if (a.z_last) {
                   const uint32_t zw[4] = {zz[m].x, zz[m].y, zz[m].z, zz[m].w};
@@ -683,19 +681,28 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
           }
           mbar_arrive(&s.pub_bar[g & (WT_PUB_RING - 1)]);   // release.cta: orders this thread's plane / membrane stores
         }
-        if (have_next) {
-          if (ahead_ok) {
-#pragma unroll
-            for (int m = 0; m < NSEG; ++m) {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) vst[m][c] = vnx[m][c];
-              zq[m] = znx[m];
-            }
-          } else {
-            request(nx.b, nx.y0, nbin, vst, zq);
-          }
-        }
-        it = nx; bin = nbin; k = nk;
+      };
+      // position of the item after `it`, and its inputs on their way into the OTHER register set
+      auto advance = [&](int g, float (&vs)[NSEG][8], uint4 (&zs)[NSEG]) -> bool {
+        if (g + 1 >= total) return false;
+        if (++nk == n_items) { nk = 0; ++nbin; nx.init(a); } else nx.next();
+        if (ahead_ok) request(nx.b, nx.y0, nx.x0, nbin, vs, zs);
+        return true;
+      };
+      // Two items per trip with the register sets swapping roles (no copies: a copy would be the first use of the loads in
+      // flight and stall on them at the end of every item - what the first version of this loop did).
+      if (total > 0) request(it.b, it.y0, it.x0, 0, vst, zq);
+      for (int g = 0; g < total;) {
+        bool have_next = advance(g, vnx, znx);
+        process(g, vst, zq);
+        if (!have_next) break;
+        if (!ahead_ok) request(nx.b, nx.y0, nx.x0, nbin, vnx, znx);   // (the next item's inputs are this item's outputs)
+        it = nx; bin = nbin; ++g;
+        have_next = advance(g, vst, zq);
+        process(g, vnx, znx);
+        if (!have_next) break;
+        if (!ahead_ok) request(nx.b, nx.y0, nx.x0, nbin, vst, zq);
+        it = nx; bin = nbin; ++g;
       }
     }
     if (a.dbg && tid == 0) {
@@ -1187,8 +1194,10 @@ int wt_env_int(const char* name, int dflt) {
 
 bool wt_plan(int H, int W, int max_chunks_per_stage, int N, uint32_t wblob_bytes, bool seq_state, int w_terms, bool tall, int* R_out,
              int* S_out,
-             uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes, int only_R) {
-  const int Wp = W + 2, n_seg = ceil_div(W, 128);
+             uint32_t* sub_bytes, uint32_t* chunk_stride, uint32_t* stage_bytes, int only_R, bool column_tiles) {
+  // column_tiles: the tile is (R rows) x (one 128-pixel segment) with a one-pixel halo, loaded row by row (W = n_col * 128)
+  const int Wp = column_tiles ? 130 : W + 2, n_seg = column_tiles ? 1 : ceil_div(W, 128);
+  if (column_tiles && (W % 128 != 0 || W <= 128)) return false;
   if (N > 32) return false;   // one 16-channel group per epilogue warp pair
   const size_t budget = (size_t)227 * 1024 - WT_HDR - WT_TAIL - align_up(wblob_bytes, 128);
   const int forced_R = only_R ? only_R : env_int("SNNFLOW_WT_R", 0), forced_S = env_int("SNNFLOW_WT_S", 0);
@@ -1242,7 +1251,9 @@ static int wt_launch(K kernel, const void* key, const WtArgs& a_in, cudaStream_t
   a.l2_prefetch = l2_pf;
   static const int exp_bits = env_int("SNNFLOW_EXP", 0);   // experiment switches (see wt_fwd_kernel); 0 in production
   a.exp = exp_bits;
-  const int n_tiles = a.n_outer * (a.H / a.R);
+  if (a.n_col < 1) a.n_col = 1;
+  a.Wsm = a.n_col > 1 ? 130 : a.Wp;   // shared-memory row pitch of an operand tile, in pixel slots
+  const int n_tiles = a.n_outer * (a.H / a.R) * a.n_col;
   {   // accumulator ring: as many buffers (2 or 4) as the 512 TMEM columns hold
     const uint32_t acc_cols = (uint32_t)(a.R * a.n_seg * a.N) * a.src[0].w_terms;
     static const int max_lg = env_int("SNNFLOW_WT_ACC_LG", 2);
