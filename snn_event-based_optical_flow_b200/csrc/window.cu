@@ -169,7 +169,7 @@ static WinWorkspace win_workspace(const snnflow_net_desc* d, const WinLayout& L,
   }
   // per-layer partial blocks: the reductions of all layers run as ONE launch at the end of the backward pass
   for (int l = 0; l < WIN_LAYERS; ++l) {
-    const int g = wg_grid(T * B, d->H, d->W, C, L.Kin[l] / 8, L.rec[l] ? C / 8 : 0);
+    const int g = wg_parts(T * B, d->H, d->W, C, L.Kin[l] / 8, L.rec[l] ? C / 8 : 0);
     W.off_wpart[l][0] = take((size_t)g * 9 * L.Kin[l] * C * sizeof(float));
     W.off_wpart[l][1] = L.rec[l] ? take((size_t)g * 9 * C * C * sizeof(float)) : W.off_wpart[l][0];
   }
@@ -600,7 +600,7 @@ extern "C" int snnflow_window_backward(const snnflow_net_desc* d, const snnflow_
       WinReduceArgs r{};
       r.wpart[0] = wpart[0]; r.wdst[0] = P_.dw_ff; r.cin_alloc[0] = L.Kin[l]; r.cin_real[0] = L.Cin[l];
       r.wpart[1] = wpart[1]; r.wdst[1] = L.rec[l] ? P_.dw_rec : nullptr; r.cin_alloc[1] = C; r.cin_real[1] = C;
-      r.n_wpart = wg_grid(T * B, H, W, C, L.Kin[l] / 8, L.rec[l] ? C / 8 : 0);
+      r.n_wpart = wg_parts(T * B, H, W, C, L.Kin[l] / 8, L.rec[l] ? C / 8 : 0);
       r.cpart = cpart; r.n_cpart = n_cpart; r.cpart_layout = cpart_layout;
       r.dlam = P_.dlam; r.dtheta = P_.dtheta; r.C = C;
       r.lam = P_.lam; r.thresh_raw = P_.thresh_raw; r.d_leak = P_.d_leak; r.d_thresh = P_.thresh_raw ? P_.d_thresh : nullptr;

@@ -122,13 +122,15 @@ struct WgArgs {
   int x_chunks[2], cin_alloc[2], cin_real[2], n_xsrc;
   const unsigned char* gp;
   unsigned long long g_img_stride, g_term_stride;
-  float* part[2];   // per source: [grid][9][cin_alloc][C]
+  float* part[2];   // per source: [wg_parts][9][cin_alloc][C]
   int n_img, H, W, Wp, R, S, C, P, n_cg, rpm, n_kyg, ksteps, x_rows;
+  int pair;         // both gradient rows of a two-row tile in ONE MMA (N = 4C); two partial blocks per CTA
   uint32_t stage_bytes, g_off;
   long long* dbg;   // optional [grid][8] cycle counters (SNNFLOW_WT_TIMING=1)
 };
 bool wg_supported(int C, int cin_chunks, int rec_chunks, int H, int W);
 int wg_grid(int n_img, int H, int W, int C, int cin_chunks, int rec_chunks);
+int wg_parts(int n_img, int H, int W, int C, int cin_chunks, int rec_chunks);   // partial blocks the launch writes per source
 int launch_wgrad_planes(WgArgs a, cudaStream_t st, double bytes, double flops);
 
 // ---- CUDA-core helpers (window_simt.cu) ---------------------------------------------------------------

@@ -12,6 +12,12 @@
 // address.  g_I comes as bf16 hi + lo planes (two MMAs per k-step); its zero border column and the zeroed pad slots
 // make the k-steps that run past the end of a row contribute nothing.
 // Each persistent CTA writes one partial block [tap][ci][co]; window_reduce sums them in a fixed order.
+//
+// Paired mode (feed-forward layers, two-row tiles): the kernel is bound by SHARED-MEMORY bandwidth - every K = 16 MMA
+// re-reads its 4 KB A tile and its B tile, 288 KB per two-row item next to the 66 KB the bulk copies write, at 128 B/clk -
+// so both gradient rows of the tile ride in ONE MMA (N = 4C: [row0 hi | row0 lo | row1 hi | row1 lo], contiguous chunk groups
+// of the gradient tile) against the four input rows y0 .. y0+3: 8 KB per two rows instead of 12.  Accumulator block
+// (input row i, gradient row c) holds vertical tap ky = i - c; the two blocks of a tap go to two partial blocks.
 #include "tcgen05.cuh"
 #include "window.cuh"
 
@@ -37,7 +43,7 @@ __device__ __forceinline__ int wg_n_items(const WgArgs& a) {
 }
 
 __device__ __forceinline__ uint32_t wg_tmem_cols(const WgArgs& a) {
-  const uint32_t need = (uint32_t)(a.n_kyg * 3 * 2 * a.C);   // [x*g_hi | x*g_lo] per (tap group, kx)
+  const uint32_t need = a.pair ? (uint32_t)(3 * 4 * a.C) : (uint32_t)(a.n_kyg * 3 * 2 * a.C);   // [x*g_hi | x*g_lo] per (tap group, kx)
   uint32_t c = 32;
   while (c < need) c <<= 1;
   return c;
@@ -127,6 +133,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
       // N = 2C: the hi and lo planes of g_I are adjacent chunk groups of one row, so ONE MMA per k-step yields both
       // partial products (columns [0,C) and [C,2C)); the read-out adds them.
       const uint32_t idesc = make_idesc(128, 2 * a.C, /*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1);
+      const uint32_t idesc_pair = make_idesc(128, 4 * a.C, /*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1);
       const uint32_t stages16 = smem_u32(stages) >> 4, pitch16 = pitch >> 4;
       const uint32_t lo_c = ((128u >> 4) << 16), d_hi = desc_hi(pitch);   // LBO = 128 B (k groups), SBO = pitch (chunk groups)
       long long t_wait = 0;
@@ -140,6 +147,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
         }
         tc_fence_after();
         const uint32_t xs16 = stages16 + ((st * a.stage_bytes) >> 4), gs16 = xs16 + (a.g_off >> 4);
+        if (a.pair) {
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const uint32_t d = tmem_base + (uint32_t)(kx * 4 * a.C);
+            uint32_t a_lo = lo_c | (xs16 + (uint32_t)kx), b_lo = lo_c | (gs16 + 1u);
+            umma_f16_split(d, a_lo, d_hi, b_lo, d_hi, idesc_pair, k > 0 ? 1u : 0u);
+#pragma unroll 4
+            for (int kk = 1; kk < a.ksteps; ++kk) {
+              a_lo += 16u;
+              b_lo += 16u;
+              umma_f16_split(d, a_lo, d_hi, b_lo, d_hi, idesc_pair, 1u);
+            }
+          }
+        } else
         for (int r = 0; r < a.R; ++r) {
           const uint32_t grow16 = gs16 + (uint32_t)(r * 2 * g_chunks) * pitch16 + 1u;
           for (int j = 0; j < a.n_kyg; ++j) {
@@ -177,6 +198,29 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
     const int si = (cg < a.x_chunks[0]) ? 0 : 1;
     const int ci = (si == 0 ? cg : cg - a.x_chunks[0]) * 8 + c;
     const bool row_used = i < a.rpm;
+    if (a.pair) {
+      // (kx, c): accumulator columns kx*4C + c*2C + [hi | lo]; this thread's input row i carries tap ky = i - c of gradient
+      // row c; partial block 2*blockIdx.x + c (every tap of a block is written by exactly one thread)
+      for (int id = par; id < 6; id += 2) {
+        const int kx = id >> 1, cb = id & 1;
+        const int ky = i - cb;
+        const bool ok = ky >= 0 && ky < 3 && ci < a.cin_real[si];
+        float* dst = a.part[si] + ((size_t)(2 * blockIdx.x + cb) * 9 + (ky * 3 + kx)) * a.cin_alloc[si] * a.C + (size_t)ci * a.C;
+        for (int g = 0; g < (a.C >> 4); ++g) {
+          float acc[16], acc1[16];
+          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kx * 4 * a.C + cb * 2 * a.C + g * 16);
+          tmem_ld16(tcol, acc);
+          tmem_ld16(tcol + (uint32_t)a.C, acc1);
+#pragma unroll
+          for (int v = 0; v < 16; ++v) acc[v] += acc1[v];
+          if (ok) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              reinterpret_cast<float4*>(dst + g * 16)[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+          }
+        }
+      }
+    } else
     for (int acc_id = par; acc_id < a.n_kyg * 3; acc_id += 2) {
       const int j = acc_id / 3, kx = acc_id - j * 3;
       const int ky = j * a.rpm + i;
@@ -204,7 +248,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
 
 // ---- host ---------------------------------------------------------------------------------------------------
 struct WgPlan {
-  int n_cg, rpm, n_kyg, ksteps, P, x_rows, R, S;
+  int n_cg, rpm, n_kyg, ksteps, P, x_rows, R, S, pair;
   uint32_t stage_bytes, g_off;
   bool ok;
 };
@@ -238,6 +282,7 @@ static WgPlan wg_plan(int C, int cin_chunks, int rec_chunks, int H, int W) {
     if (forced_S && S > forced_S) S = forced_S;
     if (S < 2) continue;
     p.R = R; p.S = S; p.x_rows = x_rows;
+    p.pair = (R == 2 && p.n_kyg == 1 && p.rpm >= 4 && 3 * 4 * C <= 512 && wg_env_int("SNNFLOW_WG_PAIR", 1)) ? 1 : 0;
     p.g_off = (uint32_t)xb;
     p.stage_bytes = (uint32_t)stage;
     p.ok = true;
@@ -255,6 +300,11 @@ int wg_grid(int n_img, int H, int W, int C, int cin_chunks, int rec_chunks) {
   return n_tiles < sm_count() ? n_tiles : sm_count();
 }
 
+int wg_parts(int n_img, int H, int W, int C, int cin_chunks, int rec_chunks) {
+  const WgPlan p = wg_plan(C, cin_chunks, rec_chunks, H, W);
+  return wg_grid(n_img, H, W, C, cin_chunks, rec_chunks) * (p.ok && p.pair ? 2 : 1);
+}
+
 int launch_wgrad_planes(WgArgs a, cudaStream_t st, double bytes, double flops) {
   const WgPlan p = wg_plan(a.C, a.x_chunks[0], a.n_xsrc > 1 ? a.x_chunks[1] : 0, a.H, a.W);
   if (!p.ok) {
@@ -262,7 +312,7 @@ int launch_wgrad_planes(WgArgs a, cudaStream_t st, double bytes, double flops) {
     return SNNFLOW_EINVAL;
   }
   a.n_cg = p.n_cg; a.rpm = p.rpm; a.n_kyg = p.n_kyg; a.ksteps = p.ksteps; a.P = p.P; a.x_rows = p.x_rows;
-  a.R = p.R; a.S = p.S; a.stage_bytes = p.stage_bytes; a.g_off = p.g_off; a.Wp = a.W + 2;
+  a.R = p.R; a.S = p.S; a.stage_bytes = p.stage_bytes; a.g_off = p.g_off; a.Wp = a.W + 2; a.pair = p.pair;
   const size_t smem = WG_HDR + (size_t)a.S * a.stage_bytes;
   static size_t attr = 0;
   if (smem > attr) {
@@ -284,8 +334,8 @@ int launch_wgrad_planes(WgArgs a, cudaStream_t st, double bytes, double flops) {
     double avg[8] = {0};
     for (int i = 0; i < grid; ++i)
       for (int j = 0; j < 8; ++j) avg[j] += (double)h[i * 8 + j] / grid;
-    fprintf(stderr, "[wt-timing] wg_planes_kernel R=%d S=%d n_cg=%d items/CTA=%.1f | producer %.0f (wait-empty %.0f) | mma %.0f (wait-full %.0f)\n",
-            a.R, a.S, a.n_cg, (double)n_tiles / grid, avg[0], avg[1], avg[2], avg[3]);
+    fprintf(stderr, "[wt-timing] wg_planes_kernel R=%d S=%d n_cg=%d pair=%d items/CTA=%.1f | producer %.0f (wait-empty %.0f) | mma %.0f (wait-full %.0f)\n",
+            a.R, a.S, a.n_cg, a.pair, (double)n_tiles / grid, avg[0], avg[1], avg[2], avg[3]);
     return check_launch("wg_planes_kernel");
   }
   SNNFLOW_CUDA(launch_pdl(wg_planes_kernel, dim3(grid), dim3(WG_THREADS), smem, st, a));
