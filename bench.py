@@ -718,7 +718,7 @@ def run_cfg0(a, snnflow, dev, n_frames=200):
     ms = ev0.elapsed_time(ev1) / n_frames
     out = {"metric": "LIFFireNet eval frames/s @128x128, batch 1, model() + compute_pol_iwe per frame (BASELINE.json configs[0])",
            "value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "frames_timed": n_frames,
-           "api": "per-bin forward() with model.graph_forward() (CUDA-graph replay of the 7 cells + flow head), eager compute_pol_iwe"}
+           "api": "per-bin forward() with model.graph_forward() (CUDA-graph replay of the streamed bin: 9 launches, state inside the engine), eager compute_pol_iwe"}
     net.graph_forward(False)
     with torch.no_grad():
         net.reset_states()

@@ -497,13 +497,16 @@ class WindowRunner:
         desc.flags |= _lib.STATE_INTERNAL | extra_flags
         return desc
 
-    def stream_forward(self, x, states):
+    def stream_forward(self, x, states, graph=False):
         """One time bin through snnflow_window_forward (T = 1, SNNFLOW_STATE_INTERNAL).  `states`: the network's NCHW state
         list - imported into the arena only when it is newer than the arena's own state (first call, reset_states(), a
-        state assigned by the caller).  Returns flow [B,2,H,W]."""
+        state assigned by the caller).  Returns flow [B,2,H,W].
+        graph=True (model.graph_forward()): the launches of a bin are replayed as a CUDA graph - one per phase of the
+        recurrent layers' ping-pong slots - from a static copy of the input; the flow map returned is the graph's own
+        buffer (overwritten two calls later).  A call that has to re-pack the weights runs eagerly."""
         L = _lib.lib()
         _bind(L)
-        layers, net = self.layers, self.net
+        layers = self.layers
         B, nb, H, W = x.shape
         dev = x.device
         x = x.float().contiguous()
@@ -513,7 +516,7 @@ class WindowRunner:
         wkey = tuple((p.data_ptr(), p._version) for l in layers for p in ((l.ff.weight, l.rec.weight, l.leak, l.thresh) if l.recurrent
                                                                         else (l.ff.weight, l.leak, l.thresh)))
         if st is None or st["shape"] != tuple(x.shape) or st["dev"] != dev:
-            st = self._stream = dict(shape=tuple(x.shape), dev=dev, phase=0, wkey=None, lam=None, theta=None)
+            st = self._stream = dict(shape=tuple(x.shape), dev=dev, phase=0, wkey=None, lam=None, theta=None, graphs=None)
             self.stream_live = False
         if not self.stream_live:      # the NCHW list is the truth: bring it into the arena
             C = layers[0].hidden_size
@@ -532,6 +535,30 @@ class WindowRunner:
         if not reuse:
             st["lam"], st["theta"] = _effective_params(self, layers)
             st["wkey"] = wkey
+        if graph and reuse and not torch.cuda.is_current_stream_capturing():
+            gs = st.get("graphs")
+            if gs is None:
+                gs = st["graphs"] = self._stream_capture(x, st, arena)
+            ph = st["phase"]
+            gs["x"].copy_(x)
+            gs["graph"][ph].replay()
+            flow = gs["flow"][ph]
+            st["phase"] = ph ^ 1
+        else:
+            flow = self._stream_launch(x, st, arena, reuse)
+        foff = L.snnflow_window_flags_offset(ctypes.byref(desc0), 0)
+        self.input_flag = arena[foff:foff + 4].view(torch.int32)
+        st["calls"] = st.get("calls", 0) + 1
+        if self.validate_input and not torch.cuda.is_current_stream_capturing() and (st["calls"] == 1 or st["calls"] % self.validate_every == 0):
+            self.check_input_flag()               # streaming: polled, not synchronised every frame
+        self.stream_live = True
+        return flow
+
+    def _stream_launch(self, x, st, arena, reuse):
+        """The launches of one streamed bin (pack input, 7 layers, flow head); toggles the phase."""
+        L = _lib.lib()
+        layers, net = self.layers, self.net
+        B, nb, H, W = x.shape
         lam, theta = st["lam"], st["theta"]
         desc = self._stream_desc(x, (_lib.STREAM_PHASE if st["phase"] else 0) | (_lib.REUSE_PACKED if reuse else 0))
         lp = (LayerPtrs * N_LAYERS)()
@@ -540,18 +567,28 @@ class WindowRunner:
             lp[i].w_rec = l.rec.weight.data_ptr() if l.recurrent else None
             lp[i].lam = lam[i].data_ptr()
             lp[i].theta = theta[i].data_ptr()
-        flow = torch.empty((1, B, 2, H, W), dtype=torch.float32, device=dev)
+        flow = torch.empty((1, B, 2, H, W), dtype=torch.float32, device=x.device)
         pw, pb = net.pred.conv2d.weight, net.pred.conv2d.bias
         _lib.check(L.snnflow_window_forward(ctypes.byref(desc), lp, pw.data_ptr(), None if pb is None else pb.data_ptr(), x.data_ptr(),
                                             None, arena.data_ptr(), flow.data_ptr(), 0, _lib.stream()), "snnflow_window_forward")
-        foff = L.snnflow_window_flags_offset(ctypes.byref(desc0), 0)
-        self.input_flag = arena[foff:foff + 4].view(torch.int32)
         st["phase"] = (st["phase"] + 1) & 1       # T = 1
-        st["calls"] = st.get("calls", 0) + 1
-        if self.validate_input and not torch.cuda.is_current_stream_capturing() and (st["calls"] == 1 or st["calls"] % self.validate_every == 0):
-            self.check_input_flag()               # streaming: polled, not synchronised every frame
-        self.stream_live = True
         return flow[0]
+
+    def _stream_capture(self, x, st, arena):
+        """Two CUDA graphs of one streamed bin: phase 0 and phase 1 (the slots the recurrent layers read / write alternate).
+        Capturing executes nothing: the arena's state and the phase are unchanged afterwards."""
+        sx = torch.empty_like(x)
+        p0 = st["phase"]
+        graphs, flows = {}, {}
+        torch.cuda.synchronize()
+        for ph in (p0, p0 ^ 1):
+            st["phase"] = ph
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                flows[ph] = self._stream_launch(sx, st, arena, True)
+            graphs[ph] = g
+        st["phase"] = p0
+        return dict(x=sx, graph=graphs, flow=flows)
 
     def stream_export(self):
         """The arena's state as the reference's list of 7 tensors [2,B,C,H,W] = stack([v, z])."""
@@ -625,6 +662,8 @@ class WindowRunner:
             warnings.warn("snnflow: this window runs on the per-step engine (shape / options / input encoding outside the "
                           "layer-major engine's envelope: C in {16, 32}, W <= 256, detached reset, count encoding)")
         fn = _LayerMajorWindowFn if use_lm else _WindowFn
+        if not torch.is_grad_enabled():      # Function.forward sees requires_grad flags, not the grad mode: nothing to save
+            params = [p if p is None else p.detach() for p in params]
         flow = fn.apply(self, cnt_window, *params)
         self.net._states = self.new_states
         return flow

@@ -126,13 +126,18 @@ class LIFFireNet(nn.Module):
         eval loop, eval_flow.py:220: one ``model()`` call per frame).  The call sequence, the arguments, the returned dict
         and the state plumbing are unchanged; what changes is ownership: the flow map and the tensors in ``_states`` returned
         by a graphed call are static buffers that the next graphed call overwrites (``.states``, which deep-clones, is safe
-        to keep).  At batch 1 a frame is launch-latency bound (7 cells + flow head, ~10 us of GPU
-        work behind ~0.5 ms of Python and launch overhead): the graph removes that overhead.  The replay ends with a copy of the
-        new state into the static buffers (16 B per neuron), so the mode pays at small batches, not at batch 16 / 256x256."""
+        to keep).  At batch 1 a frame is launch-latency bound: the graph removes the host overhead.  Where the streaming
+        mode applies (``stream_forward``: counts encoding, no residual) the graph replays the streamed bin - state inside the
+        engine, nothing copied; elsewhere it replays the 7 cells + flow head and ends with a copy of the new state into the
+        static buffers (16 B per neuron), which pays at small batches, not at batch 16 / 256x256."""
         object.__setattr__(self, "_graphs", {} if enabled else None)
         return self
 
     def _forward_graphed(self, x):
+        if self.stream_forward and self.encoding == "cnt" and self.num_bins == 2 and not self.residual:
+            flow = self._forward_streamed(x, graph=True)      # the streamed bin as a graph replay (engine.stream_forward)
+            if flow is not None:
+                return flow
         key = (tuple(x.shape), x.dtype, x.device)
         g = self._graphs.get(key)
         if g is None:
@@ -166,7 +171,7 @@ class LIFFireNet(nn.Module):
         self._states = list(g["states"])
         return g["flow"]
 
-    def _forward_streamed(self, x):
+    def _forward_streamed(self, x, graph=False):
         """Per-bin inference on the window engine with the state kept in the engine's layout between calls."""
         from .engine import WindowRunner
         r = self.__dict__.get("_window_runner")
@@ -182,7 +187,7 @@ class LIFFireNet(nn.Module):
             self._states      # another input shape: the streamed state becomes the list (and fails the shape check below, like
                               # the reference does when batch size / resolution change without reset_states())
         states = self.__dict__.get("_states_list")
-        flow = r.stream_forward(x, states)
+        flow = r.stream_forward(x, states, graph=graph)
         self.__dict__["_states_from_stream"] = False
         return flow
 

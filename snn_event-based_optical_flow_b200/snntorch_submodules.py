@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .spiking_submodules import _ConvLIFStep, _f32c, _workspace
+from .spiking_submodules import _ConvLIFStep, _f32c, _grad_arg, _workspace
 
 
 class _LeakyStep(torch.autograd.Function):
@@ -85,7 +85,7 @@ class Leaky(nn.Module):
         self.register_buffer("reset_mechanism_val", torch.tensor({"subtract": 0, "zero": 1}[reset_mechanism]))
 
     def forward(self, cur, mem):
-        return _LeakyStep.apply(cur, mem, self.beta, self.threshold, self.reset_mechanism == "subtract")
+        return _LeakyStep.apply(cur, mem, _grad_arg(self.beta), _grad_arg(self.threshold), self.reset_mechanism == "subtract")
 
 
 class _SNNtorchBase(nn.Module):
@@ -136,7 +136,7 @@ class _SNNtorchBase(nn.Module):
         state_in = None
         if self.recurrent and prev_spk is not None:
             state_in = torch.stack([torch.zeros_like(prev_spk), prev_spk])    # (v, z): v is multiplied by lam = 0
-        state, _ = _ConvLIFStep.apply(input_, state_in, self.ff.weight, self.rec.weight if self.recurrent else None,
+        state, _ = _ConvLIFStep.apply(input_, state_in, _grad_arg(self.ff.weight), _grad_arg(self.rec.weight) if self.recurrent else None,
                                       self._conv_leak, self._conv_thresh, None, True, True, 0, 10.0, packed)
         return state[0]
 

@@ -34,6 +34,12 @@ def _f32c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _grad_arg(t):
+    """A parameter as an autograd.Function argument: itself with autograd on, detached under no_grad (so that
+    ctx.needs_input_grad, which ignores the grad mode, is False and the forward kernels skip what only a backward needs)."""
+    return t if (t is None or torch.is_grad_enabled()) else t.detach()
+
+
 class _ConvLIFStep(torch.autograd.Function):
     """(x, prev_state, w_ff, w_rec, leak, thresh, residual) -> (state [2,B,C,H,W], out or None)."""
 
@@ -194,8 +200,11 @@ class _LIFBase(nn.Module):
         # tagged residual) carry the tag `_snnflow_exact16`; anything else takes the exact-fp32 CUDA-core path.
         exact16 = getattr(input_, "_snnflow_exact16", False)
         packed = self._packed_weights() if (self.use_tensor_cores and exact16) else None
+        # (_grad_arg: under no_grad the kernels must not save anything for a backward pass - Function.forward only sees
+        # the tensors' requires_grad flags, not the caller's grad mode)
         state, out = _ConvLIFStep.apply(
-            input_, prev_state, self.ff.weight, self.rec.weight if self.recurrent else None, self.leak, self.thresh,
+            input_, prev_state, _grad_arg(self.ff.weight), _grad_arg(self.rec.weight) if self.recurrent else None,
+            _grad_arg(self.leak), _grad_arg(self.thresh),
             res, self.hard_reset, self.detach, _lib.SURROGATE_ID[self.activation], self._act_width, packed)
         if out is None:
             out = state[1]

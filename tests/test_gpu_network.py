@@ -136,12 +136,15 @@ def test_graphed_per_bin_forward_equals_eager():
     assert out.requires_grad
 
 
-@pytest.mark.parametrize("kind,C,B,H,W", [("LIFFireNet", 32, 2, 24, 136), ("LIFFireFlowNet", 32, 3, 16, 128), ("LIFFireNet", 16, 1, 130, 64)])
-def test_streamed_per_bin_forward_equals_cells(kind, C, B, H, W):
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("kind,C,B,H,W", [("LIFFireNet", 32, 2, 24, 136), ("LIFFireFlowNet", 32, 3, 16, 128), ("LIFFireNet", 16, 1, 130, 64),
+                                          ("LIFFireNet", 32, 1, 8, 256)])
+def test_streamed_per_bin_forward_equals_cells(kind, C, B, H, W, graph):
     """Under no_grad the per-bin forward() runs on the window engine with the state kept in the engine's layout between calls
     (SNNFLOW_STATE_INTERNAL) and `_states` materialised lazily: flows, spikes and membranes must equal the per-bin cells bit for
     bit (2^-12-grid weights), through reads of .states, reset_states(), externally assigned states, a forward_window() call in
-    between and a switch back to autograd mode."""
+    between and a switch back to autograd mode.  graph=True: the same with model.graph_forward() - every streamed bin is a
+    CUDA-graph replay (one graph per phase of the recurrent layers' ping-pong slots).  W = 256: 128-pixel column tiles."""
     import snnflow_b200 as snnflow
     from oracle.lif import dyadic as snap
     torch.manual_seed(1)
@@ -168,9 +171,13 @@ def test_streamed_per_bin_forward_equals_cells(kind, C, B, H, W):
         s_ref = net.states
         # streamed
         net.stream_forward = True
+        if graph:
+            net.graph_forward()
         net.reset_states()
         got = [net(None, cnt[t])["flow"][0].clone() for t in range(3)]
         assert net._window_runner.stream_live, "the streamed path was not taken"
+        if graph:
+            assert net._window_runner._stream["graphs"] is not None, "the streamed bins were not replayed as graphs"
         mid = net.states                                   # lazily materialised, deep-cloned
         for a, b in zip(s_ref_3, mid):
             assert torch.equal(a, b)
