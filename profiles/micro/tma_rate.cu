@@ -22,22 +22,23 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 // per iteration: n_copies copies of copy_bytes each (lane l issues copies l, l+32, ...), slot = n_copies * copy_bytes
-__global__ void __launch_bounds__(32, 1) tma_rate_kernel(const unsigned char* src, size_t per_cta, uint32_t copy_bytes, int n_copies, int depth,
-                                                         long long* cycles) {
+// n_warps producer warps: warp w owns the iterations it = w, w + n_warps, ... (slot = it % depth)
+__global__ void __launch_bounds__(128, 1) tma_rate_kernel(const unsigned char* src, size_t per_cta, uint32_t copy_bytes, int n_copies, int depth,
+                                                          long long* cycles) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   unsigned char* ring = smem + 1024;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const uint32_t slot_bytes = copy_bytes * n_copies;
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
     for (int i = 0; i < depth; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
+  __syncthreads();
   const unsigned char* base = src + (size_t)blockIdx.x * per_cta;
   const int iters = (int)(per_cta / slot_bytes);
   const long long t0 = clock64();
-  for (int it = 0; it < iters; ++it) {
+  for (int it = warp; it < iters; it += n_warps) {
     const int st = it % depth, use = it / depth;
     if (lane == 0) {
       if (use > 0) while (!mbar_try_wait(&full[st], (use - 1) & 1)) {}
@@ -47,7 +48,8 @@ __global__ void __launch_bounds__(32, 1) tma_rate_kernel(const unsigned char* sr
     for (int c = lane; c < n_copies; c += 32)
       tma_bulk_g2s(ring + (size_t)st * slot_bytes + (size_t)c * copy_bytes, base + (size_t)it * slot_bytes + (size_t)c * copy_bytes, copy_bytes, &full[st]);
   }
-  if (lane == 0) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
     for (int it = iters > depth ? iters - depth : 0; it < iters; ++it) {
       const int st = it % depth, use = it / depth;
       while (!mbar_try_wait(&full[st], use & 1)) {}
@@ -68,20 +70,21 @@ int main() {
   cudaFuncSetAttribute(tma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   const size_t per_cta = (total / sms) & ~(size_t)((1 << 20) - 1);
   printf("SMs %d, %zu MiB per CTA\n", sms, per_cta >> 20);
-  printf("%10s %8s %6s %10s %12s %10s\n", "copy B", "copies", "depth", "ms", "GB/s", "B/clk/SM");
-  const uint32_t sizes[] = {1024, 2048, 2080, 4096, 8192, 16384, 32768};
+  printf("%10s %8s %6s %6s %10s %12s %10s\n", "copy B", "copies", "depth", "warps", "ms", "GB/s", "B/clk/SM");
+  const uint32_t sizes[] = {2080, 6240, 8192};
   for (uint32_t cb : sizes)
-    for (int nc : {1, 4, 12, 32}) {
-      for (int depth : {2, 3, 4, 6}) {
+    for (int nc : {1, 4, 12}) {
+      for (int depth : {4, 6})
+      for (int nw : {1, 2, 4}) {
         const size_t slot = (size_t)cb * nc;
         if (slot * depth > 200 * 1024 || slot < 8192) continue;
-        if ((per_cta % slot) != 0 && cb != 2080) continue;
+        if (slot * depth > 200 * 1024) continue;
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
         for (int rep = 0; rep < 2; ++rep) {
           cudaEventRecord(e0);
-          tma_rate_kernel<<<sms, 32, 1024 + slot * depth>>>(src, per_cta, cb, nc, depth, cyc);
+          tma_rate_kernel<<<sms, 32 * nw, 1024 + slot * depth>>>(src, per_cta, cb, nc, depth, cyc);
           cudaEventRecord(e1);
           cudaEventSynchronize(e1);
         }
@@ -93,7 +96,7 @@ int main() {
         for (int i = 0; i < sms; ++i) avg += (double)h[i] / sms;
         const size_t iters = per_cta / slot;
         const double bytes = (double)iters * slot * sms;
-        printf("%10u %8d %6d %10.3f %12.1f %10.2f\n", cb, nc, depth, ms, bytes / ms / 1e6, (double)iters * slot / avg);
+        printf("%10u %8d %6d %6d %10.3f %12.1f %10.2f\n", cb, nc, depth, nw, ms, bytes / ms / 1e6, (double)iters * slot / avg);
         if (cudaGetLastError() != cudaSuccess) { printf("error\n"); return 1; }
       }
     }

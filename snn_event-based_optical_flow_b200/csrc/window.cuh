@@ -51,6 +51,7 @@ struct WtArgs {
   int n_outer;   // sequence mode: B sequences (image = t*B + b) ; otherwise the number of images
   int T, B;
   int H, W, Wp, R, S, n_seg, N;   // R rows per tile, S pipeline stages, n_seg 128-pixel segments per row, N = MMA N
+  int n_prod;                     // TMA producer warps (1 or 2)
   int n_col, Wsm;                 // forward kernels: 128-pixel column tiles per row (1 = whole rows); pitch of a tile row in shared memory
   uint32_t sub_bytes, chunk_stride, stage_bytes;
   int hard_reset, surrogate;
@@ -124,6 +125,7 @@ struct WgArgs {
   unsigned long long g_img_stride, g_term_stride;
   float* part[2];   // per source: [wg_parts][9][cin_alloc][C]
   int n_img, H, W, Wp, R, S, C, P, n_cg, rpm, n_kyg, ksteps, x_rows;
+  int n_prod;       // TMA producer warps (1 or 2)
   int pair;         // both gradient rows of a two-row tile in ONE MMA (N = 4C); two partial blocks per CTA
   uint32_t stage_bytes, g_off;
   long long* dbg;   // optional [grid][8] cycle counters (SNNFLOW_WT_TIMING=1)

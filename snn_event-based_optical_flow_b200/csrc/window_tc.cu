@@ -28,8 +28,9 @@
 namespace snnflow {
 
 constexpr int WT_EPI_WARPS = 16;   // 4 TMEM lane quarters x 4 eight-channel chunks
-constexpr int WT_THREADS = (WT_EPI_WARPS + 3) * 32;   // + TMA producer, MMA issuer, tile-flag publisher (19 warps: still 5 per
-                                                      // scheduler at most, so the register cap per thread is unchanged)
+constexpr int WT_THREADS = (WT_EPI_WARPS + 4) * 32;   // + TMA producer, MMA issuer, tile-flag publisher, second TMA producer (20
+                                                      // warps = 5 per scheduler: the register cap per thread stays 96)
+constexpr int WT_PRODUCER2 = WT_EPI_WARPS + 3;        // warp index of the second producer
 constexpr int WT_PUB_RING = 8;
 constexpr int WT_MAX_STAGES = 4;
 constexpr int WT_HDR = 4096;   // barriers, TMEM slot, per-channel parameters, reduction scratch
@@ -164,10 +165,20 @@ __device__ __forceinline__ uint32_t wt_prologue(const WtArgs& a, const WtSmem& s
 }
 
 // ---- producer: one warp; lane 0 owns the barriers, lanes 0..n_chunks-1 issue one bulk copy each -------------------
+// Two producer warps share the stage ring: warp `pw` owns every second RING SLOT USE (slot use u = the u-th operand tile of
+// this CTA, in the order the MMA thread consumes them; stage u % S).  One warp spends ~570 cycles of latency per slot (barrier
+// wait -> expect_tx -> copies) plus ~50 per copy, which bounds a CTA at one tile per ~1200 cycles with 12 copies
+// (profiles/micro/tma_rate.cu: 10 -> 20 B/clk/SM with two issuing warps); the slots of two warps overlap.
+// Ownership by slot parity keeps the parity waits sound: with an even S a stage has ONE producer; with an odd S the owner of
+// use u issued use u - 2 before, which waited for the MMA to pass use u - 2 - S >= u - 2S, so the stage's barrier is never
+// more than one phase behind the waiter (ownership by ITEM breaks this when an item holds several slots: a waiter two
+// phases ahead passes a parity wait at once).
 template <bool SEQ>
-__device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
+__device__ void wt_producer(const WtArgs& a, const WtSmem& s, int pw = 0) {
   const int lane = threadIdx.x & 31;
-  if (lane == 0 && a.wblob_bytes) {
+  const int n_pw = (a.n_prod > 1 && a.aux == nullptr) ? 2 : 1;
+  if (pw >= n_pw) return;
+  if (pw == 0 && lane == 0 && a.wblob_bytes) {
     mbar_expect_tx(s.wbar, a.wblob_bytes + a.wblob2_bytes);
     tma_bulk_g2s(s.w, a.wblob, a.wblob_bytes, s.wbar);
     if (a.wblob2_bytes) tma_bulk_g2s(s.w + a.wblob_bytes, a.wblob2, a.wblob2_bytes, s.wbar);
@@ -195,6 +206,7 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
   long long t_wait = 0, t_flag = 0;
   const long long t_begin = clock64();
   const int n_bins = (!SEQ && a.n_bins > 1) ? a.n_bins : 1, dep_mask = a.bin_dep_mask;
+  int turn = 0;   // whose ring slot is next (round robin over all operand tiles of all items and bins)
   for (int bin = 0; bin < n_bins; ++bin) {
     it.init(a);
     const int n_src_b = (bin == 0 && a.n_src_bin0 > 0) ? a.n_src_bin0 : n_src;
@@ -202,6 +214,12 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
 #pragma unroll
       for (int si = 0; si < WT_MAX_SRC; ++si) {
         if (si >= n_src_b) break;
+        const bool mine = turn == pw;
+        if (++turn == n_pw) turn = 0;
+        if (!mine) {   // the other producer's ring slot
+          if (++st == (uint32_t)S) { st = 0; ++use; }
+          continue;
+        }
         if (bin > 0 && ((dep_mask >> si) & 1) && !(a.exp & 2)) {
           // rows y0-1 .. y0+R of this source were written by the epilogues of bin - 1 of this tile and of its two row
           // neighbours in the image (other CTAs): lanes 0..2 acquire one progress flag each
@@ -262,7 +280,7 @@ __device__ void wt_producer(const WtArgs& a, const WtSmem& s) {
       it.next();
     }
   }
-  if (a.dbg && lane == 0) {
+  if (a.dbg && lane == 0 && pw == 0) {
     a.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;   // producer: total
     a.dbg[blockIdx.x * 8 + 1] = t_wait + (t_flag << 32);   // producer: waiting for a free stage | for neighbour tiles (high word)
   }
@@ -417,6 +435,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_fwd_kernel(const __grid_cons
     __syncwarp();
   } else if (warp == WT_EPI_WARPS + 2) {
     if (!SEQ && lane == 0) wt_publisher(a, s);
+    __syncwarp();
+  } else if (warp == WT_PRODUCER2) {
+    wt_producer<SEQ>(a, s, 1);
     __syncwarp();
   } else {
     pdl_wait();
@@ -729,6 +750,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgrad_kernel(const __grid_co
   } else if (warp == WT_EPI_WARPS + 1) {
     if (elect_one()) wt_mma<false>(a, s, tmem_base);
     __syncwarp();
+  } else if (warp == WT_PRODUCER2) {
+    wt_producer<false>(a, s, 1);
+    __syncwarp();
   } else if (warp >= WT_EPI_WARPS + 2) {
     // (the publisher warp has no work in this kernel)
   } else {
@@ -830,6 +854,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_recbwd_kernel(const __grid_c
     __syncwarp();
   } else if (warp == WT_EPI_WARPS + 2) {
     if (MODE == 2 && lane == 0) wt_publisher(a, s);
+    __syncwarp();
+  } else if (warp == WT_PRODUCER2) {
+    if (a.has_gz) wt_producer<false>(a, s, 1);
     __syncwarp();
   } else {
     pdl_wait();
@@ -1023,6 +1050,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wt_dgpw_kernel(const __grid_con
     __syncwarp();
   } else if (warp == WT_EPI_WARPS + 1) {
     if (elect_one()) wt_mma<true>(a, s, tmem_base);
+    __syncwarp();
+  } else if (warp == WT_PRODUCER2) {
+    wt_producer<true>(a, s, 1);
     __syncwarp();
   } else if (warp >= WT_EPI_WARPS + 2) {
     // (the publisher warp has no work in this kernel)
@@ -1251,6 +1281,13 @@ static int wt_launch(K kernel, const void* key, const WtArgs& a_in, cudaStream_t
   a.l2_prefetch = l2_pf;
   static const int exp_bits = env_int("SNNFLOW_EXP", 0);   // experiment switches (see wt_fwd_kernel); 0 in production
   a.exp = exp_bits;
+  // Two producer warps where the producer is the bottleneck: the sequence-mode forward on column tiles (12 row copies per
+  // tile: eval at 256x256, 31.8k -> 34.7k frames/s).  Elsewhere one warp keeps up and the second one costs 1 - 10 % (measured
+  // per kernel at the training shape, profiles/r2_experiments.md).  SNNFLOW_PRODUCERS=1|2 forces either (read per launch).
+  {
+    const int forced = env_int("SNNFLOW_PRODUCERS", 0);
+    a.n_prod = forced ? forced : (a_in.n_prod > 0 ? a_in.n_prod : 1);
+  }
   if (a.n_col < 1) a.n_col = 1;
   a.Wsm = a.n_col > 1 ? 130 : a.Wp;   // shared-memory row pitch of an operand tile, in pixel slots
   const int n_tiles = a.n_outer * (a.H / a.R) * a.n_col;
@@ -1299,7 +1336,9 @@ static int wt_launch(K kernel, const void* key, const WtArgs& a_in, cudaStream_t
   return check_launch(what);
 }
 
-int launch_wt_fwd(const WtArgs& a, bool seq, cudaStream_t st, const char* prof_name, double bytes, double flops) {
+int launch_wt_fwd(const WtArgs& a_in, bool seq, cudaStream_t st, const char* prof_name, double bytes, double flops) {
+  WtArgs a = a_in;
+  a.n_prod = (seq && a.n_col > 1 && a.n_src == 1) ? 2 : 1;
   const int nseg = a.R * a.n_seg;
   prof_begin(prof_name, st, bytes, flops);
   const bool hard = a.hard_reset != 0;

@@ -28,7 +28,7 @@
 namespace snnflow {
 
 constexpr int WG_EPI_WARPS = 8;
-constexpr int WG_THREADS = (WG_EPI_WARPS + 2) * 32;
+constexpr int WG_THREADS = (WG_EPI_WARPS + 3) * 32;   // + two TMA producer warps (alternating items, window_tc.cu) and the MMA issuer
 constexpr int WG_MAX_STAGES = 4;
 constexpr int WG_HDR = 1024;
 
@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
   const uint32_t row_bytes = (uint32_t)a.Wp * 16, pitch = (uint32_t)a.P * 16;
   const int g_chunks = a.C >> 3;
 
-  if (warp == WG_EPI_WARPS) {
+  if (warp == WG_EPI_WARPS || warp == WG_EPI_WARPS + 2) {
+    const int pw = warp == WG_EPI_WARPS ? 0 : 1, n_pw = a.n_prod > 1 ? 2 : 1;
     // Producer warp.  A tile is (R+2)*n_cg input-row pieces + R*2*C/8 gradient-row pieces of one padded row each;
     // the lanes compute the piece addresses in parallel and each issues its own bulk copies (a single thread spends
     // ~100 issue cycles per copy next to four busy epilogue warps - measured, profiles/), lane 0 owns the barriers.
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
     const int n_xp = (a.R + 2) * a.n_cg, n_gp = a.R * 2 * g_chunks;
     long long t_wait = 0;
     const long long t_begin = clock64();
-    for (int k = 0; k < n_items; ++k) {
+    for (int k = pw; pw < n_pw && k < n_items; k += n_pw) {
       const int tile = blockIdx.x + k * gridDim.x;
       const int img = tile / tpi, y0 = (tile - img * tpi) * a.R;
       const uint32_t st = (uint32_t)k % (uint32_t)a.S, use = (uint32_t)k / (uint32_t)a.S;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
         tma_bulk_g2s(dst, src, row_bytes, &full[st]);
       }
     }
-    if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; a.dbg[blockIdx.x * 8 + 1] = t_wait; }
+    if (a.dbg && lane == 0 && pw == 0) { a.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; a.dbg[blockIdx.x * 8 + 1] = t_wait; }
     __syncwarp();
   } else if (warp == WG_EPI_WARPS + 1) {
     if (n_items > 0 && elect_one()) {
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wg_planes_kernel(const __grid_c
     pdl_wait();   // the partial buffers are read by the preceding layer's reduction
     mbar_wait(done, 0);
     tc_fence_after();
-    const int q = warp & 3, par = warp >> 2;
+    const int q = warp & 3, par = warp >> 2;   // (epilogue warps 0..7)
     const int M = q * 32 + lane;
     const int i = M / (a.n_cg * 8), cg = (M >> 3) % a.n_cg, c = M & 7;
     const int si = (cg < a.x_chunks[0]) ? 0 : 1;
@@ -313,6 +314,7 @@ int launch_wgrad_planes(WgArgs a, cudaStream_t st, double bytes, double flops) {
   }
   a.n_cg = p.n_cg; a.rpm = p.rpm; a.n_kyg = p.n_kyg; a.ksteps = p.ksteps; a.P = p.P; a.x_rows = p.x_rows;
   a.R = p.R; a.S = p.S; a.stage_bytes = p.stage_bytes; a.g_off = p.g_off; a.Wp = a.W + 2; a.pair = p.pair;
+  a.n_prod = wg_env_int("SNNFLOW_WG_PRODUCERS", wg_env_int("SNNFLOW_PRODUCERS", 2));
   const size_t smem = WG_HDR + (size_t)a.S * a.stage_bytes;
   static size_t attr = 0;
   if (smem > attr) {
