@@ -25,8 +25,9 @@ RULES = [
     (r"pred_fwd_planes", "win_pred_fwd"), (r"pack_planes_kernel", "win_pack"), (r"window_pack_weights", "win_pack_weights"),
     (r"encode_cnt_kernel", "encode_cnt"), (r"encode_voxel_kernel", "encode_voxel"), (r"encode_image_last", "encode_image_last"),
     (r"encode_image_acc", "encode_image_acc"), (r"iwe_splat_fwd_kernel", "iwe_splat_fwd"), (r"iwe_splat_bwd_kernel", "iwe_splat_bwd"),
-    (r"iwe_fix_to_float", "iwe_fix_to_float"), (r"flow_gather_fwd", "flow_gather_fwd"), (r"wl_gather", "loss_gather"),
-    (r"wl_smooth", "loss_smooth"), (r"wl_scatter", "loss_scatter"), (r"ld_scatter", "loader_scatter"),
+    (r"iwe_fix_to_float", "iwe_fix_to_float"), (r"flow_gather_fwd", "flow_gather_fwd"), (r"wl_gather_splat", "loss_gather_splat"),
+    (r"wl_splat_bwd", "loss_splat_bwd"), (r"wl_sums", "loss_sums"), (r"wl_gimg", "loss_gimg"), (r"wl_final", "loss_final"),
+    (r"wl_smooth", "loss_smooth"), (r"ld_scatter", "loader_scatter"),
     (r"convlif_fwd_tc_kernel", "convlif_fwd_tc"), (r"convlif_fwd_simt_kernel", "convlif_fwd"), (r"dp_allreduce", "dp_allreduce"),
     (r"opt_clip_adam", "opt_clip_adam"), (r"opt_sumsq", "opt_sumsq"),
 ]
