@@ -95,11 +95,15 @@ def test_layer_major_equals_per_bin(kind, C, H, W, nk):
 
 @pytest.mark.parametrize("env", [dict(SNNFLOW_FWD_PERSIST="1"), dict(SNNFLOW_RB_PERSIST="0"),
                                  dict(SNNFLOW_RB_FUSE="0"), dict(SNNFLOW_FWD_PERSIST="1", SNNFLOW_RB_PERSIST="0", SNNFLOW_RB_FUSE="0"),
-                                 dict(SNNFLOW_DP_AUX="1"), dict(SNNFLOW_RB_R="1")])
+                                 dict(SNNFLOW_DP_AUX="1"), dict(SNNFLOW_RB_R="1"),
+                                 # TMA producer warps (1 / 2 on every tensor-core kernel), unpaired weight gradient
+                                 dict(SNNFLOW_PRODUCERS="2"), dict(SNNFLOW_PRODUCERS="1", SNNFLOW_WG_PRODUCERS="1"), dict(SNNFLOW_WG_PAIR="0"),
+                                 dict(SNNFLOW_PRODUCERS="2", SNNFLOW_FWD_PERSIST="1")])
 @pytest.mark.parametrize("H,W,B", [(24, 136, 2), (130, 128, 3)])
 def test_execution_plan_switches_keep_results(env, H, W, B, monkeypatch):
     """Every execution plan of the recurrent layers - time-fused forward (SNNFLOW_FWD_PERSIST=1), per-bin BPTT launches
-    (SNNFLOW_RB_PERSIST=0), unfused data gradient (SNNFLOW_RB_FUSE=0), one-row BPTT tiles, staged epilogue inputs - gives
+    (SNNFLOW_RB_PERSIST=0), unfused data gradient (SNNFLOW_RB_FUSE=0), one-row BPTT tiles, staged epilogue inputs, one or two
+    TMA producer warps in every kernel (two of them also under the per-tile progress flags), unpaired weight gradient - gives
     the spikes / membranes / flows of the default plan bit for bit and the same gradients up to summation order.  (130 rows x
     3 images: more tiles than SMs, several tiles per CTA and bin - the per-tile progress flags across CTAs.)"""
     def run():
@@ -128,6 +132,32 @@ def test_execution_plan_switches_keep_results(env, H, W, B, monkeypatch):
     for n in g_a:
         scale = float(g_a[n].abs().max()) + 1e-12
         assert torch.allclose(g_a[n], g_b[n], rtol=1e-4, atol=1e-5 * scale), (n, float((g_a[n] - g_b[n]).abs().max()), scale)
+
+
+@pytest.mark.parametrize("env", [dict(SNNFLOW_COL_TILES="0"), dict(SNNFLOW_PRODUCERS="1"), dict(SNNFLOW_STREAM_STEP="0")])
+@pytest.mark.parametrize("kind", ["LIFFireNet", "LIFFireFlowNet"])
+def test_wide_row_plan_switches_keep_results(kind, env, monkeypatch):
+    """W = 256 (two 128-pixel MMA segments per row) under no_grad: whole-row tiles vs 128-pixel column tiles, one vs two producer
+    warps, sequence- vs step-mode kernel for the streamed bins - windows and streamed bins give the same flows and states bit for bit."""
+    def run():
+        net = make_net(kind, 32)
+        g = torch.Generator().manual_seed(21)
+        cnt = torch.poisson(torch.full((6, 2, 2, 20, 256), 0.25), generator=g).cuda()
+        with torch.no_grad():
+            net.reset_states()
+            runner_of(net, "layer_major")
+            out = list(net.forward_window(cnt[:4]))
+            out += [net(None, cnt[t])["flow"][0].clone() for t in range(4, 6)]      # streamed bins continue from the window
+        return out, [s.clone() for s in net._states]
+    f_a, s_a = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    f_b, s_b = run()
+    for t, (a, b) in enumerate(zip(f_a, f_b)):
+        assert torch.equal(a, b), f"bin {t}"
+    for i, (a, b) in enumerate(zip(s_a, s_b)):
+        assert torch.equal(a, b), f"layer {i}: states differ"
+    assert float(s_a[-1][1].mean()) > 0.01
 
 
 @pytest.mark.parametrize("kind,H,W", [("LIFFireFlowNet", 16, 130), ("LIFFireNet", 12, 64)])
