@@ -660,7 +660,8 @@ class WindowRunner:
             import warnings
             self._warned_fallback = True
             warnings.warn("snnflow: this window runs on the per-step engine (shape / options / input encoding outside the "
-                          "layer-major engine's envelope: C in {16, 32}, W <= 256, detached reset, count encoding)")
+                          "layer-major engine's envelope: C in {16, 32}; W <= 256 or a multiple of 128 without autograd, W <= 128 with it "
+                          "(256 for feed-forward networks); detached reset; count encoding)")
         fn = _LayerMajorWindowFn if use_lm else _WindowFn
         if not torch.is_grad_enabled():      # Function.forward sees requires_grad flags, not the grad mode: nothing to save
             params = [p if p is None else p.detach() for p in params]

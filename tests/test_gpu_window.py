@@ -160,12 +160,15 @@ def test_wide_row_plan_switches_keep_results(kind, env, monkeypatch):
     assert float(s_a[-1][1].mean()) > 0.01
 
 
-@pytest.mark.parametrize("kind,H,W", [("LIFFireFlowNet", 16, 130), ("LIFFireNet", 12, 64)])
+@pytest.mark.parametrize("kind,H,W", [("LIFFireFlowNet", 16, 130), ("LIFFireNet", 12, 64),
+                                      # rows of several 128-pixel segments: column tiles (forward only), up to DSEC's 480 x 640
+                                      ("LIFFireFlowNet", 8, 384), ("LIFFireNet", 6, 512), ("LIFFireNet", 480, 640)])
 def test_layer_major_eval_mode(kind, H, W):
     net = make_net(kind, 32)
     g = torch.Generator().manual_seed(6)
-    cnt = torch.poisson(torch.full((5, 2, 2, H, W), 0.25), generator=g).cuda()
+    cnt = torch.poisson(torch.full((5, 1 if H * W > 100000 else 2, 2, H, W), 0.25), generator=g).cuda()
     with torch.no_grad():
+        net.stream_forward = False      # the reference here = the per-bin cells
         net.reset_states()
         ref = torch.stack([net(None, cnt[t])["flow"][0] for t in range(5)])
         s_ref = [s.clone() for s in net._states]
