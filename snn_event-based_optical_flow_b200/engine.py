@@ -535,6 +535,11 @@ class WindowRunner:
         if not reuse:
             st["lam"], st["theta"] = _effective_params(self, layers)
             st["wkey"] = wkey
+        # the graphs bake device pointers in (weights, flow head): a parameter that moved to other storage drops them
+        pred = self.net.pred.conv2d
+        pkey = tuple(k[0] for k in wkey) + (pred.weight.data_ptr(), None if pred.bias is None else pred.bias.data_ptr())
+        if st.get("pkey") != pkey:
+            st["pkey"], st["graphs"] = pkey, None
         if graph and reuse and not torch.cuda.is_current_stream_capturing():
             gs = st.get("graphs")
             if gs is None:
